@@ -1,0 +1,204 @@
+/*
+ * pb2_engine.h -- C ABI of the B200 device-side DAG execution engine (layer L0).
+ *
+ * One engine instance drives one GPU.  It replaces, for tasks whose incarnation
+ * is GPU, the host-driven stream pipeline of the reference
+ *   parsec/mca/device/device_gpu.c:3375 (parsec_device_kernel_scheduler)
+ *   parsec/mca/device/device_gpu.c:2592 (parsec_device_progress_stream)
+ *   parsec/mca/device/device_gpu.c:2745/2873/2943 (kernel_push / _exec / _pop)
+ * and the host dependency release of
+ *   parsec/parsec.c:1609/1656/1749/1836 (update_deps_with_counter / _with_mask,
+ *   release_local_OUT_dependencies, release_dep_fct)
+ * by ONE persistent sm_100a kernel per "window" of the DAG: workers (CTAs) pop
+ * ready task descriptors from a device-resident ring, stage tiles in from
+ * host-pinned / peer memory, run the body, release successors with device
+ * atomics and append to a retire log.  No host round trip per task or per edge.
+ *
+ * Plain C, plain pointers and sizes; no torch / C++ types cross this boundary.
+ * The reference-shaped module API (parsec_device_module_t, parsec_gpu_task_t,
+ * kernel_scheduler, ...) is layered on top of this file in pb2_device.h.
+ */
+#ifndef PB2_ENGINE_H
+#define PB2_ENGINE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Error codes: same values as parsec/include/parsec/constants.h:14-26 */
+#define PB2_SUCCESS                   0
+#define PB2_ERROR                    -1
+#define PB2_ERR_OUT_OF_RESOURCE      -2
+#define PB2_ERR_NOT_FOUND            -3
+#define PB2_ERR_BAD_PARAM            -4
+#define PB2_ERR_EXISTS               -5
+#define PB2_ERR_NOT_IMPLEMENTED      -6
+#define PB2_ERR_NOT_SUPPORTED        -7
+#define PB2_ERR_VALUE_OUT_OF_BOUNDS  -8
+#define PB2_ERR_TRUNCATE             -9
+#define PB2_ERR_DEVICE              -10
+
+/* Flow access bits: same values as
+ * parsec/include/parsec/parsec_description_structures.h:62-67 */
+#define PB2_FLOW_ACCESS_NONE   0x00
+#define PB2_FLOW_ACCESS_READ   0x04
+#define PB2_FLOW_ACCESS_WRITE  0x08
+#define PB2_FLOW_ACCESS_RW     0x0c
+#define PB2_FLOW_PUSHOUT       0x40   /* engine-private: D2H the flow after the body (gpu_task->pushout bit) */
+
+/* Task bodies the persistent kernel can run in place (the "incarnations").
+ * HBM-bound bodies are coalesced 16-byte vector loops; GEMM is tcgen05. */
+enum pb2_body_e {
+    PB2_BODY_NOP        = 0,  /* empty body: tests/runtime/scheduling/ep.jdf:36-40                       */
+    PB2_BODY_FILL_I32   = 1,  /* flow0[:] = iparam[0]          (Ex05 TaskBcast: "*Aint = k", tile-wide)   */
+    PB2_BODY_CHECK_I32  = 2,  /* result = #elements of flow0 != iparam[0]; sum   (Ex05 TaskRecv)           */
+    PB2_BODY_INCR_I32   = 3,  /* flow0[:] += iparam[0]         (Ex02 "*Aint += 1"; rtt.jdf PING)           */
+    PB2_BODY_ADD_IOTA_I32 = 4,/* flow0[i] += i                 (tests/runtime/cuda/ping_kernel.cu:15)      */
+    PB2_BODY_SCALE_I32  = 5,  /* flow0[:] *= iparam[0]         (dtd_test_new_tile_cuda_kernels.cu:30)      */
+    PB2_BODY_IOTA_I32   = 6,  /* flow0[i] = i                  (dtd_test_new_tile_cuda_kernels.cu:17)      */
+    PB2_BODY_COPY       = 7,  /* flow1[:] = flow0[:]           (write_check.cu "A3=A2")                    */
+    PB2_BODY_FILL_F32   = 8,  /* flow0[:] = fparam                                                         */
+    PB2_BODY_CHECK_F32  = 9,  /* result = #elements of flow0 != fparam                                     */
+    PB2_BODY_INCR_F32   = 10, /* flow0[:] += fparam            (config 4: "T[:] += 1")                     */
+    PB2_BODY_AXPY_F32   = 11, /* flow1[:] += fparam*flow0[:]                                               */
+    PB2_BODY_MEMSET_U8  = 12, /* flow0 bytes = iparam[0]&0xff  (get_best_device_check.jdf:82 cudaMemset)   */
+    PB2_BODY_GEMM_BF16  = 16, /* flow2 (C, M x N row-major bf16) += flow0 (A, M x K row-major) *
+                               * flow1 (B, N x K row-major == K x N column-major), fp32 accumulate in TMEM
+                               * iparam[0]=M, iparam[1]=N, iparam[2]=K (each tile edge)                     */
+    PB2_BODY_MAX        = 32
+};
+
+#define PB2_MAX_FLOWS 4
+
+/* One task, 64 bytes, read-only on the device.  Mirrors what the reference keeps
+ * in parsec_task_t (parsec_internal.h:551-563: task_class, locals[], data[], priority)
+ * plus parsec_gpu_task_t (device_gpu.h:117-143: pushout, nb_flows, flow_info[]). */
+typedef struct pb2_task_s {
+    int32_t  dep_goal;      /* counter mode: #task-sourced input deps (parsec.c:1471-1556);
+                             * mask mode: tc->dependencies_goal (parsec.c:1656-1720)                        */
+    int32_t  succ_begin;    /* first entry in succ[]                                                         */
+    int32_t  succ_count;    /* number of out-edges (iterate_successors fan-out)                              */
+    int32_t  priority;      /* task priority (larger first when a priority lane is used)                      */
+    uint8_t  body;          /* enum pb2_body_e                                                                */
+    uint8_t  nb_flows;
+    uint8_t  flags;         /* PB2_TASK_* */
+    uint8_t  class_id;      /* task_class_id, for traces                                                      */
+    int32_t  tile[PB2_MAX_FLOWS];    /* tile ids, -1 = CTL / unused                                           */
+    uint8_t  access[PB2_MAX_FLOWS];  /* PB2_FLOW_ACCESS_* | PB2_FLOW_PUSHOUT                                  */
+    int32_t  iparam[3];     /* body immediates                                                               */
+    float    fparam;
+    int32_t  locals[2];     /* first two locals of the task (k, n / m, n) for traces                          */
+} pb2_task_t;                /* sizeof == 64 */
+
+#define PB2_TASK_DEPS_MASK  0x01   /* dep word is a bit mask (PARSEC_USE_DEPS_MASK) instead of a counter     */
+
+/* succ[] entry: low 27 bits = successor task id, high 5 bits = destination flow index */
+#define PB2_SUCC_MAKE(task, flow)  (((uint32_t)(flow) << 27) | (uint32_t)(task))
+#define PB2_SUCC_TASK(s)           ((int32_t)((s) & 0x07ffffffu))
+#define PB2_SUCC_FLOW(s)           ((int32_t)((s) >> 27))
+
+/* Device-side replica of one parsec_data_t on this GPU (data_internal.h:30-85), 32 bytes. */
+typedef struct pb2_tile_s {
+    void*    dev_ptr;   /* slot in this GPU's HBM (parsec_data_copy_t::device_private of the GPU copy)       */
+    void*    src_ptr;   /* device-visible address of the source/home copy: cudaHostRegister'ed host
+                         * memory (device_cuda_module.c:183-212) or a peer GPU's slot                        */
+    uint32_t bytes;     /* span to move: min(src span, dst span), device_gpu.c:1639-1644                     */
+    int32_t  state;     /* PB2_TILE_*                                                                        */
+    uint32_t version;   /* parsec_data_copy_t::version of the GPU copy                                       */
+    int32_t  src_kind;  /* PB2_SRC_HOST / PB2_SRC_PEER: which statistic the stage-in is charged to
+                         * (data_in_from_device[src], device_gpu.c:2133)                                    */
+} pb2_tile_t;
+
+#define PB2_SRC_HOST 0
+#define PB2_SRC_PEER 1
+
+#define PB2_TILE_INVALID   0   /* PARSEC_DATA_COHERENCY_INVALID, must be staged in before a READ             */
+#define PB2_TILE_STAGING   1   /* PARSEC_DATA_STATUS_UNDER_TRANSFER                                          */
+#define PB2_TILE_VALID     2   /* SHARED/OWNED + COMPLETE_TRANSFER                                           */
+
+typedef struct pb2_engine_params_s {
+    int32_t  workers_per_sm;   /* CTAs per SM for HBM-body windows (default 4)                               */
+    int32_t  threads;          /* threads per CTA for HBM-body windows (default 256)                         */
+    int32_t  max_workers;      /* 0 = all; 1 = single worker => deterministic FIFO order (tests)             */
+    int32_t  stage_mode;       /* 0 = LDG/STG vector copy, 1 = TMA bulk copy through shared memory            */
+    int32_t  queue_policy;     /* 0 = FIFO ring, 1 = successors-first (hot ring before FIFO ring)             */
+    int32_t  timeout_ms;       /* device-side watchdog: a window that makes no progress for this long aborts
+                                * (default 20000); a malformed DAG must never hang the GPU                   */
+    int32_t  reserved[2];
+} pb2_engine_params_t;
+
+typedef struct pb2_engine_info_s {
+    int32_t  cuda_device;
+    int32_t  sm_count;
+    int32_t  cc_major, cc_minor;
+    int32_t  nworkers;         /* grid size used for HBM-body windows                                        */
+    int32_t  nworkers_gemm;    /* grid size used for GEMM windows                                            */
+    int32_t  can_map_host;
+    int32_t  reserved;
+    uint64_t total_mem;
+    uint64_t free_mem;
+} pb2_engine_info_t;
+
+/* What one window run produced; device counters mirror device.h:165-171 statistics. */
+typedef struct pb2_window_stats_s {
+    uint64_t tasks_retired;
+    uint64_t bytes_h2d;        /* data_in_from_device[host]: bytes staged in by the kernel                   */
+    uint64_t bytes_d2d;        /* bytes staged in from a peer GPU slot                                       */
+    uint64_t bytes_d2h;        /* data_out_to_host: pushout bytes                                            */
+    uint64_t stage_ins;        /* nb_data_faults (count)                                                     */
+    uint64_t body_errors;      /* sum of CHECK body mismatches                                               */
+    float    kernel_ms;        /* CUDA-event time of the window kernel on its launch stream                  */
+    float    reset_ms;
+} pb2_window_stats_t;
+
+typedef struct pb2_engine_s pb2_engine_t;
+typedef struct pb2_window_s pb2_window_t;
+
+/* --- engine life cycle (parsec_cuda_module_init / _fini, device_cuda_module.c:406,660) --- */
+int  pb2_engine_create(pb2_engine_t** engine, int cuda_device, const pb2_engine_params_t* params);
+int  pb2_engine_destroy(pb2_engine_t* engine);
+int  pb2_engine_info(pb2_engine_t* engine, pb2_engine_info_t* info);
+const char* pb2_engine_last_error(pb2_engine_t* engine);
+
+/* --- device memory (parsec_device_memory_reserve device_gpu.c:866; cuda memory_allocate/free) --- */
+int  pb2_engine_malloc(pb2_engine_t* engine, size_t bytes, void** dev_ptr);
+int  pb2_engine_free(pb2_engine_t* engine, void* dev_ptr);
+/* cudaHostRegister(Portable|Mapped) of a whole collection + its device-visible alias
+ * (parsec_cuda_memory_register device_cuda_module.c:183-212). Idempotent per ptr. */
+int  pb2_engine_host_register(pb2_engine_t* engine, void* host_ptr, size_t bytes, void** dev_alias);
+int  pb2_engine_host_unregister(pb2_engine_t* engine, void* host_ptr);
+int  pb2_engine_memcpy_h2d(pb2_engine_t* engine, void* dev, const void* host, size_t bytes);
+int  pb2_engine_memcpy_d2h(pb2_engine_t* engine, void* host, const void* dev, size_t bytes);
+int  pb2_engine_synchronize(pb2_engine_t* engine);
+
+/* --- one window of the DAG ---
+ * tasks[ntasks], succ[nsucc] (CSR via succ_begin/succ_count), tiles[ntiles] and the ids of
+ * the tasks that are ready at submission (startup tasks, parsec.c:1724-1740).
+ * 'kind' selects the kernel instantiation: 0 = HBM bodies, 1 = tensor-core GEMM bodies. */
+int  pb2_window_create(pb2_engine_t* engine, pb2_window_t** window, int kind,
+                       const pb2_task_t* tasks, int32_t ntasks,
+                       const uint32_t* succ, int32_t nsucc,
+                       const pb2_tile_t* tiles, int32_t ntiles,
+                       const int32_t* ready, int32_t nready);
+int  pb2_window_destroy(pb2_window_t* window);
+/* (re)arm dependency words, ring, counters, tile states; then launch; both are stream-ordered */
+int  pb2_window_launch(pb2_window_t* window);
+/* block until the window retired all its tasks (or the watchdog tripped); fills stats */
+int  pb2_window_wait(pb2_window_t* window, pb2_window_stats_t* stats);
+/* per-task outputs, valid after wait; any pointer may be NULL */
+int  pb2_window_results(pb2_window_t* window,
+                        int32_t*  retire_order,  /* [ntasks] task ids in completion order               */
+                        uint32_t* start_seq,     /* [ntasks] global event number when the task started  */
+                        uint32_t* end_seq,       /* [ntasks] global event number when it retired        */
+                        uint32_t* seen_version,  /* [ntasks*PB2_MAX_FLOWS] tile version seen per flow   */
+                        uint64_t* result,        /* [ntasks] body result (CHECK: mismatches<<40 | sum)   */
+                        int32_t*  worker,        /* [ntasks] CTA that ran the task                       */
+                        pb2_tile_t* tiles_out);  /* [ntiles] final tile table (state, version)           */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PB2_ENGINE_H */

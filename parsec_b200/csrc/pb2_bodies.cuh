@@ -1,0 +1,206 @@
+// pb2_bodies.cuh -- HBM-bound task bodies run in place by the persistent engine kernel.
+//
+// Each body is executed by one whole CTA (the "worker") over one tile.  All payload
+// accesses are 16-byte, fully coalesced, L1-bypassing (ld.global.cg / st.global.cg) with
+// UNROLL independent requests in flight per thread; ragged tails (bytes % 16, bytes % 4)
+// are handled by scalar epilogues so empty and odd-sized tiles are legal.
+//
+// Reference bodies these restate (the reference ships them as toy <<<1,1>>> kernels or CPU code):
+//   examples/Ex05_Broadcast.jdf:33-39,53-57, examples/Ex02_Chain.jdf:44-50,
+//   tests/runtime/cuda/ping_kernel.cu:13-21,
+//   tests/dsl/dtd/dtd_test_new_tile_cuda_kernels.cu:14-56,
+//   contrib/build_with_parsec/write_check.cu:7-35,
+//   tests/runtime/cuda/get_best_device_check.jdf:82.
+#pragma once
+#include "pb2_dev_utils.cuh"
+
+namespace pb2 {
+
+constexpr int kUnroll = 4;
+
+// f(uint4& v, size_t first_elem_index) ; elements are 4-byte lanes x,y,z,w
+template <bool READ, bool WRITE, class F>
+__device__ __forceinline__ void cta_vec_loop(void* ptr, size_t bytes, F f) {
+    uint4* p = reinterpret_cast<uint4*>(ptr);
+    const size_t nvec = bytes >> 4;
+    const size_t tid = threadIdx.x, nt = blockDim.x;
+    const size_t per_iter = nt * kUnroll;
+    size_t base = 0;
+    for (; base + per_iter <= nvec; base += per_iter) {
+        uint4 v[kUnroll];
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) {
+            if (READ) v[j] = ld_stream(p + base + j * nt + tid);
+            else      v[j] = make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) {
+            f(v[j], (base + j * nt + tid) * 4);
+            if (WRITE) st_stream(p + base + j * nt + tid, v[j]);
+        }
+    }
+    for (size_t i = base + tid; i < nvec; i += nt) {
+        uint4 v = READ ? ld_stream(p + i) : make_uint4(0, 0, 0, 0);
+        f(v, i * 4);
+        if (WRITE) st_stream(p + i, v);
+    }
+    // scalar 4-byte tail (bytes not a multiple of 16)
+    const size_t nelem = bytes >> 2;
+    uint32_t* e = reinterpret_cast<uint32_t*>(ptr);
+    for (size_t i = (nvec << 2) + tid; i < nelem; i += nt) {
+        uint4 v = make_uint4(READ ? __ldcg(e + i) : 0u, 0, 0, 0);
+        // present the single element in lane x only; f must treat y,z,w as don't-care here
+        uint4 w = v;
+        f(w, i);
+        if (WRITE) __stcg(e + i, w.x);
+    }
+}
+
+// dst[:] = src[:] for arbitrary byte counts; both pointers 16-byte aligned (tile slots are).
+// 'remote' source = host-pinned or peer memory (stage-in), else local HBM.
+template <bool REMOTE_SRC>
+__device__ __forceinline__ void cta_copy(void* dst, const void* src, size_t bytes) {
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    const uint4* s = reinterpret_cast<const uint4*>(src);
+    const size_t nvec = bytes >> 4;
+    const size_t tid = threadIdx.x, nt = blockDim.x;
+    constexpr int U = REMOTE_SRC ? 8 : kUnroll;   // more bytes in flight over PCIe / NVLink
+    const size_t per_iter = nt * U;
+    size_t base = 0;
+    for (; base + per_iter <= nvec; base += per_iter) {
+        uint4 v[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j)
+            v[j] = REMOTE_SRC ? ld_remote(s + base + j * nt + tid) : ld_stream(s + base + j * nt + tid);
+#pragma unroll
+        for (int j = 0; j < U; ++j) st_stream(d + base + j * nt + tid, v[j]);
+    }
+    for (size_t i = base + tid; i < nvec; i += nt)
+        st_stream(d + i, REMOTE_SRC ? ld_remote(s + i) : ld_stream(s + i));
+    const unsigned char* sb = reinterpret_cast<const unsigned char*>(src);
+    unsigned char* db = reinterpret_cast<unsigned char*>(dst);
+    for (size_t i = (nvec << 4) + tid; i < bytes; i += nt) db[i] = sb[i];
+}
+
+// Block-wide sum of a 32-bit count; result valid in thread 0.  smem: >= 32 uint32.
+__device__ __forceinline__ uint32_t cta_reduce_sum(uint32_t v, uint32_t* smem) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) smem[warp] = v;
+    __syncthreads();
+    uint32_t r = 0;
+    if (warp == 0) {
+        r = (lane < (int)((blockDim.x + 31) >> 5)) ? smem[lane] : 0u;
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    }
+    __syncthreads();
+    return r;
+}
+
+struct BodyArgs {
+    void*    flow[4];     // device pointers of the flows' tiles
+    uint32_t bytes[4];
+    int32_t  iparam[3];
+    float    fparam;
+};
+
+// Returns the body result (only meaningful in thread 0): CHECK -> (mismatches << 32) | first element bits
+__device__ __forceinline__ uint64_t run_hbm_body(int body, const BodyArgs& a, uint32_t* red_smem) {
+    switch (body) {
+    case PB2_BODY_NOP:
+        return 0;
+    case PB2_BODY_FILL_I32: {
+        const uint32_t k = (uint32_t)a.iparam[0];
+        cta_vec_loop<false, true>(a.flow[0], a.bytes[0], [k](uint4& v, size_t) { v = make_uint4(k, k, k, k); });
+        return 0;
+    }
+    case PB2_BODY_FILL_F32: {
+        const uint32_t k = __float_as_uint(a.fparam);
+        cta_vec_loop<false, true>(a.flow[0], a.bytes[0], [k](uint4& v, size_t) { v = make_uint4(k, k, k, k); });
+        return 0;
+    }
+    case PB2_BODY_MEMSET_U8: {
+        const uint32_t b = (uint32_t)a.iparam[0] & 0xffu;
+        const uint32_t k = b | (b << 8) | (b << 16) | (b << 24);
+        cta_vec_loop<false, true>(a.flow[0], a.bytes[0] & ~3u, [k](uint4& v, size_t) { v = make_uint4(k, k, k, k); });
+        unsigned char* db = reinterpret_cast<unsigned char*>(a.flow[0]);
+        for (size_t i = (a.bytes[0] & ~3u) + threadIdx.x; i < a.bytes[0]; i += blockDim.x) db[i] = (unsigned char)b;
+        return 0;
+    }
+    case PB2_BODY_CHECK_I32:
+    case PB2_BODY_CHECK_F32: {
+        const uint32_t k = (body == PB2_BODY_CHECK_I32) ? (uint32_t)a.iparam[0] : __float_as_uint(a.fparam);
+        uint32_t bad = 0;
+        const size_t nvec_elems = ((size_t)a.bytes[0] >> 4) << 2;
+        cta_vec_loop<true, false>(a.flow[0], a.bytes[0], [&](uint4& v, size_t i) {
+            if (i < nvec_elems) bad += (v.x != k) + (v.y != k) + (v.z != k) + (v.w != k);
+            else                bad += (v.x != k);
+        });
+        const uint32_t total = cta_reduce_sum(bad, red_smem);
+        uint32_t first = 0;
+        if (threadIdx.x == 0 && a.bytes[0] >= 4) first = __ldcg(reinterpret_cast<const uint32_t*>(a.flow[0]));
+        return ((uint64_t)total << 32) | first;
+    }
+    case PB2_BODY_INCR_I32: {
+        const uint32_t k = (uint32_t)a.iparam[0];
+        cta_vec_loop<true, true>(a.flow[0], a.bytes[0], [k](uint4& v, size_t) { v.x += k; v.y += k; v.z += k; v.w += k; });
+        return 0;
+    }
+    case PB2_BODY_SCALE_I32: {
+        const int32_t k = a.iparam[0];
+        cta_vec_loop<true, true>(a.flow[0], a.bytes[0], [k](uint4& v, size_t) {
+            v.x = (uint32_t)((int32_t)v.x * k); v.y = (uint32_t)((int32_t)v.y * k);
+            v.z = (uint32_t)((int32_t)v.z * k); v.w = (uint32_t)((int32_t)v.w * k);
+        });
+        return 0;
+    }
+    case PB2_BODY_ADD_IOTA_I32: {
+        cta_vec_loop<true, true>(a.flow[0], a.bytes[0], [](uint4& v, size_t i) {
+            v.x += (uint32_t)i; v.y += (uint32_t)i + 1; v.z += (uint32_t)i + 2; v.w += (uint32_t)i + 3;
+        });
+        return 0;
+    }
+    case PB2_BODY_IOTA_I32: {
+        cta_vec_loop<false, true>(a.flow[0], a.bytes[0], [](uint4& v, size_t i) {
+            v = make_uint4((uint32_t)i, (uint32_t)i + 1, (uint32_t)i + 2, (uint32_t)i + 3);
+        });
+        return 0;
+    }
+    case PB2_BODY_INCR_F32: {
+        const float k = a.fparam;
+        cta_vec_loop<true, true>(a.flow[0], a.bytes[0], [k](uint4& v, size_t) {
+            v.x = __float_as_uint(__uint_as_float(v.x) + k); v.y = __float_as_uint(__uint_as_float(v.y) + k);
+            v.z = __float_as_uint(__uint_as_float(v.z) + k); v.w = __float_as_uint(__uint_as_float(v.w) + k);
+        });
+        return 0;
+    }
+    case PB2_BODY_COPY: {
+        const size_t n = a.bytes[0] < a.bytes[1] ? a.bytes[0] : a.bytes[1];
+        cta_copy<false>(a.flow[1], a.flow[0], n);
+        return 0;
+    }
+    case PB2_BODY_AXPY_F32: {
+        const float k = a.fparam;
+        const uint4* x = reinterpret_cast<const uint4*>(a.flow[0]);
+        const uint32_t* xe = reinterpret_cast<const uint32_t*>(a.flow[0]);
+        const size_t n = a.bytes[0] < a.bytes[1] ? a.bytes[0] : a.bytes[1];
+        const size_t nvec_elems = (n >> 4) << 2;
+        cta_vec_loop<true, true>(a.flow[1], n, [&](uint4& v, size_t i) {
+            if (i < nvec_elems) {
+                const uint4 xv = ld_stream(x + (i >> 2));
+                v.x = __float_as_uint(fmaf(k, __uint_as_float(xv.x), __uint_as_float(v.x)));
+                v.y = __float_as_uint(fmaf(k, __uint_as_float(xv.y), __uint_as_float(v.y)));
+                v.z = __float_as_uint(fmaf(k, __uint_as_float(xv.z), __uint_as_float(v.z)));
+                v.w = __float_as_uint(fmaf(k, __uint_as_float(xv.w), __uint_as_float(v.w)));
+            } else {
+                v.x = __float_as_uint(fmaf(k, __uint_as_float(__ldcg(xe + i)), __uint_as_float(v.x)));
+            }
+        });
+        return 0;
+    }
+    default:
+        return ~0ull;
+    }
+}
+
+}  // namespace pb2

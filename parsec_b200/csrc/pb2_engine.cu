@@ -1,0 +1,510 @@
+// pb2_engine.cu -- the persistent sm_100a DAG-execution kernel and its C ABI (include/pb2_engine.h).
+//
+// What it replaces in the reference (file:line in /root/reference):
+//   * the manager thread's check_in_deps / exec / get_data_out / complete_task loop,
+//     parsec/mca/device/device_gpu.c:3438-3562, and the 3-stage stream ring of
+//     parsec_device_progress_stream (:2592-2731): here every CTA is a worker that pops a task id
+//     from a device-resident ring, stages in, runs the body and retires the task itself;
+//   * parsec_device_data_stage_in / parsec_default_gpu_stage_in (:1799, :1623): the worker that first
+//     touches an INVALID tile moves it (host-pinned or peer memory -> its HBM slot) inside the kernel;
+//   * parsec_release_dep_fct -> parsec_release_local_OUT_dependencies -> update_deps_with_counter /
+//     _with_mask (parsec/parsec.c:1836, :1749, :1609, :1656): warp 0 of the worker walks the task's
+//     out-edges, one lane per edge, atomically decrements / ORs the successor's dependency word and
+//     pushes newly-ready successors into the ring with one warp-aggregated tail reservation;
+//   * parsec_device_kernel_pop / _epilog (:2943, :3179): pushout flows are copied back to their
+//     home location by the worker, versions are bumped for WRITE flows, the task id is appended to the
+//     retire log that the host drains in batches to run __parsec_complete_execution bookkeeping.
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <mutex>
+#include <map>
+
+#include "../../include/pb2_engine.h"
+#include "pb2_sched.cuh"
+#include "pb2_gemm.cuh"
+
+namespace pb2 {
+
+// ---------------------------------------------------------------------------------------------
+// reset: (re)arm one window.  dep words, ring, counters, tile table.
+// ---------------------------------------------------------------------------------------------
+__global__ void pb2_window_reset_kernel(WinDev w, const pb2_tile_t* tiles_init,
+                                        const int32_t* ready, int32_t nready) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t gsz = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = gid; i < (size_t)w.ntasks; i += gsz) {
+        const pb2_task_t& t = w.tasks[i];
+        // counter mode counts down from the goal (parsec.c:1625-1633); mask mode ORs up from 0 (:1693-1703)
+        w.dep[i] = (t.flags & PB2_TASK_DEPS_MASK) ? 0 : t.dep_goal;
+        w.start_seq[i] = 0; w.end_seq[i] = 0; w.result[i] = 0; w.worker[i] = -1; w.retire_log[i] = -1;
+        for (int f = 0; f < PB2_MAX_FLOWS; ++f) w.seen_version[i * PB2_MAX_FLOWS + f] = 0;
+    }
+    for (size_t i = gid; i <= (size_t)w.cap_mask; i += gsz)
+        w.ring[i] = (i < (size_t)nready) ? ready[i] : kEmpty;
+    for (size_t i = gid; i < (size_t)w.ntiles; i += gsz) w.tiles[i] = tiles_init[i];
+    if (gid == 0) {
+        w.ctl->head.v = 0; w.ctl->tail.v = (unsigned long long)nready; w.ctl->evt.v = 0;
+        w.ctl->retired.v = 0; w.ctl->done.v = (w.ntasks == 0) ? kDoneOK : 0;
+        w.ctl->progress_ns.v = globaltimer_ns();
+        w.ctl->bytes_h2d.v = 0; w.ctl->bytes_d2d.v = 0; w.ctl->bytes_d2h.v = 0;
+        w.ctl->stage_ins.v = 0; w.ctl->body_errors.v = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the persistent engine kernel, HBM-bound bodies
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512)
+pb2_engine_hbm_kernel(WinDev w) {
+    __shared__ pb2_task_t s_task;
+    __shared__ int32_t    s_id;
+    __shared__ int        s_decide;
+    __shared__ int        s_need;
+    __shared__ int        s_last;
+    __shared__ uint32_t   s_red[32];
+
+    for (;;) {
+        if (threadIdx.x == 0) {
+            const int32_t id = pop_task(w);
+            if (id != kEmpty) {
+                __threadfence();   // acquire side: order the tile reads below after the slot read
+                w.start_seq[id] = (uint32_t)atomicAdd(&w.ctl->evt.v, 1ull);
+                w.worker[id] = (int32_t)blockIdx.x;
+            }
+            s_id = id;
+        }
+        __syncthreads();
+        const int32_t id = s_id;
+        if (id == kEmpty) break;
+        if (threadIdx.x < 4) reinterpret_cast<uint4*>(&s_task)[threadIdx.x] =
+            __ldg(reinterpret_cast<const uint4*>(&w.tasks[id]) + threadIdx.x);
+        __syncthreads();
+        const pb2_task_t& t = s_task;
+
+        // ---- push: reserve + stage in (parsec_device_kernel_push) ----
+        // Thread 0 looks at the tile states once; the resulting mask is CTA-uniform (the states
+        // themselves may change under us, so they must not be re-read per thread around barriers).
+        if (threadIdx.x == 0) {
+            int need = 0;
+            for (int f = 0; f < t.nb_flows; ++f)
+                if (t.tile[f] >= 0 && (t.access[f] & PB2_FLOW_ACCESS_READ) &&
+                    ld_acquire_gpu(&w.tiles[t.tile[f]].state) != PB2_TILE_VALID) need |= 1 << f;
+            s_need = need;
+        }
+        __syncthreads();
+        const int need = s_need;
+        BodyArgs a;
+#pragma unroll
+        for (int f = 0; f < PB2_MAX_FLOWS; ++f) {
+            a.flow[f] = nullptr; a.bytes[f] = 0;
+            if (f < t.nb_flows && t.tile[f] >= 0) {
+                pb2_tile_t* tile = &w.tiles[t.tile[f]];
+                if ((need >> f) & 1) stage_in_flow(w, tile, t.access[f], &s_decide);
+                a.flow[f] = tile->dev_ptr; a.bytes[f] = tile->bytes;
+                if (threadIdx.x == 0)
+                    w.seen_version[id * PB2_MAX_FLOWS + f] = *reinterpret_cast<volatile uint32_t*>(&tile->version);
+            }
+        }
+        a.iparam[0] = t.iparam[0]; a.iparam[1] = t.iparam[1]; a.iparam[2] = t.iparam[2]; a.fparam = t.fparam;
+
+        // ---- exec: the body (parsec_device_kernel_exec -> submit) ----
+        const unsigned long long r = run_hbm_body(t.body, a, s_red);
+        __syncthreads();
+
+        // ---- pop: pushout + version/coherency epilog (parsec_device_kernel_pop / _epilog) ----
+#pragma unroll
+        for (int f = 0; f < PB2_MAX_FLOWS; ++f) {
+            if (f < t.nb_flows && t.tile[f] >= 0 && (t.access[f] & PB2_FLOW_PUSHOUT) &&
+                (t.access[f] & PB2_FLOW_ACCESS_WRITE)) {
+                pb2_tile_t* tile = &w.tiles[t.tile[f]];
+                cta_copy<false>(tile->src_ptr, tile->dev_ptr, tile->bytes);
+                if (threadIdx.x == 0) atomicAdd(&w.ctl->bytes_d2h.v, (unsigned long long)tile->bytes);
+            }
+        }
+        __syncthreads();
+
+        if (threadIdx.x < 32) {
+            __threadfence();   // release side: the body's stores (all threads, ordered by the barrier) become
+                               // visible before any successor can observe its dependency word / ring slot
+            if (threadIdx.x == 0) {
+                if (r == ~0ull) st_relaxed_gpu(reinterpret_cast<int32_t*>(&w.ctl->done.v), kDoneBadBody);
+                w.result[id] = r;
+                if ((t.body == PB2_BODY_CHECK_I32 || t.body == PB2_BODY_CHECK_F32) && (r >> 32))
+                    atomicAdd(&w.ctl->body_errors.v, r >> 32);
+                for (int f = 0; f < t.nb_flows; ++f) {
+                    if (t.tile[f] < 0 || !(t.access[f] & PB2_FLOW_ACCESS_WRITE)) continue;
+                    pb2_tile_t* tile = &w.tiles[t.tile[f]];
+                    // version = candidate->version + 1 for WRITE flows (device_gpu.c:2148-2152)
+                    *reinterpret_cast<volatile uint32_t*>(&tile->version) =
+                        *reinterpret_cast<volatile uint32_t*>(&tile->version) + 1;
+                    if (!(t.access[f] & PB2_FLOW_ACCESS_READ)) st_relaxed_gpu(&tile->state, PB2_TILE_VALID);
+                }
+                w.end_seq[id] = (uint32_t)atomicAdd(&w.ctl->evt.v, 1ull);
+                // the retire log is written before the out-edges are released, so that it is a linear
+                // extension of the DAG's partial order (a successor can only retire after us)
+                s_last = retire_task(w, id) ? 1 : 0;
+                __threadfence();
+            }
+            __syncwarp();
+            release_successors_warp(w, t);
+            if (threadIdx.x == 0 && s_last) {
+                __threadfence();
+                st_release_gpu(reinterpret_cast<int32_t*>(&w.ctl->done.v), kDoneOK);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace pb2
+
+// =============================================================================================
+// Host side
+// =============================================================================================
+using namespace pb2;
+
+struct pb2_engine_s {
+    int cuda_device = 0;
+    cudaDeviceProp prop{};
+    pb2_engine_params_t params{};
+    cudaStream_t stream = nullptr;
+    int nworkers = 0;
+    int nworkers_gemm = 0;
+    std::string last_error;
+    std::mutex mu;
+    std::map<void*, std::pair<size_t, void*>> registered;   // host ptr -> (bytes, device alias)
+};
+
+struct pb2_window_s {
+    pb2_engine_t* e = nullptr;
+    int kind = 0;
+    int32_t ntasks = 0, nsucc = 0, ntiles = 0, nready = 0;
+    WinDev d{};
+    pb2_task_t* d_tasks = nullptr;
+    uint32_t* d_succ = nullptr;
+    pb2_tile_t* d_tiles = nullptr;
+    pb2_tile_t* d_tiles_init = nullptr;
+    int32_t* d_ready = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    bool launched = false;
+    std::vector<void*> allocs;
+};
+
+#define PB2_CUDA(e, call)                                                                        \
+    do {                                                                                         \
+        cudaError_t err__ = (call);                                                              \
+        if (err__ != cudaSuccess) {                                                              \
+            char buf__[512];                                                                     \
+            snprintf(buf__, sizeof buf__, "%s:%d %s -> %s", __FILE__, __LINE__, #call,           \
+                     cudaGetErrorString(err__));                                                 \
+            if (e) (e)->last_error = buf__;                                                      \
+            fprintf(stderr, "pb2: CUDA error %s\n", buf__);                                      \
+            return PB2_ERR_DEVICE;                                                               \
+        }                                                                                        \
+    } while (0)
+
+template <class T>
+static int dev_alloc_copy(pb2_window_t* w, T** dptr, const T* host, size_t n) {
+    pb2_engine_t* e = w->e;
+    void* p = nullptr;
+    PB2_CUDA(e, cudaMalloc(&p, (n ? n : 1) * sizeof(T)));
+    w->allocs.push_back(p);
+    if (host && n) PB2_CUDA(e, cudaMemcpyAsync(p, host, n * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+    *dptr = reinterpret_cast<T*>(p);
+    return PB2_SUCCESS;
+}
+
+static int validate_window(pb2_engine_t* e, int kind, const pb2_task_t* tasks, int32_t ntasks,
+                           const uint32_t* succ, int32_t nsucc, int32_t ntiles,
+                           const int32_t* ready, int32_t nready) {
+    if (ntasks < 0 || nsucc < 0 || ntiles < 0 || nready < 0) return PB2_ERR_BAD_PARAM;
+    if (ntasks >= (1 << 27)) return PB2_ERR_VALUE_OUT_OF_BOUNDS;
+    for (int32_t i = 0; i < ntasks; ++i) {
+        const pb2_task_t& t = tasks[i];
+        if (t.nb_flows > PB2_MAX_FLOWS) { e->last_error = "task with more than PB2_MAX_FLOWS flows"; return PB2_ERR_BAD_PARAM; }
+        if (t.succ_count < 0 || t.succ_begin < 0 || (int64_t)t.succ_begin + t.succ_count > nsucc) {
+            e->last_error = "successor range out of bounds"; return PB2_ERR_VALUE_OUT_OF_BOUNDS; }
+        for (int f = 0; f < t.nb_flows; ++f)
+            if (t.tile[f] >= ntiles) { e->last_error = "tile id out of bounds"; return PB2_ERR_VALUE_OUT_OF_BOUNDS; }
+        const bool is_gemm = (t.body == PB2_BODY_GEMM_BF16);
+        if ((kind == 1) != is_gemm && t.body != PB2_BODY_NOP) {
+            e->last_error = "body kind does not match window kind"; return PB2_ERR_BAD_PARAM; }
+    }
+    for (int32_t i = 0; i < nsucc; ++i)
+        if (PB2_SUCC_TASK(succ[i]) >= ntasks) { e->last_error = "successor id out of bounds"; return PB2_ERR_VALUE_OUT_OF_BOUNDS; }
+    for (int32_t i = 0; i < nready; ++i)
+        if (ready[i] < 0 || ready[i] >= ntasks) { e->last_error = "ready id out of bounds"; return PB2_ERR_VALUE_OUT_OF_BOUNDS; }
+    return PB2_SUCCESS;
+}
+
+extern "C" {
+
+int pb2_engine_create(pb2_engine_t** engine, int cuda_device, const pb2_engine_params_t* params) {
+    if (!engine) return PB2_ERR_BAD_PARAM;
+    *engine = nullptr;
+    int ndev = 0;
+    cudaError_t err = cudaGetDeviceCount(&ndev);
+    if (err != cudaSuccess || ndev == 0) {
+        // The product path never falls back to a CPU implementation: no GPU => loud failure.
+        fprintf(stderr, "pb2_engine_create: no CUDA device (%s)\n", cudaGetErrorString(err));
+        return PB2_ERR_DEVICE;
+    }
+    if (cuda_device < 0 || cuda_device >= ndev) return PB2_ERR_BAD_PARAM;
+    pb2_engine_t* e = new pb2_engine_s();
+    e->cuda_device = cuda_device;
+    PB2_CUDA(e, cudaSetDevice(cuda_device));
+    PB2_CUDA(e, cudaGetDeviceProperties(&e->prop, cuda_device));
+    if (e->prop.major != 10) {
+        fprintf(stderr, "pb2_engine_create: device %d is sm_%d%d; this library only carries sm_100a code\n",
+                cuda_device, e->prop.major, e->prop.minor);
+        delete e;
+        return PB2_ERR_NOT_SUPPORTED;
+    }
+    pb2_engine_params_t p{};
+    if (params) p = *params;
+    if (p.workers_per_sm <= 0) p.workers_per_sm = 4;
+    if (p.threads <= 0) p.threads = 256;
+    if (p.threads > 512) p.threads = 512;
+    p.threads = (p.threads + 31) & ~31;
+    if (p.timeout_ms <= 0) p.timeout_ms = 20000;
+    e->params = p;
+    PB2_CUDA(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    int occ = 0;
+    PB2_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pb2_engine_hbm_kernel, p.threads, 0));
+    int per_sm = occ < p.workers_per_sm ? occ : p.workers_per_sm;
+    if (per_sm < 1) per_sm = 1;
+    e->nworkers = e->prop.multiProcessorCount * per_sm;
+    if (p.max_workers > 0 && p.max_workers < e->nworkers) e->nworkers = p.max_workers;
+    e->nworkers_gemm = pb2_gemm_nworkers(e->prop.multiProcessorCount);
+    if (p.max_workers > 0 && p.max_workers < e->nworkers_gemm) e->nworkers_gemm = p.max_workers;
+    *engine = e;
+    return PB2_SUCCESS;
+}
+
+int pb2_engine_destroy(pb2_engine_t* e) {
+    if (!e) return PB2_ERR_BAD_PARAM;
+    cudaSetDevice(e->cuda_device);
+    for (auto& kv : e->registered) cudaHostUnregister(kv.first);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return PB2_SUCCESS;
+}
+
+int pb2_engine_info(pb2_engine_t* e, pb2_engine_info_t* info) {
+    if (!e || !info) return PB2_ERR_BAD_PARAM;
+    memset(info, 0, sizeof *info);
+    info->cuda_device = e->cuda_device;
+    info->sm_count = e->prop.multiProcessorCount;
+    info->cc_major = e->prop.major; info->cc_minor = e->prop.minor;
+    info->nworkers = e->nworkers; info->nworkers_gemm = e->nworkers_gemm;
+    info->can_map_host = e->prop.canMapHostMemory;
+    size_t f = 0, t = 0;
+    PB2_CUDA(e, cudaSetDevice(e->cuda_device));
+    PB2_CUDA(e, cudaMemGetInfo(&f, &t));
+    info->total_mem = t; info->free_mem = f;
+    return PB2_SUCCESS;
+}
+
+const char* pb2_engine_last_error(pb2_engine_t* e) { return e ? e->last_error.c_str() : "null engine"; }
+
+int pb2_engine_malloc(pb2_engine_t* e, size_t bytes, void** dev_ptr) {
+    if (!e || !dev_ptr) return PB2_ERR_BAD_PARAM;
+    PB2_CUDA(e, cudaSetDevice(e->cuda_device));
+    cudaError_t err = cudaMalloc(dev_ptr, bytes ? bytes : 16);
+    if (err == cudaErrorMemoryAllocation) { cudaGetLastError(); *dev_ptr = nullptr; return PB2_ERR_OUT_OF_RESOURCE; }
+    PB2_CUDA(e, err);
+    return PB2_SUCCESS;
+}
+
+int pb2_engine_free(pb2_engine_t* e, void* dev_ptr) {
+    if (!e) return PB2_ERR_BAD_PARAM;
+    PB2_CUDA(e, cudaSetDevice(e->cuda_device));
+    PB2_CUDA(e, cudaFree(dev_ptr));
+    return PB2_SUCCESS;
+}
+
+int pb2_engine_host_register(pb2_engine_t* e, void* host_ptr, size_t bytes, void** dev_alias) {
+    if (!e || !host_ptr || !bytes) return PB2_ERR_BAD_PARAM;
+    std::lock_guard<std::mutex> lk(e->mu);
+    auto it = e->registered.find(host_ptr);
+    if (it != e->registered.end()) {   // idempotent, like dc->memory_registration_status
+        if (dev_alias) *dev_alias = it->second.second;
+        return PB2_SUCCESS;
+    }
+    PB2_CUDA(e, cudaSetDevice(e->cuda_device));
+    cudaError_t err = cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+    if (err == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); }   // e.g. torch pinned memory
+    else PB2_CUDA(e, err);
+    void* alias = nullptr;
+    PB2_CUDA(e, cudaHostGetDevicePointer(&alias, host_ptr, 0));
+    if (err != cudaErrorHostMemoryAlreadyRegistered) e->registered[host_ptr] = {bytes, alias};
+    if (dev_alias) *dev_alias = alias;
+    return PB2_SUCCESS;
+}
+
+int pb2_engine_host_unregister(pb2_engine_t* e, void* host_ptr) {
+    if (!e) return PB2_ERR_BAD_PARAM;
+    std::lock_guard<std::mutex> lk(e->mu);
+    auto it = e->registered.find(host_ptr);
+    if (it == e->registered.end()) return PB2_ERR_NOT_FOUND;
+    PB2_CUDA(e, cudaSetDevice(e->cuda_device));
+    PB2_CUDA(e, cudaHostUnregister(host_ptr));
+    e->registered.erase(it);
+    return PB2_SUCCESS;
+}
+
+int pb2_engine_memcpy_h2d(pb2_engine_t* e, void* dev, const void* host, size_t bytes) {
+    if (!e) return PB2_ERR_BAD_PARAM;
+    PB2_CUDA(e, cudaSetDevice(e->cuda_device));
+    PB2_CUDA(e, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, e->stream));
+    return PB2_SUCCESS;
+}
+
+int pb2_engine_memcpy_d2h(pb2_engine_t* e, void* host, const void* dev, size_t bytes) {
+    if (!e) return PB2_ERR_BAD_PARAM;
+    PB2_CUDA(e, cudaSetDevice(e->cuda_device));
+    PB2_CUDA(e, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, e->stream));
+    PB2_CUDA(e, cudaStreamSynchronize(e->stream));
+    return PB2_SUCCESS;
+}
+
+int pb2_engine_synchronize(pb2_engine_t* e) {
+    if (!e) return PB2_ERR_BAD_PARAM;
+    PB2_CUDA(e, cudaSetDevice(e->cuda_device));
+    PB2_CUDA(e, cudaStreamSynchronize(e->stream));
+    return PB2_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------------
+// windows
+// ---------------------------------------------------------------------------------------------
+int pb2_window_create(pb2_engine_t* e, pb2_window_t** window, int kind,
+                      const pb2_task_t* tasks, int32_t ntasks,
+                      const uint32_t* succ, int32_t nsucc,
+                      const pb2_tile_t* tiles, int32_t ntiles,
+                      const int32_t* ready, int32_t nready) {
+    if (!e || !window) return PB2_ERR_BAD_PARAM;
+    *window = nullptr;
+    if ((ntasks && !tasks) || (nsucc && !succ) || (ntiles && !tiles) || (nready && !ready)) return PB2_ERR_BAD_PARAM;
+    int rc = validate_window(e, kind, tasks, ntasks, succ, nsucc, ntiles, ready, nready);
+    if (rc != PB2_SUCCESS) return rc;
+    PB2_CUDA(e, cudaSetDevice(e->cuda_device));
+    pb2_window_t* w = new pb2_window_s();
+    w->e = e; w->kind = kind; w->ntasks = ntasks; w->nsucc = nsucc; w->ntiles = ntiles; w->nready = nready;
+#define TRY(x) do { rc = (x); if (rc != PB2_SUCCESS) { pb2_window_destroy(w); return rc; } } while (0)
+    TRY(dev_alloc_copy(w, &w->d_tasks, tasks, (size_t)ntasks));
+    TRY(dev_alloc_copy(w, &w->d_succ, succ, (size_t)nsucc));
+    TRY(dev_alloc_copy(w, &w->d_tiles_init, tiles, (size_t)ntiles));
+    TRY(dev_alloc_copy(w, &w->d_tiles, (const pb2_tile_t*)nullptr, (size_t)ntiles));
+    TRY(dev_alloc_copy(w, &w->d_ready, ready, (size_t)nready));
+    const int maxw = e->nworkers > e->nworkers_gemm ? e->nworkers : e->nworkers_gemm;
+    uint32_t cap = 1024;
+    while (cap < (uint32_t)ntasks + (uint32_t)maxw + 2u) cap <<= 1;   // every slot is used at most once per run
+    WinDev& d = w->d;
+    d.tasks = w->d_tasks; d.succ = w->d_succ; d.tiles = w->d_tiles;
+    TRY(dev_alloc_copy(w, &d.dep, (const int32_t*)nullptr, (size_t)ntasks));
+    TRY(dev_alloc_copy(w, &d.ring, (const int32_t*)nullptr, (size_t)cap));
+    TRY(dev_alloc_copy(w, &d.ctl, (const Ctl*)nullptr, 1));
+    TRY(dev_alloc_copy(w, &d.retire_log, (const int32_t*)nullptr, (size_t)ntasks));
+    TRY(dev_alloc_copy(w, &d.start_seq, (const uint32_t*)nullptr, (size_t)ntasks));
+    TRY(dev_alloc_copy(w, &d.end_seq, (const uint32_t*)nullptr, (size_t)ntasks));
+    TRY(dev_alloc_copy(w, &d.seen_version, (const uint32_t*)nullptr, (size_t)ntasks * PB2_MAX_FLOWS));
+    TRY(dev_alloc_copy(w, &d.result, (const unsigned long long*)nullptr, (size_t)ntasks));
+    TRY(dev_alloc_copy(w, &d.worker, (const int32_t*)nullptr, (size_t)ntasks));
+#undef TRY
+    d.cap_mask = cap - 1; d.ntasks = ntasks; d.ntiles = ntiles; d.stage_mode = e->params.stage_mode;
+    d.timeout_ns = (unsigned long long)e->params.timeout_ms * 1000000ull;
+    PB2_CUDA(e, cudaEventCreate(&w->ev0));
+    PB2_CUDA(e, cudaEventCreate(&w->ev1));
+    PB2_CUDA(e, cudaEventCreate(&w->ev2));
+    PB2_CUDA(e, cudaStreamSynchronize(e->stream));
+    *window = w;
+    return PB2_SUCCESS;
+}
+
+int pb2_window_destroy(pb2_window_t* w) {
+    if (!w) return PB2_ERR_BAD_PARAM;
+    cudaSetDevice(w->e->cuda_device);
+    if (w->launched) cudaStreamSynchronize(w->e->stream);
+    for (void* p : w->allocs) cudaFree(p);
+    if (w->ev0) cudaEventDestroy(w->ev0);
+    if (w->ev1) cudaEventDestroy(w->ev1);
+    if (w->ev2) cudaEventDestroy(w->ev2);
+    delete w;
+    return PB2_SUCCESS;
+}
+
+int pb2_window_launch(pb2_window_t* w) {
+    if (!w) return PB2_ERR_BAD_PARAM;
+    pb2_engine_t* e = w->e;
+    PB2_CUDA(e, cudaSetDevice(e->cuda_device));
+    PB2_CUDA(e, cudaEventRecord(w->ev0, e->stream));
+    {
+        const int threads = 256;
+        size_t n = (size_t)w->ntasks > (size_t)w->d.cap_mask + 1 ? (size_t)w->ntasks : (size_t)w->d.cap_mask + 1;
+        int blocks = (int)((n + threads - 1) / threads);
+        if (blocks > e->prop.multiProcessorCount * 8) blocks = e->prop.multiProcessorCount * 8;
+        if (blocks < 1) blocks = 1;
+        pb2_window_reset_kernel<<<blocks, threads, 0, e->stream>>>(w->d, w->d_tiles_init, w->d_ready, w->nready);
+        PB2_CUDA(e, cudaGetLastError());
+    }
+    PB2_CUDA(e, cudaEventRecord(w->ev1, e->stream));
+    if (w->ntasks > 0) {
+        if (w->kind == 0) {
+            pb2_engine_hbm_kernel<<<e->nworkers, e->params.threads, 0, e->stream>>>(w->d);
+            PB2_CUDA(e, cudaGetLastError());
+        } else {
+            int rc = pb2_gemm_launch(w->d, e->nworkers_gemm, e->stream);
+            if (rc != PB2_SUCCESS) { e->last_error = "gemm window launch failed"; return rc; }
+        }
+    }
+    PB2_CUDA(e, cudaEventRecord(w->ev2, e->stream));
+    w->launched = true;
+    return PB2_SUCCESS;
+}
+
+int pb2_window_wait(pb2_window_t* w, pb2_window_stats_t* stats) {
+    if (!w) return PB2_ERR_BAD_PARAM;
+    pb2_engine_t* e = w->e;
+    if (!w->launched) return PB2_ERR_BAD_PARAM;
+    PB2_CUDA(e, cudaSetDevice(e->cuda_device));
+    PB2_CUDA(e, cudaEventSynchronize(w->ev2));
+    Ctl c;
+    PB2_CUDA(e, cudaMemcpy(&c, w->d.ctl, sizeof c, cudaMemcpyDeviceToHost));
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->tasks_retired = c.retired.v;
+        stats->bytes_h2d = c.bytes_h2d.v; stats->bytes_d2d = c.bytes_d2d.v; stats->bytes_d2h = c.bytes_d2h.v;
+        stats->stage_ins = c.stage_ins.v; stats->body_errors = c.body_errors.v;
+        cudaEventElapsedTime(&stats->reset_ms, w->ev0, w->ev1);
+        cudaEventElapsedTime(&stats->kernel_ms, w->ev1, w->ev2);
+    }
+    const int32_t done = (int32_t)c.done.v;
+    if (done == kDoneTimeout) { e->last_error = "window watchdog: no task retired within timeout (malformed DAG?)"; return PB2_ERR_DEVICE; }
+    if (done == kDoneBadBody) { e->last_error = "window ran a task with an unknown body id"; return PB2_ERR_BAD_PARAM; }
+    if ((int64_t)c.retired.v != (int64_t)w->ntasks) { e->last_error = "window ended before all tasks retired"; return PB2_ERROR; }
+    return PB2_SUCCESS;
+}
+
+int pb2_window_results(pb2_window_t* w, int32_t* retire_order, uint32_t* start_seq, uint32_t* end_seq,
+                       uint32_t* seen_version, uint64_t* result, int32_t* worker, pb2_tile_t* tiles_out) {
+    if (!w) return PB2_ERR_BAD_PARAM;
+    pb2_engine_t* e = w->e;
+    PB2_CUDA(e, cudaSetDevice(e->cuda_device));
+    const size_t n = (size_t)w->ntasks;
+    if (retire_order && n) PB2_CUDA(e, cudaMemcpy(retire_order, w->d.retire_log, n * 4, cudaMemcpyDeviceToHost));
+    if (start_seq && n) PB2_CUDA(e, cudaMemcpy(start_seq, w->d.start_seq, n * 4, cudaMemcpyDeviceToHost));
+    if (end_seq && n) PB2_CUDA(e, cudaMemcpy(end_seq, w->d.end_seq, n * 4, cudaMemcpyDeviceToHost));
+    if (seen_version && n) PB2_CUDA(e, cudaMemcpy(seen_version, w->d.seen_version, n * 4 * PB2_MAX_FLOWS, cudaMemcpyDeviceToHost));
+    if (result && n) PB2_CUDA(e, cudaMemcpy(result, w->d.result, n * 8, cudaMemcpyDeviceToHost));
+    if (worker && n) PB2_CUDA(e, cudaMemcpy(worker, w->d.worker, n * 4, cudaMemcpyDeviceToHost));
+    if (tiles_out && w->ntiles) PB2_CUDA(e, cudaMemcpy(tiles_out, w->d_tiles, (size_t)w->ntiles * sizeof(pb2_tile_t), cudaMemcpyDeviceToHost));
+    return PB2_SUCCESS;
+}
+
+}  // extern "C"
