@@ -11,7 +11,7 @@ HDRS      := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) $(wildcard includ
 all: $(LIB) oracle
 
 $(LIB): $(CU_SRCS) $(CPP_SRCS) $(HDRS)
-	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CU_SRCS) $(CPP_SRCS) -Iinclude -lcuda 2> build_ptxas.log || (cat build_ptxas.log; exit 1)
+	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CU_SRCS) $(CPP_SRCS) -Iinclude 2> build_ptxas.log || (cat build_ptxas.log; exit 1)
 	@grep -E "error|warning" build_ptxas.log | grep -v "ptxas info" || true
 
 oracle:

@@ -56,30 +56,53 @@ __device__ __forceinline__ void cta_vec_loop(void* ptr, size_t bytes, F f) {
     }
 }
 
-// dst[:] = src[:] for arbitrary byte counts; both pointers 16-byte aligned (tile slots are).
+// dst[:] = src[:] for arbitrary byte counts and alignments.  Tile slots are 16-byte aligned; a
+// ragged collection in host memory (tile size not a multiple of 16) gives sources that are only
+// 4-byte (or 1-byte) aligned, handled by the narrower paths.
 // 'remote' source = host-pinned or peer memory (stage-in), else local HBM.
 template <bool REMOTE_SRC>
 __device__ __forceinline__ void cta_copy(void* dst, const void* src, size_t bytes) {
-    uint4* d = reinterpret_cast<uint4*>(dst);
-    const uint4* s = reinterpret_cast<const uint4*>(src);
-    const size_t nvec = bytes >> 4;
     const size_t tid = threadIdx.x, nt = blockDim.x;
-    constexpr int U = REMOTE_SRC ? 8 : kUnroll;   // more bytes in flight over PCIe / NVLink
-    const size_t per_iter = nt * U;
-    size_t base = 0;
-    for (; base + per_iter <= nvec; base += per_iter) {
-        uint4 v[U];
+    const uintptr_t al = reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src);
+    size_t done = 0;
+    if ((al & 15) == 0) {
+        uint4* d = reinterpret_cast<uint4*>(dst);
+        const uint4* s = reinterpret_cast<const uint4*>(src);
+        const size_t nvec = bytes >> 4;
+        constexpr int U = REMOTE_SRC ? 8 : kUnroll;   // more bytes in flight over PCIe / NVLink
+        const size_t per_iter = nt * U;
+        size_t base = 0;
+        for (; base + per_iter <= nvec; base += per_iter) {
+            uint4 v[U];
 #pragma unroll
-        for (int j = 0; j < U; ++j)
-            v[j] = REMOTE_SRC ? ld_remote(s + base + j * nt + tid) : ld_stream(s + base + j * nt + tid);
+            for (int j = 0; j < U; ++j)
+                v[j] = REMOTE_SRC ? ld_remote(s + base + j * nt + tid) : ld_stream(s + base + j * nt + tid);
 #pragma unroll
-        for (int j = 0; j < U; ++j) st_stream(d + base + j * nt + tid, v[j]);
+            for (int j = 0; j < U; ++j) st_stream(d + base + j * nt + tid, v[j]);
+        }
+        for (size_t i = base + tid; i < nvec; i += nt)
+            st_stream(d + i, REMOTE_SRC ? ld_remote(s + i) : ld_stream(s + i));
+        done = nvec << 4;
+    } else if ((al & 3) == 0) {
+        uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+        const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+        const size_t n = bytes >> 2;
+        constexpr int U = 8;
+        const size_t per_iter = nt * U;
+        size_t base = 0;
+        for (; base + per_iter <= n; base += per_iter) {
+            uint32_t v[U];
+#pragma unroll
+            for (int j = 0; j < U; ++j) v[j] = __ldcg(s + base + j * nt + tid);
+#pragma unroll
+            for (int j = 0; j < U; ++j) __stcg(d + base + j * nt + tid, v[j]);
+        }
+        for (size_t i = base + tid; i < n; i += nt) __stcg(d + i, __ldcg(s + i));
+        done = n << 2;
     }
-    for (size_t i = base + tid; i < nvec; i += nt)
-        st_stream(d + i, REMOTE_SRC ? ld_remote(s + i) : ld_stream(s + i));
     const unsigned char* sb = reinterpret_cast<const unsigned char*>(src);
     unsigned char* db = reinterpret_cast<unsigned char*>(dst);
-    for (size_t i = (nvec << 4) + tid; i < bytes; i += nt) db[i] = sb[i];
+    for (size_t i = done + tid; i < bytes; i += nt) db[i] = sb[i];
 }
 
 // Block-wide sum of a 32-bit count; result valid in thread 0.  smem: >= 32 uint32.

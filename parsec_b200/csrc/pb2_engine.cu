@@ -191,6 +191,7 @@ struct pb2_window_s {
     pb2_tile_t* d_tiles_init = nullptr;
     int32_t* d_ready = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    CUtensorMap* d_tmaps = nullptr;     // kind 1: one 2-D bf16 tensor map per tile (box 64 x 128, 128B swizzle)
     bool launched = false;
     std::vector<void*> allocs;
 };
@@ -240,6 +241,58 @@ static int validate_window(pb2_engine_t* e, int kind, const pb2_task_t* tasks, i
     for (int32_t i = 0; i < nready; ++i)
         if (ready[i] < 0 || ready[i] >= ntasks) { e->last_error = "ready id out of bounds"; return PB2_ERR_VALUE_OUT_OF_BOUNDS; }
     return PB2_SUCCESS;
+}
+
+
+// One tensor map per tile used as a GEMM operand: global tensor [rows][inner] bf16, row pitch inner*2 bytes,
+// box {64 (inner, 128 bytes), 128 rows}, 128-byte swizzle: exactly the K-major SWIZZLE_128B smem layout the
+// UMMA descriptors in pb2_gemm.cuh describe.  OOB rows/columns of ragged tiles are zero-filled by TMA.
+typedef CUresult (*pb2_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int build_tensor_maps(pb2_window_t* w, const pb2_task_t* tasks, int32_t ntasks,
+                             const pb2_tile_t* tiles, int32_t ntiles) {
+    pb2_engine_t* e = w->e;
+    static pb2_encode_tiled_fn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        PB2_CUDA(e, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) { e->last_error = "cuTensorMapEncodeTiled not available"; return PB2_ERR_NOT_SUPPORTED; }
+        encode = reinterpret_cast<pb2_encode_tiled_fn>(fn);
+    }
+    std::vector<int32_t> rows(ntiles, 0), inner(ntiles, 0);
+    for (int32_t i = 0; i < ntasks; ++i) {
+        const pb2_task_t& t = tasks[i];
+        if (t.body != PB2_BODY_GEMM_BF16) continue;
+        if (t.nb_flows < 3 || t.tile[0] < 0 || t.tile[1] < 0 || t.tile[2] < 0) { e->last_error = "GEMM task needs 3 data flows"; return PB2_ERR_BAD_PARAM; }
+        const int M = t.iparam[0], N = t.iparam[1], K = t.iparam[2];
+        if (M <= 0 || N <= 0 || K <= 0 || (K % 8) || (N % 8)) { e->last_error = "GEMM tile: need M,N,K > 0, K % 8 == 0, N % 8 == 0"; return PB2_ERR_NOT_SUPPORTED; }
+        const int32_t need[2][2] = {{M, K}, {N, K}};
+        for (int f = 0; f < 2; ++f) {
+            const int32_t id = t.tile[f];
+            if (rows[id] == 0) { rows[id] = need[f][0]; inner[id] = need[f][1]; }
+            else if (rows[id] != need[f][0] || inner[id] != need[f][1]) { e->last_error = "tile used with two different operand shapes"; return PB2_ERR_NOT_SUPPORTED; }
+            if ((uint64_t)need[f][0] * need[f][1] * 2 > tiles[id].bytes) { e->last_error = "GEMM operand larger than its tile"; return PB2_ERR_VALUE_OUT_OF_BOUNDS; }
+        }
+        if ((uint64_t)M * N * 2 > tiles[t.tile[2]].bytes) { e->last_error = "GEMM C larger than its tile"; return PB2_ERR_VALUE_OUT_OF_BOUNDS; }
+    }
+    std::vector<CUtensorMap> maps(ntiles ? ntiles : 1);
+    memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
+    for (int32_t i = 0; i < ntiles; ++i) {
+        if (rows[i] == 0) continue;
+        if ((uintptr_t)tiles[i].dev_ptr & 15) { e->last_error = "GEMM tile not 16-byte aligned"; return PB2_ERR_BAD_PARAM; }
+        cuuint64_t gdim[2] = {(cuuint64_t)inner[i], (cuuint64_t)rows[i]};
+        cuuint64_t gstride[1] = {(cuuint64_t)inner[i] * 2};
+        cuuint32_t box[2] = {64, 128};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, tiles[i].dev_ptr, gdim, gstride, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { e->last_error = "cuTensorMapEncodeTiled failed"; return PB2_ERR_DEVICE; }
+    }
+    return dev_alloc_copy(w, &w->d_tmaps, maps.data(), maps.size());
 }
 
 extern "C" {
@@ -402,6 +455,7 @@ int pb2_window_create(pb2_engine_t* e, pb2_window_t** window, int kind,
     TRY(dev_alloc_copy(w, &w->d_tiles_init, tiles, (size_t)ntiles));
     TRY(dev_alloc_copy(w, &w->d_tiles, (const pb2_tile_t*)nullptr, (size_t)ntiles));
     TRY(dev_alloc_copy(w, &w->d_ready, ready, (size_t)nready));
+    if (kind == 1) TRY(build_tensor_maps(w, tasks, ntasks, tiles, ntiles));
     const int maxw = e->nworkers > e->nworkers_gemm ? e->nworkers : e->nworkers_gemm;
     uint32_t cap = 1024;
     while (cap < (uint32_t)ntasks + (uint32_t)maxw + 2u) cap <<= 1;   // every slot is used at most once per run
@@ -459,7 +513,7 @@ int pb2_window_launch(pb2_window_t* w) {
             pb2_engine_hbm_kernel<<<e->nworkers, e->params.threads, 0, e->stream>>>(w->d);
             PB2_CUDA(e, cudaGetLastError());
         } else {
-            int rc = pb2_gemm_launch(w->d, e->nworkers_gemm, e->stream);
+            int rc = pb2_gemm_launch(w->d, w->d_tmaps, e->nworkers_gemm, e->stream);
             if (rc != PB2_SUCCESS) { e->last_error = "gemm window launch failed"; return rc; }
         }
     }
