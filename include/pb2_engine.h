@@ -65,6 +65,8 @@ enum pb2_body_e {
     PB2_BODY_INCR_F32   = 10, /* flow0[:] += fparam            (config 4: "T[:] += 1")                     */
     PB2_BODY_AXPY_F32   = 11, /* flow1[:] += fparam*flow0[:]                                               */
     PB2_BODY_MEMSET_U8  = 12, /* flow0 bytes = iparam[0]&0xff  (get_best_device_check.jdf:82 cudaMemset)   */
+    PB2_BODY_ADD_AT_I32 = 13, /* flow0[iparam[0]] += iparam[1]  (ping_kernel.cu:13-21 pong_kernel <<<1,1>>>,
+                               *                                 ptg_pingpong.jdf:72-73 TOKEN_CPU)          */
     PB2_BODY_GEMM_BF16  = 16, /* flow2 (C, M x N row-major bf16) += flow0 (A, M x K row-major) *
                                * flow1 (B, N x K row-major == K x N column-major), fp32 accumulate in TMEM
                                * iparam[0]=M, iparam[1]=N, iparam[2]=K (each tile edge)                     */

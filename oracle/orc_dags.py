@@ -1,9 +1,9 @@
-"""DAG builders for the reference's task graphs, as device windows (numpy, vectorised).
+"""ORACLE (test infrastructure): numpy restatement of the reference's task graphs as engine windows.
 
 Each builder restates the dataflow of one reference JDF / DTD program as the arrays the engine
 consumes: ``pb2_task_t[]``, CSR successor lists, the ids of the startup tasks and the tiles each flow
-touches.  The same graphs are produced by the C++ DSL shims (pb2_dsl.h); these numpy builders are
-the independent statement the tests cross-check them (and the oracle) against.
+touches.  The product path builds the same graphs with the C++ DSL shims (parsec_b200/csrc/pb2_dsl.cpp);
+the tests cross-check those, and the oracle's own DTD rule (orc_dtd.c), against these builders.
 
 Dependency-goal conventions follow what ``parsec-ptgpp`` emits:
   * PTG task classes use the *mask* mode (``PARSEC_USE_DEPS_MASK``): one bit per input flow that is
@@ -15,7 +15,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from . import _lib as L
+from . import orc as L
 
 
 @dataclass
@@ -233,3 +233,66 @@ def check_execution(dag, res):
     out["event_order_violations"] = int(np.sum(res["end_seq"][src].astype(np.int64) >= res["start_seq"][dst].astype(np.int64)))
     out["start_after_end"] = int(np.sum(res["start_seq"].astype(np.int64) >= res["end_seq"].astype(np.int64)))
     return out
+
+
+def ptg_pingpong(NB_TOKEN, tile_bytes=None):
+    """tests/runtime/cuda/ptg_pingpong.jdf:44-165: one token tile T hops INIT -> TOKEN_CPU(k) -> TOKEN_GPU(k,0)
+    -> TOKEN_GPU(k,1) -> TOKEN_CPU(k+1) ... -> CHECK.  INIT: tile[i] = i; TOKEN_CPU(k): tile[2k] += 2k,
+    tile[2k+1] += 2k+1; TOKEN_GPU(k,l): tile[2k+l] += 2k+l (ping_kernel.cu:15); CHECK: tile[i] == 3*i.
+    LOAD_DIST(r,d) anchors (READ D) are placement only and omitted on one device.
+    ids: INIT=0, CPU(k)=1+4k, CPUb(k)=2+4k (second element), GPU(k,0)=3+4k, GPU(k,1)=4+4k, CHECK=last.
+    TOKEN_CPU touches two elements: restated as two chained single-element updates."""
+    n = 1 + 4 * NB_TOKEN + 1
+    tb = tile_bytes or 2 * NB_TOKEN * 4
+    t = _new_tasks(n)
+    t["nb_flows"] = 1
+    t["flags"] = L.TASK_DEPS_MASK
+    t["tile"][:, 0] = 0
+    t["access"][:, 0] = L.ACCESS_RW
+    t["dep_goal"] = 0x1
+    t["body"] = L.BODY_ADD_AT_I32
+    t["body"][0] = L.BODY_IOTA_I32
+    t["access"][0, 0] = L.ACCESS_WRITE       # WRITE T <- NEW
+    t["dep_goal"][0] = 0
+    for k in range(NB_TOKEN):
+        base = 1 + 4 * k
+        for off, idx in ((0, 2 * k), (1, 2 * k + 1), (2, 2 * k), (3, 2 * k + 1)):
+            t["iparam"][base + off, 0] = idx
+            t["iparam"][base + off, 1] = idx
+            t["locals"][base + off, 0] = k
+            t["locals"][base + off, 1] = off
+        t["class_id"][base:base + 2] = 1
+        t["class_id"][base + 2:base + 4] = 2
+    t["body"][n - 1] = L.BODY_NOP                # CHECK runs on the host in the reference: the test checks
+    t["access"][n - 1, 0] = L.ACCESS_READ        # the tile the last GPU task pushed out (successor is a CPU task)
+    t["access"][n - 2, 0] = L.ACCESS_RW | L.FLOW_PUSHOUT
+    t["class_id"][n - 1] = 3
+    ids = np.arange(n - 1, dtype=np.int64)
+    begin, count, succ = _csr_from_edges(n, ids, ids + 1, np.zeros(n - 1, np.int64))
+    t["succ_begin"], t["succ_count"] = begin, count
+    return Dag(t, succ, np.array([0], np.int32), ntiles=1, tile_bytes=tb, name="ptg_pingpong",
+               meta={"NB_TOKEN": NB_TOKEN})
+
+
+def dtd_new_tile(nb_tiles, nb_elems):
+    """tests/dsl/dtd/dtd_test_new_tile.c + dtd_test_new_tile_cuda_kernels.cu:14-56: per NEW tile,
+    init (A[i] = i) -> multiply_by_two (A[i] *= 2) -> sum_add / check (A[i] == 2*i).  DTD counter mode:
+    each task depends on the previous writer of its tile."""
+    n = 3 * nb_tiles
+    t = _new_tasks(n)
+    tile = np.repeat(np.arange(nb_tiles, dtype=np.int32), 3)
+    stage = np.tile(np.arange(3, dtype=np.int32), nb_tiles)
+    t["nb_flows"] = 1
+    t["tile"][:, 0] = tile
+    t["body"] = np.choose(stage, [L.BODY_IOTA_I32, L.BODY_SCALE_I32, L.BODY_NOP])
+    t["iparam"][:, 0] = 2
+    t["access"][:, 0] = np.choose(stage, [L.ACCESS_WRITE, L.ACCESS_RW, L.ACCESS_READ | 0])
+    t["dep_goal"] = np.where(stage == 0, 0, 1)
+    t["locals"][:, 0] = tile
+    t["locals"][:, 1] = stage
+    ids = np.arange(n, dtype=np.int64)
+    m = stage < 2
+    begin, count, succ = _csr_from_edges(n, ids[m], ids[m] + 1, np.zeros(m.sum(), np.int64))
+    t["succ_begin"], t["succ_count"] = begin, count
+    return Dag(t, succ, ids[stage == 0].astype(np.int32), ntiles=nb_tiles, tile_bytes=nb_elems * 4,
+               name="dtd_new_tile", meta={"nb_tiles": nb_tiles, "nb_elems": nb_elems})

@@ -197,6 +197,13 @@ __device__ __forceinline__ uint64_t run_hbm_body(int body, const BodyArgs& a, ui
         });
         return 0;
     }
+    case PB2_BODY_ADD_AT_I32: {
+        if (threadIdx.x == 0 && (size_t)a.iparam[0] * 4 + 4 <= a.bytes[0] && a.iparam[0] >= 0) {
+            uint32_t* e = reinterpret_cast<uint32_t*>(a.flow[0]) + a.iparam[0];
+            __stcg(e, __ldcg(e) + (uint32_t)a.iparam[1]);
+        }
+        return 0;
+    }
     case PB2_BODY_COPY: {
         const size_t n = a.bytes[0] < a.bytes[1] ? a.bytes[0] : a.bytes[1];
         cta_copy<false>(a.flow[1], a.flow[0], n);

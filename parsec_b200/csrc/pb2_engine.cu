@@ -61,7 +61,7 @@ __global__ void pb2_window_reset_kernel(WinDev w, const pb2_tile_t* tiles_init,
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512)
 pb2_engine_hbm_kernel(WinDev w) {
-    __shared__ pb2_task_t s_task;
+    __shared__ __align__(16) pb2_task_t s_task;   // filled with four 16-byte loads
     __shared__ int32_t    s_id;
     __shared__ int        s_decide;
     __shared__ int        s_need;

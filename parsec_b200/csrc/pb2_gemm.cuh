@@ -110,6 +110,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 
 struct Shared {
+    alignas(16) pb2_task_t task;    // filled with four 16-byte loads
     uint64_t full[kStages];
     uint64_t empty[kStages];
     uint64_t tmem_full[2];
@@ -119,7 +120,6 @@ struct Shared {
     int32_t  need;
     int32_t  decide;
     int32_t  last;
-    pb2_task_t task;
 };
 
 }  // namespace gemm

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from parsec_b200 import _lib as L
-from parsec_b200 import dags
+from oracle import orc_dags as dags
 from parsec_b200.engine import Engine
 
 pytestmark = pytest.mark.gpu

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from parsec_b200 import _lib as L
-from parsec_b200 import dags
+from oracle import orc_dags as dags
 from parsec_b200.bf16 import bf16_bits_to_f32, f32_to_bf16_bits, round_to_bf16
 
 pytestmark = pytest.mark.gpu

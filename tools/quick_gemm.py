@@ -2,7 +2,8 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-from parsec_b200 import _lib as L, dags
+from parsec_b200 import _lib as L
+from oracle import orc_dags as dags
 from parsec_b200.engine import Engine
 
 NT = int(sys.argv[1]) if len(sys.argv) > 1 else 16
