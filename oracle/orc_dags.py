@@ -138,8 +138,10 @@ def rtt_chain(NT, FRAGS=1, tile_bytes=1024 * 1024 * 4, body=L.BODY_INCR_F32, pus
     k = np.repeat(np.arange(NT, dtype=np.int32), FRAGS)
     f = np.tile(np.arange(FRAGS, dtype=np.int32), NT)
     t["body"] = body
-    t["iparam"][:, 0] = 1
-    t["fparam"] = 1.0
+    if body == L.BODY_INCR_I32:
+        t["iparam"][:, 0] = 1
+    else:
+        t["fparam"] = 1.0
     t["nb_flows"] = 1
     t["flags"] = L.TASK_DEPS_MASK
     t["dep_goal"] = np.where(k == 0, 0, 0x1)

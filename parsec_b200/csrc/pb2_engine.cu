@@ -232,9 +232,9 @@ static int validate_window(pb2_engine_t* e, int kind, const pb2_task_t* tasks, i
             e->last_error = "successor range out of bounds"; return PB2_ERR_VALUE_OUT_OF_BOUNDS; }
         for (int f = 0; f < t.nb_flows; ++f)
             if (t.tile[f] >= ntiles) { e->last_error = "tile id out of bounds"; return PB2_ERR_VALUE_OUT_OF_BOUNDS; }
-        const bool is_gemm = (t.body == PB2_BODY_GEMM_BF16);
-        if ((kind == 1) != is_gemm && t.body != PB2_BODY_NOP) {
-            e->last_error = "body kind does not match window kind"; return PB2_ERR_BAD_PARAM; }
+        if (t.body >= PB2_BODY_MAX) { e->last_error = "unknown body id"; return PB2_ERR_BAD_PARAM; }
+        if (kind == 0 && t.body == PB2_BODY_GEMM_BF16) {
+            e->last_error = "GEMM body in an HBM-kind window (use kind 1)"; return PB2_ERR_BAD_PARAM; }
     }
     for (int32_t i = 0; i < nsucc; ++i)
         if (PB2_SUCC_TASK(succ[i]) >= ntasks) { e->last_error = "successor id out of bounds"; return PB2_ERR_VALUE_OUT_OF_BOUNDS; }

@@ -120,6 +120,7 @@ struct Shared {
     int32_t  need;
     int32_t  decide;
     int32_t  last;
+    uint32_t red[32];
 };
 
 }  // namespace gemm
@@ -194,6 +195,20 @@ pb2_engine_gemm_kernel(WinDev w, const CUtensorMap* __restrict__ tmaps) {
         }
 
         const bool is_gemm = (t.body == PB2_BODY_GEMM_BF16);
+        unsigned long long hbm_result = 0;
+        if (!is_gemm && t.body != PB2_BODY_NOP) {
+            // GEMM windows may carry a few HBM-bound tasks of the same DAG (e.g. a panel task): run them in place
+            BodyArgs a;
+            for (int f = 0; f < PB2_MAX_FLOWS; ++f) {
+                const bool has = f < t.nb_flows && t.tile[f] >= 0;
+                a.flow[f] = has ? w.tiles[t.tile[f]].dev_ptr : nullptr;
+                a.bytes[f] = has ? w.tiles[t.tile[f]].bytes : 0;
+            }
+            a.iparam[0] = t.iparam[0]; a.iparam[1] = t.iparam[1]; a.iparam[2] = t.iparam[2]; a.fparam = t.fparam;
+            hbm_result = run_hbm_body(t.body, a, sh.red);
+            fence_proxy_async();
+            __syncthreads();
+        }
         const int M = t.iparam[0], N = t.iparam[1], K = t.iparam[2];
         const int mblocks = is_gemm ? (M + BM - 1) / BM : 0;
         const int nblocks = is_gemm ? (N + BN - 1) / BN : 0;
@@ -301,7 +316,9 @@ pb2_engine_gemm_kernel(WinDev w, const CUtensorMap* __restrict__ tmaps) {
         if (threadIdx.x < 32) {
             __threadfence();
             if (threadIdx.x == 0) {
-                w.result[id] = 0;
+                w.result[id] = hbm_result;
+                if ((t.body == PB2_BODY_CHECK_I32 || t.body == PB2_BODY_CHECK_F32) && (hbm_result >> 32))
+                    atomicAdd(&w.ctl->body_errors.v, hbm_result >> 32);
                 for (int f = 0; f < t.nb_flows; ++f) {
                     if (t.tile[f] < 0 || !(t.access[f] & PB2_FLOW_ACCESS_WRITE)) continue;
                     pb2_tile_t* tile = &w.tiles[t.tile[f]];

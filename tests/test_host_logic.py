@@ -1,0 +1,306 @@
+"""Host-side logic (no GPU): C-ABI exports, 2D block-cyclic map, device heap, DTD / PTG graph construction and
+window building, device selection, coherency replay -- each checked against the oracle."""
+import ctypes as C
+import random
+import re
+
+import numpy as np
+import pytest
+
+from oracle import orc, orc_dags as dags
+from parsec_b200 import _lib as L
+from parsec_b200 import runtime as R
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads without a GPU and exports every symbol include/*.h declares."""
+    lib = L.load()
+    declared = set()
+    for hdr in ("include/pb2_engine.h", "include/pb2_parsec.h"):
+        txt = open(hdr).read()
+        declared |= set(re.findall(r"\b(pb2_[a-z0-9_]+)\s*\(", txt))
+    declared -= {"pb2_cpu_hook_t"}
+    assert declared, "no declarations found"
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    assert set(L.ENGINE_SYMBOLS) | set(R.PARSEC_SYMBOLS) >= declared
+
+
+def test_no_gpu_means_loud_failure():
+    """Without a CUDA device the product path refuses to run (no CPU fallback)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from parsec_b200.engine import Engine
+    with pytest.raises(L.Pb2Error) as ei:
+        Engine(0)
+    assert ei.value.rc == L.PB2_ERR_DEVICE
+    with pytest.raises(L.Pb2Error):
+        R.Context(cuda_devices=(0,), dry_run=False)
+
+
+@pytest.mark.parametrize("P,Q,kp,kq,ip,jq", [(1, 1, 1, 1, 0, 0), (2, 2, 1, 1, 0, 0), (2, 4, 1, 1, 1, 3), (2, 3, 2, 3, 0, 0), (3, 2, 2, 2, 1, 1)])
+def test_block_cyclic_matches_oracle(P, Q, kp, kq, ip, jq):
+    mb, nb, lm, ln = 4, 6, 4 * 11 + 1, 6 * 7
+    with R.Context(cuda_devices=(), dry_run=True) as ctx:
+        for rank in range(P * Q):
+            dc = ctx.block_cyclic(4, mb, nb, lm, ln, P=P, Q=Q, myrank=rank, kp=kp, kq=kq, ip=ip, jq=jq)
+            o = orc.twodbc(rank, mb, nb, lm, ln, P=P, Q=Q, kp=kp, kq=kq, ip=ip, jq=jq)
+            info = (C.c_int64 * 8)()
+            ctx.l.pb2_dc_info(dc, info)
+            assert list(info)[:7] == [o.lmt, o.lnt, o.mt, o.nt, o.nb_elem_r, o.nb_elem_c, o.nb_local_tiles]
+            for m in range(o.mt):
+                for n in range(o.nt):
+                    assert ctx.l.pb2_dc_rank_of(dc, m, n) == orc.lib().orc_twodbc_rank_of(C.byref(o), m, n)
+                    assert ctx.l.pb2_dc_position(dc, m, n) == orc.lib().orc_twodbc_position(C.byref(o), m, n)
+                    assert ctx.l.pb2_dc_data_key(dc, m, n) == orc.lib().orc_twodbc_key(C.byref(o), m, n)
+            ctx.l.pb2_data_collection_free(dc)
+
+
+def test_device_heap_matches_oracle():
+    """The module's slot allocator makes the same decisions as the reference's zone_malloc (via the oracle that
+    is itself pinned to the real zone_malloc.c build)."""
+    with R.Context(cuda_devices=(0,), dry_run=True, mca={"device_cuda_memory_number_of_blocks": 96, "device_cuda_memory_block_size": 512}) as ctx:
+        dev = ctx.devices[0]
+        O = orc.lib()
+        base = None
+        for seed in range(10):
+            rnd = random.Random(seed)
+            zo = O.orc_zone_init(96, 512)
+            live = []
+            for _ in range(1200):
+                if live and rnd.random() < 0.45:
+                    ptr, tid = live.pop(rnd.randrange(len(live)))
+                    assert ctx.l.pb2_device_zone_free(dev, ptr) == 0 and O.orc_zone_free(zo, tid) == 0
+                else:
+                    size = rnd.choice([1, 256, 512, 513, 1024, 2000, 4096, 8192])
+                    ptr, tid = ctx.l.pb2_device_zone_malloc(dev, size), O.orc_zone_malloc(zo, size)
+                    assert (ptr is None) == (tid < 0)
+                    if ptr is not None:
+                        if base is None:
+                            base = ptr - tid * 512
+                        assert (ptr - base) // 512 == tid
+                        live.append((ptr, tid))
+                assert ctx.l.pb2_device_zone_in_use(dev) == O.orc_zone_in_use(zo)
+            for ptr, tid in live:
+                ctx.l.pb2_device_zone_free(dev, ptr)
+            assert ctx.l.pb2_device_zone_in_use(dev) == 0
+            assert ctx.l.pb2_device_zone_free(dev, base) == L.PB2_ERR_EXISTS      # double free is reported
+            O.orc_zone_fini(zo)
+
+
+def _window_equal(win, dag):
+    """The exported window, with tasks mapped back to taskpool order, equals the oracle's graph."""
+    ids = win["task_ids"]
+    n = len(ids)
+    assert n == dag.ntasks and sorted(ids.tolist()) == list(range(n))
+    inv = np.empty(n, np.int64); inv[np.arange(n)] = ids          # window index -> pool id
+    for fld in ("body", "nb_flows", "flags", "dep_goal", "priority"):
+        assert np.array_equal(win["tasks"][fld], dag.tasks[fld][ids]), fld
+    assert np.array_equal(win["tasks"]["iparam"], dag.tasks["iparam"][ids])
+    assert np.array_equal(win["tasks"]["access"], dag.tasks["access"][ids])
+    cnt = win["tasks"]["succ_count"].astype(np.int64)
+    src = np.repeat(ids.astype(np.int64), cnt)
+    dst = ids[(win["succ"] & np.uint32(0x07FFFFFF)).astype(np.int64)].astype(np.int64)
+    fl = (win["succ"] >> np.uint32(27)).astype(np.int64)
+    es, ed, ef = dag.edges()
+    assert sorted(zip(src.tolist(), dst.tolist(), fl.tolist())) == sorted(zip(es.tolist(), ed.tolist(), ef.tolist()))
+    assert sorted(ids[win["ready"]].tolist()) == sorted(dag.ready.tolist())
+
+
+def test_ptg_ex05_window_equals_oracle_graph():
+    K, NB, tb = 12, 6, 1024
+    dag = dags.ex05_broadcast(K, NB, tb)
+    host = np.zeros(K * tb // 4, np.int32)
+    with R.Context(cuda_devices=(0,), dry_run=True) as ctx:
+        dc = ctx.block_cyclic(4, tb // 4, 1, K * tb // 4, 1, mat=host)          # K tiles of tb bytes, 1-D
+        tp = C.c_void_p(ctx.l.pb2_ptg_ex05_broadcast_new(ctx.h, dc, K, NB))
+        win = ctx.export_window(tp, ctx.devices[0])
+        _window_equal(win, dag)
+        # tiles: TaskBcast(k) and its receivers share tile k, all INVALID with the host alias as source
+        assert len(win["tiles"]) == K and np.all(win["tiles"]["state"] == L.TILE_INVALID)
+        assert np.all(win["tiles"]["bytes"] == tb)
+        t = win["tasks"]
+        for i in range(len(t)):
+            k = t["iparam"][i, 0]
+            assert win["tiles"]["src_ptr"][t["tile"][i, 0]] == host.ctypes.data + k * tb
+
+
+def test_ptg_chain_rtt_ep_windows_equal_oracle_graphs():
+    with R.Context(cuda_devices=(0,), dry_run=True) as ctx:
+        tp = C.c_void_p(ctx.l.pb2_ptg_ex02_chain_new(ctx.h, 25))
+        _window_equal(ctx.export_window(tp, ctx.devices[0]), dags.ex02_chain(25))
+    with R.Context(cuda_devices=(0,), dry_run=True) as ctx:
+        host = np.zeros(3 * 4 * 16, np.float32)
+        dc = ctx.block_cyclic(4, 4, 4, 4 * 3, 4 * 4, P=1, Q=1, mat=host)        # FRAGS x WS tiles of 4x4 floats
+        tp = C.c_void_p(ctx.l.pb2_ptg_rtt_new(ctx.h, dc, 9, 3, 4))
+        _window_equal(ctx.export_window(tp, ctx.devices[0]), dags.rtt_chain(9, 3, 64))
+    with R.Context(cuda_devices=(0,), dry_run=True) as ctx:
+        tp = C.c_void_p(ctx.l.pb2_ptg_ep_new(ctx.h, None, 16, 4))
+        _window_equal(ctx.export_window(tp, ctx.devices[0]), dags.ep(16, 4))
+
+
+def test_dtd_gemm_window_equals_oracle_graph_and_rule():
+    NT, T = 3, 64
+    dag = dags.dtd_gemm(NT, T)
+    with R.Context(cuda_devices=(0,), dry_run=True) as ctx:
+        mats = [np.zeros(NT * NT * T * T, np.uint16) for _ in range(3)]
+        dcs = [ctx.block_cyclic(2, T, T, NT * T, NT * T, mat=m) for m in mats]
+        tp = C.c_void_p(ctx.l.pb2_dtd_taskpool_new(ctx.h))
+        ops = np.array([R.INPUT, R.INPUT, R.INOUT | R.AFFINITY], np.int32)
+        tc = C.c_void_p(ctx.l.pb2_dtd_create_task_class(tp, b"GEMM", 3, ops.ctypes.data_as(C.c_void_p)))
+        assert ctx.l.pb2_dtd_task_class_add_chore(tp, tc, R.DEV_CUDA, L.BODY_GEMM_BF16, None) == 0
+        dims = np.array([T, T, T], np.int32)
+        for i in range(NT):
+            for j in range(NT):
+                for k in range(NT):
+                    tiles = (C.c_void_p * 3)(ctx.l.pb2_dtd_tile_of(tp, dcs[0], ctx.l.pb2_dc_data_key(dcs[0], i, k)),
+                                             ctx.l.pb2_dtd_tile_of(tp, dcs[1], ctx.l.pb2_dc_data_key(dcs[1], k, j)),
+                                             ctx.l.pb2_dtd_tile_of(tp, dcs[2], ctx.l.pb2_dc_data_key(dcs[2], i, j)))
+                    fo = np.array([R.INPUT, R.INPUT, (R.INOUT | R.PUSHOUT) if k == NT - 1 else R.INOUT], np.int32)
+                    tid = ctx.l.pb2_dtd_insert_task_with_task_class(tp, tc, NT ** 3 - i * NT + j, R.DEV_CUDA, tiles,
+                                                                    fo.ctypes.data_as(C.c_void_p), dims.ctypes.data_as(C.c_void_p), 0.0)
+                    assert tid == (i * NT + j) * NT + k
+        win = ctx.export_window(tp, ctx.devices[0])
+        # tile numbering differs (first-touch order); compare everything else, then the tile structure
+        ids = win["task_ids"]
+        for fld in ("body", "nb_flows", "flags", "dep_goal", "priority"):
+            assert np.array_equal(win["tasks"][fld], dag.tasks[fld][ids]), fld
+        assert np.array_equal(win["tasks"]["access"], dag.tasks["access"][ids])
+        cnt = win["tasks"]["succ_count"].astype(np.int64)
+        src = np.repeat(ids.astype(np.int64), cnt)
+        dst = ids[(win["succ"] & np.uint32(0x07FFFFFF)).astype(np.int64)]
+        es, ed, _ = dag.edges()
+        assert sorted(zip(src.tolist(), dst.tolist())) == sorted(zip(es.tolist(), ed.tolist()))
+        # same tile sharing pattern: a bijection between window tile ids and oracle tile ids
+        m = {}
+        for wi, pid in enumerate(ids):
+            for f in range(3):
+                a, b = int(win["tasks"]["tile"][wi, f]), int(dag.tasks["tile"][pid, f])
+                assert m.setdefault(a, b) == b
+        assert len(set(m.values())) == len(m) == 3 * NT * NT
+
+
+def test_dtd_rule_matches_oracle_on_random_programs():
+    """Random insert_task programs: the front end builds exactly the edges of the oracle's DTD rule."""
+    rnd = random.Random(7)
+    for trial in range(20):
+        ntiles, ntasks = 5, 40
+        with R.Context(cuda_devices=(0,), dry_run=True) as ctx:
+            tp = C.c_void_p(ctx.l.pb2_dtd_taskpool_new(ctx.h))
+            tiles = [C.c_void_p(ctx.l.pb2_dtd_tile_new(tp, 64)) for _ in range(ntiles)]
+            ops3 = np.array([R.INOUT, R.INOUT, R.INOUT], np.int32)
+            tcs = {n: C.c_void_p(ctx.l.pb2_dtd_create_task_class(tp, b"t", n, ops3.ctypes.data_as(C.c_void_p))) for n in (1, 2, 3)}
+            for tc in tcs.values():
+                ctx.l.pb2_dtd_task_class_add_chore(tp, tc, R.DEV_CUDA, L.BODY_NOP, None)
+            nbf, ft, fo = np.zeros(ntasks, np.int32), np.full((ntasks, 4), -1, np.int32), np.zeros((ntasks, 4), np.int32)
+            for t in range(ntasks):
+                nf = rnd.choice([1, 2, 3])
+                sel = rnd.sample(range(ntiles), nf)
+                kinds = [rnd.choice([orc.DTD_INPUT, orc.DTD_INPUT, orc.DTD_INOUT, orc.DTD_OUTPUT]) for _ in range(nf)]
+                nbf[t] = nf; ft[t, :nf] = sel; fo[t, :nf] = kinds
+                arr = (C.c_void_p * nf)(*[tiles[s] for s in sel])
+                opv = np.array([{1: R.INPUT, 2: R.OUTPUT, 3: R.INOUT}[k] for k in kinds], np.int32)
+                assert ctx.l.pb2_dtd_insert_task_with_task_class(tp, tcs[nf], 0, R.DEV_CUDA, arr, opv.ctypes.data_as(C.c_void_p), None, 0.0) == t
+            src, dst, fl, dep = orc.dtd_build(nbf, ft, fo, ntiles)
+            win = ctx.export_window(tp, ctx.devices[0])
+            ids = win["task_ids"]
+            assert sorted(ids.tolist()) == list(range(ntasks))            # everything is reachable on one device
+            cnt = win["tasks"]["succ_count"].astype(np.int64)
+            wsrc = np.repeat(ids.astype(np.int64), cnt)
+            wdst = ids[(win["succ"] & np.uint32(0x07FFFFFF)).astype(np.int64)]
+            wfl = (win["succ"] >> np.uint32(27)).astype(np.int64)
+            assert sorted(zip(wsrc.tolist(), wdst.tolist(), wfl.tolist())) == sorted(zip(src.tolist(), dst.tolist(), fl.tolist()))
+            assert np.array_equal(win["tasks"]["dep_goal"], dep[ids])
+
+
+def test_dry_run_execution_replays_reference_coherency():
+    """Run Ex05 end to end in dry-run mode (windows retire in order, nothing computes): the host-visible state
+    the module leaves behind equals the oracle's replay of the reference protocol, flow by flow."""
+    K, NB, tb = 6, 4, 256
+    host = np.zeros(K * tb // 4, np.int32)
+    with R.Context(cuda_devices=(0,), dry_run=True) as ctx:
+        dc = ctx.block_cyclic(4, tb // 4, 1, K * tb // 4, 1, mat=host)
+        tp = C.c_void_p(ctx.l.pb2_ptg_ex05_broadcast_new(ctx.h, dc, K, NB))
+        ctx.wait()
+        st = ctx.stats(ctx.devices[0])
+        F = NB // 2 + 1
+        assert st["executed_tasks"] == K * (1 + F)
+        assert st["data_in_from_device"][0] == K * tb                     # each tile H2D exactly once
+        assert st["required_data_in"] == K * (1 + F) * tb
+        assert st["windows_launched"] == 1 and st["tasks_released_on_device"] == K * F
+        O = orc.lib()
+        for k in range(K):
+            d = C.c_void_p(ctx.l.pb2_dc_data_of(dc, k, 0))
+            od = orc.OrcData(); O.orc_data_create(C.byref(od), 3, 0)
+            req = C.c_int()
+            assert O.orc_gpu_stage_in(C.byref(od), 2, 0, 0x0C, 0b100, C.byref(req)) == 0
+            O.orc_gpu_stage_in_complete(C.byref(od), 2, 0x0C); O.orc_gpu_task_complete(C.byref(od), 2, 0x0C, 0)
+            for _ in range(F):
+                assert O.orc_gpu_stage_in(C.byref(od), 2, 2, 0x04, 0b100, C.byref(req)) == -1
+                O.orc_gpu_task_complete(C.byref(od), 2, 0x04, 0)
+            for dev in (0, 2):
+                s = ctx.copy_state(d, dev)
+                assert (s["coherency"], s["readers"], s["version"]) == (od.copy[dev].coherency_state, od.copy[dev].readers, od.copy[dev].version), (k, dev, s)
+            assert ctx.l.pb2_data_owner_device(d) == od.owner_device == 2
+        clean, owned = C.c_int(), C.c_int()
+        ctx.l.pb2_device_lru_sizes(ctx.devices[0], C.byref(clean), C.byref(owned))
+        assert (clean.value, owned.value) == (0, K)                         # written, not pushed out: dirty LRU
+        t, dvs = ctx.trace(tp)
+        assert len(t) == K * (1 + F) and np.all(dvs == 2)
+
+
+def test_get_best_device_placement_dry_run():
+    """get_best_device_check.jdf:68-83: task(m,n) runs on GPU (n*nt + m) % ngpu (testing_get_best_device.c:158)."""
+    nt, ngpu, mb = 5, 4, 8
+    with R.Context(cuda_devices=(0,) * ngpu, dry_run=True) as ctx:
+        host = np.zeros(nt * nt * mb * mb, np.float64)
+        dc = ctx.block_cyclic(8, mb, mb, nt * mb, nt * mb, mat=host)
+        info = np.full(nt * (nt + 1) // 2, -1, np.int32)
+        tp = C.c_void_p(ctx.l.pb2_ptg_get_best_device_new(ctx.h, dc, info.ctypes.data_as(C.c_void_p)))
+        ctx.wait()
+        idx = 0
+        for m in range(nt):
+            for n in range(m + 1):
+                assert info[idx] == 2 + (n * nt + m) % ngpu, (m, n)
+                idx += 1
+        assert sum(ctx.stats(d)["executed_tasks"] for d in ctx.devices) == nt * (nt + 1) // 2
+
+
+def test_select_best_device_load_balance_matches_oracle():
+    """No affinity: least ETA with the skew rule; cross-check a random load pattern with the oracle."""
+    with R.Context(cuda_devices=(0, 0, 0), dry_run=True) as ctx:
+        tp = C.c_void_p(ctx.l.pb2_dtd_taskpool_new(ctx.h))
+        ops = np.array([R.INPUT], np.int32)
+        tc = C.c_void_p(ctx.l.pb2_dtd_create_task_class(tp, b"r", 1, ops.ctypes.data_as(C.c_void_p)))
+        ctx.l.pb2_dtd_task_class_add_chore(tp, tc, R.DEV_CUDA, L.BODY_NOP, None)
+        n = 30
+        for _ in range(n):
+            tile = C.c_void_p(ctx.l.pb2_dtd_tile_new(tp, 64))
+            arr = (C.c_void_p * 1)(tile)
+            ctx.l.pb2_dtd_insert_task_with_task_class(tp, tc, 0, R.DEV_CUDA, arr, None, None, 0.0)
+        ctx.wait()
+        _, dev = ctx.trace(tp)
+        est = ctx.stats(ctx.devices[0])["time_estimate_default"]
+        # replay with the oracle: every task adds its estimate to the chosen device until the window retires
+        loads = [0, 0, 0, 0, 0]
+        chosen = []
+        for _ in range(n):
+            devs = [(0, 0, 0, 0, 1), (0, 1, 0, 0, 1)] + [(1, 0, 1, loads[2 + g], est) for g in range(3)]
+            arr = (orc.SelDev * 5)(*[orc.SelDev(*d) for d in devs])
+            a = [np.array(x, np.int32) for x in ([0x04], [1], [-1], [0])]
+            c = orc.lib().orc_select_best_device(arr, 5, 1, *[x.ctypes.data_as(C.c_void_p) for x in a], 20, 0)
+            chosen.append(c); loads[c] += est
+        assert sorted(dev.tolist()) == sorted(chosen)
+
+
+def test_cpu_only_chain_is_config1():
+    """BASELINE config 1: Ex02_Chain, 1000 tasks, CPU-only: task k sees k, final value 999."""
+    with R.Context(cuda_devices=(), dry_run=True) as ctx:
+        tp = C.c_void_p(ctx.l.pb2_ptg_ex02_chain_new(ctx.h, 999))
+        ctx.l.pb2_taskpool_set_device_types(tp, R.DEV_CPU)
+        ctx.wait()
+        t, d = ctx.trace(tp)
+        assert np.array_equal(t, np.arange(1000)) and np.all(d == 0)
+        info = ctx.task_info(tp)
+        assert np.array_equal(info["seen_version"][:, 0], np.arange(1000))
