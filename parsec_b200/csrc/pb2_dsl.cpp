@@ -570,10 +570,18 @@ pb2_taskpool_t* pb2_ptg_get_best_device_new(pb2_context_t* ctx, pb2_data_collect
     pb2_taskpool_t* tp = expand(ctx, "get_best_device_check", defs);
     if (tp && info) {
         // after the run: which device ran task(m,n), and is B all 0x01010101 (:110-118)
-        tp->on_complete = [tp, info, nt]() {
-            int idx = 0;
-            for (auto& t : tp->tasks) if (t.tc->task_class_id == 1) { info[idx++] = t.ran_on; }
-            (void)nt;
+        // info[0 .. ntasks-1] = device that ran task(m,n) in enumeration order; info[ntasks] = number of B
+        // words that are not 0x01010101 (the check fake_task does, :110-118)
+        tp->on_complete = [tp, info]() {
+            int idx = 0, bad = 0;
+            for (auto& t : tp->tasks) {
+                if (t.tc->task_class_id != 1) continue;
+                info[idx++] = t.ran_on;
+                if (t.ran_on < 2) continue;
+                const int32_t* B = (const int32_t*)t.data[0]->device_copies[0]->device_private;
+                for (size_t i = 0; i < t.data[0]->span / 4; ++i) if (B[i] != 16843009) bad++;
+            }
+            info[idx] = bad;
         };
     }
     return tp;

@@ -256,7 +256,7 @@ def test_get_best_device_placement_dry_run():
     with R.Context(cuda_devices=(0,) * ngpu, dry_run=True) as ctx:
         host = np.zeros(nt * nt * mb * mb, np.float64)
         dc = ctx.block_cyclic(8, mb, mb, nt * mb, nt * mb, mat=host)
-        info = np.full(nt * (nt + 1) // 2, -1, np.int32)
+        info = np.full(nt * (nt + 1) // 2 + 1, -1, np.int32)
         tp = C.c_void_p(ctx.l.pb2_ptg_get_best_device_new(ctx.h, dc, info.ctypes.data_as(C.c_void_p)))
         ctx.wait()
         idx = 0
