@@ -175,6 +175,9 @@ int  pb2_engine_host_unregister(pb2_engine_t* engine, void* host_ptr);
 int  pb2_engine_memcpy_h2d(pb2_engine_t* engine, void* dev, const void* host, size_t bytes);
 int  pb2_engine_memcpy_d2h(pb2_engine_t* engine, void* host, const void* dev, size_t bytes);
 int  pb2_engine_synchronize(pb2_engine_t* engine);
+/* Enqueue all engine work on a caller-owned CUDA stream (cudaStream_t passed as void*), e.g. the stream NCCL
+ * collectives are ordered against; NULL restores the engine's own non-blocking stream. */
+int  pb2_engine_set_stream(pb2_engine_t* engine, void* cuda_stream);
 
 /* --- one window of the DAG ---
  * tasks[ntasks], succ[nsucc] (CSR via succ_begin/succ_count), tiles[ntiles] and the ids of

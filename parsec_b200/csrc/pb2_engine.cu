@@ -172,7 +172,8 @@ struct pb2_engine_s {
     int cuda_device = 0;
     cudaDeviceProp prop{};
     pb2_engine_params_t params{};
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // where engine work is enqueued
+    cudaStream_t own_stream = nullptr;   // created by the engine
     int nworkers = 0;
     int nworkers_gemm = 0;
     std::string last_error;
@@ -326,7 +327,8 @@ int pb2_engine_create(pb2_engine_t** engine, int cuda_device, const pb2_engine_p
     p.threads = (p.threads + 31) & ~31;
     if (p.timeout_ms <= 0) p.timeout_ms = 20000;
     e->params = p;
-    PB2_CUDA(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    PB2_CUDA(e, cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    e->stream = e->own_stream;
     int occ = 0;
     PB2_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pb2_engine_hbm_kernel, p.threads, 0));
     int per_sm = occ < p.workers_per_sm ? occ : p.workers_per_sm;
@@ -343,7 +345,7 @@ int pb2_engine_destroy(pb2_engine_t* e) {
     if (!e) return PB2_ERR_BAD_PARAM;
     cudaSetDevice(e->cuda_device);
     for (auto& kv : e->registered) cudaHostUnregister(kv.first);
-    if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
     return PB2_SUCCESS;
 }
@@ -423,6 +425,14 @@ int pb2_engine_memcpy_d2h(pb2_engine_t* e, void* host, const void* dev, size_t b
     PB2_CUDA(e, cudaSetDevice(e->cuda_device));
     PB2_CUDA(e, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, e->stream));
     PB2_CUDA(e, cudaStreamSynchronize(e->stream));
+    return PB2_SUCCESS;
+}
+
+int pb2_engine_set_stream(pb2_engine_t* e, void* cuda_stream) {
+    if (!e) return PB2_ERR_BAD_PARAM;
+    PB2_CUDA(e, cudaSetDevice(e->cuda_device));
+    PB2_CUDA(e, cudaStreamSynchronize(e->stream));
+    e->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : e->own_stream;
     return PB2_SUCCESS;
 }
 

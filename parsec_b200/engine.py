@@ -72,6 +72,10 @@ class Engine:
         _check(self._lib.pb2_engine_memcpy_d2h(self._h, _ptr(arr), C.c_void_p(dev_ptr), arr.nbytes), "d2h", self)
         return arr
 
+    def use_stream(self, cuda_stream):
+        """Enqueue engine work on a caller-owned stream (int cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream)."""
+        _check(self._lib.pb2_engine_set_stream(self._h, C.c_void_p(cuda_stream)), "pb2_engine_set_stream", self)
+
     def synchronize(self):
         _check(self._lib.pb2_engine_synchronize(self._h), "pb2_engine_synchronize", self)
 
