@@ -165,28 +165,46 @@ def main():
     assert ctx.l.pb2_dc_register_memory(dc, dev) == 0            # twoDBC_memory_register: pin the collection once
 
     # ---------------------------------------------------------------- e2e through the host API, host buffers
+    # One step = the application hands a freshly written collection (host memory) to a new task pool:
+    #   host_write_all  : the host copies are the newest version (what CPU producer tasks would leave behind)
+    #   ptg_new + wait  : PTG front end -> kernel_scheduler -> window; every tile is staged in from pinned host
+    #                     memory by the kernel (H2D, K * 262144 B), bodies run, successors are released on-device
+    #   task_info       : the per-task results (what TaskRecv "prints") are read back to the host (D2H)
+    tsplit = {"new": 0.0, "wait": 0.0, "read": 0.0}
+
     def e2e_step():
-        host[:] = -1
+        t0 = time.perf_counter()
+        assert ctx.l.pb2_dc_host_write_all(dc) == 0
         tp = C.c_void_p(ctx.l.pb2_ptg_ex05_broadcast_new(ctx.h, dc, K, NB))
+        t1 = time.perf_counter()
         ctx.wait()
-        assert ctx.l.pb2_device_memory_release(dev) == 0          # every dirty tile back to host memory
+        t2 = time.perf_counter()
+        info = ctx.task_info(tp)
+        recv = info["class_id"] == 1
+        ok = bool(np.all(info["result"][recv] == info["locals"][recv, 0].astype(np.uint64)))   # observed k, 0 mismatches
         ctx.l.pb2_taskpool_free(tp)
-        return int(host[5]) == 0 and int(host[-3]) == K - 1
+        t3 = time.perf_counter()
+        tsplit["new"] += t1 - t0; tsplit["wait"] += t2 - t1; tsplit["read"] += t3 - t2
+        return ok
 
     if world == 1:
         for _ in range(2):
             assert e2e_step()
+        for k in tsplit: tsplit[k] = 0.0
+        h2d0 = ctx.stats(dev)["data_in_from_device"][0]
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
             assert e2e_step()
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / args.e2e_steps
-        st0 = ctx.stats(dev)
-        h2d_step = K * TILE + ntasks * 64 + K * F * 4 + K * 32 + K * 4   # tiles (in-kernel) + descriptors
-        d2h_step = K * TILE + ntasks * 28                                 # flushed tiles + retire log/versions/results
+        h2d_tiles = (ctx.stats(dev)["data_in_from_device"][0] - h2d0) // args.e2e_steps
+        assert h2d_tiles == K * TILE                                      # every tile came from host memory, once
+        h2d_step = int(h2d_tiles) + ntasks * 64 + K * F * 4 + K * 32 + K * 4   # tiles (in-kernel) + descriptors
+        d2h_step = ntasks * (4 + 16 + 8)                                  # retire log + flow versions + results
         e2e = {"value": ntasks / e2e_s, "unit": "tasks/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
-               "ms_per_step": e2e_s * 1e3, "tile_gbs": algo_bytes / e2e_s / 1e9}
+               "ms_per_step": e2e_s * 1e3, "tile_gbs": algo_bytes / e2e_s / 1e9,
+               "ms_split": {k: v / args.e2e_steps * 1e3 for k, v in tsplit.items()}}
     else:
         e2e = None
 

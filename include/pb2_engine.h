@@ -179,6 +179,12 @@ int  pb2_engine_synchronize(pb2_engine_t* engine);
  * collectives are ordered against; NULL restores the engine's own non-blocking stream. */
 int  pb2_engine_set_stream(pb2_engine_t* engine, void* cuda_stream);
 
+/* n independent copies dst[i][0:bytes[i]] = src[i][..] in ONE kernel launch (workers grid-stride over the list);
+ * either side may be HBM, a peer GPU or cudaHostRegister'ed host memory (device-visible alias).  This is what the
+ * module uses to write a batch of dirty tiles home (parsec_gpu_create_w2r_task batches <= 20 copies per
+ * pseudo-task and pays one cudaMemcpyAsync + event per tile, transfer_gpu.c:224-304).  Stream-ordered. */
+int  pb2_engine_copy_batch(pb2_engine_t* engine, void* const* dst, const void* const* src, const uint64_t* bytes, int32_t n);
+
 /* --- one window of the DAG ---
  * tasks[ntasks], succ[nsucc] (CSR via succ_begin/succ_count), tiles[ntiles] and the ids of
  * the tasks that are ready at submission (startup tasks, parsec.c:1724-1740).

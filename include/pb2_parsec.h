@@ -195,6 +195,9 @@ int   pb2_dc_register_memory(pb2_data_collection_t* dc, pb2_device_module_t* dev
 /* map the P x Q "process" grid onto the GPUs of this process: owner rank r -> device 2 + r % ngpu, by setting
  * preferred_device on every local datum (dtd_test_simple_gemm.c:241-251 does this by hand with data_advise) */
 int   pb2_dc_distribute_on_devices(pb2_data_collection_t* dc);
+/* the application rewrote every local tile in host memory (== a CPU task with WRITE access per tile): host copies
+ * take ownership with a new version, GPU replicas become stale and are staged in again on next use */
+int   pb2_dc_host_write_all(pb2_data_collection_t* dc);
 
 /* ---------------------------------------------------------------- task pools, generic */
 int  pb2_context_add_taskpool(pb2_context_t* ctx, pb2_taskpool_t* tp);     /* scheduling.c:865 */

@@ -95,7 +95,7 @@ _lib = None
 ENGINE_SYMBOLS = [
     "pb2_engine_create", "pb2_engine_destroy", "pb2_engine_info", "pb2_engine_last_error",
     "pb2_engine_malloc", "pb2_engine_free", "pb2_engine_host_register", "pb2_engine_host_unregister",
-    "pb2_engine_memcpy_h2d", "pb2_engine_memcpy_d2h", "pb2_engine_synchronize", "pb2_engine_set_stream",
+    "pb2_engine_memcpy_h2d", "pb2_engine_memcpy_d2h", "pb2_engine_synchronize", "pb2_engine_set_stream", "pb2_engine_copy_batch",
     "pb2_window_create", "pb2_window_destroy", "pb2_window_launch", "pb2_window_wait",
     "pb2_window_results",
 ]
@@ -126,6 +126,7 @@ def load():
     lib.pb2_engine_memcpy_d2h.argtypes = [vp, vp, vp, C.c_size_t]
     lib.pb2_engine_synchronize.argtypes = [vp]
     lib.pb2_engine_set_stream.argtypes = [vp, vp]
+    lib.pb2_engine_copy_batch.argtypes = [vp, vp, vp, vp, i32]
     lib.pb2_window_create.argtypes = [vp, P(vp), C.c_int, vp, i32, vp, i32, vp, i32, vp, i32]
     lib.pb2_window_destroy.argtypes = [vp]
     lib.pb2_window_launch.argtypes = [vp]

@@ -124,6 +124,26 @@ int pb2_dc_register_memory(pb2_data_collection_t* dc, pb2_device_module_t* dev) 
     return pb2_device_memory_register(dev, dc, dc->mat, (size_t)dc->nb_local_tiles * (size_t)dc->bsiz * dc->elt_bytes);
 }
 
+// The application rewrote the whole collection in host memory (what a CPU task with WRITE access on every tile
+// does, data.c:334-458 with access WRITE on device 0): host copies become the owners with a new version, every
+// GPU replica is stale and will be staged in again by the next GPU reader.
+int pb2_dc_host_write_all(pb2_data_collection_t* dc) {
+    if (!dc) return PB2_ERR_BAD_PARAM;
+    for (pb2_data_t* d : dc->data_map) {
+        if (!d || !d->device_copies[0]) continue;
+        pb2_data_start_transfer_ownership_to_copy(dc->ctx, d, 0, PB2_FLOW_ACCESS_WRITE);
+        pb2_data_end_transfer_ownership_to_copy(d, 0, PB2_FLOW_ACCESS_WRITE);
+        uint32_t newest = d->device_copies[0]->version;
+        for (int i = 1; i < PB2_MAX_DEVICES; ++i) if (d->device_copies[i] && d->device_copies[i]->version > newest) newest = d->device_copies[i]->version;
+        d->device_copies[0]->version = newest + 1;
+        for (auto* dev : dc->ctx->devices) {
+            pb2_data_copy_t* g = d->device_copies[dev->device_index];
+            if (g && dev->device_index >= 2) pb2i_lru_push_back(dev, 1, g);      // stale replicas are reclaimable
+        }
+    }
+    return PB2_SUCCESS;
+}
+
 int pb2_dc_distribute_on_devices(pb2_data_collection_t* dc) {
     if (!dc) return PB2_ERR_BAD_PARAM;
     std::vector<int> gpus;

@@ -59,7 +59,9 @@ __global__ void pb2_window_reset_kernel(WinDev w, const pb2_tile_t* tiles_init,
 // ---------------------------------------------------------------------------------------------
 // the persistent engine kernel, HBM-bound bodies
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512)
+// 256 threads, 4 CTAs per SM (<= 64 registers): 1024 threads x 4 x 16 B loads in flight per SM saturate HBM; the
+// cold stage-in / pushout copies may spill, the body loops do not.
+__global__ void __launch_bounds__(256, 4)
 pb2_engine_hbm_kernel(WinDev w) {
     __shared__ __align__(16) pb2_task_t s_task;   // filled with four 16-byte loads
     __shared__ int32_t    s_id;
@@ -158,6 +160,16 @@ pb2_engine_hbm_kernel(WinDev w) {
             }
         }
         __syncthreads();
+    }
+}
+
+struct CopyDesc { void* dst; const void* src; unsigned long long bytes; };
+
+__global__ void __launch_bounds__(256, 4)
+pb2_copy_batch_kernel(const CopyDesc* __restrict__ d, int32_t n) {
+    for (int32_t i = blockIdx.x; i < n; i += gridDim.x) {
+        const CopyDesc c = d[i];
+        cta_copy<true>(c.dst, c.src, (size_t)c.bytes);
     }
 }
 
@@ -322,8 +334,7 @@ int pb2_engine_create(pb2_engine_t** engine, int cuda_device, const pb2_engine_p
     pb2_engine_params_t p{};
     if (params) p = *params;
     if (p.workers_per_sm <= 0) p.workers_per_sm = 4;
-    if (p.threads <= 0) p.threads = 256;
-    if (p.threads > 512) p.threads = 512;
+    if (p.threads <= 0 || p.threads > 256) p.threads = 256;     // the kernel is compiled for <= 256 threads
     p.threads = (p.threads + 31) & ~31;
     if (p.timeout_ms <= 0) p.timeout_ms = 20000;
     e->params = p;
@@ -425,6 +436,23 @@ int pb2_engine_memcpy_d2h(pb2_engine_t* e, void* host, const void* dev, size_t b
     PB2_CUDA(e, cudaSetDevice(e->cuda_device));
     PB2_CUDA(e, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, e->stream));
     PB2_CUDA(e, cudaStreamSynchronize(e->stream));
+    return PB2_SUCCESS;
+}
+
+int pb2_engine_copy_batch(pb2_engine_t* e, void* const* dst, const void* const* src, const uint64_t* bytes, int32_t n) {
+    if (!e || n < 0 || (n && (!dst || !src || !bytes))) return PB2_ERR_BAD_PARAM;
+    if (n == 0) return PB2_SUCCESS;
+    PB2_CUDA(e, cudaSetDevice(e->cuda_device));
+    std::vector<CopyDesc> h((size_t)n);
+    for (int32_t i = 0; i < n; ++i) h[i] = CopyDesc{dst[i], src[i], bytes[i]};
+    CopyDesc* d = nullptr;
+    PB2_CUDA(e, cudaMallocAsync(reinterpret_cast<void**>(&d), sizeof(CopyDesc) * (size_t)n, e->stream));
+    PB2_CUDA(e, cudaMemcpyAsync(d, h.data(), sizeof(CopyDesc) * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+    PB2_CUDA(e, cudaStreamSynchronize(e->stream));     // h is pageable: make sure the staging copy is done
+    const int grid = n < e->nworkers ? n : e->nworkers;
+    pb2_copy_batch_kernel<<<grid, 256, 0, e->stream>>>(d, n);
+    PB2_CUDA(e, cudaGetLastError());
+    PB2_CUDA(e, cudaFreeAsync(d, e->stream));
     return PB2_SUCCESS;
 }
 

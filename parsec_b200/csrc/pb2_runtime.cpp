@@ -682,27 +682,35 @@ int pb2_taskpool_free(pb2_taskpool_t* tp) {
 // the GPU device module: window building, launch, retire
 // =============================================================================================
 
-// Write back up to max_ejected dirty replicas (transfer_gpu.c:224-362, with the intended outcome: the host copy
-// gets the replica's version, both become SHARED, the replica moves to the clean LRU)
+// Write back up to max_copies dirty replicas (transfer_gpu.c:224-362, with the intended outcome: the host copy
+// gets the replica's version, both become SHARED, the replica moves to the clean LRU).  All the copies of one
+// call travel in ONE kernel launch (pb2_engine_copy_batch) instead of one cudaMemcpyAsync + event per tile.
 static int w2r_flush(pb2_device_module_t* dev, int max_copies) {
-    int n = 0;
-    pb2_data_copy_t* c = dev->lru_head[2];
-    while (c && n < max_copies) {
-        pb2_data_copy_t* next = c->lru_next;
+    std::vector<pb2_data_copy_t*> picked;
+    std::vector<void*> dst; std::vector<const void*> src; std::vector<uint64_t> bytes;
+    for (pb2_data_copy_t* c = dev->lru_head[2]; c && (int)picked.size() < max_copies; c = c->lru_next) {
         pb2_data_t* d = c->original;
         pb2_data_copy_t* h = pb2i_host_copy(d);
-        if (c->readers == 0 && c->window_tile < 0 && h && h->device_private) {
-            if (!dev->dry_run) pb2_engine_memcpy_d2h(dev->engine, h->device_private, c->device_private, d->span);
-            dev->st.data_out_to_host += d->span;
-            c->coherency_state = PB2_DATA_COHERENCY_SHARED; h->coherency_state = PB2_DATA_COHERENCY_SHARED;
-            h->version = c->version; h->flags |= PB2_DATA_FLAG_EVICTED;
-            if (d->owner_device == dev->device_index) d->owner_device = -1;
-            pb2i_lru_push_back(dev, 1, c);
-            n++;
-        }
-        c = next;
+        if (c->readers != 0 || c->window_tile >= 0 || !h || !h->device_private) continue;
+        void* alias = dev->dry_run ? h->device_private : pb2i_device_visible_host_ptr(dev, d);
+        if (!alias) continue;
+        picked.push_back(c); dst.push_back(alias); src.push_back(c->device_private); bytes.push_back(d->span);
     }
-    return n;
+    if (picked.empty()) return 0;
+    if (!dev->dry_run) {
+        if (pb2_engine_copy_batch(dev->engine, dst.data(), src.data(), bytes.data(), (int32_t)picked.size()) != PB2_SUCCESS) return 0;
+        pb2_engine_synchronize(dev->engine);
+    }
+    for (pb2_data_copy_t* c : picked) {
+        pb2_data_t* d = c->original;
+        pb2_data_copy_t* h = pb2i_host_copy(d);
+        dev->st.data_out_to_host += d->span;
+        c->coherency_state = PB2_DATA_COHERENCY_SHARED; h->coherency_state = PB2_DATA_COHERENCY_SHARED;
+        h->version = c->version; h->flags |= PB2_DATA_FLAG_EVICTED;
+        if (d->owner_device == dev->device_index) d->owner_device = -1;
+        pb2i_lru_push_back(dev, 1, c);
+    }
+    return (int)picked.size();
 }
 
 // Evict one clean replica not used by the window under construction (reserve_space :1339-1575)

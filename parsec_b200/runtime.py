@@ -36,7 +36,7 @@ PARSEC_SYMBOLS = [
     "pb2_data_get_copy", "pb2_data_copy_state", "pb2_data_owner_device", "pb2_data_preferred_device",
     "pb2_matrix_block_cyclic_new", "pb2_data_collection_free", "pb2_data_collection_set_mat", "pb2_dc_rank_of",
     "pb2_dc_data_of", "pb2_dc_data_key", "pb2_dc_position", "pb2_dc_info", "pb2_dc_register_memory",
-    "pb2_dc_distribute_on_devices", "pb2_context_add_taskpool", "pb2_context_start", "pb2_context_wait",
+    "pb2_dc_distribute_on_devices", "pb2_dc_host_write_all", "pb2_context_add_taskpool", "pb2_context_start", "pb2_context_wait",
     "pb2_taskpool_wait", "pb2_taskpool_free", "pb2_taskpool_nb_tasks", "pb2_taskpool_set_device_types",
     "pb2_taskpool_completion_trace", "pb2_taskpool_task_info", "pb2_taskpool_export_window", "pb2_dtd_taskpool_new",
     "pb2_dtd_tile_of", "pb2_dtd_tile_new", "pb2_dtd_tile_data", "pb2_dtd_create_task_class",
@@ -81,7 +81,7 @@ def lib():
         "pb2_dc_rank_of": (C.c_uint32, [vp, C.c_int, C.c_int]), "pb2_dc_data_of": (vp, [vp, C.c_int, C.c_int]),
         "pb2_dc_data_key": (C.c_uint64, [vp, C.c_int, C.c_int]), "pb2_dc_position": (C.c_int, [vp, C.c_int, C.c_int]),
         "pb2_dc_info": (C.c_int, [vp, P(C.c_int64)]), "pb2_dc_register_memory": (C.c_int, [vp, vp]),
-        "pb2_dc_distribute_on_devices": (C.c_int, [vp]),
+        "pb2_dc_distribute_on_devices": (C.c_int, [vp]), "pb2_dc_host_write_all": (C.c_int, [vp]),
         "pb2_context_add_taskpool": (C.c_int, [vp, vp]), "pb2_context_start": (C.c_int, [vp]),
         "pb2_context_wait": (C.c_int, [vp]), "pb2_taskpool_wait": (C.c_int, [vp]), "pb2_taskpool_free": (C.c_int, [vp]),
         "pb2_taskpool_nb_tasks": (C.c_int, [vp]), "pb2_taskpool_set_device_types": (C.c_int, [vp, C.c_int]),
