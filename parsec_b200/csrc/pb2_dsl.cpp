@@ -322,7 +322,14 @@ struct ClassDef {
     std::function<void(Locals, pb2_htask_t*)> bind;               // body immediates, priority
 };
 
-struct Key { int cls; int32_t L[4]; bool operator<(const Key& o) const { if (cls != o.cls) return cls < o.cls; return memcmp(L, o.L, sizeof L) < 0; } };
+struct Key { int cls; int32_t L[4]; bool operator==(const Key& o) const { return cls == o.cls && memcmp(L, o.L, sizeof L) == 0; } };
+struct KeyHash {        // make_key of the generated code: a cheap mix of the class id and the locals
+    size_t operator()(const Key& k) const {
+        uint64_t h = (uint64_t)(uint32_t)k.cls * 0x9E3779B97F4A7C15ull;
+        for (int i = 0; i < 4; ++i) h = (h ^ (uint32_t)k.L[i]) * 0x100000001B3ull;
+        return (size_t)(h ^ (h >> 29));
+    }
+};
 
 static Dep dep_task(int cls, int l0, int l1, int l2, int flow) { Dep d; d.kind = DEP_TASK; d.cls = cls; d.L[0] = l0; d.L[1] = l1; d.L[2] = l2; d.flow = flow; return d; }
 static Dep dep_mem(pb2_data_t* data) { Dep d; d.kind = data ? DEP_MEMORY : DEP_NONE; d.data = data; return d; }
@@ -331,8 +338,9 @@ static Dep dep_new(size_t bytes) { Dep d; d.kind = DEP_NEW; d.new_bytes = bytes;
 static pb2_taskpool_t* expand(pb2_context_t* ctx, const char* name, std::vector<ClassDef>& defs) {
     pb2_taskpool_t* tp = new pb2_taskpool_s();
     tp->ctx = ctx; tp->type = 1; tp->name = name;
-    std::map<Key, int32_t> ids;
+    std::unordered_map<Key, int32_t, KeyHash> ids;
     std::vector<Key> keys;
+    ids.reserve(1 << 16);
     for (size_t c = 0; c < defs.size(); ++c) {
         tp->classes.emplace_back();
         pb2_task_class_t& tc = tp->classes.back();

@@ -226,7 +226,9 @@ template <class T>
 static int dev_alloc_copy(pb2_window_t* w, T** dptr, const T* host, size_t n) {
     pb2_engine_t* e = w->e;
     void* p = nullptr;
-    PB2_CUDA(e, cudaMalloc(&p, (n ? n : 1) * sizeof(T)));
+    // stream-ordered pool allocation: after the first window of a size class this costs microseconds, whereas
+    // cudaMalloc/cudaFree next to a 170 GB slab cost hundreds of microseconds each and synchronise the device
+    PB2_CUDA(e, cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), e->stream));
     w->allocs.push_back(p);
     if (host && n) PB2_CUDA(e, cudaMemcpyAsync(p, host, n * sizeof(T), cudaMemcpyHostToDevice, e->stream));
     *dptr = reinterpret_cast<T*>(p);
@@ -340,6 +342,13 @@ int pb2_engine_create(pb2_engine_t** engine, int cuda_device, const pb2_engine_p
     e->params = p;
     PB2_CUDA(e, cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
     e->stream = e->own_stream;
+    {   // keep freed window scratch cached in the default mempool instead of returning it to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, cuda_device) == cudaSuccess) {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
     int occ = 0;
     PB2_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pb2_engine_hbm_kernel, p.threads, 0));
     int per_sm = occ < p.workers_per_sm ? occ : p.workers_per_sm;
@@ -523,7 +532,7 @@ int pb2_window_destroy(pb2_window_t* w) {
     if (!w) return PB2_ERR_BAD_PARAM;
     cudaSetDevice(w->e->cuda_device);
     if (w->launched) cudaStreamSynchronize(w->e->stream);
-    for (void* p : w->allocs) cudaFree(p);
+    for (void* p : w->allocs) cudaFreeAsync(p, w->e->stream);
     if (w->ev0) cudaEventDestroy(w->ev0);
     if (w->ev1) cudaEventDestroy(w->ev1);
     if (w->ev2) cudaEventDestroy(w->ev2);

@@ -7,9 +7,13 @@
 // but hands whole dependency-closed sets of GPU tasks ("windows") to the persistent kernel, so the per-task and
 // per-edge host round trips of the reference only remain at window boundaries and for CPU incarnations.
 #include <algorithm>
+#include <chrono>
 #include <stdio.h>
 
 #include "pb2_internal.hpp"
+
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static const bool g_timing = getenv("PB2_TIMING") != nullptr;
 
 // =============================================================================================
 // zone heap
@@ -610,6 +614,8 @@ int pb2_context_wait(pb2_context_t* ctx) {
     if (!ctx->devices_frozen) pb2_mca_device_registration_complete(ctx);
     for (;;) {
         bool progressed = false;
+        const double t_sched = now_ms();
+        const size_t nready0 = ctx->ready.size();
         while (!ctx->ready.empty()) {
             pb2_htask_t* t = ctx->ready.front();
             ctx->ready.erase(ctx->ready.begin());
@@ -617,6 +623,7 @@ int pb2_context_wait(pb2_context_t* ctx) {
             if (rc != PB2_SUCCESS) return rc;
             progressed = true;
         }
+        if (g_timing && nready0) fprintf(stderr, "pb2 wait: dispatched %zu ready tasks in %.2f ms\n", nready0, now_ms() - t_sched);
         for (auto* d : ctx->devices) {
             if (!PB2_DEV_IS_GPU(d->type) || d->pending.empty()) continue;
             int rc = device_progress(d);
@@ -831,11 +838,6 @@ static int build_window(pb2_device_module_t* dev, Window& w, std::vector<pb2_gpu
             // no room: this task (and everything behind it) waits for the next window (HOOK_RETURN_AGAIN)
             full = true;
             for (pb2_data_copy_t* g : fresh) { g->window_tile = -1; w.tile_data.pop_back(); }
-            if (t->state == 2) {
-                bool was_pending = false;
-                for (size_t i = 0; i < taken.size(); ++i) if (taken[i]->ec == t) { dev->pending.push_back(taken[i]); taken.erase(taken.begin() + i); was_pending = true; break; }
-                (void)was_pending;
-            }
             continue;
         }
         t->window_index = (int32_t)w.order.size();
@@ -850,6 +852,11 @@ static int build_window(pb2_device_module_t* dev, Window& w, std::vector<pb2_gpu
         }
     }
     for (pb2_htask_t* n : touched) n->inwin_pred = 0;
+    if (full) {      // tasks that were handed over but did not fit stay pending, in their arrival order
+        std::vector<pb2_gpu_task_t*> in;
+        for (pb2_gpu_task_t* g : taken) { if (g->ec->window_index >= 0) in.push_back(g); else dev->pending.push_back(g); }
+        taken.swap(in);
+    }
     if (w.order.empty()) { dev->ctx->last_error = "device memory too small for a single task"; return PB2_ERR_OUT_OF_RESOURCE; }
 
     // ---- tiles
@@ -979,12 +986,14 @@ static void retire_task_bookkeeping(pb2_device_module_t* dev, Window& w, pb2_hta
 
 static int device_progress(pb2_device_module_t* dev) {
     pb2_context_t* ctx = dev->ctx;
+    const double t_begin = now_ms();
     Window w;
     std::vector<pb2_gpu_task_t*> taken;
     int rc = build_window(dev, w, taken);
     if (rc != PB2_SUCCESS) return rc;
     if (w.order.empty()) return PB2_SUCCESS;
     const int32_t n = (int32_t)w.order.size();
+    const double t_built = now_ms();
     std::vector<int32_t> retire((size_t)n);
     std::vector<uint32_t> seen((size_t)n * PB2_MAX_FLOWS, 0);
     std::vector<uint64_t> result((size_t)n, 0);
@@ -1005,6 +1014,7 @@ static int device_progress(pb2_device_module_t* dev) {
         if (rc != PB2_SUCCESS) { window_release(dev, w); return rc; }
         dev->st.kernel_ms_total += st.kernel_ms;
     }
+    const double t_ran = now_ms();
     dev->st.windows_launched++;
     dev->st.tasks_released_on_device += (uint64_t)(n - (int32_t)w.ready.size());
     // the retire log is the order in which the host learns about completions
@@ -1022,6 +1032,8 @@ static int device_progress(pb2_device_module_t* dev) {
     }
     window_release(dev, w);
     for (pb2_gpu_task_t* g : taken) { dev->mutex--; delete g; }    // release_device_task
+    if (g_timing) fprintf(stderr, "pb2 window: %d tasks, build %.2f ms, create+run+results %.2f ms, retire %.2f ms\n",
+                          n, t_built - t_begin, t_ran - t_built, now_ms() - t_ran);
     return PB2_SUCCESS;
 }
 
