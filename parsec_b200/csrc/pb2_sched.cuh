@@ -60,7 +60,8 @@ __device__ __forceinline__ int32_t pop_task(const WinDev& w) {
         if ((++spins & 1023u) == 0) {
             // watchdog: a DAG whose dependency counts are wrong would spin forever
             const unsigned long long last = *reinterpret_cast<volatile unsigned long long*>(&w.ctl->progress_ns.v);
-            if (globaltimer_ns() - last > w.timeout_ns) {
+            // signed: %globaltimer read on another SM can be slightly behind the value a retiring SM just stored
+            if ((long long)(globaltimer_ns() - last) > (long long)w.timeout_ns) {
                 st_relaxed_gpu(reinterpret_cast<int32_t*>(&w.ctl->done.v), kDoneTimeout);
                 return kEmpty;
             }
