@@ -129,7 +129,9 @@ typedef struct pb2_engine_params_s {
     int32_t  queue_policy;     /* 0 = FIFO ring, 1 = successors-first (hot ring before FIFO ring)             */
     int32_t  timeout_ms;       /* device-side watchdog: a window that makes no progress for this long aborts
                                 * (default 20000); a malformed DAG must never hang the GPU                   */
-    int32_t  reserved[2];
+    int32_t  gemm_mode;        /* 0 = CTA pairs (cta_group::2) + fused k-chains (default), 1 = v1 single-CTA kernel,
+                                * 2 = CTA pairs, every task flushes C (per-task bf16 rounding, as the oracle)       */
+    int32_t  reserved[1];
 } pb2_engine_params_t;
 
 typedef struct pb2_engine_info_s {

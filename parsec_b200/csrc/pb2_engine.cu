@@ -27,6 +27,7 @@
 #include "../../include/pb2_engine.h"
 #include "pb2_sched.cuh"
 #include "pb2_gemm.cuh"
+#include "pb2_gemm2.cuh"
 
 namespace pb2 {
 
@@ -163,6 +164,15 @@ pb2_engine_hbm_kernel(WinDev w) {
     }
 }
 
+// re-arm the unit-level scheduling state of a v2 GEMM window (after pb2_window_reset_kernel re-armed the rest)
+__global__ void pb2_window2_reset_kernel(Win2Dev g, const int32_t* ready_entries, int32_t nentries) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t gsz = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = gid; i < (size_t)g.nunits; i += gsz) { g.udep[i] = g.units[i].dep_goal; g.parts_left[i] = g.units[i].nparts; }
+    for (size_t i = gid; i <= (size_t)g.w.cap_mask; i += gsz) g.w.ring[i] = (i < (size_t)nentries) ? ready_entries[i] : kEmpty;
+    if (gid == 0) g.w.ctl->tail.v = (unsigned long long)nentries;
+}
+
 struct CopyDesc { void* dst; const void* src; unsigned long long bytes; };
 
 __global__ void __launch_bounds__(256, 4)
@@ -205,6 +215,10 @@ struct pb2_window_s {
     int32_t* d_ready = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     CUtensorMap* d_tmaps = nullptr;     // kind 1: one 2-D bf16 tensor map per tile (box 64 x 128, 128B swizzle)
+    bool v2 = false;                    // kind 1 executed by the CTA-pair kernel on units
+    Win2Dev g{};
+    int32_t* d_ready_entries = nullptr;
+    int32_t nentries = 0;
     bool launched = false;
     std::vector<void*> allocs;
 };
@@ -310,6 +324,83 @@ static int build_tensor_maps(pb2_window_t* w, const pb2_task_t* tasks, int32_t n
     return dev_alloc_copy(w, &w->d_tmaps, maps.data(), maps.size());
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// v2 GEMM windows: group tasks into units (fused k-chains), see pb2_gemm2.cuh
+// ---------------------------------------------------------------------------------------------
+static int build_gemm2_units(pb2_window_t* w, const pb2_task_t* tasks, int32_t ntasks, const uint32_t* succ,
+                             const int32_t* ready, int32_t nready, bool fuse, uint32_t* ring_cap_needed) {
+    std::vector<int32_t> indeg((size_t)ntasks, 0), cpred((size_t)ntasks, -1), ccons((size_t)ntasks, 0), next((size_t)ntasks, -1);
+    auto is_gemm = [&](int32_t t) { return tasks[t].body == PB2_BODY_GEMM_BF16; };
+    for (int32_t u = 0; u < ntasks; ++u)
+        for (int32_t e = 0; e < tasks[u].succ_count; ++e) {
+            const uint32_t s = succ[tasks[u].succ_begin + e];
+            const int32_t t = PB2_SUCC_TASK(s);
+            indeg[t]++;
+            if (PB2_SUCC_FLOW(s) == 2 && is_gemm(u) && is_gemm(t) && tasks[u].tile[2] == tasks[t].tile[2]) { ccons[u]++; cpred[t] = u; }
+        }
+    if (fuse)
+        for (int32_t t = 0; t < ntasks; ++t) {
+            const int32_t u = cpred[t];
+            if (u < 0 || indeg[t] != 1 || ccons[u] != 1) continue;                 // the chain link must be t's only missing input
+            if (tasks[u].access[2] & PB2_FLOW_PUSHOUT) continue;                   // u's C has to reach the host: flush there
+            if (memcmp(tasks[u].iparam, tasks[t].iparam, sizeof tasks[u].iparam)) continue;
+            next[u] = t;
+        }
+    std::vector<uint8_t> has_pred((size_t)ntasks, 0);
+    for (int32_t u = 0; u < ntasks; ++u) if (next[u] >= 0) has_pred[next[u]] = 1;
+    std::vector<GUnit> units; std::vector<GSeg> segs; std::vector<int32_t> unit_of((size_t)ntasks, -1);
+    for (int32_t h = 0; h < ntasks; ++h) {
+        if (has_pred[h]) continue;
+        GUnit u{}; u.seg_begin = (int32_t)segs.size(); u.dep_goal = indeg[h];
+        const bool g = is_gemm(h);
+        u.flags = g ? 1 : 0; u.tileC = g ? tasks[h].tile[2] : -1;
+        u.M = tasks[h].iparam[0]; u.N = tasks[h].iparam[1]; u.K = tasks[h].iparam[2];
+        u.nparts = g ? (u.M + 255) / 256 : 1;
+        if (g && (u.N > 512 || (u.N % 16) || u.nparts > 16)) return PB2_ERR_NOT_SUPPORTED;   // caller falls back to the v1 kernel
+        for (int32_t t = h; t >= 0; t = next[t]) {
+            unit_of[t] = (int32_t)units.size();
+            segs.push_back(GSeg{t, g ? tasks[t].tile[0] : -1, g ? tasks[t].tile[1] : -1, 0});
+            if (g && (tasks[t].access[2] & PB2_FLOW_PUSHOUT)) u.flags |= 2;
+        }
+        u.seg_count = (int32_t)segs.size() - u.seg_begin;
+        units.push_back(u);
+    }
+    std::vector<int32_t> usucc;
+    for (GUnit& u : units) {
+        u.succ_begin = (int32_t)usucc.size();
+        for (int32_t i = 0; i < u.seg_count; ++i) {
+            const int32_t t = segs[u.seg_begin + i].task;
+            for (int32_t e = 0; e < tasks[t].succ_count; ++e) {
+                const int32_t d = PB2_SUCC_TASK(succ[tasks[t].succ_begin + e]);
+                if (d == next[t] && PB2_SUCC_FLOW(succ[tasks[t].succ_begin + e]) == 2) continue;   // the fused link
+                usucc.push_back(unit_of[d]);
+            }
+        }
+        u.succ_count = (int32_t)usucc.size() - u.succ_begin;
+    }
+    std::vector<int32_t> entries;
+    uint32_t total_parts = 0;
+    for (const GUnit& u : units) total_parts += (uint32_t)u.nparts;
+    for (int32_t i = 0; i < nready; ++i) {
+        const int32_t uid = unit_of[ready[i]];
+        if (units[uid].dep_goal != 0) { w->e->last_error = "ready task has in-window predecessors"; return PB2_ERR_BAD_PARAM; }
+        for (int32_t p = 0; p < units[uid].nparts; ++p) entries.push_back((int32_t)PB2_SUCC_MAKE(uid, p));
+    }
+    *ring_cap_needed = total_parts;
+    int rc;
+    GUnit* d_units = nullptr; GSeg* d_segs = nullptr; int32_t* d_usucc = nullptr;
+    if ((rc = dev_alloc_copy(w, &d_units, units.data(), units.size())) != PB2_SUCCESS) return rc;
+    if ((rc = dev_alloc_copy(w, &d_segs, segs.data(), segs.size())) != PB2_SUCCESS) return rc;
+    if ((rc = dev_alloc_copy(w, &d_usucc, usucc.data(), usucc.size())) != PB2_SUCCESS) return rc;
+    if ((rc = dev_alloc_copy(w, &w->d_ready_entries, entries.data(), entries.size())) != PB2_SUCCESS) return rc;
+    if ((rc = dev_alloc_copy(w, &w->g.udep, (const int32_t*)nullptr, units.size())) != PB2_SUCCESS) return rc;
+    if ((rc = dev_alloc_copy(w, &w->g.parts_left, (const int32_t*)nullptr, units.size())) != PB2_SUCCESS) return rc;
+    w->g.units = d_units; w->g.segs = d_segs; w->g.usucc = d_usucc; w->g.nunits = (int32_t)units.size();
+    w->nentries = (int32_t)entries.size();
+    return PB2_SUCCESS;
+}
+
 extern "C" {
 
 int pb2_engine_create(pb2_engine_t** engine, int cuda_device, const pb2_engine_params_t* params) {
@@ -357,6 +448,7 @@ int pb2_engine_create(pb2_engine_t** engine, int cuda_device, const pb2_engine_p
     if (p.max_workers > 0 && p.max_workers < e->nworkers) e->nworkers = p.max_workers;
     e->nworkers_gemm = pb2_gemm_nworkers(e->prop.multiProcessorCount);
     if (p.max_workers > 0 && p.max_workers < e->nworkers_gemm) e->nworkers_gemm = p.max_workers;
+    if (p.gemm_mode != 1 && e->nworkers_gemm < 2) e->nworkers_gemm = 2;      // v2 workers are CTA pairs
     *engine = e;
     return PB2_SUCCESS;
 }
@@ -502,10 +594,18 @@ int pb2_window_create(pb2_engine_t* e, pb2_window_t** window, int kind,
     TRY(dev_alloc_copy(w, &w->d_tiles_init, tiles, (size_t)ntiles));
     TRY(dev_alloc_copy(w, &w->d_tiles, (const pb2_tile_t*)nullptr, (size_t)ntiles));
     TRY(dev_alloc_copy(w, &w->d_ready, ready, (size_t)nready));
-    if (kind == 1) TRY(build_tensor_maps(w, tasks, ntasks, tiles, ntiles));
+    uint32_t parts_needed = 0;
+    if (kind == 1) {
+        TRY(build_tensor_maps(w, tasks, ntasks, tiles, ntiles));
+        if (e->params.gemm_mode != 1) {
+            rc = build_gemm2_units(w, tasks, ntasks, succ, ready, nready, e->params.gemm_mode == 0, &parts_needed);
+            if (rc == PB2_SUCCESS) w->v2 = true;
+            else if (rc != PB2_ERR_NOT_SUPPORTED) { pb2_window_destroy(w); return rc; }     // NOT_SUPPORTED: v1 kernel
+        }
+    }
     const int maxw = e->nworkers > e->nworkers_gemm ? e->nworkers : e->nworkers_gemm;
     uint32_t cap = 1024;
-    while (cap < (uint32_t)ntasks + (uint32_t)maxw + 2u) cap <<= 1;   // every slot is used at most once per run
+    while (cap < (uint32_t)ntasks + parts_needed + (uint32_t)maxw + 2u) cap <<= 1;   // every slot is used at most once per run
     WinDev& d = w->d;
     d.tasks = w->d_tasks; d.succ = w->d_succ; d.tiles = w->d_tiles;
     TRY(dev_alloc_copy(w, &d.dep, (const int32_t*)nullptr, (size_t)ntasks));
@@ -520,6 +620,7 @@ int pb2_window_create(pb2_engine_t* e, pb2_window_t** window, int kind,
 #undef TRY
     d.cap_mask = cap - 1; d.ntasks = ntasks; d.ntiles = ntiles; d.stage_mode = e->params.stage_mode;
     d.timeout_ns = (unsigned long long)e->params.timeout_ms * 1000000ull;
+    if (w->v2) { w->g.w = d; w->g.tmaps = w->d_tmaps; }
     PB2_CUDA(e, cudaEventCreate(&w->ev0));
     PB2_CUDA(e, cudaEventCreate(&w->ev1));
     PB2_CUDA(e, cudaEventCreate(&w->ev2));
@@ -559,6 +660,12 @@ int pb2_window_launch(pb2_window_t* w) {
         if (w->kind == 0) {
             pb2_engine_hbm_kernel<<<e->nworkers, e->params.threads, 0, e->stream>>>(w->d);
             PB2_CUDA(e, cudaGetLastError());
+        } else if (w->v2) {
+            pb2_window2_reset_kernel<<<64, 256, 0, e->stream>>>(w->g, w->d_ready_entries, w->nentries);
+            PB2_CUDA(e, cudaGetLastError());
+            PB2_CUDA(e, cudaEventRecord(w->ev1, e->stream));
+            int rc = pb2_gemm2_launch(w->g, e->nworkers_gemm, e->stream);
+            if (rc != PB2_SUCCESS) { e->last_error = "gemm v2 window launch failed"; return rc; }
         } else {
             int rc = pb2_gemm_launch(w->d, w->d_tmaps, e->nworkers_gemm, e->stream);
             if (rc != PB2_SUCCESS) { e->last_error = "gemm window launch failed"; return rc; }

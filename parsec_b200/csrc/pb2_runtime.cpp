@@ -239,6 +239,7 @@ int pb2_init(pb2_context_t** pctx, int nb_cores) {
     ctx->mca["device_engine_workers_per_sm"] = 0;
     ctx->mca["device_engine_max_workers"] = 0;
     ctx->mca["device_engine_timeout_ms"] = 0;
+    ctx->mca["device_engine_gemm_mode"] = 0;
     // index 0: the CPU; index 1: the recursive pseudo-device (device.c:1041-1110)
     for (int i = 0; i < 2; ++i) {
         pb2_device_module_t* d = new pb2_device_module_s();
@@ -281,6 +282,7 @@ int pb2_device_cuda_module_init(pb2_context_t* ctx, int cuda_index, int dry_run,
         p.workers_per_sm = (int32_t)ctx->mca["device_engine_workers_per_sm"];
         p.max_workers = (int32_t)ctx->mca["device_engine_max_workers"];
         p.timeout_ms = (int32_t)ctx->mca["device_engine_timeout_ms"];
+        p.gemm_mode = (int32_t)ctx->mca["device_engine_gemm_mode"];
         int rc = pb2_engine_create(&d->engine, cuda_index, &p);
         if (rc != PB2_SUCCESS) { delete d; return rc; }                 // no GPU => loud failure, no fallback
         pb2_engine_info_t info;
