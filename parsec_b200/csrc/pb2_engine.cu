@@ -23,6 +23,7 @@
 #include <vector>
 #include <mutex>
 #include <map>
+#include <algorithm>
 
 #include "../../include/pb2_engine.h"
 #include "pb2_sched.cuh"
@@ -382,11 +383,26 @@ static int build_gemm2_units(pb2_window_t* w, const pb2_task_t* tasks, int32_t n
     std::vector<int32_t> entries;
     uint32_t total_parts = 0;
     for (const GUnit& u : units) total_parts += (uint32_t)u.nparts;
+    // Ready GEMM units enter the ring in Z-order of their (locals[0], locals[1]) = C(i,j) coordinates: the ~37 units
+    // that run concurrently then form a compact block of C tiles that shares A rows and B columns in L2 (a FIFO
+    // ring keeps whatever order the host gives it; the reference's priority hint mt*nt*kt - i*nt + j plays the
+    // same role for its sorted pending list, device_gpu.c:2169-2174).
+    std::vector<std::pair<uint64_t, int32_t>> order;
+    auto morton = [](uint32_t x, uint32_t y) {
+        uint64_t r = 0;
+        for (int b = 0; b < 16; ++b) r |= ((uint64_t)((x >> b) & 1) << (2 * b + 1)) | ((uint64_t)((y >> b) & 1) << (2 * b));
+        return r;
+    };
     for (int32_t i = 0; i < nready; ++i) {
         const int32_t uid = unit_of[ready[i]];
         if (units[uid].dep_goal != 0) { w->e->last_error = "ready task has in-window predecessors"; return PB2_ERR_BAD_PARAM; }
-        for (int32_t p = 0; p < units[uid].nparts; ++p) entries.push_back((int32_t)PB2_SUCC_MAKE(uid, p));
+        const pb2_task_t& t = tasks[ready[i]];
+        const uint64_t key = (units[uid].flags & 1) ? morton((uint32_t)t.locals[0], (uint32_t)t.locals[1]) : 0;
+        order.emplace_back(key, uid);
     }
+    std::stable_sort(order.begin(), order.end(), [](const std::pair<uint64_t, int32_t>& a, const std::pair<uint64_t, int32_t>& b) { return a.first < b.first; });
+    for (auto& o : order)
+        for (int32_t p = 0; p < units[o.second].nparts; ++p) entries.push_back((int32_t)PB2_SUCC_MAKE(o.second, p));
     *ring_cap_needed = total_parts;
     int rc;
     GUnit* d_units = nullptr; GSeg* d_segs = nullptr; int32_t* d_usucc = nullptr;
@@ -620,7 +636,7 @@ int pb2_window_create(pb2_engine_t* e, pb2_window_t** window, int kind,
 #undef TRY
     d.cap_mask = cap - 1; d.ntasks = ntasks; d.ntiles = ntiles; d.stage_mode = e->params.stage_mode;
     d.timeout_ns = (unsigned long long)e->params.timeout_ms * 1000000ull;
-    if (w->v2) { w->g.w = d; w->g.tmaps = w->d_tmaps; }
+    if (w->v2) { w->g.w = d; w->g.tmaps = w->d_tmaps; w->g.debug = getenv("PB2_GEMM_DEBUG") ? atoi(getenv("PB2_GEMM_DEBUG")) : 0; }
     PB2_CUDA(e, cudaEventCreate(&w->ev0));
     PB2_CUDA(e, cudaEventCreate(&w->ev1));
     PB2_CUDA(e, cudaEventCreate(&w->ev2));

@@ -40,6 +40,7 @@ struct Win2Dev {
     int32_t* parts_left;
     const CUtensorMap* tmaps;
     int32_t nunits;
+    int32_t debug;                  // development only (PB2_GEMM_DEBUG): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue
 };
 
 namespace gemm2 {
@@ -81,7 +82,8 @@ __device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared::cluster.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(addr) : "memory");
+    // no cluster-scope release: the arrival publishes no data (the TMA bytes are tracked by complete_tx)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(addr) : "memory");
 }
 // TMA load of this CTA's share into its own smem; completion bytes are credited to the LEADER's barrier
 __device__ __forceinline__ void tma_load_2sm(void* smem_dst, const CUtensorMap* tmap, uint32_t leader_bar, int c0, int c1) {
@@ -277,16 +279,25 @@ pb2_engine_gemm2_kernel(Win2Dev g) {
                         const GSeg sg = g.segs[job.seg_begin + s];
                         const CUtensorMap* mapA = &g.tmaps[sg.tileA];
                         const CUtensorMap* mapB = &g.tmaps[sg.tileB];
+                        if (s + 1 < job.seg_count) {        // the next member's descriptors: fetch them now, not on first use
+                            const GSeg nx = g.segs[job.seg_begin + s + 1];
+                            asm volatile("prefetch.tensormap [%0];" :: "l"(&g.tmaps[nx.tileA]) : "memory");
+                            asm volatile("prefetch.tensormap [%0];" :: "l"(&g.tmaps[nx.tileB]) : "memory");
+                        }
                         for (int kb = 0; kb < kblocks; ++kb) {
                             mbar_wait(&sh.empty[p_stage], p_phase ^ 1);
                             uint8_t* sa = smem + p_stage * kStage2;
                             const uint32_t bar = leader_full0 + p_stage * 8;
+                            if (g.debug & 1) {
+                                if (leader) mbar_arrive(&sh.full[p_stage]); else mbar_arrive_cluster(bar);
+                            } else {
                             if (leader) mbar_expect_tx(&sh.full[p_stage], (uint32_t)(kAStage + nhalves * kBHalf) * 2);
                             else        mbar_arrive_cluster(bar);
                             tma_load_2sm(sa, mapA, bar, kb * BK, job.m0 + (int)rank * 128);
                             for (int h = 0; h < nhalves; ++h) {
                                 const int nh = min(256, job.N - 256 * h);
                                 tma_load_2sm(sa + kAStage + h * kBHalf, mapB, bar, kb * BK, 256 * h + (int)rank * (nh / 2));
+                            }
                             }
                             if (++p_stage == kStages2) { p_stage = 0; p_phase ^= 1; }
                         }
@@ -301,7 +312,7 @@ pb2_engine_gemm2_kernel(Win2Dev g) {
                             tc_fence_after();
                             const uint32_t sa = smem_u32(smem + c_stage * kStage2);
                             const uint64_t da = make_desc(sa);
-                            for (int h = 0; h < nhalves; ++h) {
+                            for (int h = 0; h < nhalves && !(g.debug & 2); ++h) {
                                 const int nh = min(256, job.N - 256 * h);
                                 const uint32_t idesc = make_idesc(256, nh);
                                 const uint64_t db = make_desc(sa + kAStage + h * kBHalf);
@@ -323,12 +334,17 @@ pb2_engine_gemm2_kernel(Win2Dev g) {
             } else if (warp >= 4) {
                 // ===== epilogue (both CTAs): C rows m0 + rank*128 + quadrant*32 + lane
                 const int q = warp & 3;
-                mbar_wait(&sh.tmem_full, tfull_phase);
-                tc_fence_after();
                 uint8_t* Cbase = reinterpret_cast<uint8_t*>(w.tiles[job.tileC].dev_ptr);
                 const int row = job.m0 + (int)rank * 128 + q * 32 + lane;
+                // these warps idle during the main loop: pull this thread's C row into L2 now, so that the
+                // read-modify-write below does not pay DRAM latency sixteen times in a row
+                if (row < job.M)
+                    for (int b = 0; b < job.N * 2; b += 128)
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(Cbase + (size_t)row * job.N * 2 + b));
+                mbar_wait(&sh.tmem_full, tfull_phase);
+                tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-                const int nchunks = (job.N + 31) / 32;
+                const int nchunks = (g.debug & 4) ? 0 : (job.N + 31) / 32;
                 const bool row_ok = row < job.M;
                 uint4 cv[4];
                 auto load_c = [&](int c) {

@@ -35,7 +35,7 @@ def test_dtd_gemm_chain(mode, NT, T):
     dag = dags.dtd_gemm(NT, T)
     tb = T * T * 2
     host = np.concatenate([f32_to_bf16_bits(A).ravel(), f32_to_bf16_bits(B).ravel(), f32_to_bf16_bits(C).ravel()])
-    with Engine(0, gemm_mode=mode) as engine:
+    with Engine(0, gemm_mode=mode, timeout_ms=4000) as engine:
         slab = engine.malloc(dag.ntiles * tb)
         alias = engine.host_register(host)
         tiles = np.zeros(dag.ntiles, L.TILE_DTYPE)
