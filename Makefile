@@ -1,7 +1,8 @@
 # Builds the in-tree native library (sm_100a only) and the CPU oracle.
 NVCC      ?= /usr/local/cuda/bin/nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVCCFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v
+EXTRA     ?=
+NVCCFLAGS := $(EXTRA) -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v
 CSRC      := parsec_b200/csrc
 LIB       := parsec_b200/libparsec_b200.so
 CU_SRCS   := $(CSRC)/pb2_engine.cu

@@ -131,7 +131,8 @@ typedef struct pb2_engine_params_s {
                                 * (default 20000); a malformed DAG must never hang the GPU                   */
     int32_t  gemm_mode;        /* 0 = CTA pairs (cta_group::2) + fused k-chains (default), 1 = v1 single-CTA kernel,
                                 * 2 = CTA pairs, every task flushes C (per-task bf16 rounding, as the oracle)       */
-    int32_t  reserved[1];
+    int32_t  part_bytes;       /* HBM bodies: a task whose largest tile exceeds this many bytes is run as up to 32
+                                * parts (byte slices) by different workers (default 256 KiB, <0 = never split)   */
 } pb2_engine_params_t;
 
 typedef struct pb2_engine_info_s {

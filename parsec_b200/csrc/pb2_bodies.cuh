@@ -16,7 +16,10 @@
 
 namespace pb2 {
 
-constexpr int kUnroll = 4;
+#ifndef PB2_UNROLL
+#define PB2_UNROLL 4
+#endif
+constexpr int kUnroll = PB2_UNROLL;
 
 // f(uint4& v, size_t first_elem_index) ; elements are 4-byte lanes x,y,z,w
 template <bool READ, bool WRITE, class F>
@@ -121,8 +124,10 @@ __device__ __forceinline__ uint32_t cta_reduce_sum(uint32_t v, uint32_t* smem) {
 }
 
 struct BodyArgs {
-    void*    flow[4];     // device pointers of the flows' tiles
-    uint32_t bytes[4];
+    void*    flow[4];     // device pointers of this part's slice of the flows' tiles
+    uint32_t bytes[4];    // bytes of the slice
+    uint32_t elem0;       // index of the slice's first 4-byte element inside the tile (IOTA-style bodies)
+    uint32_t part;        // part index (CHECK reports the tile's first element from part 0 only)
     int32_t  iparam[3];
     float    fparam;
 };
@@ -161,7 +166,7 @@ __device__ __forceinline__ uint64_t run_hbm_body(int body, const BodyArgs& a, ui
         });
         const uint32_t total = cta_reduce_sum(bad, red_smem);
         uint32_t first = 0;
-        if (threadIdx.x == 0 && a.bytes[0] >= 4) first = __ldcg(reinterpret_cast<const uint32_t*>(a.flow[0]));
+        if (threadIdx.x == 0 && a.part == 0 && a.bytes[0] >= 4) first = __ldcg(reinterpret_cast<const uint32_t*>(a.flow[0]));
         return ((uint64_t)total << 32) | first;
     }
     case PB2_BODY_INCR_I32: {
@@ -178,14 +183,18 @@ __device__ __forceinline__ uint64_t run_hbm_body(int body, const BodyArgs& a, ui
         return 0;
     }
     case PB2_BODY_ADD_IOTA_I32: {
-        cta_vec_loop<true, true>(a.flow[0], a.bytes[0], [](uint4& v, size_t i) {
-            v.x += (uint32_t)i; v.y += (uint32_t)i + 1; v.z += (uint32_t)i + 2; v.w += (uint32_t)i + 3;
+        const uint32_t e0 = a.elem0;
+        cta_vec_loop<true, true>(a.flow[0], a.bytes[0], [e0](uint4& v, size_t i) {
+            const uint32_t j = e0 + (uint32_t)i;
+            v.x += j; v.y += j + 1; v.z += j + 2; v.w += j + 3;
         });
         return 0;
     }
     case PB2_BODY_IOTA_I32: {
-        cta_vec_loop<false, true>(a.flow[0], a.bytes[0], [](uint4& v, size_t i) {
-            v = make_uint4((uint32_t)i, (uint32_t)i + 1, (uint32_t)i + 2, (uint32_t)i + 3);
+        const uint32_t e0 = a.elem0;
+        cta_vec_loop<false, true>(a.flow[0], a.bytes[0], [e0](uint4& v, size_t i) {
+            const uint32_t j = e0 + (uint32_t)i;
+            v = make_uint4(j, j + 1, j + 2, j + 3);
         });
         return 0;
     }
@@ -198,8 +207,9 @@ __device__ __forceinline__ uint64_t run_hbm_body(int body, const BodyArgs& a, ui
         return 0;
     }
     case PB2_BODY_ADD_AT_I32: {
-        if (threadIdx.x == 0 && (size_t)a.iparam[0] * 4 + 4 <= a.bytes[0] && a.iparam[0] >= 0) {
-            uint32_t* e = reinterpret_cast<uint32_t*>(a.flow[0]) + a.iparam[0];
+        const long long rel = (long long)a.iparam[0] - (long long)a.elem0;     // the element may live in another part
+        if (threadIdx.x == 0 && rel >= 0 && (size_t)rel * 4 + 4 <= a.bytes[0]) {
+            uint32_t* e = reinterpret_cast<uint32_t*>(a.flow[0]) + rel;
             __stcg(e, __ldcg(e) + (uint32_t)a.iparam[1]);
         }
         return 0;

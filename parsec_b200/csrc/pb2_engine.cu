@@ -43,6 +43,7 @@ __global__ void pb2_window_reset_kernel(WinDev w, const pb2_tile_t* tiles_init,
         const pb2_task_t& t = w.tasks[i];
         // counter mode counts down from the goal (parsec.c:1625-1633); mask mode ORs up from 0 (:1693-1703)
         w.dep[i] = (t.flags & PB2_TASK_DEPS_MASK) ? 0 : t.dep_goal;
+        if (w.parts_left) w.parts_left[i] = PB2_TASK_NPARTS(t.flags);
         w.start_seq[i] = 0; w.end_seq[i] = 0; w.result[i] = 0; w.worker[i] = -1; w.retire_log[i] = -1;
         for (int f = 0; f < PB2_MAX_FLOWS; ++f) w.seen_version[i * PB2_MAX_FLOWS + f] = 0;
     }
@@ -63,7 +64,15 @@ __global__ void pb2_window_reset_kernel(WinDev w, const pb2_tile_t* tiles_init,
 // ---------------------------------------------------------------------------------------------
 // 256 threads, 4 CTAs per SM (<= 64 registers): 1024 threads x 4 x 16 B loads in flight per SM saturate HBM; the
 // cold stage-in / pushout copies may spill, the body loops do not.
-__global__ void __launch_bounds__(256, 4)
+// 64-thread workers, 24 per SM (1536 threads, <= 40 registers): measured best on B200 (sweep in DESIGN.md):
+// many small workers overlap the serial pop / release sections of one task with the streaming of the others.
+#ifndef PB2_HBM_MINB
+#define PB2_HBM_MINB 24
+#endif
+#ifndef PB2_HBM_THREADS
+#define PB2_HBM_THREADS 64
+#endif
+__global__ void __launch_bounds__(PB2_HBM_THREADS, PB2_HBM_MINB)
 pb2_engine_hbm_kernel(WinDev w) {
     __shared__ __align__(16) pb2_task_t s_task;   // filled with four 16-byte loads
     __shared__ int32_t    s_id;
@@ -74,21 +83,19 @@ pb2_engine_hbm_kernel(WinDev w) {
 
     for (;;) {
         if (threadIdx.x == 0) {
-            const int32_t id = pop_task(w);
-            if (id != kEmpty) {
-                __threadfence();   // acquire side: order the tile reads below after the slot read
-                w.start_seq[id] = (uint32_t)atomicAdd(&w.ctl->evt.v, 1ull);
-                w.worker[id] = (int32_t)blockIdx.x;
-            }
-            s_id = id;
+            const int32_t e = pop_task(w);
+            if (e != kEmpty) __threadfence();   // acquire side: order the tile reads below after the slot read
+            s_id = e;
         }
         __syncthreads();
-        const int32_t id = s_id;
-        if (id == kEmpty) break;
+        if (s_id == kEmpty) break;
+        const int32_t id = PB2_SUCC_TASK((uint32_t)s_id);
+        const int part = PB2_SUCC_FLOW((uint32_t)s_id);
         if (threadIdx.x < 4) reinterpret_cast<uint4*>(&s_task)[threadIdx.x] =
             __ldg(reinterpret_cast<const uint4*>(&w.tasks[id]) + threadIdx.x);
         __syncthreads();
         const pb2_task_t& t = s_task;
+        const int nparts = PB2_TASK_NPARTS(t.flags);
 
         // ---- push: reserve + stage in (parsec_device_kernel_push) ----
         // Thread 0 looks at the tile states once; the resulting mask is CTA-uniform (the states
@@ -99,18 +106,29 @@ pb2_engine_hbm_kernel(WinDev w) {
                 if (t.tile[f] >= 0 && (t.access[f] & PB2_FLOW_ACCESS_READ) &&
                     ld_acquire_gpu(&w.tiles[t.tile[f]].state) != PB2_TILE_VALID) need |= 1 << f;
             s_need = need;
+            if (part == 0) {
+                w.start_seq[id] = (uint32_t)atomicAdd(&w.ctl->evt.v, 1ull);
+                w.worker[id] = (int32_t)blockIdx.x;
+            }
         }
         __syncthreads();
         const int need = s_need;
         BodyArgs a;
+        a.part = (uint32_t)part; a.elem0 = 0;
 #pragma unroll
         for (int f = 0; f < PB2_MAX_FLOWS; ++f) {
             a.flow[f] = nullptr; a.bytes[f] = 0;
             if (f < t.nb_flows && t.tile[f] >= 0) {
                 pb2_tile_t* tile = &w.tiles[t.tile[f]];
                 if ((need >> f) & 1) stage_in_flow(w, tile, t.access[f], &s_decide);
-                a.flow[f] = tile->dev_ptr; a.bytes[f] = tile->bytes;
-                if (threadIdx.x == 0)
+                // this part's slice: 16-byte aligned cut points, the last part takes the remainder
+                const uint32_t bytes = tile->bytes;
+                const uint32_t per = ((bytes / (uint32_t)nparts) + 15u) & ~15u;
+                const uint32_t off = per * (uint32_t)part < bytes ? per * (uint32_t)part : bytes;
+                const uint32_t len = (part == nparts - 1) ? bytes - off : (off + per <= bytes ? per : bytes - off);
+                a.flow[f] = reinterpret_cast<uint8_t*>(tile->dev_ptr) + off; a.bytes[f] = len;
+                if (f == 0) a.elem0 = off >> 2;
+                if (threadIdx.x == 0 && part == 0)
                     w.seen_version[id * PB2_MAX_FLOWS + f] = *reinterpret_cast<volatile uint32_t*>(&tile->version);
             }
         }
@@ -126,8 +144,9 @@ pb2_engine_hbm_kernel(WinDev w) {
             if (f < t.nb_flows && t.tile[f] >= 0 && (t.access[f] & PB2_FLOW_PUSHOUT) &&
                 (t.access[f] & PB2_FLOW_ACCESS_WRITE)) {
                 pb2_tile_t* tile = &w.tiles[t.tile[f]];
-                cta_copy<false>(tile->src_ptr, tile->dev_ptr, tile->bytes);
-                if (threadIdx.x == 0) atomicAdd(&w.ctl->bytes_d2h.v, (unsigned long long)tile->bytes);
+                const size_t off = reinterpret_cast<uint8_t*>(a.flow[f]) - reinterpret_cast<uint8_t*>(tile->dev_ptr);
+                cta_copy<false>(reinterpret_cast<uint8_t*>(tile->src_ptr) + off, a.flow[f], a.bytes[f]);
+                if (threadIdx.x == 0) atomicAdd(&w.ctl->bytes_d2h.v, (unsigned long long)a.bytes[f]);
             }
         }
         __syncthreads();
@@ -137,25 +156,33 @@ pb2_engine_hbm_kernel(WinDev w) {
                                // visible before any successor can observe its dependency word / ring slot
             if (threadIdx.x == 0) {
                 if (r == ~0ull) st_relaxed_gpu(reinterpret_cast<int32_t*>(&w.ctl->done.v), kDoneBadBody);
-                w.result[id] = r;
-                if ((t.body == PB2_BODY_CHECK_I32 || t.body == PB2_BODY_CHECK_F32) && (r >> 32))
-                    atomicAdd(&w.ctl->body_errors.v, r >> 32);
-                for (int f = 0; f < t.nb_flows; ++f) {
-                    if (t.tile[f] < 0 || !(t.access[f] & PB2_FLOW_ACCESS_WRITE)) continue;
-                    pb2_tile_t* tile = &w.tiles[t.tile[f]];
-                    // version = candidate->version + 1 for WRITE flows (device_gpu.c:2148-2152)
-                    *reinterpret_cast<volatile uint32_t*>(&tile->version) =
-                        *reinterpret_cast<volatile uint32_t*>(&tile->version) + 1;
-                    if (!(t.access[f] & PB2_FLOW_ACCESS_READ)) st_relaxed_gpu(&tile->state, PB2_TILE_VALID);
+                if (t.body == PB2_BODY_CHECK_I32 || t.body == PB2_BODY_CHECK_F32) {
+                    // parts add their mismatch counts; part 0 also carries the tile's first element
+                    if (nparts == 1) w.result[id] = r; else if (r) atomicAdd(&w.result[id], r);
+                    if (r >> 32) atomicAdd(&w.ctl->body_errors.v, r >> 32);
+                } else if (part == 0) w.result[id] = r;
+                // the last part to finish retires the task (fence / RMW chain orders every part's stores before it)
+                int last = 1;
+                if (nparts > 1) { last = atomicSub(&w.parts_left[id], 1) == 1; __threadfence(); }
+                s_last = 0; s_need = last;
+                if (last) {
+                    for (int f = 0; f < t.nb_flows; ++f) {
+                        if (t.tile[f] < 0 || !(t.access[f] & PB2_FLOW_ACCESS_WRITE)) continue;
+                        pb2_tile_t* tile = &w.tiles[t.tile[f]];
+                        // version = candidate->version + 1 for WRITE flows (device_gpu.c:2148-2152)
+                        *reinterpret_cast<volatile uint32_t*>(&tile->version) =
+                            *reinterpret_cast<volatile uint32_t*>(&tile->version) + 1;
+                        if (!(t.access[f] & PB2_FLOW_ACCESS_READ)) st_relaxed_gpu(&tile->state, PB2_TILE_VALID);
+                    }
+                    w.end_seq[id] = (uint32_t)atomicAdd(&w.ctl->evt.v, 1ull);
+                    // the retire log is written before the out-edges are released, so that it is a linear
+                    // extension of the DAG's partial order (a successor can only retire after us)
+                    s_last = retire_task(w, id) ? 1 : 0;
+                    __threadfence();
                 }
-                w.end_seq[id] = (uint32_t)atomicAdd(&w.ctl->evt.v, 1ull);
-                // the retire log is written before the out-edges are released, so that it is a linear
-                // extension of the DAG's partial order (a successor can only retire after us)
-                s_last = retire_task(w, id) ? 1 : 0;
-                __threadfence();
             }
             __syncwarp();
-            release_successors_warp(w, t);
+            if (s_need) release_successors_warp(w, t);
             if (threadIdx.x == 0 && s_last) {
                 __threadfence();
                 st_release_gpu(reinterpret_cast<int32_t*>(&w.ctl->done.v), kDoneOK);
@@ -207,7 +234,7 @@ struct pb2_engine_s {
 struct pb2_window_s {
     pb2_engine_t* e = nullptr;
     int kind = 0;
-    int32_t ntasks = 0, nsucc = 0, ntiles = 0, nready = 0;
+    int32_t ntasks = 0, nsucc = 0, ntiles = 0, nready = 0, nready_entries = 0;
     WinDev d{};
     pb2_task_t* d_tasks = nullptr;
     uint32_t* d_succ = nullptr;
@@ -442,10 +469,11 @@ int pb2_engine_create(pb2_engine_t** engine, int cuda_device, const pb2_engine_p
     }
     pb2_engine_params_t p{};
     if (params) p = *params;
-    if (p.workers_per_sm <= 0) p.workers_per_sm = 4;
-    if (p.threads <= 0 || p.threads > 256) p.threads = 256;     // the kernel is compiled for <= 256 threads
+    if (p.workers_per_sm <= 0) p.workers_per_sm = PB2_HBM_MINB;
+    if (p.threads <= 0 || p.threads > PB2_HBM_THREADS) p.threads = PB2_HBM_THREADS;     // the kernel is compiled for this CTA size
     p.threads = (p.threads + 31) & ~31;
     if (p.timeout_ms <= 0) p.timeout_ms = 20000;
+    if (p.part_bytes == 0) p.part_bytes = 256 * 1024;
     e->params = p;
     PB2_CUDA(e, cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
     e->stream = e->own_stream;
@@ -605,11 +633,28 @@ int pb2_window_create(pb2_engine_t* e, pb2_window_t** window, int kind,
     pb2_window_t* w = new pb2_window_s();
     w->e = e; w->kind = kind; w->ntasks = ntasks; w->nsucc = nsucc; w->ntiles = ntiles; w->nready = nready;
 #define TRY(x) do { rc = (x); if (rc != PB2_SUCCESS) { pb2_window_destroy(w); return rc; } } while (0)
-    TRY(dev_alloc_copy(w, &w->d_tasks, tasks, (size_t)ntasks));
+    // device copy of the descriptors: bits 3..7 of flags carry the number of parts - 1 (wide tasks, HBM windows)
+    std::vector<pb2_task_t> dtasks(tasks, tasks + ntasks);
+    std::vector<int32_t> entries;
+    uint32_t extra_parts = 0;
+    for (int32_t i = 0; i < ntasks; ++i) {
+        pb2_task_t& t = dtasks[i];
+        t.flags &= 0x07;
+        if (kind != 0 || t.body == PB2_BODY_NOP || e->params.part_bytes < 0) continue;
+        uint32_t big = 0;
+        for (int f = 0; f < t.nb_flows; ++f) if (t.tile[f] >= 0 && tiles[t.tile[f]].bytes > big) big = tiles[t.tile[f]].bytes;
+        uint32_t np = (big + (uint32_t)e->params.part_bytes - 1) / (uint32_t)e->params.part_bytes;
+        if (np > 32) np = 32;
+        if (np > 1) { t.flags |= (uint8_t)((np - 1) << 3); extra_parts += np - 1; }
+    }
+    for (int32_t i = 0; i < nready; ++i)
+        for (int p = 0; p < PB2_TASK_NPARTS(dtasks[ready[i]].flags); ++p) entries.push_back((int32_t)PB2_SUCC_MAKE(ready[i], p));
+    TRY(dev_alloc_copy(w, &w->d_tasks, dtasks.data(), (size_t)ntasks));
     TRY(dev_alloc_copy(w, &w->d_succ, succ, (size_t)nsucc));
     TRY(dev_alloc_copy(w, &w->d_tiles_init, tiles, (size_t)ntiles));
     TRY(dev_alloc_copy(w, &w->d_tiles, (const pb2_tile_t*)nullptr, (size_t)ntiles));
-    TRY(dev_alloc_copy(w, &w->d_ready, ready, (size_t)nready));
+    TRY(dev_alloc_copy(w, &w->d_ready, entries.data(), entries.size()));
+    w->nready_entries = (int32_t)entries.size();
     uint32_t parts_needed = 0;
     if (kind == 1) {
         TRY(build_tensor_maps(w, tasks, ntasks, tiles, ntiles));
@@ -621,7 +666,7 @@ int pb2_window_create(pb2_engine_t* e, pb2_window_t** window, int kind,
     }
     const int maxw = e->nworkers > e->nworkers_gemm ? e->nworkers : e->nworkers_gemm;
     uint32_t cap = 1024;
-    while (cap < (uint32_t)ntasks + parts_needed + (uint32_t)maxw + 2u) cap <<= 1;   // every slot is used at most once per run
+    while (cap < (uint32_t)ntasks + extra_parts + parts_needed + (uint32_t)maxw + 2u) cap <<= 1;   // every slot is used at most once per run
     WinDev& d = w->d;
     d.tasks = w->d_tasks; d.succ = w->d_succ; d.tiles = w->d_tiles;
     TRY(dev_alloc_copy(w, &d.dep, (const int32_t*)nullptr, (size_t)ntasks));
@@ -633,6 +678,8 @@ int pb2_window_create(pb2_engine_t* e, pb2_window_t** window, int kind,
     TRY(dev_alloc_copy(w, &d.seen_version, (const uint32_t*)nullptr, (size_t)ntasks * PB2_MAX_FLOWS));
     TRY(dev_alloc_copy(w, &d.result, (const unsigned long long*)nullptr, (size_t)ntasks));
     TRY(dev_alloc_copy(w, &d.worker, (const int32_t*)nullptr, (size_t)ntasks));
+    d.parts_left = nullptr;
+    if (kind == 0 && extra_parts) TRY(dev_alloc_copy(w, &d.parts_left, (const int32_t*)nullptr, (size_t)ntasks));
 #undef TRY
     d.cap_mask = cap - 1; d.ntasks = ntasks; d.ntiles = ntiles; d.stage_mode = e->params.stage_mode;
     d.timeout_ns = (unsigned long long)e->params.timeout_ms * 1000000ull;
@@ -668,7 +715,7 @@ int pb2_window_launch(pb2_window_t* w) {
         int blocks = (int)((n + threads - 1) / threads);
         if (blocks > e->prop.multiProcessorCount * 8) blocks = e->prop.multiProcessorCount * 8;
         if (blocks < 1) blocks = 1;
-        pb2_window_reset_kernel<<<blocks, threads, 0, e->stream>>>(w->d, w->d_tiles_init, w->d_ready, w->nready);
+        pb2_window_reset_kernel<<<blocks, threads, 0, e->stream>>>(w->d, w->d_tiles_init, w->d_ready, w->nready_entries);
         PB2_CUDA(e, cudaGetLastError());
     }
     PB2_CUDA(e, cudaEventRecord(w->ev1, e->stream));

@@ -204,6 +204,7 @@ pb2_engine_gemm_kernel(WinDev w, const CUtensorMap* __restrict__ tmaps) {
                 a.flow[f] = has ? w.tiles[t.tile[f]].dev_ptr : nullptr;
                 a.bytes[f] = has ? w.tiles[t.tile[f]].bytes : 0;
             }
+            a.elem0 = 0; a.part = 0;
             a.iparam[0] = t.iparam[0]; a.iparam[1] = t.iparam[1]; a.iparam[2] = t.iparam[2]; a.fparam = t.fparam;
             hbm_result = run_hbm_body(t.body, a, sh.red);
             fence_proxy_async();

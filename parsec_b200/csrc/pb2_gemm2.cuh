@@ -392,6 +392,7 @@ pb2_engine_gemm2_kernel(Win2Dev g) {
                 a.flow[f] = has ? w.tiles[t.tile[f]].dev_ptr : nullptr;
                 a.bytes[f] = has ? w.tiles[t.tile[f]].bytes : 0;
             }
+            a.elem0 = 0; a.part = 0;
             a.iparam[0] = t.iparam[0]; a.iparam[1] = t.iparam[1]; a.iparam[2] = t.iparam[2]; a.fparam = t.fparam;
             const unsigned long long r = run_hbm_body(t.body, a, sh.red);
             if (threadIdx.x == 0) {

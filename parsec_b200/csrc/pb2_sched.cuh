@@ -42,7 +42,14 @@ struct WinDev {
     int32_t           ntiles;
     int32_t           stage_mode;
     unsigned long long timeout_ns;
+    int32_t*          parts_left;     // HBM windows: parts of a task still running (wide tasks)
 };
+
+// A task whose tiles are large is executed as several PARTS (byte slices of its tiles) by different workers;
+// the number of parts (1..32) is kept in bits 3..7 of the DEVICE copy of pb2_task_t::flags, ring entries are
+// (part << 27) | task.  One tile at HBM speed needs the whole GPU: a 4 MiB tile is 1.3 us of the machine, not
+// 1 ms of one CTA.
+#define PB2_TASK_NPARTS(flags)  ((((int)(flags)) >> 3) + 1)
 
 // ---------------------------------------------------------------------------------------------
 // scheduling primitives shared by the HBM and the GEMM engine kernels
@@ -94,15 +101,17 @@ __device__ __forceinline__ void release_successors_warp(const WinDev& w, const p
                 ready = (atomicSub(&w.dep[sid], 1) == 1);
             }
         }
-        const uint32_t m = __ballot_sync(0xffffffffu, ready);
-        if (m) {
+        // a ready successor contributes one ring entry per part: exclusive scan of the part counts over the warp
+        const int nparts = ready ? PB2_TASK_NPARTS(w.tasks[sid].flags) : 0;
+        int incl = nparts;
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total) {
             unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&w.ctl->tail.v, (unsigned long long)__popc(m));
+            if (lane == 0) base = atomicAdd(&w.ctl->tail.v, (unsigned long long)total);
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (ready) {
-                const uint32_t pos = (uint32_t)base + __popc(m & lanemask_lt());
-                st_release_gpu(&w.ring[pos & w.cap_mask], sid);
-            }
+            for (int p = 0; p < nparts; ++p)
+                st_release_gpu(&w.ring[((uint32_t)base + (uint32_t)(incl - nparts + p)) & w.cap_mask], (int32_t)PB2_SUCC_MAKE(sid, p));
         }
     }
 }

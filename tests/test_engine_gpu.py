@@ -124,3 +124,73 @@ def test_malformed_dag_trips_watchdog():
         assert ei.value.rc == L.PB2_ERR_DEVICE
         assert w.stats["tasks_retired"] == 2
         w.close()
+
+
+@pytest.mark.parametrize("tile_bytes,part_bytes", [(1 << 20, 64 * 1024), ((1 << 20) + 4, 100 * 1000), (4 << 20, 0), (40, 16)])
+def test_wide_tasks_match_oracle(tile_bytes, part_bytes):
+    """Tasks on large tiles run as parts (byte slices) on many workers: every body, the pushout, the versions and
+    the CHECK results are bit-identical to the oracle's sequential run."""
+    from oracle import orc
+    n = tile_bytes // 4
+    t = np.zeros(9, L.TASK_DTYPE)
+    t["tile"][:] = -1
+    t["nb_flows"] = 1
+    t["tile"][:, 0] = 0
+    t["access"][:, 0] = L.ACCESS_RW
+    t["dep_goal"] = 1
+    t["dep_goal"][0] = 0
+    seq = [(L.BODY_IOTA_I32, 0, 0), (L.BODY_ADD_IOTA_I32, 0, 0), (L.BODY_SCALE_I32, 3, 0), (L.BODY_INCR_I32, -7, 0),
+           (L.BODY_ADD_AT_I32, n - 1, 1000), (L.BODY_ADD_AT_I32, n // 2, 77), (L.BODY_CHECK_I32, 5, 0),
+           (L.BODY_COPY, 0, 0), (L.BODY_CHECK_I32, 123, 0)]
+    for i, (b, p0, p1) in enumerate(seq):
+        t["body"][i], t["iparam"][i, 0], t["iparam"][i, 1] = b, p0, p1
+    t["access"][0, 0] = L.ACCESS_WRITE
+    t["access"][6, 0] = L.ACCESS_READ
+    t["nb_flows"][7] = 2; t["tile"][7, 1] = 1; t["access"][7, 0] = L.ACCESS_READ; t["access"][7, 1] = L.ACCESS_WRITE | L.FLOW_PUSHOUT
+    t["tile"][8, 0] = 1; t["access"][8, 0] = L.ACCESS_READ
+    t["succ_begin"] = np.arange(9); t["succ_count"] = 1; t["succ_count"][8] = 0
+    succ = np.arange(1, 10, dtype=np.uint32)
+    host = np.full(2 * n, 123, np.int32)
+    ohost = host.copy()
+    spec = np.zeros(2, orc.TILE_DTYPE); spec["bytes"] = tile_bytes; spec["src_ptr"] = [0, tile_bytes]
+    spec["state"] = [orc.TILE_VALID, orc.TILE_INVALID]
+    ref = orc.run_window(t, succ[:9], spec, np.array([0], np.int32), ohost)
+    assert ref["rc"] == 0
+    with Engine(0, part_bytes=part_bytes) as e:
+        slab = e.malloc(2 * tile_bytes + 1024)
+        alias = e.host_register(host)
+        tiles = np.zeros(2, L.TILE_DTYPE)
+        tiles["dev_ptr"] = [slab, slab + (tile_bytes + 511) // 512 * 512]
+        tiles["src_ptr"] = [alias, alias + tile_bytes]
+        tiles["bytes"] = tile_bytes
+        tiles["state"] = [L.TILE_VALID, L.TILE_INVALID]
+        w = e.window(0, t, succ[:9], tiles, np.array([0], np.int32))
+        st = w.run(); res = w.results(); w.close()
+        got0 = np.empty(n, np.int32); e.d2h(got0, int(tiles["dev_ptr"][0]))
+        e.host_unregister(host)
+    assert np.array_equal(res["retire_order"], np.arange(9))
+    assert np.array_equal(res["result"], ref["result"])
+    assert np.array_equal(res["seen_version"], ref["seen_version"])
+    assert np.array_equal(got0, ref["device"][0].view(np.int32)[:n])
+    assert np.array_equal(host, ohost)                                   # pushout of tile 1, slice by slice
+    assert st["body_errors"] == ref["stats"]["body_errors"] and st["bytes_d2h"] == tile_bytes
+    assert st["bytes_h2d"] == ref["stats"]["bytes_h2d"]
+
+
+def test_big_tile_chain_uses_the_whole_gpu():
+    """Config-4 body on one GPU: a serial chain of 4 MiB tiles; with parts one hop is spread over up to 32 workers."""
+    NT, tb = 64, 4 << 20
+    dag = dags.rtt_chain(NT, 1, tb)
+    host = np.zeros(tb // 4, np.float32)
+    times = {}
+    for pb in (-1, 0):
+        with Engine(0, part_bytes=pb) as e:
+            tiles, slab, slot = make_tiles(e, dag, host)
+            w = e.window(0, dag.tasks, dag.succ, tiles, dag.ready)
+            w.run(); host[:] = 0
+            st = w.run(); res = w.results(); w.close()
+            assert all(v == 0 for v in dags.check_execution(dag, res).values())
+            assert np.all(host == NT)
+            times[pb] = st["kernel_ms"]
+            e.host_unregister(host)
+    assert times[0] < times[-1] / 4, times
