@@ -57,7 +57,7 @@ class ClockSampler:
     def start(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -101,7 +101,7 @@ def cpu_reference_arm(steps, warmup, sample_groups):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--groups", type=int, default=K_GROUPS, help="broadcast groups per GPU (config value: 4096)")
@@ -260,12 +260,13 @@ def main():
     out = {"metric": "tasks/s", "value": value, "unit": "tasks/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32",
            "data": "synthetic", "config": cfg, "tile_gbs": world * algo_bytes / (ms_per_step / 1e3) / 1e9,
-           "gpu_launches": launches_per_step * args.steps, "clocks": clocks}
+           "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+           "engine": {"hbm_worker": "64 threads x 24 per SM", "gemm_worker": "CTA pair, cta_group::2, fused k-chains"}}
     if world == 1:
         peak, how = peaks()
         ach = algo_bytes / (only_kernel_ms / 1e3) / 1e9
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_ex05_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r01_ex05_traffic.json")   # from the committed ncu --set full capture
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         out["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
