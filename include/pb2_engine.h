@@ -188,6 +188,16 @@ int  pb2_engine_set_stream(pb2_engine_t* engine, void* cuda_stream);
  * pseudo-task and pays one cudaMemcpyAsync + event per tile, transfer_gpu.c:224-304).  Stream-ordered. */
 int  pb2_engine_copy_batch(pb2_engine_t* engine, void* const* dst, const void* const* src, const uint64_t* bytes, int32_t n);
 
+/* --- multi-GPU (one process per GPU): peer-visible memory ---
+ * 64-byte CUDA IPC handles of cudaMalloc'ed memory; a peer process opens them to get a pointer its kernels can
+ * load from / store to over NVLink (parsec_cuda_all_devices_attached enables the same peer access inside one
+ * process, device_cuda_module.c:144-181). */
+int  pb2_engine_ipc_export(pb2_engine_t* engine, void* dev_ptr, unsigned char handle[64]);
+int  pb2_engine_ipc_open(pb2_engine_t* engine, const unsigned char handle[64], void** dev_ptr);
+int  pb2_engine_ipc_close(pb2_engine_t* engine, void* dev_ptr);
+/* all windows created after this call keep their scheduling arrays in IPC-exportable memory */
+int  pb2_engine_set_shared_windows(pb2_engine_t* engine, int on);
+
 /* --- one window of the DAG ---
  * tasks[ntasks], succ[nsucc] (CSR via succ_begin/succ_count), tiles[ntiles] and the ids of
  * the tasks that are ready at submission (startup tasks, parsec.c:1724-1740).
@@ -211,6 +221,54 @@ int  pb2_window_results(pb2_window_t* window,
                         uint64_t* result,        /* [ntasks] body result (CHECK: mismatches<<40 | sum)   */
                         int32_t*  worker,        /* [ntasks] CTA that ran the task                       */
                         pb2_tile_t* tiles_out);  /* [ntiles] final tile table (state, version)           */
+
+/* --- windows that release dependencies of tasks living in OTHER GPUs' windows (remote_dep edges, remote_dep.h:42-58,
+ * without the host: the activation is a device atomic on the peer's dependency word plus a ring write over NVLink).
+ * Handle of this window's scheduling arrays, to be given to the peers: */
+typedef struct pb2_window_handle_s {
+    unsigned char dep[64], ring[64], ctl[64];
+    uint32_t cap_mask;
+    int32_t  ntasks;
+} pb2_window_handle_t;
+int  pb2_window_export(pb2_window_t* window, pb2_window_handle_t* handle);
+/* remote out-edges of this window: for task t, entries rs_begin[t] .. rs_begin[t+1]-1 of (rank[], target[]) where
+ * target = PB2_SUCC_MAKE(task id in that rank's window, nparts-1 of that task); remote successors are counter-mode.
+ * peers[r] is rank r's exported handle (peers[my_rank] is ignored). */
+int  pb2_window_set_remote(pb2_window_t* window, int32_t my_rank, int32_t nranks, const pb2_window_handle_t* peers,
+                           const int32_t* rs_begin, const int32_t* rs_rank, const uint32_t* rs_target, int32_t nrs);
+/* two-phase launch for windows that are released into by peers: every rank arms, all ranks synchronise, every
+ * rank starts.  pb2_window_launch == arm + start. */
+int  pb2_window_arm(pb2_window_t* window);
+int  pb2_window_start(pb2_window_t* window);
+
+/* --- splitting one window over the GPUs of a box (host logic, no device work) ------------------------------------
+ * What remote_dep.c does per task at run time (parsec_remote_dep_activate, remote_dep.c:451: which ranks own the
+ * successors of this task, per output flow) is done once per window: every edge whose end points live on different
+ * ranks becomes a remote edge of the producer's window, and the consumer's flow gets a tile descriptor that pulls the
+ * producer's copy over NVLink (src_kind PEER) the first time a local task needs that version.
+ *   task_rank[t] : rank that runs task t (rank_of of its affinity datum, two_dim_rectangle_cyclic.c:258-286)
+ *   tile_rank[i] : rank whose slab holds the initial / final copy of tile i
+ * A rank that overwrites a tile it has sent is held back by a write-after-read edge from the remote readers, the
+ * rule parsec_dtd_ordering_correctly applies to local readers (insert_function.c:2603). */
+typedef struct pb2_partition_s pb2_partition_t;
+typedef struct pb2_partition_sizes_s {
+    int32_t  ntasks, nsucc, ntiles, nready, nremote, nslots;
+    uint64_t slab_bytes;           /* bytes of the rank's tile slab (every slot 256-byte aligned) */
+} pb2_partition_sizes_t;
+int  pb2_partition_create(pb2_partition_t** partition, const pb2_task_t* tasks, int32_t ntasks,
+                          const uint32_t* succ, int32_t nsucc, const pb2_tile_t* tiles, int32_t ntiles,
+                          const int32_t* ready, int32_t nready, const int32_t* task_rank, const int32_t* tile_rank,
+                          int32_t nranks, int32_t part_bytes);
+int  pb2_partition_sizes(const pb2_partition_t* partition, int32_t rank, pb2_partition_sizes_t* sizes);
+/* slab_base[r]: address of rank r's slab as seen from `rank` (own allocation / IPC mapping).  Arrays sized by
+ * pb2_partition_sizes; rs_begin has ntasks+1 entries; global_id[t] is the id the local task had in the input;
+ * slot_tile / slot_offset describe the slab (global tile id and byte offset of each slot). */
+int  pb2_partition_get(const pb2_partition_t* partition, int32_t rank, const uint64_t* slab_base,
+                       pb2_task_t* tasks, uint32_t* succ, pb2_tile_t* tiles, int32_t* ready,
+                       int32_t* rs_begin, int32_t* rs_rank, uint32_t* rs_target, int32_t* global_id,
+                       int32_t* slot_tile, uint64_t* slot_offset);
+void pb2_partition_destroy(pb2_partition_t* partition);
+const char* pb2_partition_error(void);
 
 #ifdef __cplusplus
 }

@@ -149,6 +149,33 @@ def run_window(tasks, succ, tiles_spec, ready, host=None):
     return out
 
 
+def run_window_raw(tasks, succ, tiles, ready, policy=0, seed=1):
+    """orc_run_window on descriptors whose dev_ptr / src_ptr are real host addresses owned by the caller (several
+    descriptors may alias one buffer: that is how a window split over ranks is replayed as one merged DAG)."""
+    L = lib()
+    tasks = np.ascontiguousarray(tasks, dtype=TASK_DTYPE)
+    succ = np.ascontiguousarray(succ, dtype=np.uint32)
+    ready = np.ascontiguousarray(ready, dtype=np.int32)
+    tiles = np.array(tiles, dtype=TILE_DTYPE, copy=True)
+    n = len(tasks)
+    out = {
+        "retire_order": np.full(n, -1, np.int32), "start_seq": np.zeros(n, np.uint32), "end_seq": np.zeros(n, np.uint32),
+        "seen_version": np.zeros((n, 4), np.uint32), "result": np.zeros(n, np.uint64),
+    }
+    st = OrcStats()
+    L.orc_set_policy(policy, seed)
+    try:
+        rc = L.orc_run_window(_p(tasks), n, _p(succ), len(succ), _p(tiles), len(tiles), _p(ready), len(ready),
+                              _p(out["retire_order"]), _p(out["start_seq"]), _p(out["end_seq"]),
+                              _p(out["seen_version"]), _p(out["result"]), C.byref(st))
+    finally:
+        L.orc_set_policy(0, 1)
+    out["rc"] = rc
+    out["stats"] = {f[0]: getattr(st, f[0]) for f in OrcStats._fields_}
+    out["tiles"] = tiles
+    return out
+
+
 def cpu_sched_run(tasks, succ, tiles, ready, nthreads):
     """Multi-threaded CPU scheduler port (the CPU baseline).  tiles[].dev_ptr must be host pointers."""
     L = lib()

@@ -101,6 +101,13 @@ static uint64_t run_body(const pb2_task_t* t, void* flow[PB2_MAX_FLOWS], const u
  * memory owned by the caller).  Outputs mirror pb2_window_results.  Returns 0, or -1 if the DAG deadlocks
  * (tasks left with unsatisfied dependencies), -2 on an unknown body.
  */
+/* Order in which ready tasks are picked: 0 FIFO (the engine's order with one worker), 1 LIFO, 2 seeded random.
+ * Any order is a legal execution of the DAG; the non-FIFO ones are used by the tests to shake out missing
+ * write-after-read edges (a stage-in reads its source when the task runs, not when it was released). */
+static int g_policy = 0;
+static uint32_t g_rng = 1;
+void orc_set_policy(int policy, uint32_t seed) { g_policy = policy; g_rng = seed ? seed : 1; }
+
 int orc_run_window(const pb2_task_t* tasks, int32_t ntasks, const uint32_t* succ, int32_t nsucc,
                    pb2_tile_t* tiles, int32_t ntiles, const int32_t* ready, int32_t nready,
                    int32_t* retire_order, uint32_t* start_seq, uint32_t* end_seq, uint32_t* seen_version,
@@ -115,7 +122,16 @@ int orc_run_window(const pb2_task_t* tasks, int32_t ntasks, const uint32_t* succ
     for (int32_t i = 0; i < ntasks; ++i) dep[i] = (tasks[i].flags & PB2_TASK_DEPS_MASK) ? 0 : tasks[i].dep_goal;
     for (int32_t i = 0; i < nready; ++i) fifo[tail++] = ready[i];
     while (head < tail) {
-        const int32_t id = fifo[head++];
+        int32_t id;
+        if (g_policy == 1) id = fifo[--tail];
+        else {
+            if (g_policy == 2) {
+                g_rng ^= g_rng << 13; g_rng ^= g_rng >> 17; g_rng ^= g_rng << 5;
+                const int32_t j = head + (int32_t)(g_rng % (uint32_t)(tail - head));
+                const int32_t tmp = fifo[head]; fifo[head] = fifo[j]; fifo[j] = tmp;
+            }
+            id = fifo[head++];
+        }
         const pb2_task_t* t = &tasks[id];
         void* flow[PB2_MAX_FLOWS] = {0};
         uint32_t bytes[PB2_MAX_FLOWS] = {0};

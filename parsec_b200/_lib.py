@@ -83,6 +83,16 @@ class WindowStats(C.Structure):
                 ("kernel_ms", C.c_float), ("reset_ms", C.c_float)]
 
 
+class WindowHandle(C.Structure):
+    _fields_ = [("dep", C.c_ubyte * 64), ("ring", C.c_ubyte * 64), ("ctl", C.c_ubyte * 64),
+                ("cap_mask", C.c_uint32), ("ntasks", C.c_int32)]
+
+
+class PartitionSizes(C.Structure):
+    _fields_ = [("ntasks", C.c_int32), ("nsucc", C.c_int32), ("ntiles", C.c_int32), ("nready", C.c_int32),
+                ("nremote", C.c_int32), ("nslots", C.c_int32), ("slab_bytes", C.c_uint64)]
+
+
 class Pb2Error(RuntimeError):
     def __init__(self, rc, what, detail=""):
         self.rc = rc
@@ -95,9 +105,12 @@ _lib = None
 ENGINE_SYMBOLS = [
     "pb2_engine_create", "pb2_engine_destroy", "pb2_engine_info", "pb2_engine_last_error",
     "pb2_engine_malloc", "pb2_engine_free", "pb2_engine_host_register", "pb2_engine_host_unregister",
-    "pb2_engine_memcpy_h2d", "pb2_engine_memcpy_d2h", "pb2_engine_synchronize", "pb2_engine_set_stream", "pb2_engine_copy_batch",
+    "pb2_engine_memcpy_h2d", "pb2_engine_memcpy_d2h", "pb2_engine_synchronize", "pb2_engine_set_stream", "pb2_engine_copy_batch", "pb2_engine_ipc_export", "pb2_engine_ipc_open",
+    "pb2_engine_ipc_close", "pb2_engine_set_shared_windows", "pb2_window_export", "pb2_window_set_remote",
+    "pb2_window_arm", "pb2_window_start",
     "pb2_window_create", "pb2_window_destroy", "pb2_window_launch", "pb2_window_wait",
     "pb2_window_results",
+    "pb2_partition_create", "pb2_partition_sizes", "pb2_partition_get", "pb2_partition_destroy", "pb2_partition_error",
 ]
 
 
@@ -127,13 +140,27 @@ def load():
     lib.pb2_engine_synchronize.argtypes = [vp]
     lib.pb2_engine_set_stream.argtypes = [vp, vp]
     lib.pb2_engine_copy_batch.argtypes = [vp, vp, vp, vp, i32]
+    lib.pb2_engine_ipc_export.argtypes = [vp, vp, vp]
+    lib.pb2_engine_ipc_open.argtypes = [vp, vp, P(vp)]
+    lib.pb2_engine_ipc_close.argtypes = [vp, vp]
+    lib.pb2_engine_set_shared_windows.argtypes = [vp, C.c_int]
+    lib.pb2_window_export.argtypes = [vp, vp]
+    lib.pb2_window_set_remote.argtypes = [vp, i32, i32, vp, vp, vp, vp, i32]
+    lib.pb2_window_arm.argtypes = [vp]
+    lib.pb2_window_start.argtypes = [vp]
     lib.pb2_window_create.argtypes = [vp, P(vp), C.c_int, vp, i32, vp, i32, vp, i32, vp, i32]
     lib.pb2_window_destroy.argtypes = [vp]
     lib.pb2_window_launch.argtypes = [vp]
     lib.pb2_window_wait.argtypes = [vp, P(WindowStats)]
     lib.pb2_window_results.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.pb2_partition_create.argtypes = [P(vp), vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, i32, i32]
+    lib.pb2_partition_sizes.argtypes = [vp, i32, P(PartitionSizes)]
+    lib.pb2_partition_get.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.pb2_partition_destroy.argtypes = [vp]
     for name in ENGINE_SYMBOLS:
-        if name != "pb2_engine_last_error":
+        if name not in ("pb2_engine_last_error", "pb2_partition_error", "pb2_partition_destroy"):
             getattr(lib, name).restype = C.c_int
+    lib.pb2_partition_error.restype = C.c_char_p
+    lib.pb2_partition_destroy.restype = None
     _lib = lib
     return lib

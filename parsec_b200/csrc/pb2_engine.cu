@@ -182,7 +182,7 @@ pb2_engine_hbm_kernel(WinDev w) {
                 }
             }
             __syncwarp();
-            if (s_need) release_successors_warp(w, t);
+            if (s_need) { release_successors_warp(w, t); release_remote_warp(w, id); }
             if (threadIdx.x == 0 && s_last) {
                 __threadfence();
                 st_release_gpu(reinterpret_cast<int32_t*>(&w.ctl->done.v), kDoneOK);
@@ -228,6 +228,7 @@ struct pb2_engine_s {
     int nworkers_gemm = 0;
     std::string last_error;
     std::mutex mu;
+    bool shared_windows = false;
     std::map<void*, std::pair<size_t, void*>> registered;   // host ptr -> (bytes, device alias)
 };
 
@@ -248,7 +249,9 @@ struct pb2_window_s {
     int32_t* d_ready_entries = nullptr;
     int32_t nentries = 0;
     bool launched = false;
+    bool shared = false;
     std::vector<void*> allocs;
+    std::vector<void*> peer_ptrs;
 };
 
 #define PB2_CUDA(e, call)                                                                        \
@@ -270,7 +273,8 @@ static int dev_alloc_copy(pb2_window_t* w, T** dptr, const T* host, size_t n) {
     void* p = nullptr;
     // stream-ordered pool allocation: after the first window of a size class this costs microseconds, whereas
     // cudaMalloc/cudaFree next to a 170 GB slab cost hundreds of microseconds each and synchronise the device
-    PB2_CUDA(e, cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), e->stream));
+    if (w->shared) { PB2_CUDA(e, cudaMalloc(&p, (n ? n : 1) * sizeof(T))); }     // IPC needs cudaMalloc memory
+    else PB2_CUDA(e, cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), e->stream));
     w->allocs.push_back(p);
     if (host && n) PB2_CUDA(e, cudaMemcpyAsync(p, host, n * sizeof(T), cudaMemcpyHostToDevice, e->stream));
     *dptr = reinterpret_cast<T*>(p);
@@ -601,6 +605,30 @@ int pb2_engine_copy_batch(pb2_engine_t* e, void* const* dst, const void* const* 
     return PB2_SUCCESS;
 }
 
+int pb2_engine_ipc_export(pb2_engine_t* e, void* dev_ptr, unsigned char handle[64]) {
+    if (!e || !dev_ptr || !handle) return PB2_ERR_BAD_PARAM;
+    PB2_CUDA(e, cudaSetDevice(e->cuda_device));
+    cudaIpcMemHandle_t ih;
+    PB2_CUDA(e, cudaIpcGetMemHandle(&ih, dev_ptr));
+    memcpy(handle, &ih, 64);
+    return PB2_SUCCESS;
+}
+int pb2_engine_ipc_open(pb2_engine_t* e, const unsigned char handle[64], void** dev_ptr) {
+    if (!e || !dev_ptr || !handle) return PB2_ERR_BAD_PARAM;
+    PB2_CUDA(e, cudaSetDevice(e->cuda_device));
+    cudaIpcMemHandle_t ih;
+    memcpy(&ih, handle, 64);
+    PB2_CUDA(e, cudaIpcOpenMemHandle(dev_ptr, ih, cudaIpcMemLazyEnablePeerAccess));
+    return PB2_SUCCESS;
+}
+int pb2_engine_ipc_close(pb2_engine_t* e, void* dev_ptr) {
+    if (!e || !dev_ptr) return PB2_ERR_BAD_PARAM;
+    PB2_CUDA(e, cudaSetDevice(e->cuda_device));
+    PB2_CUDA(e, cudaIpcCloseMemHandle(dev_ptr));
+    return PB2_SUCCESS;
+}
+int pb2_engine_set_shared_windows(pb2_engine_t* e, int on) { if (!e) return PB2_ERR_BAD_PARAM; e->shared_windows = on != 0; return PB2_SUCCESS; }
+
 int pb2_engine_set_stream(pb2_engine_t* e, void* cuda_stream) {
     if (!e) return PB2_ERR_BAD_PARAM;
     PB2_CUDA(e, cudaSetDevice(e->cuda_device));
@@ -631,6 +659,7 @@ int pb2_window_create(pb2_engine_t* e, pb2_window_t** window, int kind,
     if (rc != PB2_SUCCESS) return rc;
     PB2_CUDA(e, cudaSetDevice(e->cuda_device));
     pb2_window_t* w = new pb2_window_s();
+    w->shared = e->shared_windows;
     w->e = e; w->kind = kind; w->ntasks = ntasks; w->nsucc = nsucc; w->ntiles = ntiles; w->nready = nready;
 #define TRY(x) do { rc = (x); if (rc != PB2_SUCCESS) { pb2_window_destroy(w); return rc; } } while (0)
     // device copy of the descriptors: bits 3..7 of flags carry the number of parts - 1 (wide tasks, HBM windows)
@@ -678,7 +707,7 @@ int pb2_window_create(pb2_engine_t* e, pb2_window_t** window, int kind,
     TRY(dev_alloc_copy(w, &d.seen_version, (const uint32_t*)nullptr, (size_t)ntasks * PB2_MAX_FLOWS));
     TRY(dev_alloc_copy(w, &d.result, (const unsigned long long*)nullptr, (size_t)ntasks));
     TRY(dev_alloc_copy(w, &d.worker, (const int32_t*)nullptr, (size_t)ntasks));
-    d.parts_left = nullptr;
+    d.parts_left = nullptr; d.rs_begin = nullptr; d.rs_rank = nullptr; d.rs_target = nullptr; d.peers = nullptr; d.shared = w->shared ? 1 : 0;
     if (kind == 0 && extra_parts) TRY(dev_alloc_copy(w, &d.parts_left, (const int32_t*)nullptr, (size_t)ntasks));
 #undef TRY
     d.cap_mask = cap - 1; d.ntasks = ntasks; d.ntiles = ntiles; d.stage_mode = e->params.stage_mode;
@@ -696,7 +725,8 @@ int pb2_window_destroy(pb2_window_t* w) {
     if (!w) return PB2_ERR_BAD_PARAM;
     cudaSetDevice(w->e->cuda_device);
     if (w->launched) cudaStreamSynchronize(w->e->stream);
-    for (void* p : w->allocs) cudaFreeAsync(p, w->e->stream);
+    for (void* p : w->peer_ptrs) cudaIpcCloseMemHandle(p);
+    for (void* p : w->allocs) { if (w->shared) cudaFree(p); else cudaFreeAsync(p, w->e->stream); }
     if (w->ev0) cudaEventDestroy(w->ev0);
     if (w->ev1) cudaEventDestroy(w->ev1);
     if (w->ev2) cudaEventDestroy(w->ev2);
@@ -704,7 +734,7 @@ int pb2_window_destroy(pb2_window_t* w) {
     return PB2_SUCCESS;
 }
 
-int pb2_window_launch(pb2_window_t* w) {
+int pb2_window_arm(pb2_window_t* w) {
     if (!w) return PB2_ERR_BAD_PARAM;
     pb2_engine_t* e = w->e;
     PB2_CUDA(e, cudaSetDevice(e->cuda_device));
@@ -718,15 +748,23 @@ int pb2_window_launch(pb2_window_t* w) {
         pb2_window_reset_kernel<<<blocks, threads, 0, e->stream>>>(w->d, w->d_tiles_init, w->d_ready, w->nready_entries);
         PB2_CUDA(e, cudaGetLastError());
     }
+    if (w->ntasks > 0 && w->kind == 1 && w->v2) {
+        pb2_window2_reset_kernel<<<64, 256, 0, e->stream>>>(w->g, w->d_ready_entries, w->nentries);
+        PB2_CUDA(e, cudaGetLastError());
+    }
     PB2_CUDA(e, cudaEventRecord(w->ev1, e->stream));
+    return PB2_SUCCESS;
+}
+
+int pb2_window_start(pb2_window_t* w) {
+    if (!w) return PB2_ERR_BAD_PARAM;
+    pb2_engine_t* e = w->e;
+    PB2_CUDA(e, cudaSetDevice(e->cuda_device));
     if (w->ntasks > 0) {
         if (w->kind == 0) {
             pb2_engine_hbm_kernel<<<e->nworkers, e->params.threads, 0, e->stream>>>(w->d);
             PB2_CUDA(e, cudaGetLastError());
         } else if (w->v2) {
-            pb2_window2_reset_kernel<<<64, 256, 0, e->stream>>>(w->g, w->d_ready_entries, w->nentries);
-            PB2_CUDA(e, cudaGetLastError());
-            PB2_CUDA(e, cudaEventRecord(w->ev1, e->stream));
             int rc = pb2_gemm2_launch(w->g, e->nworkers_gemm, e->stream);
             if (rc != PB2_SUCCESS) { e->last_error = "gemm v2 window launch failed"; return rc; }
         } else {
@@ -736,6 +774,60 @@ int pb2_window_launch(pb2_window_t* w) {
     }
     PB2_CUDA(e, cudaEventRecord(w->ev2, e->stream));
     w->launched = true;
+    return PB2_SUCCESS;
+}
+
+int pb2_window_launch(pb2_window_t* w) {
+    int rc = pb2_window_arm(w);
+    return rc == PB2_SUCCESS ? pb2_window_start(w) : rc;
+}
+
+int pb2_window_export(pb2_window_t* w, pb2_window_handle_t* h) {
+    if (!w || !h) return PB2_ERR_BAD_PARAM;
+    pb2_engine_t* e = w->e;
+    if (!w->shared) { e->last_error = "window was not created with shared windows enabled"; return PB2_ERR_NOT_SUPPORTED; }
+    PB2_CUDA(e, cudaSetDevice(e->cuda_device));
+    memset(h, 0, sizeof *h);
+    cudaIpcMemHandle_t ih;
+    PB2_CUDA(e, cudaIpcGetMemHandle(&ih, w->d.dep));  memcpy(h->dep, &ih, 64);
+    PB2_CUDA(e, cudaIpcGetMemHandle(&ih, w->d.ring)); memcpy(h->ring, &ih, 64);
+    PB2_CUDA(e, cudaIpcGetMemHandle(&ih, w->d.ctl));  memcpy(h->ctl, &ih, 64);
+    h->cap_mask = w->d.cap_mask; h->ntasks = w->ntasks;
+    return PB2_SUCCESS;
+}
+
+int pb2_window_set_remote(pb2_window_t* w, int32_t my_rank, int32_t nranks, const pb2_window_handle_t* peers,
+                          const int32_t* rs_begin, const int32_t* rs_rank, const uint32_t* rs_target, int32_t nrs) {
+    if (!w || nranks <= 0 || my_rank < 0 || my_rank >= nranks || !peers || !rs_begin || nrs < 0) return PB2_ERR_BAD_PARAM;
+    pb2_engine_t* e = w->e;
+    PB2_CUDA(e, cudaSetDevice(e->cuda_device));
+    for (int32_t i = 0; i < nrs; ++i) {
+        if (rs_rank[i] < 0 || rs_rank[i] >= nranks || rs_rank[i] == my_rank) { e->last_error = "remote edge to a bad rank"; return PB2_ERR_BAD_PARAM; }
+        if (PB2_SUCC_TASK(rs_target[i]) >= peers[rs_rank[i]].ntasks) { e->last_error = "remote edge target out of bounds"; return PB2_ERR_VALUE_OUT_OF_BOUNDS; }
+    }
+    if (rs_begin[w->ntasks] != nrs) return PB2_ERR_BAD_PARAM;
+    std::vector<PeerWin> pw((size_t)nranks);
+    for (int32_t r = 0; r < nranks; ++r) {
+        memset(&pw[r], 0, sizeof(PeerWin));
+        if (r == my_rank) continue;
+        void *pd = nullptr, *pr = nullptr, *pc = nullptr;
+        cudaIpcMemHandle_t ih;
+        memcpy(&ih, peers[r].dep, 64);  PB2_CUDA(e, cudaIpcOpenMemHandle(&pd, ih, cudaIpcMemLazyEnablePeerAccess));
+        memcpy(&ih, peers[r].ring, 64); PB2_CUDA(e, cudaIpcOpenMemHandle(&pr, ih, cudaIpcMemLazyEnablePeerAccess));
+        memcpy(&ih, peers[r].ctl, 64);  PB2_CUDA(e, cudaIpcOpenMemHandle(&pc, ih, cudaIpcMemLazyEnablePeerAccess));
+        w->peer_ptrs.push_back(pd); w->peer_ptrs.push_back(pr); w->peer_ptrs.push_back(pc);
+        pw[r].dep = reinterpret_cast<int32_t*>(pd); pw[r].ring = reinterpret_cast<int32_t*>(pr);
+        pw[r].ctl = reinterpret_cast<Ctl*>(pc); pw[r].cap_mask = peers[r].cap_mask;
+    }
+    int rc;
+    PeerWin* d_pw = nullptr; int32_t* d_b = nullptr; int32_t* d_r = nullptr; uint32_t* d_t = nullptr;
+    if ((rc = dev_alloc_copy(w, &d_pw, pw.data(), pw.size())) != PB2_SUCCESS) return rc;
+    if ((rc = dev_alloc_copy(w, &d_b, rs_begin, (size_t)w->ntasks + 1)) != PB2_SUCCESS) return rc;
+    if ((rc = dev_alloc_copy(w, &d_r, rs_rank, (size_t)nrs)) != PB2_SUCCESS) return rc;
+    if ((rc = dev_alloc_copy(w, &d_t, rs_target, (size_t)nrs)) != PB2_SUCCESS) return rc;
+    PB2_CUDA(e, cudaStreamSynchronize(e->stream));
+    w->d.peers = d_pw; w->d.rs_begin = d_b; w->d.rs_rank = d_r; w->d.rs_target = d_t;
+    if (w->v2) w->g.w = w->d;
     return PB2_SUCCESS;
 }
 

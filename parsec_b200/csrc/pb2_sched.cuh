@@ -43,7 +43,15 @@ struct WinDev {
     int32_t           stage_mode;
     unsigned long long timeout_ns;
     int32_t*          parts_left;     // HBM windows: parts of a task still running (wide tasks)
+    // remote out-edges (other GPUs' windows), see pb2_window_set_remote
+    const int32_t*    rs_begin;
+    const int32_t*    rs_rank;
+    const uint32_t*   rs_target;
+    const struct PeerWin* peers;
+    int32_t           shared;         // scheduling arrays are written by peers: poll / publish at system scope
 };
+
+struct PeerWin { int32_t* dep; int32_t* ring; Ctl* ctl; uint32_t cap_mask; int32_t pad; };
 
 // A task whose tiles are large is executed as several PARTS (byte slices of its tiles) by different workers;
 // the number of parts (1..32) is kept in bits 3..7 of the DEVICE copy of pb2_task_t::flags, ring entries are
@@ -62,7 +70,7 @@ __device__ __forceinline__ int32_t pop_task(const WinDev& w) {
     int32_t* slot = &w.ring[ticket & w.cap_mask];
     uint32_t spins = 0;
     int32_t id;
-    while ((id = ld_acquire_gpu(slot)) == kEmpty) {
+    while ((id = (w.shared ? ld_acquire_sys(slot) : ld_acquire_gpu(slot))) == kEmpty) {
         if (ld_relaxed_gpu(reinterpret_cast<const int32_t*>(&w.ctl->done.v)) != 0) return kEmpty;
         if ((++spins & 1023u) == 0) {
             // watchdog: a DAG whose dependency counts are wrong would spin forever
@@ -112,6 +120,32 @@ __device__ __forceinline__ void release_successors_warp(const WinDev& w, const p
             base = __shfl_sync(0xffffffffu, base, 0);
             for (int p = 0; p < nparts; ++p)
                 st_release_gpu(&w.ring[((uint32_t)base + (uint32_t)(incl - nparts + p)) & w.cap_mask], (int32_t)PB2_SUCC_MAKE(sid, p));
+        }
+    }
+}
+
+// Whole warp: release the out-edges that lead into other GPUs' windows.  The activation message of the reference
+// (remote_dep_mpi.c:1860 remote_dep_mpi_recv_activate -> release of the local successors) becomes a system-scope
+// atomic on the peer's dependency word and, when it reaches zero, ring entries written into the peer's HBM over
+// NVLink.  The tile itself is pulled by the peer's worker from this GPU's slot when the task runs (stage_in_flow).
+__device__ __forceinline__ void release_remote_warp(const WinDev& w, int32_t id) {
+    if (!w.rs_begin) return;
+    const int lane = threadIdx.x & 31;
+    const int32_t b = w.rs_begin[id], e1 = w.rs_begin[id + 1];
+    if (b == e1) return;
+    __threadfence_system();            // our tile bytes are visible to the peers before they can see the release
+    for (int32_t e0 = b; e0 < e1; e0 += 32) {
+        const int32_t e = e0 + lane;
+        if (e < e1) {
+            const PeerWin pw = w.peers[w.rs_rank[e]];
+            const uint32_t tgt = w.rs_target[e];
+            const int32_t sid = PB2_SUCC_TASK(tgt);
+            if (atomicSub_system(&pw.dep[sid], 1) == 1) {
+                const int nparts = PB2_SUCC_FLOW(tgt) + 1;
+                const unsigned long long base = atomicAdd_system(&pw.ctl->tail.v, (unsigned long long)nparts);
+                for (int p = 0; p < nparts; ++p)
+                    st_release_sys(&pw.ring[((uint32_t)base + (uint32_t)p) & pw.cap_mask], (int32_t)PB2_SUCC_MAKE(sid, p));
+            }
         }
     }
 }

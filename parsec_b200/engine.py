@@ -76,6 +76,20 @@ class Engine:
         """Enqueue engine work on a caller-owned stream (int cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream)."""
         _check(self._lib.pb2_engine_set_stream(self._h, C.c_void_p(cuda_stream)), "pb2_engine_set_stream", self)
 
+    def set_shared_windows(self, on=True):
+        _check(self._lib.pb2_engine_set_shared_windows(self._h, 1 if on else 0), "set_shared_windows", self)
+
+    def ipc_export(self, dev_ptr):
+        h = (C.c_ubyte * 64)()
+        _check(self._lib.pb2_engine_ipc_export(self._h, C.c_void_p(dev_ptr), h), "ipc_export", self)
+        return bytes(h)
+
+    def ipc_open(self, handle):
+        h = (C.c_ubyte * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        _check(self._lib.pb2_engine_ipc_open(self._h, h, C.byref(p)), "ipc_open", self)
+        return p.value
+
     def synchronize(self):
         _check(self._lib.pb2_engine_synchronize(self._h), "pb2_engine_synchronize", self)
 
@@ -124,6 +138,26 @@ class Window:
 
     def launch(self):
         _check(self._lib.pb2_window_launch(self._h), "pb2_window_launch", self.engine)
+
+    def arm(self):
+        _check(self._lib.pb2_window_arm(self._h), "pb2_window_arm", self.engine)
+
+    def start(self):
+        _check(self._lib.pb2_window_start(self._h), "pb2_window_start", self.engine)
+
+    def export(self):
+        h = L.WindowHandle()
+        _check(self._lib.pb2_window_export(self._h, C.byref(h)), "pb2_window_export", self.engine)
+        return bytes(h)
+
+    def set_remote(self, my_rank, handles, rs_begin, rs_rank, rs_target):
+        """handles: list of bytes (one exported WindowHandle per rank)."""
+        arr = (L.WindowHandle * len(handles))(*[L.WindowHandle.from_buffer_copy(h) for h in handles])
+        rs_begin = np.ascontiguousarray(rs_begin, np.int32)
+        rs_rank = np.ascontiguousarray(rs_rank, np.int32)
+        rs_target = np.ascontiguousarray(rs_target, np.uint32)
+        _check(self._lib.pb2_window_set_remote(self._h, my_rank, len(handles), arr, _ptr(rs_begin), _ptr(rs_rank),
+                                               _ptr(rs_target), len(rs_rank)), "pb2_window_set_remote", self.engine)
 
     def wait(self):
         st = L.WindowStats()

@@ -9,11 +9,160 @@ window produced for remote successors travel in one NCCL exchange (send/recv pai
 window that consumes them -- the ACTIVATE/GET/PUT hand-shake of a whole dependency frontier batched into one
 collective step, no per-edge host round trip.
 
+Two data paths are kept:
+  * "direct" (default): ONE window per GPU for the whole pool; an edge that crosses GPUs is released by the producer's
+    worker CTA with a system-scope atomic on the consumer GPU's dependency word plus a ring write over NVLink
+    (release_remote_warp), and the consumer's worker pulls the tile out of the producer's slab when the task runs
+    (stage_in_flow, src_kind PEER).  No host and no collective on the data path; NCCL is only the per-step
+    barrier that orders "every rank has reset its window" before "any rank starts".
+  * "exchange": two windows per GPU with one batched NCCL send/recv of the frontier in between (kept as the
+    library baseline the direct path is measured against).
+
 Host logic only (numpy + torch.distributed plumbing); the kernels are the engine's.
 """
+import ctypes as C
+
 import numpy as np
 
 from . import _lib as L
+
+
+class Partition:
+    """pb2_partition_* (include/pb2_engine.h): split a dependency-closed window over `nranks` GPUs."""
+
+    def __init__(self, tasks, succ, tiles, ready, task_rank, tile_rank, nranks, part_bytes=0):
+        self._lib = L.load()
+        self._h = C.c_void_p()
+        tasks = np.ascontiguousarray(tasks, L.TASK_DTYPE)
+        succ = np.ascontiguousarray(succ, np.uint32)
+        tiles = np.ascontiguousarray(tiles, L.TILE_DTYPE)
+        ready = np.ascontiguousarray(ready, np.int32)
+        task_rank = np.ascontiguousarray(task_rank, np.int32)
+        tile_rank = np.ascontiguousarray(tile_rank, np.int32)
+        assert len(task_rank) == len(tasks) and len(tile_rank) == len(tiles)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        rc = self._lib.pb2_partition_create(C.byref(self._h), vp(tasks), len(tasks), vp(succ), len(succ), vp(tiles), len(tiles),
+                                            vp(ready), len(ready), vp(task_rank), vp(tile_rank), nranks, part_bytes)
+        if rc != L.PB2_SUCCESS:
+            raise L.Pb2Error(rc, "pb2_partition_create", (self._lib.pb2_partition_error() or b"").decode())
+        self.nranks = nranks
+
+    def sizes(self, rank):
+        s = L.PartitionSizes()
+        rc = self._lib.pb2_partition_sizes(self._h, rank, C.byref(s))
+        if rc != L.PB2_SUCCESS:
+            raise L.Pb2Error(rc, "pb2_partition_sizes", "")
+        return {f[0]: getattr(s, f[0]) for f in L.PartitionSizes._fields_}
+
+    def get(self, rank, slab_base):
+        """slab_base[r] = address of rank r's slab as seen from `rank`."""
+        z = self.sizes(rank)
+        out = {
+            "tasks": np.zeros(z["ntasks"], L.TASK_DTYPE), "succ": np.zeros(z["nsucc"], np.uint32),
+            "tiles": np.zeros(z["ntiles"], L.TILE_DTYPE), "ready": np.zeros(z["nready"], np.int32),
+            "rs_begin": np.zeros(z["ntasks"] + 1, np.int32), "rs_rank": np.zeros(z["nremote"], np.int32),
+            "rs_target": np.zeros(z["nremote"], np.uint32), "global_id": np.zeros(z["ntasks"], np.int32),
+            "slot_tile": np.zeros(z["nslots"], np.int32), "slot_offset": np.zeros(z["nslots"], np.uint64),
+        }
+        base = np.ascontiguousarray(slab_base, np.uint64)
+        assert len(base) == self.nranks
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        rc = self._lib.pb2_partition_get(self._h, rank, vp(base), *[vp(out[k]) for k in (
+            "tasks", "succ", "tiles", "ready", "rs_begin", "rs_rank", "rs_target", "global_id", "slot_tile", "slot_offset")])
+        if rc != L.PB2_SUCCESS:
+            raise L.Pb2Error(rc, "pb2_partition_get", "")
+        out["slab_bytes"] = z["slab_bytes"]
+        return out
+
+    def close(self):
+        if self._h:
+            self._lib.pb2_partition_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def ex05_global(K_total, NB, world, tile_bytes):
+    """Ex05_Broadcast (examples/Ex05_Broadcast.jdf:24-58) over `world` ranks as ONE window + owner maps.
+
+    TaskBcast(k) : RW A <- mydata(k), -> A TaskRecv(k, 0..NB..2); runs on rank_of(mydata(k)) = k % world
+    TaskRecv(k,n): READ A <- A TaskBcast(k);                       runs on rank_of(mydata(k + n)) (loc = k + n, :45-47)
+    Returns (tasks, succ, tiles, ready, task_rank, tile_rank)."""
+    ns = np.arange(0, NB + 1, 2, dtype=np.int32)
+    F = len(ns)
+    n = K_total * (1 + F)
+    t = np.zeros(n, L.TASK_DTYPE)
+    t["tile"][:] = -1
+    k = np.arange(K_total, dtype=np.int32)
+    b = t[:K_total]
+    b["body"], b["nb_flows"], b["flags"] = L.BODY_FILL_I32, 1, L.TASK_DEPS_MASK
+    b["tile"][:, 0], b["access"][:, 0], b["iparam"][:, 0], b["locals"][:, 0] = k, L.ACCESS_RW, k, k
+    b["succ_begin"], b["succ_count"] = k * F, F
+    r = t[K_total:]
+    kk = np.repeat(k, F)
+    r["body"], r["nb_flows"], r["flags"], r["class_id"], r["dep_goal"] = L.BODY_CHECK_I32, 1, L.TASK_DEPS_MASK, 1, 0x1
+    r["tile"][:, 0], r["access"][:, 0], r["iparam"][:, 0] = kk, L.ACCESS_READ, kk
+    r["locals"][:, 0], r["locals"][:, 1] = kk, np.tile(ns, K_total)
+    succ = (K_total + np.arange(K_total * F)).astype(np.uint32)
+    tiles = np.zeros(K_total, L.TILE_DTYPE)
+    tiles["bytes"], tiles["state"] = tile_bytes, L.TILE_VALID
+    task_rank = np.concatenate([k % world, (kk + np.tile(ns, K_total)) % world]).astype(np.int32)
+    return t, succ, tiles, np.arange(K_total, dtype=np.int32), task_rank, (k % world).astype(np.int32)
+
+
+def rtt_global(ntasks, world, tile_bytes):
+    """tests/runtime/cuda/rtt.jdf: PING(k) RW T <- (k == 0) ? A(0) : T PING(k-1), runs on rank k % world (the
+    reference sets one data per rank and moves the tile around the ring).  Every task adds 1 to every element."""
+    t = np.zeros(ntasks, L.TASK_DTYPE)
+    t["tile"][:] = -1
+    k = np.arange(ntasks, dtype=np.int32)
+    t["body"], t["nb_flows"], t["flags"] = L.BODY_INCR_I32, 1, L.TASK_DEPS_MASK
+    t["tile"][:, 0], t["access"][:, 0], t["locals"][:, 0] = 0, L.ACCESS_RW, k
+    t["dep_goal"] = np.where(k > 0, 1, 0)
+    t["succ_begin"], t["succ_count"] = k, np.where(k < ntasks - 1, 1, 0)
+    succ = (k[:-1] + 1).astype(np.uint32)
+    tiles = np.zeros(1, L.TILE_DTYPE)
+    tiles["bytes"], tiles["state"] = tile_bytes, L.TILE_VALID
+    return t, succ, tiles, np.zeros(1, np.int32), (k % world).astype(np.int32), np.zeros(1, np.int32)
+
+
+class SharedRun:
+    """One rank's half of a window that was split over the GPUs of the box ("direct" path).
+
+    `dist` is torch.distributed (any backend for the handle exchange; the per-step barrier is an all_reduce on
+    torch's current CUDA stream, i.e. stream-ordered between the window reset and the worker kernel)."""
+
+    def __init__(self, eng, part, rank, world, dist, torch):
+        self.eng, self.rank, self.world, self.dist, self.torch = eng, rank, world, dist, torch
+        z = part.sizes(rank)
+        self.slab_bytes = max(int(z["slab_bytes"]), 256)
+        self.slab = eng.malloc(self.slab_bytes)
+        eng.h2d(self.slab, np.zeros(self.slab_bytes, np.uint8))
+        eng.synchronize()
+        handles = [None] * world
+        dist.all_gather_object(handles, eng.ipc_export(self.slab))
+        self.base = [self.slab if r == rank else eng.ipc_open(handles[r]) for r in range(world)]
+        self.p = part.get(rank, self.base)
+        eng.set_shared_windows(True)
+        self.w = eng.window(0, self.p["tasks"], self.p["succ"], self.p["tiles"], self.p["ready"])
+        eng.set_shared_windows(False)
+        wh = [None] * world
+        dist.all_gather_object(wh, self.w.export())
+        self.w.set_remote(rank, wh, self.p["rs_begin"], self.p["rs_rank"], self.p["rs_target"])
+        self._flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+        dist.barrier()
+
+    def step(self):
+        self.w.arm()                                   # reset dependency words, ring and tile states
+        self.dist.all_reduce(self._flag)               # every rank's reset is complete before any worker starts
+        self.w.start()
+
+    def wait(self):
+        return self.w.wait()
 
 
 def owner_1xN(k, world):
@@ -136,3 +285,25 @@ def ex05_multi_gpu_step_factory(ctx, dev, dc, K, NB, tile_bytes, rank, world, lo
         return keep
 
     return step, finish, (4 if wb is not None else 2)
+
+
+def ex05_direct_step_factory(K, NB, tile_bytes, rank, world, local_rank):
+    """Ex05 over `world` GPUs, one window per GPU, cross-GPU edges released by the device ("direct" path)."""
+    import torch
+    import torch.distributed as dist
+    from .engine import Engine
+
+    g = ex05_global(K * world, NB, world, tile_bytes)
+    part = Partition(*g, nranks=world)
+    eng = Engine(local_rank)
+    eng.use_stream(torch.cuda.current_stream().cuda_stream)
+    run = SharedRun(eng, part, rank, world, dist, torch)
+    ntasks = len(run.p["tasks"])
+
+    def finish():
+        torch.cuda.synchronize()
+        st = run.wait()
+        assert st["body_errors"] == 0 and st["tasks_retired"] == ntasks, st
+        return run
+
+    return run.step, finish, 3, ntasks

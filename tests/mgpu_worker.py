@@ -1,0 +1,65 @@
+"""One rank of tests/test_multigpu_gpu.py (run under torch.distributed.run)."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from oracle import orc
+    from parsec_b200 import multigpu as M
+    from parsec_b200.engine import Engine
+
+    case = sys.argv[1]
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if case == "ex05":
+        g = M.ex05_global(64 * world, 14, world, 65536)
+    elif case == "rtt":
+        g = M.rtt_global(200, world, 1 << 20)
+    else:
+        import test_partition as T
+        g = T.drop_cross_rank_control_edges(T.random_dtd(400, 6, world, 4242, tile_bytes=4096))
+    tasks, succ, tiles, ready, task_rank, tile_rank = g
+    glob = orc.run_window(tasks, succ, tiles, ready)
+    assert glob["rc"] == 0
+    part = M.Partition(*g, nranks=world)
+    eng = Engine(local, timeout_ms=20000)
+    eng.use_stream(torch.cuda.current_stream().cuda_stream)
+    run = M.SharedRun(eng, part, rank, world, dist, torch)
+    ok = True
+    d2d = 0
+    zeros = np.zeros(run.slab_bytes, np.uint8)
+    for it in range(3):                       # the window is re-armed and re-run: reset + barrier protocol
+        eng.h2d(run.slab, zeros)
+        eng.synchronize()
+        dist.barrier()
+        run.step()
+        torch.cuda.synchronize()
+        st = run.wait()
+        res = run.w.results()
+        gid = run.p["global_id"]
+        ok = ok and st["tasks_retired"] == len(gid) and st["body_errors"] == 0
+        if it == 0:
+            ok = ok and bool(np.array_equal(res["result"], glob["result"][gid]))
+        d2d += int(st["bytes_d2d"])
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    tot = torch.tensor([d2d, len(run.p["rs_rank"])], device="cuda")
+    dist.all_reduce(tot)
+    if rank == 0:
+        print(json.dumps({"ok": bool(flag.item()), "world": world, "case": case, "bytes_d2d": int(tot[0].item()),
+                          "remote_edges": int(tot[1].item())}))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
