@@ -74,6 +74,8 @@ class Engine:
 
     def use_stream(self, cuda_stream):
         """Enqueue engine work on a caller-owned stream (int cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream)."""
+        if not cuda_stream:
+            raise ValueError("use_stream needs a real stream handle (the legacy default stream is 0: create a torch.cuda.Stream)")
         _check(self._lib.pb2_engine_set_stream(self._h, C.c_void_p(cuda_stream)), "pb2_engine_set_stream", self)
 
     def set_shared_windows(self, on=True):

@@ -130,6 +130,15 @@ def rtt_global(ntasks, world, tile_bytes):
     return t, succ, tiles, np.zeros(1, np.int32), (k % world).astype(np.int32), np.zeros(1, np.int32)
 
 
+def work_stream(torch):
+    """Make a non-default CUDA stream torch's current stream and return its handle: the engine and the NCCL barrier
+    are enqueued on it, so "reset -> barrier -> workers" is stream-ordered (the legacy default stream has handle 0,
+    which pb2_engine_set_stream reads as "use the engine's own stream")."""
+    if torch.cuda.current_stream().cuda_stream == 0:
+        torch.cuda.set_stream(torch.cuda.Stream())
+    return torch.cuda.current_stream().cuda_stream
+
+
 class SharedRun:
     """One rank's half of a window that was split over the GPUs of the box ("direct" path).
 
@@ -252,7 +261,7 @@ def ex05_multi_gpu_step_factory(ctx, dev, dc, K, NB, tile_bytes, rank, world, lo
 
     sh = ex05_shard(K, NB, world, rank, tile_bytes)
     eng = Engine(local_rank)
-    eng.use_stream(torch.cuda.current_stream().cuda_stream)
+    eng.use_stream(work_stream(torch))
     slab = torch.zeros(K * tile_bytes // 4, dtype=torch.int32, device="cuda")
     recv = [torch.empty(K * tile_bytes // 4, dtype=torch.int32, device="cuda") for _ in sh["recv_from"]]
 
@@ -287,16 +296,25 @@ def ex05_multi_gpu_step_factory(ctx, dev, dc, K, NB, tile_bytes, rank, world, lo
     return step, finish, (4 if wb is not None else 2)
 
 
-def ex05_direct_step_factory(K, NB, tile_bytes, rank, world, local_rank):
-    """Ex05 over `world` GPUs, one window per GPU, cross-GPU edges released by the device ("direct" path)."""
+def ex05_direct_step_factory(K, NB, tile_bytes, rank, world, local_rank, eng=None, host_tiles=None):
+    """Ex05 over `world` GPUs, one window per GPU, cross-GPU edges released by the device ("direct" path).
+
+    host_tiles: device-visible alias of this rank's K tiles in pinned host memory (pb2_engine_host_register); when
+    given, every step stages the rank's tiles in from host memory inside the kernel (the end-to-end variant)."""
     import torch
     import torch.distributed as dist
     from .engine import Engine
 
-    g = ex05_global(K * world, NB, world, tile_bytes)
+    g = list(ex05_global(K * world, NB, world, tile_bytes))
+    if host_tiles is not None:
+        tiles = g[2]
+        mine = np.nonzero(g[5] == rank)[0]
+        tiles["state"][:] = L.TILE_INVALID
+        tiles["src_ptr"][mine] = np.uint64(host_tiles) + (mine // world).astype(np.uint64) * np.uint64(tile_bytes)
     part = Partition(*g, nranks=world)
-    eng = Engine(local_rank)
-    eng.use_stream(torch.cuda.current_stream().cuda_stream)
+    if eng is None:
+        eng = Engine(local_rank)
+        eng.use_stream(work_stream(torch))
     run = SharedRun(eng, part, rank, world, dist, torch)
     ntasks = len(run.p["tasks"])
 
