@@ -28,9 +28,11 @@ def main():
         g = M.rtt_global(200, world, 1 << 20)
     else:
         import test_partition as T
-        g = T.drop_cross_rank_control_edges(T.random_dtd(400, 6, world, 4242, tile_bytes=4096))
+        # the oracle runs the fully ordered (DTD) window; the partitioner gets it WITHOUT the cross-rank control edges
+        full = T.random_dtd(400, 6, world, 4242, tile_bytes=4096)
+        g = T.drop_cross_rank_control_edges(full)
     tasks, succ, tiles, ready, task_rank, tile_rank = g
-    glob = orc.run_window(tasks, succ, tiles, ready)
+    glob = orc.run_window(*(full if case == "random_dtd" else g)[:4])
     assert glob["rc"] == 0
     part = M.Partition(*g, nranks=world)
     eng = Engine(local, timeout_ms=20000)
@@ -49,11 +51,16 @@ def main():
         st = run.wait()
         res = run.w.results()
         gid = run.p["global_id"]
-        ok = ok and st["tasks_retired"] == len(gid)
+        if st["tasks_retired"] != len(gid):
+            print("rank", rank, "iteration", it, "retired", st["tasks_retired"], "of", len(gid), flush=True)
+            ok = False
         if it == 0:
             # CHECK bodies count elements != iparam[0]: the split run must count what the unsplit oracle run counts
             chk = tasks["body"][gid] == L.BODY_CHECK_I32
-            ok = ok and st["body_errors"] == int((glob["result"][gid][chk] >> np.uint64(32)).sum())
+            want = int((glob["result"][gid][chk] >> np.uint64(32)).sum())
+            if st["body_errors"] != want:
+                print("rank", rank, "body_errors", st["body_errors"], "oracle", want, flush=True)
+                ok = False
             same = res["result"] == glob["result"][gid]
             if not same.all():
                 bad = np.nonzero(~same)[0][:5]

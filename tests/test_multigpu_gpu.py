@@ -28,7 +28,9 @@ def _run(world, case, extra=()):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert lines, r.stdout[-2000:]
-    return json.loads(lines[-1])
+    out = json.loads(lines[-1])
+    out["log"] = [l for l in r.stdout.splitlines() if l.startswith("rank")][:20]
+    return out
 
 
 @pytest.mark.gpu
