@@ -131,8 +131,9 @@ typedef struct pb2_engine_params_s {
                                 * (default 20000); a malformed DAG must never hang the GPU                   */
     int32_t  gemm_mode;        /* 0 = CTA pairs (cta_group::2) + fused k-chains (default), 1 = v1 single-CTA kernel,
                                 * 2 = CTA pairs, every task flushes C (per-task bf16 rounding, as the oracle)       */
-    int32_t  part_bytes;       /* HBM bodies: a task whose largest tile exceeds this many bytes is run as up to 32
-                                * parts (byte slices) by different workers (default 256 KiB, <0 = never split)   */
+    int32_t  part_bytes;       /* HBM bodies: a task whose largest tile exceeds this many bytes is run as up to 512
+                                * parts (byte slices) by different workers (default 256 KiB, <0 = never split);
+                                * pb2_engine_set_part_bytes changes it for the windows created afterwards       */
 } pb2_engine_params_t;
 
 typedef struct pb2_engine_info_s {
@@ -197,6 +198,9 @@ int  pb2_engine_ipc_open(pb2_engine_t* engine, const unsigned char handle[64], v
 int  pb2_engine_ipc_close(pb2_engine_t* engine, void* dev_ptr);
 /* all windows created after this call keep their scheduling arrays in IPC-exportable memory */
 int  pb2_engine_set_shared_windows(pb2_engine_t* engine, int on);
+/* part size for the windows created from now on (a serial chain of large tiles wants small parts: a 64-thread
+ * worker keeps only 4 KiB in flight; wide DAGs want one part per tile) */
+int  pb2_engine_set_part_bytes(pb2_engine_t* engine, int32_t part_bytes);
 
 /* --- one window of the DAG ---
  * tasks[ntasks], succ[nsucc] (CSR via succ_begin/succ_count), tiles[ntiles] and the ids of
@@ -232,7 +236,8 @@ typedef struct pb2_window_handle_s {
 } pb2_window_handle_t;
 int  pb2_window_export(pb2_window_t* window, pb2_window_handle_t* handle);
 /* remote out-edges of this window: for task t, entries rs_begin[t] .. rs_begin[t+1]-1 of (rank[], target[]) where
- * target = PB2_SUCC_MAKE(task id in that rank's window, nparts-1 of that task); remote successors are counter-mode.
+ * target = ((nparts - 1) << 22) | task id in that rank's window (nparts: parts of that task, 1..512, the rule of
+ * pb2_engine_params_t::part_bytes); remote successors are counter-mode.
  * peers[r] is rank r's exported handle (peers[my_rank] is ignored). */
 int  pb2_window_set_remote(pb2_window_t* window, int32_t my_rank, int32_t nranks, const pb2_window_handle_t* peers,
                            const int32_t* rs_begin, const int32_t* rs_rank, const uint32_t* rs_target, int32_t nrs);

@@ -43,13 +43,19 @@ __global__ void pb2_window_reset_kernel(WinDev w, const pb2_tile_t* tiles_init,
         const pb2_task_t& t = w.tasks[i];
         // counter mode counts down from the goal (parsec.c:1625-1633); mask mode ORs up from 0 (:1693-1703)
         w.dep[i] = (t.flags & PB2_TASK_DEPS_MASK) ? 0 : t.dep_goal;
-        if (w.parts_left) w.parts_left[i] = PB2_TASK_NPARTS(t.flags);
+        if (w.parts_left) w.parts_left[i] = task_nparts(w, (int32_t)i);
         w.start_seq[i] = 0; w.end_seq[i] = 0; w.result[i] = 0; w.worker[i] = -1; w.retire_log[i] = -1;
         for (int f = 0; f < PB2_MAX_FLOWS; ++f) w.seen_version[i * PB2_MAX_FLOWS + f] = 0;
     }
     for (size_t i = gid; i <= (size_t)w.cap_mask; i += gsz)
         w.ring[i] = (i < (size_t)nready) ? ready[i] : kEmpty;
-    for (size_t i = gid; i < (size_t)w.ntiles; i += gsz) w.tiles[i] = tiles_init[i];
+    for (size_t i = gid; i < (size_t)w.ntiles; i += gsz) {
+        w.tiles[i] = tiles_init[i];
+        if (w.slice_claim) {
+            for (int k = 0; k < PB2_SLICE_WORDS; ++k) w.slice_claim[i * PB2_SLICE_WORDS + k] = 0;
+            for (int k = 0; k <= PB2_SLICE_WORDS; ++k) w.slice_done[i * (PB2_SLICE_WORDS + 1) + k] = 0;
+        }
+    }
     if (gid == 0) {
         w.ctl->head.v = 0; w.ctl->tail.v = (unsigned long long)nready; w.ctl->evt.v = 0;
         w.ctl->retired.v = 0; w.ctl->done.v = (w.ntasks == 0) ? kDoneOK : 0;
@@ -89,13 +95,13 @@ pb2_engine_hbm_kernel(WinDev w) {
         }
         __syncthreads();
         if (s_id == kEmpty) break;
-        const int32_t id = PB2_SUCC_TASK((uint32_t)s_id);
-        const int part = PB2_SUCC_FLOW((uint32_t)s_id);
+        const int32_t id = PB2_ENT_TASK(s_id);
+        const int part = PB2_ENT_PART(s_id);
         if (threadIdx.x < 4) reinterpret_cast<uint4*>(&s_task)[threadIdx.x] =
             __ldg(reinterpret_cast<const uint4*>(&w.tasks[id]) + threadIdx.x);
         __syncthreads();
         const pb2_task_t& t = s_task;
-        const int nparts = PB2_TASK_NPARTS(t.flags);
+        const int nparts = task_nparts(w, id);
 
         // ---- push: reserve + stage in (parsec_device_kernel_push) ----
         // Thread 0 looks at the tile states once; the resulting mask is CTA-uniform (the states
@@ -115,17 +121,35 @@ pb2_engine_hbm_kernel(WinDev w) {
         const int need = s_need;
         BodyArgs a;
         a.part = (uint32_t)part; a.elem0 = 0;
+        uint32_t widest = 0;
+        if (nparts > 1)
+            for (int f = 0; f < t.nb_flows; ++f)
+                if (t.tile[f] >= 0 && w.tiles[t.tile[f]].bytes > widest) widest = w.tiles[t.tile[f]].bytes;
 #pragma unroll
         for (int f = 0; f < PB2_MAX_FLOWS; ++f) {
             a.flow[f] = nullptr; a.bytes[f] = 0;
             if (f < t.nb_flows && t.tile[f] >= 0) {
                 pb2_tile_t* tile = &w.tiles[t.tile[f]];
-                if ((need >> f) & 1) stage_in_flow(w, tile, t.access[f], &s_decide);
-                // this part's slice: 16-byte aligned cut points, the last part takes the remainder
+                // this part's slice: every flow is cut at the same byte offsets (those of the task's widest tile,
+                // 16-byte aligned, the last part takes the remainder), so two-flow bodies pair equal offsets
                 const uint32_t bytes = tile->bytes;
-                const uint32_t per = ((bytes / (uint32_t)nparts) + 15u) & ~15u;
+                const uint32_t per = ((widest / (uint32_t)nparts) + 15u) & ~15u;
                 const uint32_t off = per * (uint32_t)part < bytes ? per * (uint32_t)part : bytes;
                 const uint32_t len = (part == nparts - 1) ? bytes - off : (off + per <= bytes ? per : bytes - off);
+                if ((need >> f) & 1) {
+                    const int ns = tile_slices(w, bytes);
+                    if (ns == 1) stage_in_flow(w, tile, t.access[f], &s_decide);
+                    else if (ns == nparts && bytes == widest) stage_in_slices(w, t.tile[f], ns, part, part + 1, &s_decide);   // my slice only
+                    else {
+                        // the task is cut differently from the tile (its widest flow is another tile)
+                        const uint32_t sper = ((bytes / (uint32_t)ns) + 15u) & ~15u;
+                        int s0 = (int)(off / sper), s1 = (int)((off + len + sper - 1) / sper);
+                        if (s0 > ns - 1) s0 = ns - 1;
+                        if (s1 > ns) s1 = ns;
+                        if (len == 0) s1 = s0;
+                        stage_in_slices(w, t.tile[f], ns, s0, s1, &s_decide);
+                    }
+                }
                 a.flow[f] = reinterpret_cast<uint8_t*>(tile->dev_ptr) + off; a.bytes[f] = len;
                 if (f == 0) a.elem0 = off >> 2;
                 if (threadIdx.x == 0 && part == 0)
@@ -627,6 +651,11 @@ int pb2_engine_ipc_close(pb2_engine_t* e, void* dev_ptr) {
     PB2_CUDA(e, cudaIpcCloseMemHandle(dev_ptr));
     return PB2_SUCCESS;
 }
+int pb2_engine_set_part_bytes(pb2_engine_t* e, int32_t part_bytes) {
+    if (!e) return PB2_ERR_BAD_PARAM;
+    e->params.part_bytes = part_bytes == 0 ? 256 * 1024 : part_bytes;
+    return PB2_SUCCESS;
+}
 int pb2_engine_set_shared_windows(pb2_engine_t* e, int on) { if (!e) return PB2_ERR_BAD_PARAM; e->shared_windows = on != 0; return PB2_SUCCESS; }
 
 int pb2_engine_set_stream(pb2_engine_t* e, void* cuda_stream) {
@@ -662,22 +691,23 @@ int pb2_window_create(pb2_engine_t* e, pb2_window_t** window, int kind,
     w->shared = e->shared_windows;
     w->e = e; w->kind = kind; w->ntasks = ntasks; w->nsucc = nsucc; w->ntiles = ntiles; w->nready = nready;
 #define TRY(x) do { rc = (x); if (rc != PB2_SUCCESS) { pb2_window_destroy(w); return rc; } } while (0)
-    // device copy of the descriptors: bits 3..7 of flags carry the number of parts - 1 (wide tasks, HBM windows)
+    // wide tasks (HBM windows): parts per task = ceil(widest tile / part_bytes), at most PB2_MAX_PARTS
     std::vector<pb2_task_t> dtasks(tasks, tasks + ntasks);
+    std::vector<uint16_t> nparts((size_t)ntasks, 1);
     std::vector<int32_t> entries;
     uint32_t extra_parts = 0;
     for (int32_t i = 0; i < ntasks; ++i) {
         pb2_task_t& t = dtasks[i];
         t.flags &= 0x07;
-        if (kind != 0 || t.body == PB2_BODY_NOP || e->params.part_bytes < 0) continue;
+        if (kind != 0 || t.body == PB2_BODY_NOP || e->params.part_bytes < 0 || ntasks >= (1 << 22)) continue;
         uint32_t big = 0;
         for (int f = 0; f < t.nb_flows; ++f) if (t.tile[f] >= 0 && tiles[t.tile[f]].bytes > big) big = tiles[t.tile[f]].bytes;
         uint32_t np = (big + (uint32_t)e->params.part_bytes - 1) / (uint32_t)e->params.part_bytes;
-        if (np > 32) np = 32;
-        if (np > 1) { t.flags |= (uint8_t)((np - 1) << 3); extra_parts += np - 1; }
+        if (np > PB2_MAX_PARTS) np = PB2_MAX_PARTS;
+        if (np > 1) { nparts[(size_t)i] = (uint16_t)np; extra_parts += np - 1; }
     }
     for (int32_t i = 0; i < nready; ++i)
-        for (int p = 0; p < PB2_TASK_NPARTS(dtasks[ready[i]].flags); ++p) entries.push_back((int32_t)PB2_SUCC_MAKE(ready[i], p));
+        for (int p = 0; p < (int)nparts[(size_t)ready[i]]; ++p) entries.push_back(PB2_ENT_MAKE(ready[i], p));
     TRY(dev_alloc_copy(w, &w->d_tasks, dtasks.data(), (size_t)ntasks));
     TRY(dev_alloc_copy(w, &w->d_succ, succ, (size_t)nsucc));
     TRY(dev_alloc_copy(w, &w->d_tiles_init, tiles, (size_t)ntiles));
@@ -708,7 +738,16 @@ int pb2_window_create(pb2_engine_t* e, pb2_window_t** window, int kind,
     TRY(dev_alloc_copy(w, &d.result, (const unsigned long long*)nullptr, (size_t)ntasks));
     TRY(dev_alloc_copy(w, &d.worker, (const int32_t*)nullptr, (size_t)ntasks));
     d.parts_left = nullptr; d.rs_begin = nullptr; d.rs_rank = nullptr; d.rs_target = nullptr; d.peers = nullptr; d.shared = w->shared ? 1 : 0;
-    if (kind == 0 && extra_parts) TRY(dev_alloc_copy(w, &d.parts_left, (const int32_t*)nullptr, (size_t)ntasks));
+    d.slice_claim = nullptr; d.slice_done = nullptr; d.part_bytes = e->params.part_bytes;
+    d.nparts = nullptr;
+    if (kind == 0 && extra_parts) {
+        uint16_t* d_np = nullptr;
+        TRY(dev_alloc_copy(w, &d_np, nparts.data(), (size_t)ntasks));
+        d.nparts = d_np;
+        TRY(dev_alloc_copy(w, &d.parts_left, (const int32_t*)nullptr, (size_t)ntasks));
+        TRY(dev_alloc_copy(w, &d.slice_claim, (const uint32_t*)nullptr, (size_t)ntiles * PB2_SLICE_WORDS));
+        TRY(dev_alloc_copy(w, &d.slice_done, (const uint32_t*)nullptr, (size_t)ntiles * (PB2_SLICE_WORDS + 1)));
+    }
 #undef TRY
     d.cap_mask = cap - 1; d.ntasks = ntasks; d.ntiles = ntiles; d.stage_mode = e->params.stage_mode;
     d.timeout_ns = (unsigned long long)e->params.timeout_ms * 1000000ull;
@@ -803,7 +842,7 @@ int pb2_window_set_remote(pb2_window_t* w, int32_t my_rank, int32_t nranks, cons
     PB2_CUDA(e, cudaSetDevice(e->cuda_device));
     for (int32_t i = 0; i < nrs; ++i) {
         if (rs_rank[i] < 0 || rs_rank[i] >= nranks || rs_rank[i] == my_rank) { e->last_error = "remote edge to a bad rank"; return PB2_ERR_BAD_PARAM; }
-        if (PB2_SUCC_TASK(rs_target[i]) >= peers[rs_rank[i]].ntasks) { e->last_error = "remote edge target out of bounds"; return PB2_ERR_VALUE_OUT_OF_BOUNDS; }
+        if ((int32_t)(rs_target[i] & 0x3FFFFFu) >= peers[rs_rank[i]].ntasks) { e->last_error = "remote edge target out of bounds"; return PB2_ERR_VALUE_OUT_OF_BOUNDS; }
     }
     if (rs_begin[w->ntasks] != nrs) return PB2_ERR_BAD_PARAM;
     std::vector<PeerWin> pw((size_t)nranks);

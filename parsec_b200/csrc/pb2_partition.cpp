@@ -113,11 +113,11 @@ int pb2_partition_create(pb2_partition_t** out, const pb2_task_t* tasks, int32_t
             indeg[(size_t)s]++;
             if (f < tasks[s].nb_flows && tasks[s].tile[f] >= 0 && writes(p, tasks[s].tile[f])) prod[(size_t)s * PB2_MAX_FLOWS + f] = p;
         }
-        if (k.body != PB2_BODY_NOP && part_bytes > 0) {
+        if (k.body != PB2_BODY_NOP && part_bytes > 0 && ntasks < (1 << 22)) {
             uint32_t big = 0;
             for (int f = 0; f < k.nb_flows; ++f) if (k.tile[f] >= 0 && tiles[k.tile[f]].bytes > big) big = tiles[k.tile[f]].bytes;
             uint32_t np = (big + (uint32_t)part_bytes - 1) / (uint32_t)part_bytes;
-            nparts[(size_t)p] = (int32_t)(np > 32 ? 32 : (np < 1 ? 1 : np));
+            nparts[(size_t)p] = (int32_t)(np > 512 ? 512 : (np < 1 ? 1 : np));
         }
     }
     for (int32_t t = 0; t < ntasks; ++t) {
@@ -299,7 +299,7 @@ int pb2_partition_create(pb2_partition_t** out, const pb2_task_t* tasks, int32_t
             rp.rs_begin[l] = (int32_t)rp.rs_rank.size();
             auto edge = [&](int32_t s, int f) {
                 if (task_rank[s] == r) rp.succ.push_back(PB2_SUCC_MAKE(P->lid[(size_t)s], f));
-                else { rp.rs_rank.push_back(task_rank[s]); rp.rs_target.push_back(PB2_SUCC_MAKE(P->lid[(size_t)s], nparts[(size_t)s] - 1)); }
+                else { rp.rs_rank.push_back(task_rank[s]); rp.rs_target.push_back(((uint32_t)(nparts[(size_t)s] - 1) << 22) | (uint32_t)P->lid[(size_t)s]); }
             };
             for (int32_t e = k.succ_begin; e < k.succ_begin + k.succ_count; ++e) edge((int32_t)PB2_SUCC_TASK(succ[e]), (int)PB2_SUCC_FLOW(succ[e]));
             for (auto& w : war[(size_t)t]) edge(w.first, PB2_MAX_FLOWS);       // control edge: no flow of the successor

@@ -49,15 +49,48 @@ struct WinDev {
     const uint32_t*   rs_target;
     const struct PeerWin* peers;
     int32_t           shared;         // scheduling arrays are written by peers: poll / publish at system scope
+    // sliced stage-in of tiles larger than part_bytes (HBM windows): which slices are claimed / staged
+    uint32_t*         slice_claim;
+    uint32_t*         slice_done;
+    int32_t           part_bytes;
+    const uint16_t*   nparts;         // HBM windows with wide tasks: parts per task (null: every task is one part)
 };
 
 struct PeerWin { int32_t* dep; int32_t* ring; Ctl* ctl; uint32_t cap_mask; int32_t pad; };
 
-// A task whose tiles are large is executed as several PARTS (byte slices of its tiles) by different workers;
-// the number of parts (1..32) is kept in bits 3..7 of the DEVICE copy of pb2_task_t::flags, ring entries are
-// (part << 27) | task.  One tile at HBM speed needs the whole GPU: a 4 MiB tile is 1.3 us of the machine, not
-// 1 ms of one CTA.
-#define PB2_TASK_NPARTS(flags)  ((((int)(flags)) >> 3) + 1)
+// A task whose tiles are large is executed as several PARTS (byte slices of its tiles) by different workers: one
+// tile at HBM / NVLink speed needs the whole GPU (a 64-thread CTA keeps 4 KiB in flight; a 4 MiB tile is 1.3 us of
+// the machine, not 1 ms of one CTA).  Parts per task (1..512) live in WinDev::nparts; ring entries of HBM windows
+// are (part << 22) | task, so such a window holds at most 2^22 tasks when it has wide tasks.
+#define PB2_MAX_PARTS 512
+#define PB2_ENT_MAKE(task, part) ((int32_t)(((uint32_t)(part) << 22) | (uint32_t)(task)))
+#define PB2_ENT_TASK(e)          ((int32_t)((uint32_t)(e) & 0x3FFFFFu))
+#define PB2_ENT_PART(e)          ((int)((uint32_t)(e) >> 22))
+
+__device__ __forceinline__ int task_nparts(const WinDev& w, int32_t id) { return w.nparts ? (int)w.nparts[id] : 1; }
+
+// Whole warp: lanes with np > 0 own a ready task `sid` whose entries go to ring[first .. first + np).  Tasks with
+// hundreds of parts are written by all 32 lanes together.
+template <bool SYS>
+__device__ __forceinline__ void push_entries_warp(int32_t* ring, uint32_t cap_mask, int32_t sid, int np, uint32_t first) {
+    const int lane = threadIdx.x & 31;
+    const unsigned many = __ballot_sync(0xffffffffu, np > 4);
+    if (np > 0 && np <= 4)
+        for (int p = 0; p < np; ++p) {
+            if (SYS) st_release_sys(&ring[(first + (uint32_t)p) & cap_mask], PB2_ENT_MAKE(sid, p));
+            else st_release_gpu(&ring[(first + (uint32_t)p) & cap_mask], PB2_ENT_MAKE(sid, p));
+        }
+    for (unsigned m = many; m; m &= m - 1) {
+        const int src = __ffs(m) - 1;
+        const int32_t s2 = __shfl_sync(0xffffffffu, sid, src);
+        const int n2 = __shfl_sync(0xffffffffu, np, src);
+        const uint32_t f2 = __shfl_sync(0xffffffffu, first, src);
+        for (int p = lane; p < n2; p += 32) {
+            if (SYS) st_release_sys(&ring[(f2 + (uint32_t)p) & cap_mask], PB2_ENT_MAKE(s2, p));
+            else st_release_gpu(&ring[(f2 + (uint32_t)p) & cap_mask], PB2_ENT_MAKE(s2, p));
+        }
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // scheduling primitives shared by the HBM and the GEMM engine kernels
@@ -110,7 +143,7 @@ __device__ __forceinline__ void release_successors_warp(const WinDev& w, const p
             }
         }
         // a ready successor contributes one ring entry per part: exclusive scan of the part counts over the warp
-        const int nparts = ready ? PB2_TASK_NPARTS(w.tasks[sid].flags) : 0;
+        const int nparts = ready ? task_nparts(w, sid) : 0;
         int incl = nparts;
         for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
@@ -118,8 +151,7 @@ __device__ __forceinline__ void release_successors_warp(const WinDev& w, const p
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(&w.ctl->tail.v, (unsigned long long)total);
             base = __shfl_sync(0xffffffffu, base, 0);
-            for (int p = 0; p < nparts; ++p)
-                st_release_gpu(&w.ring[((uint32_t)base + (uint32_t)(incl - nparts + p)) & w.cap_mask], (int32_t)PB2_SUCC_MAKE(sid, p));
+            push_entries_warp<false>(w.ring, w.cap_mask, sid, nparts, (uint32_t)base + (uint32_t)(incl - nparts));
         }
     }
 }
@@ -136,16 +168,29 @@ __device__ __forceinline__ void release_remote_warp(const WinDev& w, int32_t id)
     __threadfence_system();            // our tile bytes are visible to the peers before they can see the release
     for (int32_t e0 = b; e0 < e1; e0 += 32) {
         const int32_t e = e0 + lane;
+        int np = 0;
+        int32_t sid = 0;
+        uint32_t first = 0;
+        PeerWin pw = w.peers[w.rs_rank[e < e1 ? e : b]];
         if (e < e1) {
-            const PeerWin pw = w.peers[w.rs_rank[e]];
             const uint32_t tgt = w.rs_target[e];
-            const int32_t sid = PB2_SUCC_TASK(tgt);
+            sid = PB2_ENT_TASK(tgt);
             if (atomicSub_system(&pw.dep[sid], 1) == 1) {
-                const int nparts = PB2_SUCC_FLOW(tgt) + 1;
-                const unsigned long long base = atomicAdd_system(&pw.ctl->tail.v, (unsigned long long)nparts);
-                for (int p = 0; p < nparts; ++p)
-                    st_release_sys(&pw.ring[((uint32_t)base + (uint32_t)p) & pw.cap_mask], (int32_t)PB2_SUCC_MAKE(sid, p));
+                np = PB2_ENT_PART(tgt) + 1;
+                first = (uint32_t)atomicAdd_system(&pw.ctl->tail.v, (unsigned long long)np);
             }
+        }
+        // entries of one ready task go to ONE peer: lanes cooperate per ready lane, the ring pointer travels with it
+        const unsigned many = __ballot_sync(0xffffffffu, np > 0);
+        for (unsigned m = many; m; m &= m - 1) {
+            const int src = __ffs(m) - 1;
+            const int32_t s2 = __shfl_sync(0xffffffffu, sid, src);
+            const int n2 = __shfl_sync(0xffffffffu, np, src);
+            const uint32_t f2 = __shfl_sync(0xffffffffu, first, src);
+            const unsigned long long rp = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)pw.ring, src);
+            const uint32_t cm = __shfl_sync(0xffffffffu, pw.cap_mask, src);
+            int32_t* ring = reinterpret_cast<int32_t*>((uintptr_t)rp);
+            for (int p = lane; p < n2; p += 32) st_release_sys(&ring[(f2 + (uint32_t)p) & cm], PB2_ENT_MAKE(s2, p));
         }
     }
 }
@@ -189,6 +234,57 @@ __device__ __forceinline__ void stage_in_flow(const WinDev& w, pb2_tile_t* tile,
                       (unsigned long long)tile->bytes);
             atomicAdd(&w.ctl->stage_ins.v, 1ull);
         }
+    }
+    __syncthreads();
+}
+
+
+// Number of stage-in slices of a tile: the same rule pb2_window_create uses for the parts of a wide task.
+#define PB2_SLICE_WORDS (PB2_MAX_PARTS / 32)
+__device__ __forceinline__ int tile_slices(const WinDev& w, uint32_t bytes) {
+    if (w.part_bytes <= 0 || !w.slice_claim) return 1;
+    const uint32_t n = (bytes + (uint32_t)w.part_bytes - 1) / (uint32_t)w.part_bytes;
+    return n > PB2_MAX_PARTS ? PB2_MAX_PARTS : (n < 1 ? 1 : (int)n);
+}
+
+// Stage in the slices [s0, s1) of a tile larger than part_bytes.  Every slice is moved by exactly one CTA (claim
+// bit), so the parts of a wide task -- and the parts of other readers of the same version -- pull the tile in
+// parallel instead of one CTA moving 4 MiB alone; a CTA that finds a slice claimed by someone else only waits
+// for it.  The worker whose slice completes the tile publishes PB2_TILE_VALID.
+__device__ __noinline__ void stage_in_slices(const WinDev& w, int32_t tile_id, int nslices, int s0, int s1, int* s_decide) {
+    pb2_tile_t* tile = &w.tiles[tile_id];
+    const uint32_t bytes = tile->bytes;
+    const uint32_t sper = ((bytes / (uint32_t)nslices) + 15u) & ~15u;
+    uint32_t* claim = w.slice_claim + (size_t)tile_id * PB2_SLICE_WORDS;
+    uint32_t* done = w.slice_done + (size_t)tile_id * (PB2_SLICE_WORDS + 1);     // last word: number of staged slices
+    for (int sl = s0; sl < s1; ++sl) {
+        const uint32_t bit = 1u << (sl & 31);
+        if (threadIdx.x == 0) *s_decide = (atomicOr(&claim[sl >> 5], bit) & bit) ? 0 : 1;
+        __syncthreads();
+        if (*s_decide) {
+            const uint32_t off = sper * (uint32_t)sl < bytes ? sper * (uint32_t)sl : bytes;
+            const uint32_t len = (sl == nslices - 1) ? bytes - off : (off + sper <= bytes ? sper : bytes - off);
+            cta_copy<true>(reinterpret_cast<uint8_t*>(tile->dev_ptr) + off, reinterpret_cast<const uint8_t*>(tile->src_ptr) + off, len);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                atomicOr(&done[sl >> 5], bit);
+                atomicAdd(tile->src_kind == PB2_SRC_PEER ? &w.ctl->bytes_d2d.v : &w.ctl->bytes_h2d.v, (unsigned long long)len);
+                if ((int)atomicAdd(&done[PB2_SLICE_WORDS], 1u) + 1 == nslices) {
+                    __threadfence();
+                    st_release_gpu(&tile->state, PB2_TILE_VALID);
+                    atomicAdd(&w.ctl->stage_ins.v, 1ull);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        for (int sl = s0; sl < s1; ++sl) {
+            const uint32_t bit = 1u << (sl & 31);
+            while (!(ld_acquire_gpu(reinterpret_cast<const int32_t*>(&done[sl >> 5])) & bit)) __nanosleep(64);
+        }
+        __threadfence();
     }
     __syncthreads();
 }

@@ -81,6 +81,9 @@ class Engine:
     def set_shared_windows(self, on=True):
         _check(self._lib.pb2_engine_set_shared_windows(self._h, 1 if on else 0), "set_shared_windows", self)
 
+    def set_part_bytes(self, part_bytes):
+        _check(self._lib.pb2_engine_set_part_bytes(self._h, part_bytes), "set_part_bytes", self)
+
     def ipc_export(self, dev_ptr):
         h = (C.c_ubyte * 64)()
         _check(self._lib.pb2_engine_ipc_export(self._h, C.c_void_p(dev_ptr), h), "ipc_export", self)

@@ -114,20 +114,26 @@ def ex05_global(K_total, NB, world, tile_bytes):
     return t, succ, tiles, np.arange(K_total, dtype=np.int32), task_rank, (k % world).astype(np.int32)
 
 
-def rtt_global(ntasks, world, tile_bytes):
-    """tests/runtime/cuda/rtt.jdf: PING(k) RW T <- (k == 0) ? A(0) : T PING(k-1), runs on rank k % world (the
-    reference sets one data per rank and moves the tile around the ring).  Every task adds 1 to every element."""
-    t = np.zeros(ntasks, L.TASK_DTYPE)
+def rtt_global(nt, world, tile_bytes, frags=1):
+    """tests/runtime/cuda/rtt.jdf:26-34: PING(k, f), k = 0..NT-1, f = 0..FRAGS-1, RW T <- (k == 0) ? A(f, 0) : T PING(k-1, f),
+    placed on A(f, k % WS) with a 1 x WS grid: FRAGS independent chains that hop to the next GPU at every task.
+    Every task adds 1 to every element (BASELINE configs[3] body).  Task id = k * frags + f."""
+    n = nt * frags
+    t = np.zeros(n, L.TASK_DTYPE)
     t["tile"][:] = -1
-    k = np.arange(ntasks, dtype=np.int32)
+    i = np.arange(n, dtype=np.int32)
+    k, f = i // frags, i % frags
     t["body"], t["nb_flows"], t["flags"] = L.BODY_INCR_I32, 1, L.TASK_DEPS_MASK
-    t["tile"][:, 0], t["access"][:, 0], t["locals"][:, 0] = 0, L.ACCESS_RW, k
+    t["iparam"][:, 0] = 1
+    t["tile"][:, 0], t["access"][:, 0], t["locals"][:, 0], t["locals"][:, 1] = f, L.ACCESS_RW, k, f
     t["dep_goal"] = np.where(k > 0, 1, 0)
-    t["succ_begin"], t["succ_count"] = k, np.where(k < ntasks - 1, 1, 0)
-    succ = (k[:-1] + 1).astype(np.uint32)
-    tiles = np.zeros(1, L.TILE_DTYPE)
+    last = k == nt - 1
+    t["succ_count"] = np.where(last, 0, 1)
+    t["succ_begin"] = np.minimum(i, n - frags)
+    succ = (i[~last] + frags).astype(np.uint32)
+    tiles = np.zeros(frags, L.TILE_DTYPE)
     tiles["bytes"], tiles["state"] = tile_bytes, L.TILE_VALID
-    return t, succ, tiles, np.zeros(1, np.int32), (k % world).astype(np.int32), np.zeros(1, np.int32)
+    return t, succ, tiles, np.arange(frags, dtype=np.int32), (k % world).astype(np.int32), np.zeros(frags, np.int32)
 
 
 def work_stream(torch):

@@ -177,6 +177,66 @@ def test_wide_tasks_match_oracle(tile_bytes, part_bytes):
     assert st["bytes_h2d"] == ref["stats"]["bytes_h2d"]
 
 
+@pytest.mark.parametrize("big,small,part_bytes", [(1 << 20, 1 << 20, 64 * 1024), ((1 << 20) + 20, 300 * 1000, 100 * 1000), (4 << 20, 64 * 1024, 0)])
+def test_sliced_stage_in_of_wide_tiles(big, small, part_bytes):
+    """Tiles larger than part_bytes that start INVALID are staged in slice by slice by the parts of their readers
+    (each slice moved exactly once, also when two wide readers of the same version run at the same time and when a
+    task is cut differently from the tile): bytes staged == tile bytes, values == oracle."""
+    from oracle import orc
+    nb, ns = big // 4, small // 4
+    # tiles: 0 big (host, INVALID), 1 small (host, INVALID), 2 big scratch (VALID), 3 small scratch (VALID)
+    t = np.zeros(6, L.TASK_DTYPE)
+    t["tile"][:] = -1
+    # 0: RW INCR on tile 0 (sliced stage-in by its own parts, then in-place update)
+    t["body"][0], t["nb_flows"][0], t["iparam"][0, 0] = L.BODY_INCR_I32, 1, 5
+    t["tile"][0, 0], t["access"][0, 0] = 0, L.ACCESS_RW
+    # 1, 2: two concurrent readers of tile 1's first version... tile 1 is INVALID: COPY small -> big scratch (cut by the big tile)
+    t["body"][1], t["nb_flows"][1] = L.BODY_COPY, 2
+    t["tile"][1, 0], t["access"][1, 0], t["tile"][1, 1], t["access"][1, 1] = 1, L.ACCESS_READ, 2, L.ACCESS_WRITE
+    t["body"][2], t["nb_flows"][2], t["iparam"][2, 0] = L.BODY_CHECK_I32, 1, 123
+    t["tile"][2, 0], t["access"][2, 0] = 1, L.ACCESS_READ
+    # 3: reader of tile 0 after the update; 4: COPY big -> small scratch (task cut by the big tile, small one whole)
+    t["body"][3], t["nb_flows"][3], t["iparam"][3, 0], t["dep_goal"][3] = L.BODY_CHECK_I32, 1, 128, 1
+    t["tile"][3, 0], t["access"][3, 0] = 0, L.ACCESS_READ
+    t["body"][4], t["nb_flows"][4], t["dep_goal"][4] = L.BODY_COPY, 2, 1
+    t["tile"][4, 0], t["access"][4, 0], t["tile"][4, 1], t["access"][4, 1] = 0, L.ACCESS_READ, 3, L.ACCESS_WRITE
+    t["body"][5], t["nb_flows"][5], t["iparam"][5, 0], t["dep_goal"][5] = L.BODY_CHECK_I32, 1, 128, 1
+    t["tile"][5, 0], t["access"][5, 0] = 3, L.ACCESS_READ
+    t["succ_begin"] = [0, 2, 2, 2, 2, 3]; t["succ_count"] = [2, 0, 0, 0, 1, 0]
+    succ = np.array([3, 4, 5], np.uint32)
+    ready = np.array([0, 1, 2], np.int32)
+    host = np.full(nb + ns, 123, np.int32)
+    spec = np.zeros(4, orc.TILE_DTYPE)
+    spec["bytes"] = [big, small, big, small]
+    spec["src_ptr"] = [0, big, 0, 0]
+    spec["state"] = [orc.TILE_INVALID, orc.TILE_INVALID, orc.TILE_VALID, orc.TILE_VALID]
+    ref = orc.run_window(t, succ, spec, ready, host.copy())
+    assert ref["rc"] == 0
+    with Engine(0, part_bytes=part_bytes) as e:
+        offs = np.cumsum([0] + [(b + 511) // 512 * 512 for b in (big, small, big, small)])
+        slab = e.malloc(int(offs[-1]))
+        e.h2d(slab, np.zeros(int(offs[-1]), np.uint8))
+        alias = e.host_register(host)
+        tiles = np.zeros(4, L.TILE_DTYPE)
+        tiles["dev_ptr"] = slab + offs[:4].astype(np.uint64)
+        tiles["src_ptr"] = [alias, alias + big, 0, 0]
+        tiles["bytes"] = [big, small, big, small]
+        tiles["state"] = [L.TILE_INVALID, L.TILE_INVALID, L.TILE_VALID, L.TILE_VALID]
+        w = e.window(0, t, succ, tiles, ready)
+        for _ in range(3):                                    # re-armed windows stage again
+            st = w.run(); res = w.results()
+            assert np.array_equal(res["result"], ref["result"])
+            assert st["bytes_h2d"] == big + small == ref["stats"]["bytes_h2d"]
+            assert st["body_errors"] == ref["stats"]["body_errors"]
+        got = [np.empty(b // 4, np.int32) for b in (big, small, big, small)]
+        for i in range(4):
+            e.d2h(got[i], int(tiles["dev_ptr"][i]))
+        w.close()
+        e.host_unregister(host)
+    for i in range(4):
+        assert np.array_equal(got[i], ref["device"][i].view(np.int32)[:len(got[i])]), i
+
+
 def test_big_tile_chain_uses_the_whole_gpu():
     """Config-4 body on one GPU: a serial chain of 4 MiB tiles; with parts one hop is spread over up to 32 workers."""
     NT, tb = 64, 4 << 20

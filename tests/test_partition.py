@@ -37,7 +37,7 @@ def merged_run(part, world, policy=0, seed=1):
             loc = ((loc >> 27) << 27) | ((loc & 0x7FFFFFF) + toff[r])
             rem = []
             for e in range(p["rs_begin"][l], p["rs_begin"][l + 1]):
-                rem.append((int(p["rs_target"][e]) & 0x7FFFFFF) + toff[p["rs_rank"][e]])
+                rem.append((int(p["rs_target"][e]) & 0x3FFFFF) + toff[p["rs_rank"][e]])
             sb[l] = nsucc
             succ.extend(int(x) for x in loc)
             succ.extend(rem)
@@ -196,7 +196,7 @@ def test_remote_edge_targets_are_consistent():
         for q, o in enumerate(parts):
             m = o["rs_rank"] == r
             assert q != r or not m.any()
-            np.add.at(indeg, (o["rs_target"][m] & 0x7FFFFFF).astype(np.int64), 1)
+            np.add.at(indeg, (o["rs_target"][m] & 0x3FFFFF).astype(np.int64), 1)
         assert np.array_equal(indeg, p["tasks"]["dep_goal"].astype(np.int64))
         assert not (p["tasks"]["flags"] & L.TASK_DEPS_MASK).any()
         assert np.array_equal(np.sort(p["ready"]), np.nonzero(p["tasks"]["dep_goal"] == 0)[0])
