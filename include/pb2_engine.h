@@ -196,8 +196,11 @@ int  pb2_engine_copy_batch(pb2_engine_t* engine, void* const* dst, const void* c
 int  pb2_engine_ipc_export(pb2_engine_t* engine, void* dev_ptr, unsigned char handle[64]);
 int  pb2_engine_ipc_open(pb2_engine_t* engine, const unsigned char handle[64], void** dev_ptr);
 int  pb2_engine_ipc_close(pb2_engine_t* engine, void* dev_ptr);
-/* all windows created after this call keep their scheduling arrays in IPC-exportable memory */
-int  pb2_engine_set_shared_windows(pb2_engine_t* engine, int on);
+/* all windows created after this call keep their scheduling arrays in IPC-exportable memory and treat their tasks'
+ * dependency goals as counting in-edges from other GPUs too.  next_rs_begin (may be NULL; ntasks+1 entries, must stay
+ * valid until the next pb2_window_create returns) is the remote out-edge CSR of the next window: a task with remote
+ * successors is never fused into the middle of a GEMM k-chain unit. */
+int  pb2_engine_set_shared_windows(pb2_engine_t* engine, int on, const int32_t* next_rs_begin);
 /* part size for the windows created from now on (a serial chain of large tiles wants small parts: a 64-thread
  * worker keeps only 4 KiB in flight; wide DAGs want one part per tile) */
 int  pb2_engine_set_part_bytes(pb2_engine_t* engine, int32_t part_bytes);
@@ -233,11 +236,16 @@ typedef struct pb2_window_handle_s {
     unsigned char dep[64], ring[64], ctl[64];
     uint32_t cap_mask;
     int32_t  ntasks;
+    int32_t  entry_kind;   /* 0: dep words and ring entries are per task, 1: per fused GEMM unit */
+    int32_t  reserved;
 } pb2_window_handle_t;
+/* entry[t] = what a remote producer must put in rs_target to release task t of THIS window (index of the
+ * dependency word + number of ring entries, in this window's own encoding).  Exchange it with the peers. */
+int  pb2_window_task_entries(pb2_window_t* window, int32_t* entry);
 int  pb2_window_export(pb2_window_t* window, pb2_window_handle_t* handle);
 /* remote out-edges of this window: for task t, entries rs_begin[t] .. rs_begin[t+1]-1 of (rank[], target[]) where
- * target = ((nparts - 1) << 22) | task id in that rank's window (nparts: parts of that task, 1..512, the rule of
- * pb2_engine_params_t::part_bytes); remote successors are counter-mode.
+ * target = the destination window's pb2_window_task_entries value of the destination task; remote successors are
+ * counter-mode.
  * peers[r] is rank r's exported handle (peers[my_rank] is ignored). */
 int  pb2_window_set_remote(pb2_window_t* window, int32_t my_rank, int32_t nranks, const pb2_window_handle_t* peers,
                            const int32_t* rs_begin, const int32_t* rs_rank, const uint32_t* rs_target, int32_t nrs);
@@ -266,7 +274,9 @@ int  pb2_partition_create(pb2_partition_t** partition, const pb2_task_t* tasks, 
                           int32_t nranks, int32_t part_bytes);
 int  pb2_partition_sizes(const pb2_partition_t* partition, int32_t rank, pb2_partition_sizes_t* sizes);
 /* slab_base[r]: address of rank r's slab as seen from `rank` (own allocation / IPC mapping).  Arrays sized by
- * pb2_partition_sizes; rs_begin has ntasks+1 entries; global_id[t] is the id the local task had in the input;
+ * pb2_partition_sizes; rs_begin has ntasks+1 entries; rs_target[e] is the LOCAL TASK ID in rank rs_rank[e]'s part
+ * (translate it with that rank's pb2_window_task_entries before pb2_window_set_remote); global_id[t] is the id the
+ * local task had in the input; part_bytes of pb2_partition_create is reserved (pass 0);
  * slot_tile / slot_offset describe the slab (global tile id and byte offset of each slot). */
 int  pb2_partition_get(const pb2_partition_t* partition, int32_t rank, const uint64_t* slab_base,
                        pb2_task_t* tasks, uint32_t* succ, pb2_tile_t* tiles, int32_t* ready,

@@ -253,6 +253,7 @@ struct pb2_engine_s {
     std::string last_error;
     std::mutex mu;
     bool shared_windows = false;
+    const int32_t* next_rs_begin = nullptr;   // remote out-degree CSR of the next shared window (not owned)
     std::map<void*, std::pair<size_t, void*>> registered;   // host ptr -> (bytes, device alias)
 };
 
@@ -274,6 +275,7 @@ struct pb2_window_s {
     int32_t nentries = 0;
     bool launched = false;
     bool shared = false;
+    std::vector<int32_t> task_entry;          // per task: its ring entry with (parts - 1) in the part field
     std::vector<void*> allocs;
     std::vector<void*> peer_ptrs;
 };
@@ -385,7 +387,8 @@ static int build_tensor_maps(pb2_window_t* w, const pb2_task_t* tasks, int32_t n
 // v2 GEMM windows: group tasks into units (fused k-chains), see pb2_gemm2.cuh
 // ---------------------------------------------------------------------------------------------
 static int build_gemm2_units(pb2_window_t* w, const pb2_task_t* tasks, int32_t ntasks, const uint32_t* succ,
-                             const int32_t* ready, int32_t nready, bool fuse, uint32_t* ring_cap_needed) {
+                             const int32_t* ready, int32_t nready, bool fuse, uint32_t* ring_cap_needed,
+                             const int32_t* rs_begin) {
     std::vector<int32_t> indeg((size_t)ntasks, 0), cpred((size_t)ntasks, -1), ccons((size_t)ntasks, 0), next((size_t)ntasks, -1);
     auto is_gemm = [&](int32_t t) { return tasks[t].body == PB2_BODY_GEMM_BF16; };
     for (int32_t u = 0; u < ntasks; ++u)
@@ -395,10 +398,19 @@ static int build_gemm2_units(pb2_window_t* w, const pb2_task_t* tasks, int32_t n
             indeg[t]++;
             if (PB2_SUCC_FLOW(s) == 2 && is_gemm(u) && is_gemm(t) && tasks[u].tile[2] == tasks[t].tile[2]) { ccons[u]++; cpred[t] = u; }
         }
+    // A window that peers release into: the tasks' dependency goals (counter mode, set by the partitioner) also
+    // count the in-edges that come from other GPUs; the local CSR does not show them.
+    if (w->shared)
+        for (int32_t t = 0; t < ntasks; ++t) {
+            const int32_t need = (tasks[t].flags & PB2_TASK_DEPS_MASK) ? __builtin_popcount((unsigned)tasks[t].dep_goal) : tasks[t].dep_goal;
+            if (need < indeg[t]) { w->e->last_error = "dependency goal smaller than the in-window in-degree"; return PB2_ERR_BAD_PARAM; }
+            indeg[t] = need;
+        }
     if (fuse)
         for (int32_t t = 0; t < ntasks; ++t) {
             const int32_t u = cpred[t];
             if (u < 0 || indeg[t] != 1 || ccons[u] != 1) continue;                 // the chain link must be t's only missing input
+            if (rs_begin && rs_begin[u + 1] > rs_begin[u]) continue;               // u's result is awaited on another GPU: retire it on its own
             if (tasks[u].access[2] & PB2_FLOW_PUSHOUT) continue;                   // u's C has to reach the host: flush there
             if (memcmp(tasks[u].iparam, tasks[t].iparam, sizeof tasks[u].iparam)) continue;
             next[u] = t;
@@ -467,6 +479,8 @@ static int build_gemm2_units(pb2_window_t* w, const pb2_task_t* tasks, int32_t n
     if ((rc = dev_alloc_copy(w, &w->d_ready_entries, entries.data(), entries.size())) != PB2_SUCCESS) return rc;
     if ((rc = dev_alloc_copy(w, &w->g.udep, (const int32_t*)nullptr, units.size())) != PB2_SUCCESS) return rc;
     if ((rc = dev_alloc_copy(w, &w->g.parts_left, (const int32_t*)nullptr, units.size())) != PB2_SUCCESS) return rc;
+    w->task_entry.assign((size_t)ntasks, -1);
+    for (int32_t t = 0; t < ntasks; ++t) w->task_entry[(size_t)t] = (int32_t)PB2_SUCC_MAKE(unit_of[t], units[(size_t)unit_of[t]].nparts - 1);
     w->g.units = d_units; w->g.segs = d_segs; w->g.usucc = d_usucc; w->g.nunits = (int32_t)units.size();
     w->nentries = (int32_t)entries.size();
     return PB2_SUCCESS;
@@ -656,7 +670,18 @@ int pb2_engine_set_part_bytes(pb2_engine_t* e, int32_t part_bytes) {
     e->params.part_bytes = part_bytes == 0 ? 256 * 1024 : part_bytes;
     return PB2_SUCCESS;
 }
-int pb2_engine_set_shared_windows(pb2_engine_t* e, int on) { if (!e) return PB2_ERR_BAD_PARAM; e->shared_windows = on != 0; return PB2_SUCCESS; }
+int pb2_engine_set_shared_windows(pb2_engine_t* e, int on, const int32_t* next_rs_begin) {
+    if (!e) return PB2_ERR_BAD_PARAM;
+    e->shared_windows = on != 0; e->next_rs_begin = on ? next_rs_begin : nullptr;
+    return PB2_SUCCESS;
+}
+
+int pb2_window_task_entries(pb2_window_t* w, int32_t* entry) {
+    if (!w || !entry) return PB2_ERR_BAD_PARAM;
+    if ((int32_t)w->task_entry.size() != w->ntasks) return PB2_ERR_NOT_SUPPORTED;
+    memcpy(entry, w->task_entry.data(), w->task_entry.size() * sizeof(int32_t));
+    return PB2_SUCCESS;
+}
 
 int pb2_engine_set_stream(pb2_engine_t* e, void* cuda_stream) {
     if (!e) return PB2_ERR_BAD_PARAM;
@@ -708,6 +733,8 @@ int pb2_window_create(pb2_engine_t* e, pb2_window_t** window, int kind,
     }
     for (int32_t i = 0; i < nready; ++i)
         for (int p = 0; p < (int)nparts[(size_t)ready[i]]; ++p) entries.push_back(PB2_ENT_MAKE(ready[i], p));
+    w->task_entry.resize((size_t)ntasks);
+    for (int32_t i = 0; i < ntasks; ++i) w->task_entry[(size_t)i] = PB2_ENT_MAKE(i, (int)nparts[(size_t)i] - 1);
     TRY(dev_alloc_copy(w, &w->d_tasks, dtasks.data(), (size_t)ntasks));
     TRY(dev_alloc_copy(w, &w->d_succ, succ, (size_t)nsucc));
     TRY(dev_alloc_copy(w, &w->d_tiles_init, tiles, (size_t)ntiles));
@@ -718,7 +745,8 @@ int pb2_window_create(pb2_engine_t* e, pb2_window_t** window, int kind,
     if (kind == 1) {
         TRY(build_tensor_maps(w, tasks, ntasks, tiles, ntiles));
         if (e->params.gemm_mode != 1) {
-            rc = build_gemm2_units(w, tasks, ntasks, succ, ready, nready, e->params.gemm_mode == 0, &parts_needed);
+            rc = build_gemm2_units(w, tasks, ntasks, succ, ready, nready, e->params.gemm_mode == 0, &parts_needed,
+                                   w->shared ? e->next_rs_begin : nullptr);
             if (rc == PB2_SUCCESS) w->v2 = true;
             else if (rc != PB2_ERR_NOT_SUPPORTED) { pb2_window_destroy(w); return rc; }     // NOT_SUPPORTED: v1 kernel
         }
@@ -739,7 +767,7 @@ int pb2_window_create(pb2_engine_t* e, pb2_window_t** window, int kind,
     TRY(dev_alloc_copy(w, &d.worker, (const int32_t*)nullptr, (size_t)ntasks));
     d.parts_left = nullptr; d.rs_begin = nullptr; d.rs_rank = nullptr; d.rs_target = nullptr; d.peers = nullptr; d.shared = w->shared ? 1 : 0;
     d.slice_claim = nullptr; d.slice_done = nullptr; d.part_bytes = e->params.part_bytes;
-    d.nparts = nullptr;
+    d.nparts = nullptr; d.remote_units = 0;
     if (kind == 0 && extra_parts) {
         uint16_t* d_np = nullptr;
         TRY(dev_alloc_copy(w, &d_np, nparts.data(), (size_t)ntasks));
@@ -828,10 +856,10 @@ int pb2_window_export(pb2_window_t* w, pb2_window_handle_t* h) {
     PB2_CUDA(e, cudaSetDevice(e->cuda_device));
     memset(h, 0, sizeof *h);
     cudaIpcMemHandle_t ih;
-    PB2_CUDA(e, cudaIpcGetMemHandle(&ih, w->d.dep));  memcpy(h->dep, &ih, 64);
+    PB2_CUDA(e, cudaIpcGetMemHandle(&ih, w->v2 ? w->g.udep : w->d.dep));  memcpy(h->dep, &ih, 64);   // fused-GEMM windows: unit words
     PB2_CUDA(e, cudaIpcGetMemHandle(&ih, w->d.ring)); memcpy(h->ring, &ih, 64);
     PB2_CUDA(e, cudaIpcGetMemHandle(&ih, w->d.ctl));  memcpy(h->ctl, &ih, 64);
-    h->cap_mask = w->d.cap_mask; h->ntasks = w->ntasks;
+    h->cap_mask = w->d.cap_mask; h->ntasks = w->ntasks; h->entry_kind = w->v2 ? 1 : 0;
     return PB2_SUCCESS;
 }
 
@@ -840,9 +868,13 @@ int pb2_window_set_remote(pb2_window_t* w, int32_t my_rank, int32_t nranks, cons
     if (!w || nranks <= 0 || my_rank < 0 || my_rank >= nranks || !peers || !rs_begin || nrs < 0) return PB2_ERR_BAD_PARAM;
     pb2_engine_t* e = w->e;
     PB2_CUDA(e, cudaSetDevice(e->cuda_device));
+    const int32_t my_kind = w->v2 ? 1 : 0;
+    for (int32_t r = 0; r < nranks; ++r)
+        if (r != my_rank && peers[r].entry_kind != my_kind) { e->last_error = "peers run a different kind of window (fused GEMM units vs tasks)"; return PB2_ERR_NOT_SUPPORTED; }
     for (int32_t i = 0; i < nrs; ++i) {
         if (rs_rank[i] < 0 || rs_rank[i] >= nranks || rs_rank[i] == my_rank) { e->last_error = "remote edge to a bad rank"; return PB2_ERR_BAD_PARAM; }
-        if ((int32_t)(rs_target[i] & 0x3FFFFFu) >= peers[rs_rank[i]].ntasks) { e->last_error = "remote edge target out of bounds"; return PB2_ERR_VALUE_OUT_OF_BOUNDS; }
+        const int32_t idx = my_kind ? (int32_t)PB2_SUCC_TASK(rs_target[i]) : (int32_t)(rs_target[i] & 0x3FFFFFu);
+        if (idx >= peers[rs_rank[i]].ntasks) { e->last_error = "remote edge target out of bounds"; return PB2_ERR_VALUE_OUT_OF_BOUNDS; }
     }
     if (rs_begin[w->ntasks] != nrs) return PB2_ERR_BAD_PARAM;
     std::vector<PeerWin> pw((size_t)nranks);
@@ -865,7 +897,7 @@ int pb2_window_set_remote(pb2_window_t* w, int32_t my_rank, int32_t nranks, cons
     if ((rc = dev_alloc_copy(w, &d_r, rs_rank, (size_t)nrs)) != PB2_SUCCESS) return rc;
     if ((rc = dev_alloc_copy(w, &d_t, rs_target, (size_t)nrs)) != PB2_SUCCESS) return rc;
     PB2_CUDA(e, cudaStreamSynchronize(e->stream));
-    w->d.peers = d_pw; w->d.rs_begin = d_b; w->d.rs_rank = d_r; w->d.rs_target = d_t;
+    w->d.peers = d_pw; w->d.rs_begin = d_b; w->d.rs_rank = d_r; w->d.rs_target = d_t; w->d.remote_units = my_kind;
     if (w->v2) w->g.w = w->d;
     return PB2_SUCCESS;
 }

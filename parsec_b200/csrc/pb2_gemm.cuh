@@ -333,6 +333,7 @@ pb2_engine_gemm_kernel(WinDev w, const CUtensorMap* __restrict__ tmaps) {
             }
             __syncwarp();
             release_successors_warp(w, t);
+            release_remote_warp(w, id);
             if (threadIdx.x == 0 && sh.last) {
                 __threadfence();
                 st_release_gpu(reinterpret_cast<int32_t*>(&w.ctl->done.v), kDoneOK);

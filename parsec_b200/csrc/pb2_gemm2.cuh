@@ -173,6 +173,9 @@ __device__ __forceinline__ void retire_unit_warp(const Win2Dev& g, const GUnit& 
                 st_release_gpu(&w.ring[((uint32_t)base + (uint32_t)(incl - nparts + p)) & w.cap_mask], (int32_t)PB2_SUCC_MAKE(sid, p));
         }
     }
+    // out-edges into other GPUs' windows, member by member (a member with remote successors is always the last of
+    // its unit: build_gemm2_units does not fuse across it)
+    if (w.rs_begin) for (int i = 0; i < L; ++i) release_remote_warp(w, g.segs[u.seg_begin + i].task);
     if (lane == 0 && (int32_t)(rbase + L) == w.ntasks) {
         __threadfence();
         st_release_gpu(reinterpret_cast<int32_t*>(&w.ctl->done.v), kDoneOK);

@@ -26,6 +26,7 @@ struct Desc {            // one tile descriptor of a rank's window
     int32_t src_rank;    // -1: keep the global tile's host source / state; >= 0: pull from that rank's slot
     int32_t src_slot;
     int32_t state;
+    int32_t ver;         // writers of the tile before the first user of this descriptor: its version on arrival
 };
 
 struct RankPart {
@@ -74,7 +75,7 @@ int pb2_partition_create(pb2_partition_t** out, const pb2_task_t* tasks, int32_t
                          const int32_t* task_rank, const int32_t* tile_rank, int32_t nranks, int32_t part_bytes) {
     if (!out || ntasks < 0 || nsucc < 0 || ntiles < 0 || nready < 0 || nranks <= 0 || (ntasks && (!tasks || !task_rank)) ||
         (ntiles && (!tiles || !tile_rank))) { g_err = "bad argument"; return PB2_ERR_BAD_PARAM; }
-    if (part_bytes == 0) part_bytes = 256 * 1024;
+    (void)part_bytes;
     pb2_partition_s* P = new pb2_partition_s();
     P->nranks = nranks; P->ntasks = ntasks;
     P->tasks.assign(tasks, tasks + ntasks);
@@ -88,7 +89,6 @@ int pb2_partition_create(pb2_partition_t** out, const pb2_task_t* tasks, int32_t
         if (task_rank[t] < 0 || task_rank[t] >= nranks) FAIL(PB2_ERR_BAD_PARAM, "task_rank out of range");
         const pb2_task_t& k = tasks[t];
         if (k.nb_flows > PB2_MAX_FLOWS) FAIL(PB2_ERR_BAD_PARAM, "task with more than PB2_MAX_FLOWS flows");
-        if (k.body == PB2_BODY_GEMM_BF16) FAIL(PB2_ERR_NOT_SUPPORTED, "GEMM windows are not partitioned yet");
         if (k.succ_count < 0 || k.succ_begin < 0 || (int64_t)k.succ_begin + k.succ_count > nsucc) FAIL(PB2_ERR_VALUE_OUT_OF_BOUNDS, "successor range out of bounds");
         for (int f = 0; f < k.nb_flows; ++f) if (k.tile[f] >= ntiles) FAIL(PB2_ERR_VALUE_OUT_OF_BOUNDS, "tile id out of bounds");
         RankPart& rp = P->parts[(size_t)task_rank[t]];
@@ -99,7 +99,7 @@ int pb2_partition_create(pb2_partition_t** out, const pb2_task_t* tasks, int32_t
     for (int32_t i = 0; i < nsucc; ++i) if (PB2_SUCC_TASK(succ[i]) >= ntasks) FAIL(PB2_ERR_VALUE_OUT_OF_BOUNDS, "successor id out of bounds");
 
     // in-degree, data producer of every (task, flow), number of parts (same rule as pb2_window_create)
-    std::vector<int32_t> indeg((size_t)ntasks, 0), prod((size_t)ntasks * PB2_MAX_FLOWS, -1), nparts((size_t)ntasks, 1);
+    std::vector<int32_t> indeg((size_t)ntasks, 0), prod((size_t)ntasks * PB2_MAX_FLOWS, -1);
     auto writes = [&](int32_t p, int32_t tile) {
         const pb2_task_t& k = tasks[p];
         for (int g = 0; g < k.nb_flows; ++g) if (k.tile[g] == tile && (k.access[g] & PB2_FLOW_ACCESS_WRITE)) return true;
@@ -112,12 +112,6 @@ int pb2_partition_create(pb2_partition_t** out, const pb2_task_t* tasks, int32_t
             const int f = (int)PB2_SUCC_FLOW(succ[e]);
             indeg[(size_t)s]++;
             if (f < tasks[s].nb_flows && tasks[s].tile[f] >= 0 && writes(p, tasks[s].tile[f])) prod[(size_t)s * PB2_MAX_FLOWS + f] = p;
-        }
-        if (k.body != PB2_BODY_NOP && part_bytes > 0 && ntasks < (1 << 22)) {
-            uint32_t big = 0;
-            for (int f = 0; f < k.nb_flows; ++f) if (k.tile[f] >= 0 && tiles[k.tile[f]].bytes > big) big = tiles[k.tile[f]].bytes;
-            uint32_t np = (big + (uint32_t)part_bytes - 1) / (uint32_t)part_bytes;
-            nparts[(size_t)p] = (int32_t)(np > 512 ? 512 : (np < 1 ? 1 : np));
         }
     }
     for (int32_t t = 0; t < ntasks; ++t) {
@@ -241,7 +235,7 @@ int pb2_partition_create(pb2_partition_t** out, const pb2_task_t* tasks, int32_t
                 else {
                     const int32_t pr = task_rank[p];
                     d = (int32_t)rp.descs.size();
-                    rp.descs.push_back({tile, slot_for(P, r, tile), pr, slot_for(P, pr, tile), PB2_TILE_INVALID});
+                    rp.descs.push_back({tile, slot_for(P, r, tile), pr, slot_for(P, pr, tile), PB2_TILE_INVALID, v});
                     pulled[(size_t)r][key] = d;
                     SlotUsers& su = slot_users[{r, tile}];
                     su.prev.swap(su.cur); su.cur.clear();
@@ -264,10 +258,10 @@ int pb2_partition_create(pb2_partition_t** out, const pb2_task_t* tasks, int32_t
                 else {
                     const int32_t home = tile_rank[tile];
                     d = (int32_t)rp.descs.size();
-                    if (home == r) rp.descs.push_back({tile, slot_for(P, r, tile), -1, -1, tiles[tile].state});
-                    else if (!(k.access[f] & PB2_FLOW_ACCESS_READ)) rp.descs.push_back({tile, slot_for(P, r, tile), -1, -1, PB2_TILE_VALID});
+                    if (home == r) rp.descs.push_back({tile, slot_for(P, r, tile), -1, -1, tiles[tile].state, v});
+                    else if (!(k.access[f] & PB2_FLOW_ACCESS_READ)) rp.descs.push_back({tile, slot_for(P, r, tile), -1, -1, PB2_TILE_VALID, v});
                     else if (tiles[tile].state == PB2_TILE_VALID)
-                        rp.descs.push_back({tile, slot_for(P, r, tile), home, slot_for(P, home, tile), PB2_TILE_INVALID});
+                        rp.descs.push_back({tile, slot_for(P, r, tile), home, slot_for(P, home, tile), PB2_TILE_INVALID, v});
                     else FAIL(PB2_ERR_NOT_SUPPORTED, "a rank reads the initial copy of a tile that is not resident on its home rank");
                     cur[(size_t)r][tile] = d;
                 }
@@ -299,7 +293,7 @@ int pb2_partition_create(pb2_partition_t** out, const pb2_task_t* tasks, int32_t
             rp.rs_begin[l] = (int32_t)rp.rs_rank.size();
             auto edge = [&](int32_t s, int f) {
                 if (task_rank[s] == r) rp.succ.push_back(PB2_SUCC_MAKE(P->lid[(size_t)s], f));
-                else { rp.rs_rank.push_back(task_rank[s]); rp.rs_target.push_back(((uint32_t)(nparts[(size_t)s] - 1) << 22) | (uint32_t)P->lid[(size_t)s]); }
+                else { rp.rs_rank.push_back(task_rank[s]); rp.rs_target.push_back((uint32_t)P->lid[(size_t)s]); }
             };
             for (int32_t e = k.succ_begin; e < k.succ_begin + k.succ_count; ++e) edge((int32_t)PB2_SUCC_TASK(succ[e]), (int)PB2_SUCC_FLOW(succ[e]));
             for (auto& w : war[(size_t)t]) edge(w.first, PB2_MAX_FLOWS);       // control edge: no flow of the successor
@@ -343,6 +337,7 @@ int pb2_partition_get(const pb2_partition_t* P, int32_t rank, const uint64_t* sl
         pb2_tile_t t = P->tiles[(size_t)d.tile];
         t.dev_ptr = reinterpret_cast<void*>(slab_base[rank] + rp.slot_off[(size_t)d.slot]);
         t.state = d.state;
+        t.version += (uint32_t)d.ver;                   // every task sees the version the unsplit window would show it
         if (d.src_rank >= 0) {
             t.src_ptr = reinterpret_cast<void*>(slab_base[d.src_rank] + P->parts[(size_t)d.src_rank].slot_off[(size_t)d.src_slot]);
             t.src_kind = PB2_SRC_PEER;

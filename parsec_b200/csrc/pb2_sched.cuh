@@ -54,6 +54,7 @@ struct WinDev {
     uint32_t*         slice_done;
     int32_t           part_bytes;
     const uint16_t*   nparts;         // HBM windows with wide tasks: parts per task (null: every task is one part)
+    int32_t           remote_units;   // remote targets are (parts-1) << 27 | unit of a fused-GEMM window, not << 22 | task
 };
 
 struct PeerWin { int32_t* dep; int32_t* ring; Ctl* ctl; uint32_t cap_mask; int32_t pad; };
@@ -174,9 +175,9 @@ __device__ __forceinline__ void release_remote_warp(const WinDev& w, int32_t id)
         PeerWin pw = w.peers[w.rs_rank[e < e1 ? e : b]];
         if (e < e1) {
             const uint32_t tgt = w.rs_target[e];
-            sid = PB2_ENT_TASK(tgt);
+            sid = w.remote_units ? (int32_t)PB2_SUCC_TASK(tgt) : PB2_ENT_TASK(tgt);
             if (atomicSub_system(&pw.dep[sid], 1) == 1) {
-                np = PB2_ENT_PART(tgt) + 1;
+                np = (w.remote_units ? (int)PB2_SUCC_FLOW(tgt) : PB2_ENT_PART(tgt)) + 1;
                 first = (uint32_t)atomicAdd_system(&pw.ctl->tail.v, (unsigned long long)np);
             }
         }
@@ -190,7 +191,8 @@ __device__ __forceinline__ void release_remote_warp(const WinDev& w, int32_t id)
             const unsigned long long rp = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)pw.ring, src);
             const uint32_t cm = __shfl_sync(0xffffffffu, pw.cap_mask, src);
             int32_t* ring = reinterpret_cast<int32_t*>((uintptr_t)rp);
-            for (int p = lane; p < n2; p += 32) st_release_sys(&ring[(f2 + (uint32_t)p) & cm], PB2_ENT_MAKE(s2, p));
+            for (int p = lane; p < n2; p += 32)
+                st_release_sys(&ring[(f2 + (uint32_t)p) & cm], w.remote_units ? (int32_t)PB2_SUCC_MAKE(s2, p) : PB2_ENT_MAKE(s2, p));
         }
     }
 }

@@ -78,8 +78,10 @@ class Engine:
             raise ValueError("use_stream needs a real stream handle (the legacy default stream is 0: create a torch.cuda.Stream)")
         _check(self._lib.pb2_engine_set_stream(self._h, C.c_void_p(cuda_stream)), "pb2_engine_set_stream", self)
 
-    def set_shared_windows(self, on=True):
-        _check(self._lib.pb2_engine_set_shared_windows(self._h, 1 if on else 0), "set_shared_windows", self)
+    def set_shared_windows(self, on=True, next_rs_begin=None):
+        """next_rs_begin: int32 remote out-edge CSR of the NEXT window (kept alive by the caller until it is created)."""
+        self._rs_keep = None if next_rs_begin is None else np.ascontiguousarray(next_rs_begin, np.int32)
+        _check(self._lib.pb2_engine_set_shared_windows(self._h, 1 if on else 0, _ptr(self._rs_keep)), "set_shared_windows", self)
 
     def set_part_bytes(self, part_bytes):
         _check(self._lib.pb2_engine_set_part_bytes(self._h, part_bytes), "set_part_bytes", self)
@@ -154,6 +156,11 @@ class Window:
         h = L.WindowHandle()
         _check(self._lib.pb2_window_export(self._h, C.byref(h)), "pb2_window_export", self.engine)
         return bytes(h)
+
+    def task_entries(self):
+        out = np.empty(self.ntasks, np.int32)
+        _check(self._lib.pb2_window_task_entries(self._h, _ptr(out)), "pb2_window_task_entries", self.engine)
+        return out
 
     def set_remote(self, my_rank, handles, rs_begin, rs_rank, rs_target):
         """handles: list of bytes (one exported WindowHandle per rank)."""

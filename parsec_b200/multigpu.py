@@ -145,13 +145,97 @@ def work_stream(torch):
     return torch.cuda.current_stream().cuda_stream
 
 
+def cholesky_global(NT, nb, P, Q, elem_bytes=2):
+    """Right-looking tile Cholesky DAG shape (BASELINE configs[4]; the classes of pb2_ptg_cholesky_shape_new):
+      POTRF(k)      RW T(k,k)                                  <- SYRK(k,k-1)           body NOP (panel step not modelled)
+      TRSM(m,k)     READ T(k,k) x2, RW C(m,k)   m > k          <- POTRF(k), GEMM(m,k,k-1)
+      SYRK(m,k)     READ A(m,k) x2, RW T(m,m)   m > k          <- TRSM(m,k), SYRK(m,k-1)
+      GEMM(m,n,k)   READ A(m,k), B(n,k), RW C(m,n)  m > n > k  <- TRSM(m,k), TRSM(n,k), GEMM(m,n,k-1)
+    GEMM-class bodies C += A * B^T on nb x nb bf16 tiles; owner of a task = rank_of(its RW tile) on a P x Q grid
+    (two_dim_rectangle_cyclic.c:281-283).  Tile id of (m,n), m >= n: m*(m+1)/2 + n.
+    Returns (tasks, succ, tiles, ready, task_rank, tile_rank)."""
+    tid = lambda m, n: m * (m + 1) // 2 + n
+    ntiles = NT * (NT + 1) // 2
+    ids, rows = {}, []
+
+    def add(cls, m, n, k, body, flows):
+        ids[(cls, m, n, k)] = len(rows)
+        rows.append((cls, m, n, k, body, flows))
+
+    R, RW = L.ACCESS_READ, L.ACCESS_RW
+    for k in range(NT):
+        add(0, k, 0, 0, L.BODY_NOP, [(tid(k, k), RW)])
+    for k in range(NT):
+        for m in range(k + 1, NT):
+            add(1, m, k, 0, L.BODY_GEMM_BF16, [(tid(k, k), R), (tid(k, k), R), (tid(m, k), RW)])
+    for m in range(1, NT):
+        for k in range(m):
+            add(2, m, k, 0, L.BODY_GEMM_BF16, [(tid(m, k), R), (tid(m, k), R), (tid(m, m), RW)])
+    for m in range(2, NT):
+        for n in range(1, m):
+            for k in range(n):
+                add(3, m, n, k, L.BODY_GEMM_BF16, [(tid(m, k), R), (tid(n, k), R), (tid(m, n), RW)])
+    n_t = len(rows)
+    t = np.zeros(n_t, L.TASK_DTYPE)
+    t["tile"][:] = -1
+    edges = [[] for _ in range(n_t)]
+
+    def edge(src, dst_key, flow):
+        d = ids.get(dst_key)
+        if d is not None:
+            edges[src].append((d, flow))
+
+    for i, (cls, m, n, k, body, flows) in enumerate(rows):
+        t["body"][i], t["nb_flows"][i], t["class_id"][i], t["flags"][i] = body, len(flows), cls, L.TASK_DEPS_MASK
+        for f, (tile, acc) in enumerate(flows):
+            t["tile"][i, f], t["access"][i, f] = tile, acc
+        t["locals"][i, 0], t["locals"][i, 1] = m, n
+        t["iparam"][i] = (nb, nb, nb) if body == L.BODY_GEMM_BF16 else (0, 0, 0)
+        if cls == 0:                                   # POTRF(k=m) -> TRSM(p, k) flows 0, 1
+            for p in range(m + 1, NT):
+                edge(i, (1, p, m, 0), 0); edge(i, (1, p, m, 0), 1)
+        elif cls == 1:                                 # TRSM(m, k=n)
+            kk = n
+            edge(i, (2, m, kk, 0), 0); edge(i, (2, m, kk, 0), 1)
+            for nn in range(kk + 1, m):
+                edge(i, (3, m, nn, kk), 0)
+            for p in range(m + 1, NT):
+                edge(i, (3, p, m, kk), 1)
+        elif cls == 2:                                 # SYRK(m, k=n) -> SYRK(m, k+1) | POTRF(m)
+            if n < m - 1:
+                edge(i, (2, m, n + 1, 0), 2)
+            else:
+                edge(i, (0, m, 0, 0), 0)
+        else:                                          # GEMM(m, n, k) -> GEMM(m, n, k+1) | TRSM(m, n)
+            if k < n - 1:
+                edge(i, (3, m, n, k + 1), 2)
+            else:
+                edge(i, (1, m, n, 0), 2)
+    succ, begin = [], np.zeros(n_t, np.int32)
+    goal = np.zeros(n_t, np.int32)
+    for i, es in enumerate(edges):
+        begin[i] = len(succ)
+        for d, f in es:
+            succ.append((f << 27) | d)
+            goal[d] |= 1 << f
+    t["succ_begin"], t["succ_count"], t["dep_goal"] = begin, [len(e) for e in edges], goal
+    tiles = np.zeros(ntiles, L.TILE_DTYPE)
+    tiles["bytes"], tiles["state"] = nb * nb * elem_bytes, L.TILE_VALID
+    mm = np.array([m for m in range(NT) for n in range(m + 1)])
+    nn = np.array([n for m in range(NT) for n in range(m + 1)])
+    tile_rank = ((mm % P) * Q + (nn % Q)).astype(np.int32)
+    rw_tile = np.array([r[5][-1][0] for r in rows])
+    ready = np.nonzero(goal == 0)[0].astype(np.int32)
+    return t, np.array(succ, np.uint32), tiles, ready, tile_rank[rw_tile].astype(np.int32), tile_rank
+
+
 class SharedRun:
     """One rank's half of a window that was split over the GPUs of the box ("direct" path).
 
     `dist` is torch.distributed (any backend for the handle exchange; the per-step barrier is an all_reduce on
     torch's current CUDA stream, i.e. stream-ordered between the window reset and the worker kernel)."""
 
-    def __init__(self, eng, part, rank, world, dist, torch):
+    def __init__(self, eng, part, rank, world, dist, torch, kind=0):
         self.eng, self.rank, self.world, self.dist, self.torch = eng, rank, world, dist, torch
         z = part.sizes(rank)
         self.slab_bytes = max(int(z["slab_bytes"]), 256)
@@ -162,14 +246,42 @@ class SharedRun:
         dist.all_gather_object(handles, eng.ipc_export(self.slab))
         self.base = [self.slab if r == rank else eng.ipc_open(handles[r]) for r in range(world)]
         self.p = part.get(rank, self.base)
-        eng.set_shared_windows(True)
-        self.w = eng.window(0, self.p["tasks"], self.p["succ"], self.p["tiles"], self.p["ready"])
+        eng.set_shared_windows(True, self.p["rs_begin"])
+        self.w = eng.window(kind, self.p["tasks"], self.p["succ"], self.p["tiles"], self.p["ready"])
         eng.set_shared_windows(False)
         wh = [None] * world
-        dist.all_gather_object(wh, self.w.export())
-        self.w.set_remote(rank, wh, self.p["rs_begin"], self.p["rs_rank"], self.p["rs_target"])
+        dist.all_gather_object(wh, (self.w.export(), self.w.task_entries()))
+        # the partitioner names a remote successor by its local task id; the owner's window says how to release it
+        tgt = self.p["rs_target"].copy()
+        for r in range(world):
+            m = self.p["rs_rank"] == r
+            if m.any():
+                tgt[m] = wh[r][1][self.p["rs_target"][m].astype(np.int64)].astype(np.uint32)
+        self.w.set_remote(rank, [h[0] for h in wh], self.p["rs_begin"], self.p["rs_rank"], tgt)
         self._flag = torch.zeros(1, dtype=torch.int32, device="cuda")
         dist.barrier()
+
+    def slot_of(self, tile):
+        """(device address, bytes) of this rank's slot for global tile `tile`, or None if the rank never touches it."""
+        hit = np.nonzero(self.p["slot_tile"] == tile)[0]
+        if not len(hit):
+            return None
+        return self.slab + int(self.p["slot_offset"][int(hit[0])])
+
+    def load_home_tiles(self, tile_rank, data):
+        """data[tile] (numpy, tile bytes): initial contents; every rank fills the slots of the tiles it is home of."""
+        for tile in np.nonzero(np.asarray(tile_rank) == self.rank)[0]:
+            addr = self.slot_of(int(tile))
+            if addr is not None:
+                self.eng.h2d(addr, np.ascontiguousarray(data[int(tile)]))
+        self.eng.synchronize()
+        self.dist.barrier()
+
+    def read_tile(self, tile, nbytes):
+        out = np.empty(nbytes, np.uint8)
+        self.eng.d2h(out, self.slot_of(tile))
+        self.eng.synchronize()
+        return out
 
     def step(self):
         self.w.arm()                                   # reset dependency words, ring and tile states

@@ -34,18 +34,19 @@ def _run(world, case, extra=()):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", ["ex05", "rtt", "random_dtd"])
+@pytest.mark.parametrize("case", ["ex05", "rtt", "random_dtd", "cholesky", "cholesky_unfused"])
 def test_direct_path_two_gpus(case):
     if _ngpus() < 2:
         pytest.skip("needs 2 GPUs")
     out = _run(2, case)
     assert out["ok"] and out["world"] == 2, out
+    assert out.get("exact_range", True), out
     if case != "ex05":            # NB = 14, n even: with two ranks every TaskRecv(k, n) lives on TaskBcast(k)'s rank
         assert out["remote_edges"] > 0 and out["bytes_d2d"] > 0, out
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", ["ex05", "rtt", "random_dtd"])
+@pytest.mark.parametrize("case", ["ex05", "rtt", "random_dtd", "cholesky"])
 def test_direct_path_four_gpus(case):
     if _ngpus() < 4:
         pytest.skip("needs 4 GPUs")

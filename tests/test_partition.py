@@ -37,7 +37,7 @@ def merged_run(part, world, policy=0, seed=1):
             loc = ((loc >> 27) << 27) | ((loc & 0x7FFFFFF) + toff[r])
             rem = []
             for e in range(p["rs_begin"][l], p["rs_begin"][l + 1]):
-                rem.append((int(p["rs_target"][e]) & 0x3FFFFF) + toff[p["rs_rank"][e]])
+                rem.append(int(p["rs_target"][e]) + toff[p["rs_rank"][e]])
             sb[l] = nsucc
             succ.extend(int(x) for x in loc)
             succ.extend(rem)
@@ -63,6 +63,7 @@ def check_split(g, world, tile_data_check=True, split_input=None):
         assert res["rc"] == 0, (policy, seed)
         assert res["stats"]["tasks_retired"] == len(tasks)
         assert np.array_equal(res["result"], glob["result"][gid]), (policy, seed)
+        assert np.array_equal(res["seen_version"], glob["seen_version"][gid]), (policy, seed)   # same version per flow
         if tile_data_check:
             # the rank that ran the last writer of a tile holds its final version
             last = {}
@@ -184,6 +185,61 @@ def test_partitioner_restores_cross_rank_ordering(seed):
     check_split(g, world, split_input=g2)
 
 
+@pytest.mark.parametrize("world,P,Q", [(2, 1, 2), (4, 2, 2), (8, 2, 4)])
+def test_cholesky_shape_split(world, P, Q):
+    """BASELINE configs[4] shape (reduced): GEMM-class bodies, 2D block-cyclic owners; the split replays to the same
+    tiles (sparse +-1 data, exact) and the same per-flow versions as the unsplit window."""
+    from parsec_b200.bf16 import f32_to_bf16_bits
+    NT, nb = 3, 32
+    g = M.cholesky_global(NT, nb, P, Q)
+    tasks, succ, tiles, ready, task_rank, tile_rank = g
+    assert len(tasks) == NT + 2 * (NT * (NT - 1) // 2) + NT * (NT - 1) * (NT - 2) // 6
+    rng = np.random.default_rng(3)
+    vals = (rng.random((len(tiles), nb, nb)) < 1 / 48) * rng.choice([-1.0, 1.0], (len(tiles), nb, nb))
+    bits = f32_to_bf16_bits(vals.astype(np.float32)).reshape(len(tiles), -1)
+    spec = np.zeros(len(tiles), orc.TILE_DTYPE)
+    spec["bytes"], spec["state"] = nb * nb * 2, orc.TILE_INVALID
+    spec["src_ptr"] = np.arange(len(tiles), dtype=np.uint64) * np.uint64(nb * nb * 2)
+    glob = orc.run_window(tasks, succ, spec, ready, bits.copy().reshape(-1))
+    assert glob["rc"] == 0
+    part = M.Partition(*g, nranks=world)
+    sizes = [part.sizes(r) for r in range(world)]
+    slabs = [np.zeros(max(int(z["slab_bytes"]), 8), np.uint8) for z in sizes]
+    parts = [part.get(r, [s.ctypes.data for s in slabs]) for r in range(world)]
+    for r, p in enumerate(parts):                                  # initial contents into the home slots
+        for sl, tile in enumerate(p["slot_tile"]):
+            if tile_rank[tile] == r:
+                o = int(p["slot_offset"][sl])
+                slabs[r][o:o + nb * nb * 2] = bits[tile].view(np.uint8)
+    # merged replay (same construction as merged_run, on the pre-filled slabs)
+    toff = np.cumsum([0] + [len(p["tasks"]) for p in parts]); doff = np.cumsum([0] + [len(p["tiles"]) for p in parts])
+    mt, ms, mr = [], [], []
+    for r, p in enumerate(parts):
+        t = p["tasks"].copy(); tl = t["tile"]; tl[tl >= 0] += doff[r]; t["tile"] = tl
+        sb = np.zeros(len(t), np.int32)
+        for l in range(len(t)):
+            loc = p["succ"][t["succ_begin"][l]: t["succ_begin"][l] + t["succ_count"][l]]
+            sb[l] = len(ms)
+            ms.extend(int(((x >> 27) << 27) | ((x & 0x7FFFFFF) + toff[r])) for x in loc)
+            ms.extend(int(p["rs_target"][e]) + int(toff[p["rs_rank"][e]]) for e in range(p["rs_begin"][l], p["rs_begin"][l + 1]))
+        t["succ_count"] = t["succ_count"] + np.diff(p["rs_begin"]); t["succ_begin"] = sb
+        mt.append(t); mr.extend(int(x) + int(toff[r]) for x in p["ready"])
+    gid = np.concatenate([p["global_id"] for p in parts])
+    for policy, seed in [(0, 1), (1, 1), (2, 5)]:
+        for r, p in enumerate(parts):
+            for sl, tile in enumerate(p["slot_tile"]):
+                o = int(p["slot_offset"][sl])
+                slabs[r][o:o + nb * nb * 2] = bits[tile].view(np.uint8) if tile_rank[tile] == r else 0
+        res = orc.run_window_raw(np.concatenate(mt), np.array(ms, np.uint32), np.concatenate([p["tiles"] for p in parts]),
+                                 np.array(mr, np.int32), policy, seed)
+        assert res["rc"] == 0 and res["stats"]["tasks_retired"] == len(tasks)
+        assert np.array_equal(res["seen_version"], glob["seen_version"][gid])
+        for tile in range(len(tiles)):
+            r = int(tile_rank[tile])                              # the RW chain of a tile lives on its home rank
+            p = parts[r]; sl = int(np.nonzero(p["slot_tile"] == tile)[0][0]); o = int(p["slot_offset"][sl])
+            assert np.array_equal(slabs[r][o:o + nb * nb * 2], glob["device"][tile]), (policy, tile)
+
+
 def test_remote_edge_targets_are_consistent():
     """every rank's dep_goal == local in-edges + remote in-edges addressed to it by the other ranks"""
     world = 4
@@ -196,7 +252,7 @@ def test_remote_edge_targets_are_consistent():
         for q, o in enumerate(parts):
             m = o["rs_rank"] == r
             assert q != r or not m.any()
-            np.add.at(indeg, (o["rs_target"][m] & 0x3FFFFF).astype(np.int64), 1)
+            np.add.at(indeg, o["rs_target"][m].astype(np.int64), 1)
         assert np.array_equal(indeg, p["tasks"]["dep_goal"].astype(np.int64))
         assert not (p["tasks"]["flags"] & L.TASK_DEPS_MASK).any()
         assert np.array_equal(np.sort(p["ready"]), np.nonzero(p["tasks"]["dep_goal"] == 0)[0])
