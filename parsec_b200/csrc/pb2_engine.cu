@@ -424,8 +424,8 @@ static int build_gemm2_units(pb2_window_t* w, const pb2_task_t* tasks, int32_t n
         const bool g = is_gemm(h);
         u.flags = g ? 1 : 0; u.tileC = g ? tasks[h].tile[2] : -1;
         u.M = tasks[h].iparam[0]; u.N = tasks[h].iparam[1]; u.K = tasks[h].iparam[2];
-        u.nparts = g ? (u.M + 255) / 256 : 1;
-        if (g && (u.N > 512 || (u.N % 16) || u.nparts > 16)) return PB2_ERR_NOT_SUPPORTED;   // caller falls back to the v1 kernel
+        u.nparts = g ? ((u.M + 255) / 256) * ((u.N + 511) / 512) : 1;       // 256-row x 512-column blocks of C (TMEM: 512 columns)
+        if (g && ((u.N % 16) || u.nparts > 16)) return PB2_ERR_NOT_SUPPORTED;       // caller falls back to the v1 kernel
         for (int32_t t = h; t >= 0; t = next[t]) {
             unit_of[t] = (int32_t)units.size();
             segs.push_back(GSeg{t, g ? tasks[t].tile[0] : -1, g ? tasks[t].tile[1] : -1, 0});
@@ -773,6 +773,13 @@ int pb2_window_create(pb2_engine_t* e, pb2_window_t** window, int kind,
         TRY(dev_alloc_copy(w, &d_np, nparts.data(), (size_t)ntasks));
         d.nparts = d_np;
         TRY(dev_alloc_copy(w, &d.parts_left, (const int32_t*)nullptr, (size_t)ntasks));
+        TRY(dev_alloc_copy(w, &d.slice_claim, (const uint32_t*)nullptr, (size_t)ntiles * PB2_SLICE_WORDS));
+        TRY(dev_alloc_copy(w, &d.slice_done, (const uint32_t*)nullptr, (size_t)ntiles * (PB2_SLICE_WORDS + 1)));
+    }
+    if (kind == 1 && w->v2) {
+        // operand tiles that have to be staged in (host or peer GPU) are pulled in 64 KiB slices by every CTA pair
+        // that needs them (the parts of one unit, the units that share an operand) instead of by one CTA alone
+        d.part_bytes = 64 * 1024;
         TRY(dev_alloc_copy(w, &d.slice_claim, (const uint32_t*)nullptr, (size_t)ntiles * PB2_SLICE_WORDS));
         TRY(dev_alloc_copy(w, &d.slice_done, (const uint32_t*)nullptr, (size_t)ntiles * (PB2_SLICE_WORDS + 1)));
     }

@@ -57,6 +57,7 @@ struct Job {
     int32_t unit, part, stop, is_gemm;
     int32_t seg_begin, seg_count, tileC, m0;
     int32_t M, N, K, pushout;
+    int32_t n0, Nj, pad0, pad1;     // this part's columns [n0, n0 + Nj) of the N-wide tile (Nj <= 512: TMEM columns)
 };
 
 struct Shared2 {
@@ -227,7 +228,9 @@ pb2_engine_gemm2_kernel(Win2Dev g) {
                     const GUnit u = g.units[j.unit];
                     j.is_gemm = u.flags & 1; j.pushout = (u.flags >> 1) & 1;
                     j.seg_begin = u.seg_begin; j.seg_count = u.seg_count; j.tileC = u.tileC;
-                    j.m0 = j.part * 256; j.M = u.M; j.N = u.N; j.K = u.K;
+                    const int mparts = (u.M + 255) / 256;
+                    j.m0 = (j.part % mparts) * 256; j.M = u.M; j.N = u.N; j.K = u.K;
+                    j.n0 = (j.part / mparts) * 512; j.Nj = min(512, u.N - j.n0);
                 }
                 sh.job = j;
             }
@@ -242,7 +245,12 @@ pb2_engine_gemm2_kernel(Win2Dev g) {
                     pb2_tile_t* tile = &w.tiles[tile_id];
                     if (threadIdx.x == 0) sh.need = ld_acquire_gpu(&tile->state) != PB2_TILE_VALID;
                     __syncthreads();
-                    if (sh.need) { stage_in_flow(w, tile, acc, &sh.decide); fence_proxy_async(); }
+                    if (sh.need) {
+                        const int ns = tile_slices(w, tile->bytes);
+                        if (ns == 1) stage_in_flow(w, tile, acc, &sh.decide);
+                        else stage_in_slices(w, tile_id, ns, 0, ns, &sh.decide);     // take what nobody has claimed, wait for the rest
+                        fence_proxy_async();
+                    }
                     __syncthreads();
                 }
                 if (!sh.job.is_gemm) {
@@ -272,7 +280,7 @@ pb2_engine_gemm2_kernel(Win2Dev g) {
 
         if (job.is_gemm) {
             const int kblocks = (job.K + BK - 1) / BK;
-            const int nhalves = (job.N + 255) / 256;
+            const int nhalves = (job.Nj + 255) / 256;
             if (warp == 1) {
                 // ===== TMA producer (both CTAs): my 128 rows of A, my half of each N=256 block of B
                 if (lane == 0) {
@@ -298,8 +306,8 @@ pb2_engine_gemm2_kernel(Win2Dev g) {
                             else        mbar_arrive_cluster(bar);
                             tma_load_2sm(sa, mapA, bar, kb * BK, job.m0 + (int)rank * 128);
                             for (int h = 0; h < nhalves; ++h) {
-                                const int nh = min(256, job.N - 256 * h);
-                                tma_load_2sm(sa + kAStage + h * kBHalf, mapB, bar, kb * BK, 256 * h + (int)rank * (nh / 2));
+                                const int nh = min(256, job.Nj - 256 * h);
+                                tma_load_2sm(sa + kAStage + h * kBHalf, mapB, bar, kb * BK, job.n0 + 256 * h + (int)rank * (nh / 2));
                             }
                             }
                             if (++p_stage == kStages2) { p_stage = 0; p_phase ^= 1; }
@@ -316,7 +324,7 @@ pb2_engine_gemm2_kernel(Win2Dev g) {
                             const uint32_t sa = smem_u32(smem + c_stage * kStage2);
                             const uint64_t da = make_desc(sa);
                             for (int h = 0; h < nhalves && !(g.debug & 2); ++h) {
-                                const int nh = min(256, job.N - 256 * h);
+                                const int nh = min(256, job.Nj - 256 * h);
                                 const uint32_t idesc = make_idesc(256, nh);
                                 const uint64_t db = make_desc(sa + kAStage + h * kBHalf);
 #pragma unroll
@@ -342,19 +350,19 @@ pb2_engine_gemm2_kernel(Win2Dev g) {
                 // these warps idle during the main loop: pull this thread's C row into L2 now, so that the
                 // read-modify-write below does not pay DRAM latency sixteen times in a row
                 if (row < job.M)
-                    for (int b = 0; b < job.N * 2; b += 128)
-                        asm volatile("prefetch.global.L2 [%0];" :: "l"(Cbase + (size_t)row * job.N * 2 + b));
+                    for (int b = 0; b < job.Nj * 2; b += 128)
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(Cbase + ((size_t)row * job.N + job.n0) * 2 + b));
                 mbar_wait(&sh.tmem_full, tfull_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-                const int nchunks = (g.debug & 4) ? 0 : (job.N + 31) / 32;
+                const int nchunks = (g.debug & 4) ? 0 : (job.Nj + 31) / 32;
                 const bool row_ok = row < job.M;
                 uint4 cv[4];
                 auto load_c = [&](int c) {
                     const int col0 = c * 32;
-                    const uint4* cp = reinterpret_cast<const uint4*>(Cbase + ((size_t)row * job.N + col0) * 2);
+                    const uint4* cp = reinterpret_cast<const uint4*>(Cbase + ((size_t)row * job.N + job.n0 + col0) * 2);
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) cv[v] = (row_ok && col0 + v * 8 < job.N) ? ld_stream(cp + v) : make_uint4(0, 0, 0, 0);
+                    for (int v = 0; v < 4; ++v) cv[v] = (row_ok && col0 + v * 8 < job.Nj) ? ld_stream(cp + v) : make_uint4(0, 0, 0, 0);
                 };
                 load_c(0);
 #pragma unroll 1
@@ -368,10 +376,10 @@ pb2_engine_gemm2_kernel(Win2Dev g) {
                     tc_wait_ld();
                     const int col0 = c * 32;
                     if (row_ok) {
-                        uint4* cp = reinterpret_cast<uint4*>(Cbase + ((size_t)row * job.N + col0) * 2);
+                        uint4* cp = reinterpret_cast<uint4*>(Cbase + ((size_t)row * job.N + job.n0 + col0) * 2);
 #pragma unroll
                         for (int v = 0; v < 4; ++v) {
-                            if (col0 + v * 8 < job.N) {
+                            if (col0 + v * 8 < job.Nj) {
                                 uint4 o;
                                 o.x = pack_bf16(bf16_lo(cur[v].x) + __uint_as_float(acc[v * 8 + 0]), bf16_hi(cur[v].x) + __uint_as_float(acc[v * 8 + 1]));
                                 o.y = pack_bf16(bf16_lo(cur[v].y) + __uint_as_float(acc[v * 8 + 2]), bf16_hi(cur[v].y) + __uint_as_float(acc[v * 8 + 3]));
@@ -419,10 +427,17 @@ pb2_engine_gemm2_kernel(Win2Dev g) {
                 pb2_tile_t* tile = &w.tiles[job.tileC];
                 const size_t row_bytes = (size_t)job.N * 2;
                 const int rows = min(256, job.M - job.m0);
-                if (rows > 0) {
+                if (rows > 0 && job.Nj == job.N) {
                     cta_copy<false>(reinterpret_cast<uint8_t*>(tile->src_ptr) + (size_t)job.m0 * row_bytes,
                                     reinterpret_cast<const uint8_t*>(tile->dev_ptr) + (size_t)job.m0 * row_bytes, (size_t)rows * row_bytes);
                     if (threadIdx.x == 0) atomicAdd(&w.ctl->bytes_d2h.v, (unsigned long long)rows * row_bytes);
+                } else if (rows > 0) {
+                    // a column block of a tile wider than 512: row segments
+                    for (int r = 0; r < rows; ++r) {
+                        const size_t o = (size_t)(job.m0 + r) * row_bytes + (size_t)job.n0 * 2;
+                        cta_copy<false>(reinterpret_cast<uint8_t*>(tile->src_ptr) + o, reinterpret_cast<const uint8_t*>(tile->dev_ptr) + o, (size_t)job.Nj * 2);
+                    }
+                    if (threadIdx.x == 0) atomicAdd(&w.ctl->bytes_d2h.v, (unsigned long long)rows * (unsigned long long)job.Nj * 2ull);
                 }
                 __syncthreads();
             }
