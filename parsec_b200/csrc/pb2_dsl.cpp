@@ -335,12 +335,18 @@ static Dep dep_task(int cls, int l0, int l1, int l2, int flow) { Dep d; d.kind =
 static Dep dep_mem(pb2_data_t* data) { Dep d; d.kind = data ? DEP_MEMORY : DEP_NONE; d.data = data; return d; }
 static Dep dep_new(size_t bytes) { Dep d; d.kind = DEP_NEW; d.new_bytes = bytes; return d; }
 
+static double expand_now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 static pb2_taskpool_t* expand(pb2_context_t* ctx, const char* name, std::vector<ClassDef>& defs) {
+    const bool timing = getenv("PB2_TIMING") != nullptr;
+    const double t_0 = expand_now_ms();
     pb2_taskpool_t* tp = new pb2_taskpool_s();
     tp->ctx = ctx; tp->type = 1; tp->name = name;
-    std::unordered_map<Key, int32_t, KeyHash> ids;
+    // key -> task id: open addressing, filled once after the task space is known (no node per task)
     std::vector<Key> keys;
-    ids.reserve(1 << 16);
+    std::vector<int32_t> table;
+    size_t tmask = 0;
+    KeyHash hasher;
     for (size_t c = 0; c < defs.size(); ++c) {
         tp->classes.emplace_back();
         pb2_task_class_t& tc = tp->classes.back();
@@ -356,15 +362,29 @@ static pb2_taskpool_t* expand(pb2_context_t* ctx, const char* name, std::vector<
             pb2_htask_t* t = pb2i_new_task(tp, &tp->classes[c]);
             for (int i = 0; i < 4; ++i) t->locals[i] = k.L[i];
             for (int f = 0; f < defs[c].nb_flows; ++f) t->access[f] = defs[c].access[f];
-            ids[k] = t->id; keys.push_back(k);
+            keys.push_back(k);
         });
+    }
+    {
+        size_t cap = 64;
+        while (cap < 2 * keys.size()) cap <<= 1;
+        table.assign(cap, -1); tmask = cap - 1;
+        for (size_t i = 0; i < keys.size(); ++i) {
+            size_t h = hasher(keys[i]) & tmask;
+            while (table[h] >= 0) h = (h + 1) & tmask;
+            table[h] = (int32_t)i;
+        }
     }
     auto find = [&](int cls, const int32_t* L) -> int32_t {
         Key k; k.cls = cls; memset(k.L, 0, sizeof k.L);
         for (int i = 0; i < defs[cls].nb_locals && i < 4; ++i) k.L[i] = L[i];
-        auto it = ids.find(k);
-        return it == ids.end() ? -1 : it->second;
+        for (size_t h = hasher(k) & tmask;; h = (h + 1) & tmask) {
+            const int32_t id = table[h];
+            if (id < 0) return -1;
+            if (keys[(size_t)id] == k) return id;
+        }
     };
+    const double t_1 = expand_now_ms();
     // ---- which datum does each flow carry: follow the input deps back to memory / NEW (iteratively)
     const size_t n = tp->tasks.size();
     std::vector<uint8_t> resolved(n * PB2_MAX_FLOWS, 0);
@@ -391,6 +411,7 @@ static pb2_taskpool_t* expand(pb2_context_t* ctx, const char* name, std::vector<
             for (auto& pf : path) { tp->tasks[pf.first].data[pf.second] = found; resolved[(size_t)pf.first * PB2_MAX_FLOWS + pf.second] = 1; }
         }
     }
+    const double t_2 = expand_now_ms();
     // ---- edges, pushout, startup tasks
     std::vector<std::pair<pb2_data_t*, pb2_data_t*>> finals;
     for (size_t id = 0; id < n; ++id) {
@@ -418,7 +439,10 @@ static pb2_taskpool_t* expand(pb2_context_t* ctx, const char* name, std::vector<
         }
         if (cd.bind) cd.bind(k.L, &t);
     }
+    const double t_3 = expand_now_ms();
     for (size_t id = 0; id < n; ++id) if (tp->tasks[id].npred_unsat == 0) pb2i_schedule(ctx, &tp->tasks[id]);
+    if (timing) fprintf(stderr, "pb2 ptg expand: %zu tasks, space %.2f ms, data %.2f ms, edges %.2f ms, startup %.2f ms\n",
+                        n, t_1 - t_0, t_2 - t_1, t_3 - t_2, expand_now_ms() - t_3);
     if (!finals.empty())
         tp->on_complete = [finals]() {
             for (auto& sd : finals) {
@@ -602,7 +626,8 @@ pb2_taskpool_t* pb2_ptg_get_best_device_new(pb2_context_t* ctx, pb2_data_collect
         // words that are not 0x01010101 (the check fake_task does, :110-118)
         tp->on_complete = [tp, info]() {
             int idx = 0, bad = 0;
-            for (auto& t : tp->tasks) {
+            for (size_t ti = 0; ti < tp->tasks.size(); ++ti) {
+                pb2_htask_t& t = tp->tasks[ti];
                 if (t.tc->task_class_id != 1) continue;
                 info[idx++] = t.ran_on;
                 if (t.ran_on < 2) continue;

@@ -64,6 +64,33 @@ struct pb2_task_class_s {
     bool use_mask = false;
 };
 
+// Successor list of a host task: up to 8 out-edges inline (a broadcast of Ex05 has 8, a GEMM chain member 1-3), heap
+// beyond that.  The reference keeps out-edges implicit in generated code; the per-task malloc of a std::vector was
+// the largest single cost of building a PTG pool.
+struct pb2_succ_list {
+    uint32_t inl[8];
+    uint32_t* heap = nullptr;
+    uint32_t n = 0, cap = 8;
+    pb2_succ_list() = default;
+    pb2_succ_list(const pb2_succ_list&) = delete;
+    pb2_succ_list& operator=(const pb2_succ_list&) = delete;
+    ~pb2_succ_list() { free(heap); }
+    void push_back(uint32_t v) {
+        if (n == cap) {
+            const uint32_t ncap = cap * 2;
+            uint32_t* nh = static_cast<uint32_t*>(malloc(sizeof(uint32_t) * ncap));
+            memcpy(nh, data(), sizeof(uint32_t) * n);
+            free(heap); heap = nh; cap = ncap;
+        }
+        (heap ? heap : inl)[n++] = v;
+    }
+    const uint32_t* data() const { return heap ? heap : inl; }
+    const uint32_t* begin() const { return data(); }
+    const uint32_t* end() const { return data() + n; }
+    size_t size() const { return n; }
+    uint32_t operator[](size_t i) const { return data()[i]; }
+};
+
 struct pb2_htask_s {
     pb2_taskpool_t* tp = nullptr;
     pb2_task_class_t* tc = nullptr;
@@ -80,7 +107,7 @@ struct pb2_htask_s {
     int32_t dep_goal = 0;           // counter: number of task-sourced inputs; mask: dependencies_goal
     int32_t dep_word = 0;           // counter: remaining; mask: satisfied bits
     int32_t npred_unsat = 0;        // unsatisfied in-edges
-    std::vector<uint32_t> succ;     // PB2_SUCC_MAKE(task id, dst flow)
+    pb2_succ_list succ;             // PB2_SUCC_MAKE(task id, dst flow)
     uint8_t body = 0;
     int32_t iparam[3] = {0, 0, 0};
     float fparam = 0.f;
@@ -112,11 +139,32 @@ struct pb2_dtd_tile_s {
     bool flushed = false;
 };
 
+// Tasks of a pool: stable addresses, id == index, allocated in chunks of 2048 (a std::deque of 270-byte elements does
+// one malloc per task).
+struct pb2_task_store {
+    static constexpr size_t kChunk = 2048;
+    std::vector<pb2_htask_s*> chunks;
+    size_t n = 0;
+    pb2_task_store() = default;
+    pb2_task_store(const pb2_task_store&) = delete;
+    pb2_task_store& operator=(const pb2_task_store&) = delete;
+    ~pb2_task_store() { for (pb2_htask_s* c : chunks) delete[] c; }
+    pb2_htask_s& emplace_back() {
+        if (n == chunks.size() * kChunk) chunks.push_back(new pb2_htask_s[kChunk]);
+        ++n;
+        return back();
+    }
+    pb2_htask_s& operator[](size_t i) { return chunks[i / kChunk][i % kChunk]; }
+    const pb2_htask_s& operator[](size_t i) const { return chunks[i / kChunk][i % kChunk]; }
+    pb2_htask_s& back() { return (*this)[n - 1]; }
+    size_t size() const { return n; }
+};
+
 struct pb2_taskpool_s {
     pb2_context_t* ctx = nullptr;
     int type = 0;                            // 0 DTD, 1 PTG
     std::string name;
-    std::deque<pb2_htask_s> tasks;           // stable addresses; id == index
+    pb2_task_store tasks;                    // stable addresses; id == index
     std::deque<pb2_task_class_s> classes;
     std::vector<pb2_data_t*> temporaries;    // NEW data owned by the pool
     int32_t nb_done = 0;

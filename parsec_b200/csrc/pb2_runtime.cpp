@@ -646,7 +646,7 @@ int pb2_taskpool_wait(pb2_taskpool_t* tp) { return tp ? pb2_context_wait(tp->ctx
 int pb2_taskpool_nb_tasks(pb2_taskpool_t* tp) { return tp ? (int)tp->tasks.size() : 0; }
 int pb2_taskpool_set_device_types(pb2_taskpool_t* tp, int types) {
     if (!tp) return PB2_ERR_BAD_PARAM;
-    for (auto& t : tp->tasks) { t.allowed_types = (uint8_t)types; t.selected_device = nullptr; }
+    for (size_t i = 0; i < tp->tasks.size(); ++i) { pb2_htask_t& t = tp->tasks[i]; t.allowed_types = (uint8_t)types; t.selected_device = nullptr; }
     return PB2_SUCCESS;
 }
 
