@@ -100,6 +100,7 @@ struct pb2_data_copy_s {
     pb2_data_copy_t *lru_prev, *lru_next;
     int32_t   lru_list;            /* 0 none, 1 gpu_mem_lru (clean), 2 gpu_mem_owned_lru (dirty) */
     int32_t   window_tile;         /* tile id inside the window being built/run, -1 otherwise */
+    const void* window_owner;      /* which in-flight window window_tile refers to */
 };
 
 /* data_internal.h:30-49 */

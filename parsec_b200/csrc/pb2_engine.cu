@@ -248,6 +248,7 @@ struct pb2_engine_s {
     pb2_engine_params_t params{};
     cudaStream_t stream = nullptr;       // where engine work is enqueued
     cudaStream_t own_stream = nullptr;   // created by the engine
+    cudaStream_t up_stream = nullptr;    // descriptor uploads of the NEXT window: not ordered behind the running one
     int nworkers = 0;
     int nworkers_gemm = 0;
     std::string last_error;
@@ -300,9 +301,9 @@ static int dev_alloc_copy(pb2_window_t* w, T** dptr, const T* host, size_t n) {
     // stream-ordered pool allocation: after the first window of a size class this costs microseconds, whereas
     // cudaMalloc/cudaFree next to a 170 GB slab cost hundreds of microseconds each and synchronise the device
     if (w->shared) { PB2_CUDA(e, cudaMalloc(&p, (n ? n : 1) * sizeof(T))); }     // IPC needs cudaMalloc memory
-    else PB2_CUDA(e, cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), e->stream));
+    else PB2_CUDA(e, cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), e->up_stream));
     w->allocs.push_back(p);
-    if (host && n) PB2_CUDA(e, cudaMemcpyAsync(p, host, n * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+    if (host && n) PB2_CUDA(e, cudaMemcpyAsync(p, host, n * sizeof(T), cudaMemcpyHostToDevice, e->up_stream));
     *dptr = reinterpret_cast<T*>(p);
     return PB2_SUCCESS;
 }
@@ -518,6 +519,7 @@ int pb2_engine_create(pb2_engine_t** engine, int cuda_device, const pb2_engine_p
     if (p.part_bytes == 0) p.part_bytes = 256 * 1024;
     e->params = p;
     PB2_CUDA(e, cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    PB2_CUDA(e, cudaStreamCreateWithFlags(&e->up_stream, cudaStreamNonBlocking));
     e->stream = e->own_stream;
     {   // keep freed window scratch cached in the default mempool instead of returning it to the driver
         cudaMemPool_t pool;
@@ -544,6 +546,7 @@ int pb2_engine_destroy(pb2_engine_t* e) {
     cudaSetDevice(e->cuda_device);
     for (auto& kv : e->registered) cudaHostUnregister(kv.first);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    if (e->up_stream) cudaStreamDestroy(e->up_stream);
     delete e;
     return PB2_SUCCESS;
 }
@@ -790,7 +793,10 @@ int pb2_window_create(pb2_engine_t* e, pb2_window_t** window, int kind,
     PB2_CUDA(e, cudaEventCreate(&w->ev0));
     PB2_CUDA(e, cudaEventCreate(&w->ev1));
     PB2_CUDA(e, cudaEventCreate(&w->ev2));
-    PB2_CUDA(e, cudaStreamSynchronize(e->stream));
+    // every descriptor array is on the device when this returns (the host vectors above are temporaries); the
+    // upload stream is not ordered behind the engine stream, so creating the next window does not wait for the
+    // window that is running
+    PB2_CUDA(e, cudaStreamSynchronize(e->up_stream));
     *window = w;
     return PB2_SUCCESS;
 }
@@ -798,7 +804,7 @@ int pb2_window_create(pb2_engine_t* e, pb2_window_t** window, int kind,
 int pb2_window_destroy(pb2_window_t* w) {
     if (!w) return PB2_ERR_BAD_PARAM;
     cudaSetDevice(w->e->cuda_device);
-    if (w->launched) cudaStreamSynchronize(w->e->stream);
+    if (w->launched) cudaEventSynchronize(w->ev2);        // this window only: a later one may be running
     for (void* p : w->peer_ptrs) cudaIpcCloseMemHandle(p);
     for (void* p : w->allocs) { if (w->shared) cudaFree(p); else cudaFreeAsync(p, w->e->stream); }
     if (w->ev0) cudaEventDestroy(w->ev0);
@@ -903,7 +909,7 @@ int pb2_window_set_remote(pb2_window_t* w, int32_t my_rank, int32_t nranks, cons
     if ((rc = dev_alloc_copy(w, &d_b, rs_begin, (size_t)w->ntasks + 1)) != PB2_SUCCESS) return rc;
     if ((rc = dev_alloc_copy(w, &d_r, rs_rank, (size_t)nrs)) != PB2_SUCCESS) return rc;
     if ((rc = dev_alloc_copy(w, &d_t, rs_target, (size_t)nrs)) != PB2_SUCCESS) return rc;
-    PB2_CUDA(e, cudaStreamSynchronize(e->stream));
+    PB2_CUDA(e, cudaStreamSynchronize(e->up_stream));
     w->d.peers = d_pw; w->d.rs_begin = d_b; w->d.rs_rank = d_r; w->d.rs_target = d_t; w->d.remote_units = my_kind;
     if (w->v2) w->g.w = w->d;
     return PB2_SUCCESS;

@@ -184,6 +184,8 @@ struct pb2_device_module_s {
     int major = 0, minor = 0;
     bool dry_run = false;
     pb2_engine_t* engine = nullptr;
+    std::deque<void*> inflight;              // windows launched and not yet retired (oldest first), pb2_runtime.cpp
+    size_t pipe_chunk = 0;                   // roots per window while a large batch of pending tasks is being cut up
     pb2_device_stats_t st{};
     uint32_t peer_access_mask = 0;
     // memory: one slab carved by the zone heap (parsec_device_memory_reserve, device_gpu.c:866-991)
@@ -206,6 +208,7 @@ struct pb2_context_s {
     std::map<std::string, int64_t> mca;
     std::vector<pb2_taskpool_t*> taskpools;
     std::vector<pb2_htask_t*> ready;         // priority-sorted ready list (parsec_list_push_sorted)
+    size_t ready_head = 0;                   // entries before it have been handed out (pb2_context_wait)
     bool started = false;
     std::string last_error;
 };

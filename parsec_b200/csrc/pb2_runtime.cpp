@@ -108,7 +108,7 @@ void pb2i_lru_push_back(pb2_device_module_t* dev, int list, pb2_data_copy_t* c) 
 static pb2_data_copy_t* new_copy(pb2_data_t* d, int device, uint8_t flags) {
     pb2_data_copy_t* c = new pb2_data_copy_t();
     memset(c, 0, sizeof *c);
-    c->device_index = (int8_t)device; c->flags = flags; c->original = d; c->window_tile = -1;
+    c->device_index = (int8_t)device; c->flags = flags; c->original = d; c->window_tile = -1; c->window_owner = nullptr;
     c->coherency_state = PB2_DATA_COHERENCY_INVALID;
     d->device_copies[device] = c; d->nb_copies++;
     return c;
@@ -240,6 +240,10 @@ int pb2_init(pb2_context_t** pctx, int nb_cores) {
     ctx->mca["device_engine_max_workers"] = 0;
     ctx->mca["device_engine_timeout_ms"] = 0;
     ctx->mca["device_engine_gemm_mode"] = 0;
+    // a batch of at least _min_roots ready GPU tasks is cut into _pipeline windows of whole dependency closures:
+    // while one window runs, the host builds the next one and replays the bookkeeping of the previous one
+    ctx->mca["device_engine_pipeline"] = 4;
+    ctx->mca["device_engine_pipeline_min_roots"] = 2048;
     // index 0: the CPU; index 1: the recursive pseudo-device (device.c:1041-1110)
     for (int i = 0; i < 2; ++i) {
         pb2_device_module_t* d = new pb2_device_module_s();
@@ -472,7 +476,8 @@ selected:
 void pb2i_schedule(pb2_context_t* ctx, pb2_htask_t* t) {
     t->state = 1;
     auto it = ctx->ready.end();
-    while (it != ctx->ready.begin() && (*(it - 1))->priority < t->priority) --it;
+    const auto first = ctx->ready.begin() + (long)ctx->ready_head;
+    while (it != first && (*(it - 1))->priority < t->priority) --it;
     ctx->ready.insert(it, t);
 }
 
@@ -618,16 +623,18 @@ int pb2_context_wait(pb2_context_t* ctx) {
         bool progressed = false;
         const double t_sched = now_ms();
         const size_t nready0 = ctx->ready.size();
-        while (!ctx->ready.empty()) {
-            pb2_htask_t* t = ctx->ready.front();
-            ctx->ready.erase(ctx->ready.begin());
+        // pop from the front without shifting the vector each time: ready_head marks what has been taken, and
+        // pb2i_schedule never inserts in front of it
+        while (ctx->ready_head < ctx->ready.size()) {
+            pb2_htask_t* t = ctx->ready[ctx->ready_head++];
             int rc = execute_task(ctx, t);
-            if (rc != PB2_SUCCESS) return rc;
+            if (rc != PB2_SUCCESS) { ctx->ready.erase(ctx->ready.begin(), ctx->ready.begin() + (long)ctx->ready_head); ctx->ready_head = 0; return rc; }
             progressed = true;
         }
+        ctx->ready.clear(); ctx->ready_head = 0;
         if (g_timing && nready0) fprintf(stderr, "pb2 wait: dispatched %zu ready tasks in %.2f ms\n", nready0, now_ms() - t_sched);
         for (auto* d : ctx->devices) {
-            if (!PB2_DEV_IS_GPU(d->type) || d->pending.empty()) continue;
+            if (!PB2_DEV_IS_GPU(d->type) || (d->pending.empty() && d->inflight.empty())) continue;
             int rc = device_progress(d);
             if (rc != PB2_SUCCESS) return rc;
             progressed = true;
@@ -804,7 +811,7 @@ static bool predicted_on_device(pb2_device_module_t* dev, pb2_htask_t* s) {
 }
 
 // Build the dependency-closed window reachable from the pending tasks of one taskpool.
-static int build_window(pb2_device_module_t* dev, Window& w, std::vector<pb2_gpu_task_t*>& taken) {
+static int build_window(pb2_device_module_t* dev, Window& w, std::vector<pb2_gpu_task_t*>& taken, size_t max_roots) {
     if (dev->pending.empty()) return PB2_SUCCESS;
     w.tp = dev->pending.front()->ec->tp;
     const bool want_gemm = dev->pending.front()->ec->body == PB2_BODY_GEMM_BF16;
@@ -813,7 +820,7 @@ static int build_window(pb2_device_module_t* dev, Window& w, std::vector<pb2_gpu
     std::deque<pb2_gpu_task_t*> keep;
     for (pb2_gpu_task_t* g : dev->pending) {
         const bool is_gemm = g->ec->body == PB2_BODY_GEMM_BF16;
-        if (g->ec->tp == w.tp && (is_gemm == want_gemm || g->ec->body == PB2_BODY_NOP)) { queue.push_back(g->ec); taken.push_back(g); }
+        if (taken.size() < max_roots && g->ec->tp == w.tp && (is_gemm == want_gemm || g->ec->body == PB2_BODY_NOP)) { queue.push_back(g->ec); taken.push_back(g); }
         else keep.push_back(g);
     }
     dev->pending.swap(keep);
@@ -829,8 +836,10 @@ static int build_window(pb2_device_module_t* dev, Window& w, std::vector<pb2_gpu
                 if (!d) continue;
                 pb2_data_copy_t* g = reserve_space(dev, d);
                 if (!g) { ok = false; break; }
+                if (g->window_tile >= 0 && g->window_owner != &w) { ok = false; break; }   // in use by the window that is running
                 if (g->window_tile < 0) {
                     g->window_tile = (int32_t)w.tile_data.size();
+                    g->window_owner = &w;
                     w.tile_data.push_back(d);
                     fresh.push_back(g);
                 }
@@ -839,7 +848,7 @@ static int build_window(pb2_device_module_t* dev, Window& w, std::vector<pb2_gpu
         if (!ok) {
             // no room: this task (and everything behind it) waits for the next window (HOOK_RETURN_AGAIN)
             full = true;
-            for (pb2_data_copy_t* g : fresh) { g->window_tile = -1; w.tile_data.pop_back(); }
+            for (pb2_data_copy_t* g : fresh) { g->window_tile = -1; g->window_owner = nullptr; w.tile_data.pop_back(); }
             continue;
         }
         t->window_index = (int32_t)w.order.size();
@@ -859,7 +868,10 @@ static int build_window(pb2_device_module_t* dev, Window& w, std::vector<pb2_gpu
         for (pb2_gpu_task_t* g : taken) { if (g->ec->window_index >= 0) in.push_back(g); else dev->pending.push_back(g); }
         taken.swap(in);
     }
-    if (w.order.empty()) { dev->ctx->last_error = "device memory too small for a single task"; return PB2_ERR_OUT_OF_RESOURCE; }
+    if (w.order.empty()) {
+        if (!dev->inflight.empty()) return PB2_SUCCESS;             // everything waits for the window that is running
+        dev->ctx->last_error = "device memory too small for a single task"; return PB2_ERR_OUT_OF_RESOURCE;
+    }
 
     // ---- tiles
     w.tiles.resize(w.tile_data.size());
@@ -922,7 +934,9 @@ static int build_window(pb2_device_module_t* dev, Window& w, std::vector<pb2_gpu
 
 static void window_release(pb2_device_module_t* dev, Window& w) {
     for (pb2_htask_t* t : w.order) t->window_index = -1;
-    for (pb2_data_t* d : w.tile_data) if (d->device_copies[dev->device_index]) d->device_copies[dev->device_index]->window_tile = -1;
+    for (pb2_data_t* d : w.tile_data) if (d->device_copies[dev->device_index]) {
+        d->device_copies[dev->device_index]->window_tile = -1; d->device_copies[dev->device_index]->window_owner = nullptr;
+    }
 }
 
 // Host-visible bookkeeping of one retired task, replayed in retire order exactly as the reference's manager
@@ -986,16 +1000,52 @@ static void retire_task_bookkeeping(pb2_device_module_t* dev, Window& w, pb2_hta
     dev->st.executed_tasks++;
 }
 
-static int device_progress(pb2_device_module_t* dev) {
-    pb2_context_t* ctx = dev->ctx;
-    const double t_begin = now_ms();
+struct InFlight {
     Window w;
     std::vector<pb2_gpu_task_t*> taken;
-    int rc = build_window(dev, w, taken);
-    if (rc != PB2_SUCCESS) return rc;
-    if (w.order.empty()) return PB2_SUCCESS;
+    pb2_window_t* win = nullptr;
+    double t_begin = 0, t_built = 0, t_launched = 0;
+};
+
+// build one window from the pending tasks and start it (asynchronously)
+static int launch_one(pb2_device_module_t* dev, bool* launched) {
+    pb2_context_t* ctx = dev->ctx;
+    *launched = false;
+    InFlight* f = new InFlight();
+    f->t_begin = now_ms();
+    const size_t pipe = (size_t)std::max<int64_t>(1, ctx->mca["device_engine_pipeline"]);
+    const size_t min_roots = (size_t)std::max<int64_t>(1, ctx->mca["device_engine_pipeline_min_roots"]);
+    if (dev->pipe_chunk == 0 && pipe > 1 && dev->pending.size() >= min_roots)
+        dev->pipe_chunk = (dev->pending.size() + pipe - 1) / pipe;
+    const size_t max_roots = dev->pipe_chunk ? dev->pipe_chunk : (size_t)-1;
+    int rc = build_window(dev, f->w, f->taken, max_roots);
+    if (rc != PB2_SUCCESS || f->w.order.empty()) { delete f; return rc; }
+    if (dev->pending.empty()) dev->pipe_chunk = 0;
+    f->t_built = now_ms();
+    if (!dev->dry_run) {
+        Window& w = f->w;
+        const int32_t n = (int32_t)w.order.size();
+        rc = pb2_window_create(dev->engine, &f->win, w.kind, w.tasks.data(), n, w.succ.data(), (int32_t)w.succ.size(),
+                               w.tiles.data(), (int32_t)w.tiles.size(), w.ready.data(), (int32_t)w.ready.size());
+        if (rc != PB2_SUCCESS) ctx->last_error = std::string("window_create: ") + pb2_engine_last_error(dev->engine);
+        if (rc == PB2_SUCCESS && (rc = pb2_window_launch(f->win)) != PB2_SUCCESS)
+            ctx->last_error = std::string("window launch: ") + pb2_engine_last_error(dev->engine);
+        if (rc != PB2_SUCCESS) { if (f->win) pb2_window_destroy(f->win); window_release(dev, w); delete f; return rc; }
+    }
+    f->t_launched = now_ms();
+    dev->inflight.push_back(f);
+    *launched = true;
+    return PB2_SUCCESS;
+}
+
+// wait for the oldest window and replay its bookkeeping
+static int retire_one(pb2_device_module_t* dev) {
+    pb2_context_t* ctx = dev->ctx;
+    InFlight* f = reinterpret_cast<InFlight*>(dev->inflight.front());
+    dev->inflight.pop_front();
+    Window& w = f->w;
     const int32_t n = (int32_t)w.order.size();
-    const double t_built = now_ms();
+    const double t_wait = now_ms();
     std::vector<int32_t> retire((size_t)n);
     std::vector<uint32_t> seen((size_t)n * PB2_MAX_FLOWS, 0);
     std::vector<uint64_t> result((size_t)n, 0);
@@ -1003,17 +1053,12 @@ static int device_progress(pb2_device_module_t* dev) {
         // no device: retire in window order so the host logic can be exercised end to end
         for (int32_t i = 0; i < n; ++i) retire[i] = i;
     } else {
-        pb2_window_t* win = nullptr;
-        rc = pb2_window_create(dev->engine, &win, w.kind, w.tasks.data(), n, w.succ.data(), (int32_t)w.succ.size(),
-                               w.tiles.data(), (int32_t)w.tiles.size(), w.ready.data(), (int32_t)w.ready.size());
-        if (rc != PB2_SUCCESS) { ctx->last_error = std::string("window_create: ") + pb2_engine_last_error(dev->engine); window_release(dev, w); return rc; }
-        rc = pb2_window_launch(win);
         pb2_window_stats_t st{};
-        if (rc == PB2_SUCCESS) rc = pb2_window_wait(win, &st);
-        if (rc == PB2_SUCCESS) rc = pb2_window_results(win, retire.data(), nullptr, nullptr, seen.data(), result.data(), nullptr, nullptr);
+        int rc = pb2_window_wait(f->win, &st);
+        if (rc == PB2_SUCCESS) rc = pb2_window_results(f->win, retire.data(), nullptr, nullptr, seen.data(), result.data(), nullptr, nullptr);
         if (rc != PB2_SUCCESS) ctx->last_error = std::string("window run: ") + pb2_engine_last_error(dev->engine);
-        pb2_window_destroy(win);
-        if (rc != PB2_SUCCESS) { window_release(dev, w); return rc; }
+        pb2_window_destroy(f->win);
+        if (rc != PB2_SUCCESS) { window_release(dev, w); delete f; return rc; }
         dev->st.kernel_ms_total += st.kernel_ms;
     }
     const double t_ran = now_ms();
@@ -1033,9 +1078,22 @@ static int device_progress(pb2_device_module_t* dev) {
         pb2i_lru_push_back(dev, g->coherency_state == PB2_DATA_COHERENCY_OWNED ? 2 : 1, g);
     }
     window_release(dev, w);
-    for (pb2_gpu_task_t* g : taken) { dev->mutex--; delete g; }    // release_device_task
-    if (g_timing) fprintf(stderr, "pb2 window: %d tasks, build %.2f ms, create+run+results %.2f ms, retire %.2f ms\n",
-                          n, t_built - t_begin, t_ran - t_built, now_ms() - t_ran);
+    for (pb2_gpu_task_t* g : f->taken) { dev->mutex--; delete g; }    // release_device_task
+    if (g_timing) fprintf(stderr, "pb2 window: %d tasks, build %.2f ms, create+launch %.2f ms, waited %.2f ms, retire %.2f ms\n",
+                          n, f->t_built - f->t_begin, f->t_launched - f->t_built, t_ran - t_wait, now_ms() - t_ran);
+    delete f;
+    return PB2_SUCCESS;
+}
+
+// The manager's loop body (device_gpu.c:3438-3562), two windows deep: launch what is pending, then retire the oldest.
+static int device_progress(pb2_device_module_t* dev) {
+    const size_t depth = 2;
+    bool launched = true;
+    while (launched && !dev->pending.empty() && dev->inflight.size() < depth) {
+        int rc = launch_one(dev, &launched);
+        if (rc != PB2_SUCCESS) return rc;
+    }
+    if (!dev->inflight.empty()) return retire_one(dev);
     return PB2_SUCCESS;
 }
 
@@ -1061,7 +1119,7 @@ int pb2_taskpool_export_window(pb2_taskpool_t* tp, pb2_device_module_t* dev,
     ctx->ready.swap(keep);
     Window w;
     std::vector<pb2_gpu_task_t*> taken;
-    int rc = build_window(dev, w, taken);
+    int rc = build_window(dev, w, taken, (size_t)-1);
     if (rc != PB2_SUCCESS) return rc;
     const bool fill = tasks && succ && tiles && ready &&
                       *ntasks >= (int32_t)w.tasks.size() && *nsucc >= (int32_t)w.succ.size() &&

