@@ -177,6 +177,13 @@ int  pb2_engine_free(pb2_engine_t* engine, void* dev_ptr);
 int  pb2_engine_host_register(pb2_engine_t* engine, void* host_ptr, size_t bytes, void** dev_alias);
 int  pb2_engine_host_unregister(pb2_engine_t* engine, void* host_ptr);
 int  pb2_engine_memcpy_h2d(pb2_engine_t* engine, void* dev, const void* host, size_t bytes);
+/* Copy-engine prefetch for the NEXT window that is armed: queued on a DMA stream that runs beside the window in
+ * flight; pb2_window_arm makes the engine stream wait for everything queued here.  `host` must be pinned
+ * (pb2_engine_host_register).  One call moves `rows` equally spaced tiles (cudaMemcpy2DAsync; a zone heap with
+ * 512 KiB units holds 256 KiB tiles at a 512 KiB pitch).  Large runs reach the PCIe DMA rate (54 GB/s on this box) where worker
+ * CTAs reading host memory reach 46 GB/s; the caller marks the tiles it prefetched PB2_TILE_VALID. */
+int  pb2_engine_prefetch_h2d(pb2_engine_t* engine, void* dev, size_t dev_pitch, const void* host, size_t host_pitch,
+                             size_t width_bytes, size_t rows);   /* rows tiles of width_bytes, constant strides */
 int  pb2_engine_memcpy_d2h(pb2_engine_t* engine, void* host, const void* dev, size_t bytes);
 int  pb2_engine_synchronize(pb2_engine_t* engine);
 /* Enqueue all engine work on a caller-owned CUDA stream (cudaStream_t passed as void*), e.g. the stream NCCL

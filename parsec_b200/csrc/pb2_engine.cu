@@ -249,6 +249,9 @@ struct pb2_engine_s {
     cudaStream_t stream = nullptr;       // where engine work is enqueued
     cudaStream_t own_stream = nullptr;   // created by the engine
     cudaStream_t up_stream = nullptr;    // descriptor uploads of the NEXT window: not ordered behind the running one
+    cudaStream_t dma_stream = nullptr;   // pb2_engine_prefetch_h2d
+    cudaEvent_t dma_ev = nullptr;
+    bool dma_pending = false;
     int nworkers = 0;
     int nworkers_gemm = 0;
     std::string last_error;
@@ -520,6 +523,8 @@ int pb2_engine_create(pb2_engine_t** engine, int cuda_device, const pb2_engine_p
     e->params = p;
     PB2_CUDA(e, cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
     PB2_CUDA(e, cudaStreamCreateWithFlags(&e->up_stream, cudaStreamNonBlocking));
+    PB2_CUDA(e, cudaStreamCreateWithFlags(&e->dma_stream, cudaStreamNonBlocking));
+    PB2_CUDA(e, cudaEventCreateWithFlags(&e->dma_ev, cudaEventDisableTiming));
     e->stream = e->own_stream;
     {   // keep freed window scratch cached in the default mempool instead of returning it to the driver
         cudaMemPool_t pool;
@@ -547,6 +552,8 @@ int pb2_engine_destroy(pb2_engine_t* e) {
     for (auto& kv : e->registered) cudaHostUnregister(kv.first);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->up_stream) cudaStreamDestroy(e->up_stream);
+    if (e->dma_stream) cudaStreamDestroy(e->dma_stream);
+    if (e->dma_ev) cudaEventDestroy(e->dma_ev);
     delete e;
     return PB2_SUCCESS;
 }
@@ -618,6 +625,18 @@ int pb2_engine_memcpy_h2d(pb2_engine_t* e, void* dev, const void* host, size_t b
     if (!e) return PB2_ERR_BAD_PARAM;
     PB2_CUDA(e, cudaSetDevice(e->cuda_device));
     PB2_CUDA(e, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, e->stream));
+    return PB2_SUCCESS;
+}
+
+int pb2_engine_prefetch_h2d(pb2_engine_t* e, void* dev, size_t dev_pitch, const void* host, size_t host_pitch,
+                            size_t width_bytes, size_t rows) {
+    if (!e || !dev || !host || !width_bytes || !rows) return PB2_ERR_BAD_PARAM;
+    PB2_CUDA(e, cudaSetDevice(e->cuda_device));
+    if (rows == 1 || (dev_pitch == width_bytes && host_pitch == width_bytes))
+        PB2_CUDA(e, cudaMemcpyAsync(dev, host, width_bytes * rows, cudaMemcpyHostToDevice, e->dma_stream));
+    else
+        PB2_CUDA(e, cudaMemcpy2DAsync(dev, dev_pitch, host, host_pitch, width_bytes, rows, cudaMemcpyHostToDevice, e->dma_stream));
+    e->dma_pending = true;
     return PB2_SUCCESS;
 }
 
@@ -818,6 +837,11 @@ int pb2_window_arm(pb2_window_t* w) {
     if (!w) return PB2_ERR_BAD_PARAM;
     pb2_engine_t* e = w->e;
     PB2_CUDA(e, cudaSetDevice(e->cuda_device));
+    if (e->dma_pending) {                       // prefetches queued for this window land before its first worker starts
+        PB2_CUDA(e, cudaEventRecord(e->dma_ev, e->dma_stream));
+        PB2_CUDA(e, cudaStreamWaitEvent(e->stream, e->dma_ev, 0));
+        e->dma_pending = false;
+    }
     PB2_CUDA(e, cudaEventRecord(w->ev0, e->stream));
     {
         const int threads = 256;

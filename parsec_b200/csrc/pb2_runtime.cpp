@@ -242,6 +242,9 @@ int pb2_init(pb2_context_t** pctx, int nb_cores) {
     ctx->mca["device_engine_gemm_mode"] = 0;
     // a batch of at least _min_roots ready GPU tasks is cut into _pipeline windows of whole dependency closures:
     // while one window runs, the host builds the next one and replays the bookkeeping of the previous one
+    // tiles a window has to read from pinned host memory: runs of at least this many contiguous bytes (host and
+    // device side) go through the copy engine before the window starts, the rest is staged by the worker CTAs
+    ctx->mca["device_engine_dma_prefetch_min_bytes"] = 1 << 20;      // 0 disables
     ctx->mca["device_engine_pipeline"] = 4;
     ctx->mca["device_engine_pipeline_min_roots"] = 2048;
     // index 0: the CPU; index 1: the recursive pseudo-device (device.c:1041-1110)
@@ -1007,6 +1010,54 @@ struct InFlight {
     double t_begin = 0, t_built = 0, t_launched = 0;
 };
 
+// Host-resident tiles whose first use in the window is a READ, laid out contiguously on both sides, are moved by the
+// copy engine in a few large cudaMemcpyAsync (parsec_cuda_memcpy_async, device_cuda_module.c:318-344, issues one per
+// flow: 4096 calls of 256 KiB reach 29 GB/s on this box, one call per run 54 GB/s, worker CTAs 46 GB/s).
+static int dma_prefetch(pb2_device_module_t* dev, Window& w) {
+    const int64_t min_bytes = dev->ctx->mca["device_engine_dma_prefetch_min_bytes"];
+    if (min_bytes <= 0) return PB2_SUCCESS;
+    std::vector<int8_t> first((size_t)w.tiles.size(), -1);          // 1: first access reads the tile
+    for (size_t i = 0; i < w.tasks.size(); ++i) {
+        const pb2_task_t& t = w.tasks[i];
+        for (int f = 0; f < t.nb_flows; ++f)
+            if (t.tile[f] >= 0 && first[(size_t)t.tile[f]] < 0) first[(size_t)t.tile[f]] = (t.access[f] & PB2_FLOW_ACCESS_READ) ? 1 : 0;
+    }
+    std::vector<std::pair<uintptr_t, size_t>> cand;                  // (device address, tile index)
+    for (size_t i = 0; i < w.tiles.size(); ++i) {
+        const pb2_tile_t& tl = w.tiles[i];
+        if (tl.state != PB2_TILE_INVALID || tl.src_kind != PB2_SRC_HOST || !tl.src_ptr || first[i] != 1) continue;
+        pb2_data_copy_t* h = pb2i_host_copy(w.tile_data[i]);
+        if (!h || !h->device_private) continue;
+        cand.emplace_back((uintptr_t)tl.dev_ptr, i);
+    }
+    std::sort(cand.begin(), cand.end());
+    auto host_of = [&](size_t c) { return (uintptr_t)pb2i_host_copy(w.tile_data[cand[c].second])->device_private; };
+    size_t i = 0;
+    while (i < cand.size()) {
+        // longest run of equally sized tiles with constant strides on both sides, starting at candidate i
+        const uint32_t width = w.tiles[cand[i].second].bytes;
+        size_t j = i + 1;
+        uintptr_t dpitch = width, hpitch = width;
+        if (j < cand.size() && w.tiles[cand[j].second].bytes == width && host_of(j) > host_of(i)) {
+            dpitch = cand[j].first - cand[i].first; hpitch = host_of(j) - host_of(i);
+            if (dpitch >= width && hpitch >= width) {
+                ++j;
+                while (j < cand.size() && w.tiles[cand[j].second].bytes == width &&
+                       cand[j].first - cand[j - 1].first == dpitch && host_of(j) - host_of(j - 1) == hpitch) ++j;
+            } else { dpitch = hpitch = width; }
+        }
+        const size_t rows = j - i;
+        if ((int64_t)((size_t)width * rows) >= min_bytes) {
+            int rc = pb2_engine_prefetch_h2d(dev->engine, reinterpret_cast<void*>(cand[i].first), dpitch,
+                                             reinterpret_cast<const void*>(host_of(i)), hpitch, width, rows);
+            if (rc != PB2_SUCCESS) { dev->ctx->last_error = std::string("prefetch: ") + pb2_engine_last_error(dev->engine); return rc; }
+            for (size_t k = i; k < j; ++k) w.tiles[cand[k].second].state = PB2_TILE_VALID;   // resident when the window starts
+        }
+        i = j;
+    }
+    return PB2_SUCCESS;
+}
+
 // build one window from the pending tasks and start it (asynchronously)
 static int launch_one(pb2_device_module_t* dev, bool* launched) {
     pb2_context_t* ctx = dev->ctx;
@@ -1025,6 +1076,8 @@ static int launch_one(pb2_device_module_t* dev, bool* launched) {
     if (!dev->dry_run) {
         Window& w = f->w;
         const int32_t n = (int32_t)w.order.size();
+        rc = dma_prefetch(dev, w);
+        if (rc != PB2_SUCCESS) { window_release(dev, w); delete f; return rc; }
         rc = pb2_window_create(dev->engine, &f->win, w.kind, w.tasks.data(), n, w.succ.data(), (int32_t)w.succ.size(),
                                w.tiles.data(), (int32_t)w.tiles.size(), w.ready.data(), (int32_t)w.ready.size());
         if (rc != PB2_SUCCESS) ctx->last_error = std::string("window_create: ") + pb2_engine_last_error(dev->engine);
