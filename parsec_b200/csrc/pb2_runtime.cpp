@@ -1013,9 +1013,13 @@ struct InFlight {
 // Host-resident tiles whose first use in the window is a READ, laid out contiguously on both sides, are moved by the
 // copy engine in a few large cudaMemcpyAsync (parsec_cuda_memcpy_async, device_cuda_module.c:318-344, issues one per
 // flow: 4096 calls of 256 KiB reach 29 GB/s on this box, one call per run 54 GB/s, worker CTAs 46 GB/s).
-static int dma_prefetch(pb2_device_module_t* dev, Window& w) {
+struct DmaRun { void* dev; size_t dpitch; const void* host; size_t hpitch; size_t width, rows; };
+
+// plans the runs and marks their tiles resident; the copies are issued after the window's descriptors have been
+// uploaded (small uploads queued behind a 256 MiB transfer on the same copy engine would block pb2_window_create)
+static void dma_plan(pb2_device_module_t* dev, Window& w, std::vector<DmaRun>& runs) {
     const int64_t min_bytes = dev->ctx->mca["device_engine_dma_prefetch_min_bytes"];
-    if (min_bytes <= 0) return PB2_SUCCESS;
+    if (min_bytes <= 0) return;
     std::vector<int8_t> first((size_t)w.tiles.size(), -1);          // 1: first access reads the tile
     for (size_t i = 0; i < w.tasks.size(); ++i) {
         const pb2_task_t& t = w.tasks[i];
@@ -1048,14 +1052,11 @@ static int dma_prefetch(pb2_device_module_t* dev, Window& w) {
         }
         const size_t rows = j - i;
         if ((int64_t)((size_t)width * rows) >= min_bytes) {
-            int rc = pb2_engine_prefetch_h2d(dev->engine, reinterpret_cast<void*>(cand[i].first), dpitch,
-                                             reinterpret_cast<const void*>(host_of(i)), hpitch, width, rows);
-            if (rc != PB2_SUCCESS) { dev->ctx->last_error = std::string("prefetch: ") + pb2_engine_last_error(dev->engine); return rc; }
+            runs.push_back(DmaRun{reinterpret_cast<void*>(cand[i].first), dpitch, reinterpret_cast<const void*>(host_of(i)), hpitch, width, rows});
             for (size_t k = i; k < j; ++k) w.tiles[cand[k].second].state = PB2_TILE_VALID;   // resident when the window starts
         }
         i = j;
     }
-    return PB2_SUCCESS;
 }
 
 // build one window from the pending tasks and start it (asynchronously)
@@ -1076,11 +1077,15 @@ static int launch_one(pb2_device_module_t* dev, bool* launched) {
     if (!dev->dry_run) {
         Window& w = f->w;
         const int32_t n = (int32_t)w.order.size();
-        rc = dma_prefetch(dev, w);
-        if (rc != PB2_SUCCESS) { window_release(dev, w); delete f; return rc; }
+        std::vector<DmaRun> runs;
+        dma_plan(dev, w, runs);
         rc = pb2_window_create(dev->engine, &f->win, w.kind, w.tasks.data(), n, w.succ.data(), (int32_t)w.succ.size(),
                                w.tiles.data(), (int32_t)w.tiles.size(), w.ready.data(), (int32_t)w.ready.size());
         if (rc != PB2_SUCCESS) ctx->last_error = std::string("window_create: ") + pb2_engine_last_error(dev->engine);
+        for (size_t r = 0; r < runs.size() && rc == PB2_SUCCESS; ++r) {
+            rc = pb2_engine_prefetch_h2d(dev->engine, runs[r].dev, runs[r].dpitch, runs[r].host, runs[r].hpitch, runs[r].width, runs[r].rows);
+            if (rc != PB2_SUCCESS) ctx->last_error = std::string("prefetch: ") + pb2_engine_last_error(dev->engine);
+        }
         if (rc == PB2_SUCCESS && (rc = pb2_window_launch(f->win)) != PB2_SUCCESS)
             ctx->last_error = std::string("window launch: ") + pb2_engine_last_error(dev->engine);
         if (rc != PB2_SUCCESS) { if (f->win) pb2_window_destroy(f->win); window_release(dev, w); delete f; return rc; }
