@@ -169,8 +169,9 @@ def main():
     # ---------------------------------------------------------------- e2e through the host API, host buffers
     # One step = the application hands a freshly written collection (host memory) to a new task pool:
     #   host_write_all  : the host copies are the newest version (what CPU producer tasks would leave behind)
-    #   ptg_new + wait  : PTG front end -> kernel_scheduler -> window; every tile is staged in from pinned host
-    #                     memory by the kernel (H2D, K * 262144 B), bodies run, successors are released on-device
+    #   ptg_new + wait  : PTG front end -> kernel_scheduler -> 4 pipelined windows (two in flight); every tile comes
+    #                     from pinned host memory (H2D, K * 262144 B: strided runs through the copy engine, anything
+    #                     else staged by the worker CTAs), bodies run, successors are released on-device
     #   task_info       : the per-task results (what TaskRecv "prints") are read back to the host (D2H)
     tsplit = {"new": 0.0, "wait": 0.0, "read": 0.0}
 
@@ -258,7 +259,8 @@ def main():
         finish = lambda: w.wait()
         launches_per_step = 2
     elif args.mgpu == "direct":
-        step, finish, launches_per_step, nt_rank = ex05_direct_step_factory(K, NB, TILE, rank, world, local_rank)
+        step, finish, _, nt_rank = ex05_direct_step_factory(K, NB, TILE, rank, world, local_rank)
+        launches_per_step = 2                                     # re-arm + persistent kernel (the NCCL barrier kernel is not ours)
         assert nt_rank == ntasks
         cfg["multi_gpu"] = "one window per GPU; cross-GPU edges released by the producer's CTA (system-scope atomics over NVLink), tiles pulled by the consumer; NCCL only as the per-step barrier"
     else:
