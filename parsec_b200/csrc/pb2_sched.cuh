@@ -209,7 +209,7 @@ __device__ __forceinline__ bool retire_task(const WinDev& w, int32_t id) {
 // stage-in / stage-out of one flow by the whole CTA
 // ---------------------------------------------------------------------------------------------
 // Thread 0 decides (s_decide[0]): 1 = this CTA moves the tile, 0 = already valid (possibly after waiting)
-__device__ __forceinline__ void stage_in_flow(const WinDev& w, pb2_tile_t* tile, uint8_t access, int* s_decide) {
+__device__ __noinline__ void stage_in_flow(const WinDev& w, pb2_tile_t* tile, uint8_t access, int* s_decide) {
     if (threadIdx.x == 0) {
         int decide = 0;
         if (access & PB2_FLOW_ACCESS_READ) {

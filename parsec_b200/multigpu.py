@@ -229,6 +229,18 @@ def cholesky_global(NT, nb, P, Q, elem_bytes=2):
     return t, np.array(succ, np.uint32), tiles, ready, tile_rank[rw_tile].astype(np.int32), tile_rank
 
 
+def translate_remote_targets(part, entries_by_rank):
+    """The partitioner names a remote successor by its local task id on the owning rank; that rank's window says how
+    to release it (pb2_window_task_entries: index of the dependency word + number of ring entries, in the window's
+    own encoding).  entries_by_rank[r] is rank r's table."""
+    tgt = part["rs_target"].copy()
+    for r, table in enumerate(entries_by_rank):
+        m = part["rs_rank"] == r
+        if m.any():
+            tgt[m] = np.asarray(table)[part["rs_target"][m].astype(np.int64)].astype(np.uint32)
+    return tgt
+
+
 class SharedRun:
     """One rank's half of a window that was split over the GPUs of the box ("direct" path).
 
@@ -251,12 +263,7 @@ class SharedRun:
         eng.set_shared_windows(False)
         wh = [None] * world
         dist.all_gather_object(wh, (self.w.export(), self.w.task_entries()))
-        # the partitioner names a remote successor by its local task id; the owner's window says how to release it
-        tgt = self.p["rs_target"].copy()
-        for r in range(world):
-            m = self.p["rs_rank"] == r
-            if m.any():
-                tgt[m] = wh[r][1][self.p["rs_target"][m].astype(np.int64)].astype(np.uint32)
+        tgt = translate_remote_targets(self.p, [h[1] for h in wh])
         self.w.set_remote(rank, [h[0] for h in wh], self.p["rs_begin"], self.p["rs_rank"], tgt)
         self._flag = torch.zeros(1, dtype=torch.int32, device="cuda")
         dist.barrier()

@@ -321,8 +321,6 @@ def test_large_batches_are_cut_into_pipelined_windows():
         assert st["windows_launched"] == 4
         assert st["executed_tasks"] == K * (1 + F) and st["tasks_released_on_device"] == K * F
         assert st["data_in_from_device"][0] == K * tb
-        info = ctx.task_info(tp)
-        assert np.all(info["seen_version"][info["class_id"] == 1, 0] == 0) or True
         ctx.l.pb2_taskpool_free(tp)
 
 

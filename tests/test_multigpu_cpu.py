@@ -85,3 +85,53 @@ def test_owner_map_matches_collection():
             for k in range(32):
                 assert ctx.l.pb2_dc_rank_of(dcq, 0, k) == mg.owner_1xN(k, world)
             ctx.l.pb2_data_collection_free(dc); ctx.l.pb2_data_collection_free(dcq)
+
+
+def _direct_worker(rank, world, port, q):
+    """Host protocol of the direct path, one process per rank, no GPU: every rank partitions the same global window,
+    publishes (fake) slab addresses and its window's release table like SharedRun does with IPC handles, translates
+    its remote edges, and the ranks cross-check that what the peers will release adds up to every task's goal."""
+    import torch.distributed as dist
+    from parsec_b200 import multigpu as mg
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    P, Q = {2: (1, 2), 4: (2, 2)}[world]
+    g = mg.cholesky_global(5, 64, P, Q)
+    part = mg.Partition(*g, nranks=world)
+    bases = [None] * world
+    dist.all_gather_object(bases, 0x10000000000 * (rank + 1))          # stands for the IPC-mapped slab of each rank
+    p = part.get(rank, bases)
+    # what pb2_window_task_entries returns for an HBM window without wide tasks: entry = task id, one ring entry
+    tables = [None] * world
+    dist.all_gather_object(tables, np.arange(len(p["tasks"]), dtype=np.int32) + 0)
+    tgt = mg.translate_remote_targets(p, tables)
+    sent = [np.bincount(tgt[p["rs_rank"] == r].astype(np.int64), minlength=len(tables[r])) for r in range(world)]
+    allsent = [None] * world
+    dist.all_gather_object(allsent, sent)
+    indeg = np.zeros(len(p["tasks"]), np.int64)
+    np.add.at(indeg, (p["succ"] & 0x7FFFFFF).astype(np.int64), 1)
+    for r in range(world):
+        indeg += allsent[r][rank]
+    peers_pull_from = sorted({int(a) // 0x10000000000 - 1 for a in p["tiles"]["src_ptr"][p["tiles"]["src_kind"] == 1]})
+    q.put((rank, bool(np.array_equal(indeg, p["tasks"]["dep_goal"])), int(len(p["rs_rank"])), peers_pull_from,
+           int(len(p["tasks"])), int((p["tiles"]["src_kind"] == 1).sum())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_direct_path_host_protocol_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_direct_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs: p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res)                                   # goals == local + remote in-edges on every rank
+    assert sum(r[2] for r in res) > 0 and sum(r[5] for r in res) > 0
+    assert sum(r[4] for r in res) == 5 + 2 * 10 + 10                 # POTRF + TRSM + SYRK + GEMM of NT = 5
+    for r in res:
+        assert r[0] not in r[3]                                     # a rank never pulls from itself
