@@ -70,6 +70,8 @@ enum pb2_body_e {
     PB2_BODY_GEMM_BF16  = 16, /* flow2 (C, M x N row-major bf16) += flow0 (A, M x K row-major) *
                                * flow1 (B, N x K row-major == K x N column-major), fp32 accumulate in TMEM
                                * iparam[0]=M, iparam[1]=N, iparam[2]=K (each tile edge)                     */
+    PB2_BODY_USER       = 31, /* host-side only: the chore is a user `submit` callback that enqueues its own CUDA work
+                               * on a stream (device_gpu.h:49-51); such tasks never enter an engine window           */
     PB2_BODY_MAX        = 32
 };
 
@@ -189,6 +191,7 @@ int  pb2_engine_synchronize(pb2_engine_t* engine);
 /* Enqueue all engine work on a caller-owned CUDA stream (cudaStream_t passed as void*), e.g. the stream NCCL
  * collectives are ordered against; NULL restores the engine's own non-blocking stream. */
 int  pb2_engine_set_stream(pb2_engine_t* engine, void* cuda_stream);
+void* pb2_engine_get_stream(pb2_engine_t* engine);       /* the cudaStream_t engine work is enqueued on */
 
 /* n independent copies dst[i][0:bytes[i]] = src[i][..] in ONE kernel launch (workers grid-stride over the list);
  * either side may be HBM, a peer GPU or cudaHostRegister'ed host memory (device-visible alias).  This is what the

@@ -233,6 +233,17 @@ pb2_task_class_t* pb2_dtd_create_task_class(pb2_taskpool_t* tp, const char* name
 /* parsec_dtd_task_class_add_chore (:2503).  GPU chores name an in-engine body (enum pb2_body_e); CPU chores a host fn */
 typedef int (*pb2_cpu_hook_t)(pb2_htask_t* task, void** flow_ptrs, const int32_t* iparam, float fparam);
 int  pb2_dtd_task_class_add_chore(pb2_taskpool_t* tp, pb2_task_class_t* tc, int device_type, int body, pb2_cpu_hook_t cpu_hook);
+/* A GPU chore that is an opaque user function, the reference's own kind of CUDA body: parsec_advance_task_function_t
+ * submit(gpu_device, gpu_task, gpu_stream) (device_gpu.h:49-51; dtd_test_simple_gemm.c:470-540).  It is called on the
+ * host once every flow is resident on `dev`, enqueues its work on `cuda_stream` and returns PB2_HOOK_RETURN_DONE
+ * (AGAIN: call me again after the stream has drained; anything negative else is fatal).  Such tasks run on a
+ * host-driven stream lane, in dependency order, between engine windows; pb2_gpu_task_flow_ptr gives the device
+ * address of a flow (parsec_dtd_get_dev_ptr, insert_function.c:3714-3726). */
+typedef int (*pb2_gpu_submit_t)(pb2_device_module_t* dev, pb2_gpu_task_t* gpu_task, void* cuda_stream);
+int  pb2_dtd_task_class_add_submit(pb2_taskpool_t* tp, pb2_task_class_t* tc, pb2_gpu_submit_t submit);
+void* pb2_gpu_task_flow_ptr(pb2_device_module_t* dev, pb2_gpu_task_t* gpu_task, int flow);
+size_t pb2_gpu_task_flow_bytes(pb2_gpu_task_t* gpu_task, int flow);
+const int32_t* pb2_gpu_task_iparam(pb2_gpu_task_t* gpu_task);
 /* parsec_dtd_insert_task_with_task_class (:3333): flow_ops may add PB2_PUSHOUT per call, like the reference */
 int  pb2_dtd_insert_task_with_task_class(pb2_taskpool_t* tp, pb2_task_class_t* tc, int priority, int device_type,
                                          pb2_dtd_tile_t* const* tiles, const int32_t* flow_ops,

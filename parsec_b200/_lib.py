@@ -105,7 +105,7 @@ _lib = None
 ENGINE_SYMBOLS = [
     "pb2_engine_create", "pb2_engine_destroy", "pb2_engine_info", "pb2_engine_last_error",
     "pb2_engine_malloc", "pb2_engine_free", "pb2_engine_host_register", "pb2_engine_host_unregister",
-    "pb2_engine_memcpy_h2d", "pb2_engine_prefetch_h2d", "pb2_engine_memcpy_d2h", "pb2_engine_synchronize", "pb2_engine_set_stream", "pb2_engine_copy_batch", "pb2_engine_ipc_export", "pb2_engine_ipc_open",
+    "pb2_engine_memcpy_h2d", "pb2_engine_prefetch_h2d", "pb2_engine_memcpy_d2h", "pb2_engine_synchronize", "pb2_engine_set_stream", "pb2_engine_get_stream", "pb2_engine_copy_batch", "pb2_engine_ipc_export", "pb2_engine_ipc_open",
     "pb2_engine_ipc_close", "pb2_engine_set_shared_windows", "pb2_engine_set_part_bytes", "pb2_window_export", "pb2_window_set_remote", "pb2_window_task_entries",
     "pb2_window_arm", "pb2_window_start",
     "pb2_window_create", "pb2_window_destroy", "pb2_window_launch", "pb2_window_wait",
@@ -160,8 +160,10 @@ def load():
     lib.pb2_partition_get.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.pb2_partition_destroy.argtypes = [vp]
     for name in ENGINE_SYMBOLS:
-        if name not in ("pb2_engine_last_error", "pb2_partition_error", "pb2_partition_destroy"):
+        if name not in ("pb2_engine_last_error", "pb2_partition_error", "pb2_partition_destroy", "pb2_engine_get_stream"):
             getattr(lib, name).restype = C.c_int
+    lib.pb2_engine_get_stream.argtypes = [vp]
+    lib.pb2_engine_get_stream.restype = vp
     lib.pb2_partition_error.restype = C.c_char_p
     lib.pb2_partition_destroy.restype = None
     _lib = lib

@@ -221,6 +221,24 @@ int pb2_dtd_task_class_add_chore(pb2_taskpool_t* tp, pb2_task_class_t* tc, int d
     return PB2_SUCCESS;
 }
 
+int pb2_dtd_task_class_add_submit(pb2_taskpool_t* tp, pb2_task_class_t* tc, pb2_gpu_submit_t submit) {
+    if (!tp || !tc || !submit) return PB2_ERR_BAD_PARAM;
+    tc->gpu_body = PB2_BODY_USER; tc->submit = submit; tc->chore_types |= PB2_DEV_CUDA;
+    for (auto* d : tp->ctx->devices) if (d->type & PB2_DEV_CUDA) tp->devices_index_mask |= 1u << d->device_index;
+    return PB2_SUCCESS;
+}
+
+void* pb2_gpu_task_flow_ptr(pb2_device_module_t* dev, pb2_gpu_task_t* g, int flow) {
+    if (!dev || !g || !g->ec || flow < 0 || flow >= g->ec->nb_flows || !g->ec->data[flow]) return nullptr;
+    pb2_data_copy_t* c = g->ec->data[flow]->device_copies[dev->device_index];
+    return c ? c->device_private : nullptr;
+}
+size_t pb2_gpu_task_flow_bytes(pb2_gpu_task_t* g, int flow) {
+    if (!g || !g->ec || flow < 0 || flow >= g->ec->nb_flows || !g->ec->data[flow]) return 0;
+    return g->ec->data[flow]->span;
+}
+const int32_t* pb2_gpu_task_iparam(pb2_gpu_task_t* g) { return (g && g->ec) ? g->ec->iparam : nullptr; }
+
 int pb2_dtd_insert_task_with_task_class(pb2_taskpool_t* tp, pb2_task_class_t* tc, int priority, int device_type,
                                         pb2_dtd_tile_t* const* tiles, const int32_t* flow_ops,
                                         const int32_t* iparam3, float fparam) {

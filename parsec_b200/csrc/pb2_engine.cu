@@ -323,7 +323,7 @@ static int validate_window(pb2_engine_t* e, int kind, const pb2_task_t* tasks, i
             e->last_error = "successor range out of bounds"; return PB2_ERR_VALUE_OUT_OF_BOUNDS; }
         for (int f = 0; f < t.nb_flows; ++f)
             if (t.tile[f] >= ntiles) { e->last_error = "tile id out of bounds"; return PB2_ERR_VALUE_OUT_OF_BOUNDS; }
-        if (t.body >= PB2_BODY_MAX) { e->last_error = "unknown body id"; return PB2_ERR_BAD_PARAM; }
+        if (t.body >= PB2_BODY_MAX || t.body == PB2_BODY_USER) { e->last_error = "unknown body id"; return PB2_ERR_BAD_PARAM; }
         if (kind == 0 && t.body == PB2_BODY_GEMM_BF16) {
             e->last_error = "GEMM body in an HBM-kind window (use kind 1)"; return PB2_ERR_BAD_PARAM; }
     }
@@ -712,6 +712,8 @@ int pb2_engine_set_stream(pb2_engine_t* e, void* cuda_stream) {
     e->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : e->own_stream;
     return PB2_SUCCESS;
 }
+
+void* pb2_engine_get_stream(pb2_engine_t* e) { return e ? reinterpret_cast<void*>(e->stream) : nullptr; }
 
 int pb2_engine_synchronize(pb2_engine_t* e) {
     if (!e) return PB2_ERR_BAD_PARAM;

@@ -61,6 +61,7 @@ struct pb2_task_class_s {
     uint8_t chore_types = 0;                          // PB2_DEV_* with an incarnation
     int gpu_body = -1;
     pb2_cpu_hook_t cpu_hook = nullptr;
+    pb2_gpu_submit_t submit = nullptr;                // PB2_BODY_USER: the user's own stream-enqueue function
     bool use_mask = false;
 };
 

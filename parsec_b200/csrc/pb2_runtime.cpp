@@ -818,12 +818,16 @@ static int build_window(pb2_device_module_t* dev, Window& w, std::vector<pb2_gpu
     if (dev->pending.empty()) return PB2_SUCCESS;
     w.tp = dev->pending.front()->ec->tp;
     const bool want_gemm = dev->pending.front()->ec->body == PB2_BODY_GEMM_BF16;
-    w.kind = want_gemm ? 1 : 0;
+    const bool want_user = dev->pending.front()->ec->body == PB2_BODY_USER;      // the host-driven stream lane
+    w.kind = want_user ? 2 : (want_gemm ? 1 : 0);
+    auto fits = [&](const pb2_htask_t* t) {
+        if (want_user || t->body == PB2_BODY_USER) return want_user && t->body == PB2_BODY_USER;
+        return (t->body == PB2_BODY_GEMM_BF16) == want_gemm || t->body == PB2_BODY_NOP;
+    };
     std::deque<pb2_htask_t*> queue;
     std::deque<pb2_gpu_task_t*> keep;
     for (pb2_gpu_task_t* g : dev->pending) {
-        const bool is_gemm = g->ec->body == PB2_BODY_GEMM_BF16;
-        if (taken.size() < max_roots && g->ec->tp == w.tp && (is_gemm == want_gemm || g->ec->body == PB2_BODY_NOP)) { queue.push_back(g->ec); taken.push_back(g); }
+        if (taken.size() < max_roots && g->ec->tp == w.tp && fits(g->ec)) { queue.push_back(g->ec); taken.push_back(g); }
         else keep.push_back(g);
     }
     dev->pending.swap(keep);
@@ -860,8 +864,7 @@ static int build_window(pb2_device_module_t* dev, Window& w, std::vector<pb2_gpu
             pb2_htask_t* n = &w.tp->tasks[PB2_SUCC_TASK(s)];
             if (n->inwin_pred == 0) touched.push_back(n);
             n->inwin_pred++;
-            if (n->state == 0 && n->inwin_pred == n->npred_unsat && predicted_on_device(dev, n) &&
-                ((n->body == PB2_BODY_GEMM_BF16) == want_gemm || n->body == PB2_BODY_NOP))
+            if (n->state == 0 && n->inwin_pred == n->npred_unsat && predicted_on_device(dev, n) && fits(n))
                 queue.push_back(n);
         }
     }
@@ -1007,8 +1010,69 @@ struct InFlight {
     Window w;
     std::vector<pb2_gpu_task_t*> taken;
     pb2_window_t* win = nullptr;
+    std::vector<uint32_t> lane_seen;        // kind 2 (user submit lane): versions seen, filled when the lane ran
     double t_begin = 0, t_built = 0, t_launched = 0;
 };
+
+// Tasks whose CUDA chore is a user `submit` function (PB2_BODY_USER): the host does for them what the reference's
+// manager does for every task -- stage the inputs in (kernel_push), call submit on the stream (kernel_exec,
+// device_gpu.c:2873-2934), write pushout flows back (kernel_pop) -- but for a whole dependency-closed chain of
+// them at once and with batched copies: one copy kernel for all stage-ins, one for all write-backs.
+static int run_submit_lane(pb2_device_module_t* dev, InFlight* f) {
+    pb2_context_t* ctx = dev->ctx;
+    Window& w = f->w;
+    const size_t n = w.order.size();
+    std::vector<void*> dst; std::vector<const void*> src; std::vector<uint64_t> len;
+    std::vector<int8_t> first(w.tiles.size(), -1);
+    for (size_t i = 0; i < n; ++i)
+        for (int fl = 0; fl < w.tasks[i].nb_flows; ++fl) {
+            const int32_t tile = w.tasks[i].tile[fl];
+            if (tile >= 0 && first[(size_t)tile] < 0) first[(size_t)tile] = (w.tasks[i].access[fl] & PB2_FLOW_ACCESS_READ) ? 1 : 0;
+        }
+    for (size_t i = 0; i < w.tiles.size(); ++i) {
+        const pb2_tile_t& tl = w.tiles[i];
+        if (tl.state != PB2_TILE_INVALID || first[i] != 1 || !tl.src_ptr) continue;
+        dst.push_back(tl.dev_ptr); src.push_back(tl.src_ptr); len.push_back(tl.bytes);
+    }
+    int rc = pb2_engine_copy_batch(dev->engine, dst.data(), src.data(), len.data(), (int32_t)dst.size());
+    if (rc != PB2_SUCCESS) { ctx->last_error = std::string("submit lane stage-in: ") + pb2_engine_last_error(dev->engine); return rc; }
+    void* stream = pb2_engine_get_stream(dev->engine);
+    std::vector<uint32_t> ver(w.tiles.size());
+    for (size_t i = 0; i < w.tiles.size(); ++i) ver[i] = w.tiles[i].version;
+    f->lane_seen.assign(n * PB2_MAX_FLOWS, 0);
+    dst.clear(); src.clear(); len.clear();
+    for (size_t i = 0; i < n; ++i) {
+        pb2_htask_t* t = w.order[i];
+        if (!t->tc || !t->tc->submit) { ctx->last_error = "PB2_BODY_USER task without a submit function"; return PB2_ERR_BAD_PARAM; }
+        pb2_gpu_task_s g;
+        g.ec = t; g.pushout = t->pushout; g.nb_flows = (uint32_t)t->nb_flows;
+        for (int fl = 0; fl < t->nb_flows; ++fl) g.flow_span[fl] = t->data[fl] ? t->data[fl]->span : 0;
+        int hr = t->tc->submit(dev, &g, stream);
+        for (int again = 0; hr == PB2_HOOK_RETURN_AGAIN && again < 1000; ++again) {      // device_gpu.c:2634-2641
+            pb2_engine_synchronize(dev->engine);
+            hr = t->tc->submit(dev, &g, stream);
+        }
+        if (hr != PB2_HOOK_RETURN_DONE && hr != PB2_HOOK_RETURN_ASYNC) { ctx->last_error = "submit function failed"; return PB2_ERROR; }
+        for (int fl = 0; fl < t->nb_flows; ++fl) {
+            const int32_t tile = w.tasks[i].tile[fl];
+            if (tile < 0) continue;
+            f->lane_seen[i * PB2_MAX_FLOWS + (size_t)fl] = ver[(size_t)tile];
+            if (w.tasks[i].access[fl] & PB2_FLOW_ACCESS_WRITE) {
+                ver[(size_t)tile]++;
+                if (w.tasks[i].access[fl] & PB2_FLOW_PUSHOUT) {        // newest version goes home; a later writer overrides it
+                    const pb2_tile_t& tl = w.tiles[(size_t)tile];
+                    bool dup = false;
+                    for (size_t k = 0; k < dst.size(); ++k) if (dst[k] == tl.src_ptr) dup = true;
+                    if (!dup) { dst.push_back(tl.src_ptr); src.push_back(tl.dev_ptr); len.push_back(tl.bytes); }
+                }
+            }
+        }
+    }
+    rc = pb2_engine_copy_batch(dev->engine, dst.data(), src.data(), len.data(), (int32_t)dst.size());   // stream-ordered after the bodies
+    if (rc == PB2_SUCCESS) rc = pb2_engine_synchronize(dev->engine);
+    if (rc != PB2_SUCCESS) ctx->last_error = std::string("submit lane: ") + pb2_engine_last_error(dev->engine);
+    return rc;
+}
 
 // Host-resident tiles whose first use in the window is a READ, laid out contiguously on both sides, are moved by the
 // copy engine in a few large cudaMemcpyAsync (parsec_cuda_memcpy_async, device_cuda_module.c:318-344, issues one per
@@ -1074,7 +1138,10 @@ static int launch_one(pb2_device_module_t* dev, bool* launched) {
     if (rc != PB2_SUCCESS || f->w.order.empty()) { delete f; return rc; }
     if (dev->pending.empty()) dev->pipe_chunk = 0;
     f->t_built = now_ms();
-    if (!dev->dry_run) {
+    if (!dev->dry_run && f->w.kind == 2) {
+        rc = run_submit_lane(dev, f);
+        if (rc != PB2_SUCCESS) { window_release(dev, f->w); delete f; return rc; }
+    } else if (!dev->dry_run) {
         Window& w = f->w;
         const int32_t n = (int32_t)w.order.size();
         std::vector<DmaRun> runs;
@@ -1107,9 +1174,10 @@ static int retire_one(pb2_device_module_t* dev) {
     std::vector<int32_t> retire((size_t)n);
     std::vector<uint32_t> seen((size_t)n * PB2_MAX_FLOWS, 0);
     std::vector<uint64_t> result((size_t)n, 0);
-    if (dev->dry_run) {
-        // no device: retire in window order so the host logic can be exercised end to end
+    if (dev->dry_run || w.kind == 2) {
+        // no device (dry run), or the submit lane, which ran its tasks in window order
         for (int32_t i = 0; i < n; ++i) retire[i] = i;
+        if (!f->lane_seen.empty()) seen = f->lane_seen;
     } else {
         pb2_window_stats_t st{};
         int rc = pb2_window_wait(f->win, &st);
@@ -1121,7 +1189,7 @@ static int retire_one(pb2_device_module_t* dev) {
     }
     const double t_ran = now_ms();
     dev->st.windows_launched++;
-    dev->st.tasks_released_on_device += (uint64_t)(n - (int32_t)w.ready.size());
+    if (w.kind != 2) dev->st.tasks_released_on_device += (uint64_t)(n - (int32_t)w.ready.size());
     // the retire log is the order in which the host learns about completions
     for (int32_t i = 0; i < n; ++i) {
         pb2_htask_t* t = w.order[retire[i]];

@@ -41,6 +41,7 @@ PARSEC_SYMBOLS = [
     "pb2_taskpool_completion_trace", "pb2_taskpool_task_info", "pb2_taskpool_export_window", "pb2_dtd_taskpool_new",
     "pb2_dtd_tile_of", "pb2_dtd_tile_new", "pb2_dtd_tile_data", "pb2_dtd_create_task_class",
     "pb2_dtd_task_class_add_chore", "pb2_dtd_insert_task_with_task_class", "pb2_dtd_data_flush_all",
+    "pb2_dtd_task_class_add_submit", "pb2_gpu_task_flow_ptr", "pb2_gpu_task_flow_bytes", "pb2_gpu_task_iparam",
     "pb2_dtd_data_flush", "pb2_ptg_ex02_chain_new", "pb2_ptg_ex05_broadcast_new", "pb2_ptg_rtt_new",
     "pb2_ptg_ep_new", "pb2_ptg_pingpong_new", "pb2_ptg_get_best_device_new", "pb2_ptg_cholesky_shape_new",
     "pb2_app_dtd_simple_gemm",
@@ -93,6 +94,9 @@ def lib():
         "pb2_dtd_create_task_class": (vp, [vp, C.c_char_p, C.c_int, vp]),
         "pb2_dtd_task_class_add_chore": (C.c_int, [vp, vp, C.c_int, C.c_int, vp]),
         "pb2_dtd_insert_task_with_task_class": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, vp, C.c_float]),
+        "pb2_dtd_task_class_add_submit": (C.c_int, [vp, vp, GPU_SUBMIT]),
+        "pb2_gpu_task_flow_ptr": (vp, [vp, vp, C.c_int]), "pb2_gpu_task_flow_bytes": (C.c_size_t, [vp, C.c_int]),
+        "pb2_gpu_task_iparam": (P(i32), [vp]),
         "pb2_dtd_data_flush_all": (C.c_int, [vp, vp]), "pb2_dtd_data_flush": (C.c_int, [vp, vp]),
         "pb2_ptg_ex02_chain_new": (vp, [vp, C.c_int]), "pb2_ptg_ex05_broadcast_new": (vp, [vp, vp, C.c_int, C.c_int]),
         "pb2_ptg_rtt_new": (vp, [vp, vp, C.c_int, C.c_int, C.c_int]), "pb2_ptg_ep_new": (vp, [vp, vp, C.c_int, C.c_int]),
@@ -105,6 +109,10 @@ def lib():
         f.restype, f.argtypes = res, args
     _bound = True
     return l
+
+
+# pb2_gpu_submit_t: int submit(pb2_device_module_t* dev, pb2_gpu_task_t* gpu_task, void* cuda_stream)
+GPU_SUBMIT = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p)
 
 
 def _chk(rc, what):

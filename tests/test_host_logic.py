@@ -343,3 +343,31 @@ def test_pipelined_windows_never_share_a_tile():
         assert st["executed_tasks"] == NT ** 3
         assert st["windows_launched"] >= 3
         ctx.l.pb2_taskpool_free(keep)
+
+
+def test_user_submit_tasks_get_their_own_lane():
+    """PB2_BODY_USER chores (user `submit` functions) never enter an engine window: FILL -> user -> CHECK on one tile is
+    three windows (engine, host-driven stream lane, engine), in dependency order, versions 0 -> 1 -> 2."""
+    with R.Context(cuda_devices=(0,), dry_run=True) as ctx:
+        cb = R.GPU_SUBMIT(lambda d, g, s: 0)
+        tp = C.c_void_p(ctx.l.pb2_dtd_taskpool_new(ctx.h))
+        op = np.array([R.INOUT], np.int32)
+        nc = lambda: C.c_void_p(ctx.l.pb2_dtd_create_task_class(tp, b"k", 1, op.ctypes.data_as(C.c_void_p)))
+        fill, user, chk = nc(), nc(), nc()
+        assert ctx.l.pb2_dtd_task_class_add_chore(tp, fill, R.DEV_CUDA, L.BODY_FILL_I32, None) == 0
+        assert ctx.l.pb2_dtd_task_class_add_submit(tp, user, cb) == 0
+        assert ctx.l.pb2_dtd_task_class_add_submit(tp, user, R.GPU_SUBMIT()) != 0          # NULL function is refused
+        assert ctx.l.pb2_dtd_task_class_add_chore(tp, chk, R.DEV_CUDA, L.BODY_CHECK_I32, None) == 0
+        p = lambda *v: np.array(v, np.int32).ctypes.data_as(C.c_void_p)
+        for _ in range(3):
+            arr = (C.c_void_p * 1)(C.c_void_p(ctx.l.pb2_dtd_tile_new(tp, 4096)))
+            ctx.l.pb2_dtd_insert_task_with_task_class(tp, fill, 0, R.DEV_CUDA, arr, p(R.OUTPUT), p(7, 0, 0), 0.0)
+            ctx.l.pb2_dtd_insert_task_with_task_class(tp, user, 0, R.DEV_CUDA, arr, p(R.INOUT), p(1, 0, 0), 0.0)
+            ctx.l.pb2_dtd_insert_task_with_task_class(tp, chk, 0, R.DEV_CUDA, arr, p(R.INPUT), p(0x01010101, 0, 0), 0.0)
+        ctx.wait()
+        st = ctx.stats(ctx.devices[0])
+        assert st["executed_tasks"] == 9 and st["windows_launched"] == 3
+        t, dev = ctx.trace(tp)
+        pos = {int(task): i for i, task in enumerate(t)}
+        for tile in range(3):
+            assert pos[3 * tile] < pos[3 * tile + 1] < pos[3 * tile + 2]

@@ -181,3 +181,62 @@ def test_cholesky_shaped_dag_completes():
         t, dev = ctx.trace(tp)
         assert sorted(t.tolist()) == list(range(n)) and np.all(dev == 2)
         assert np.all(np.isfinite(bf16_bits_to_f32(bits)))
+
+
+def _cudart():
+    import ctypes.util
+    for name in ("libcudart.so.12", "libcudart.so", ctypes.util.find_library("cudart") or ""):
+        try:
+            if name:
+                return C.CDLL(name)
+        except OSError:
+            continue
+    import glob, os, torch                                            # torch ships its own runtime
+    for p in glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "cuda_runtime", "lib", "libcudart.so*")):
+        return C.CDLL(p)
+    raise RuntimeError("libcudart not found")
+
+
+def test_user_submit_chore_runs_between_engine_windows():
+    """A GPU chore that is an opaque user `submit(device, gpu_task, stream)` function (device_gpu.h:49-51, the kind of
+    body dtd_test_simple_gemm.c and every generated BODY [type=CUDA] use): the host lane stages the flows in, calls
+    it on the stream, and the task chains with in-engine bodies before and after it on the same tiles.
+      tile: FILL 7 (engine) -> user memset 0x01 per byte (submit) -> CHECK == 0x01010101 (engine), then flushed home."""
+    import torch  # noqa: F401  (loads the CUDA runtime this process uses)
+    rt = _cudart()
+    rt.cudaMemsetAsync.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p]
+    nb, ntiles = 4096, 5
+    calls = []
+    with R.Context(cuda_devices=(0,)) as ctx:
+        def submit(dev, gtask, stream):
+            ptr = ctx.l.pb2_gpu_task_flow_ptr(dev, gtask, 0)
+            nbytes = ctx.l.pb2_gpu_task_flow_bytes(gtask, 0)
+            val = ctx.l.pb2_gpu_task_iparam(gtask)[0]
+            calls.append((ptr, nbytes, val))
+            return 0 if rt.cudaMemsetAsync(ptr, val, nbytes, stream) == 0 else -5
+        cb = R.GPU_SUBMIT(submit)
+        tp = C.c_void_p(ctx.l.pb2_dtd_taskpool_new(ctx.h))
+        op = np.array([R.INOUT], np.int32)
+        new_class = lambda: C.c_void_p(ctx.l.pb2_dtd_create_task_class(tp, b"k", 1, op.ctypes.data_as(C.c_void_p)))
+        fill, user, chk = new_class(), new_class(), new_class()
+        assert ctx.l.pb2_dtd_task_class_add_chore(tp, fill, R.DEV_CUDA, L.BODY_FILL_I32, None) == 0
+        assert ctx.l.pb2_dtd_task_class_add_submit(tp, user, cb) == 0
+        assert ctx.l.pb2_dtd_task_class_add_chore(tp, chk, R.DEV_CUDA, L.BODY_CHECK_I32, None) == 0
+        tiles = [C.c_void_p(ctx.l.pb2_dtd_tile_new(tp, nb * 4)) for _ in range(ntiles)]
+        p = lambda *v: np.array(v, np.int32).ctypes.data_as(C.c_void_p)
+        ids = []
+        for t in tiles:
+            arr = (C.c_void_p * 1)(t)
+            ctx.l.pb2_dtd_insert_task_with_task_class(tp, fill, 0, R.DEV_CUDA, arr, p(R.OUTPUT), p(7, 0, 0), 0.0)
+            ctx.l.pb2_dtd_insert_task_with_task_class(tp, user, 0, R.DEV_CUDA, arr, p(R.INOUT), p(1, 0, 0), 0.0)
+            ids.append(ctx.l.pb2_dtd_insert_task_with_task_class(tp, chk, 0, R.DEV_CUDA, arr, p(R.INPUT), p(0x01010101, 0, 0), 0.0))
+        ctx.wait()
+        info = ctx.task_info(tp)
+        st = ctx.stats(ctx.devices[0])
+        assert st["executed_tasks"] == 3 * ntiles
+        assert len(calls) == ntiles and all(c[1] == nb * 4 and c[2] == 1 for c in calls)
+        for i in ids:                                               # the engine's CHECK saw the user kernel's bytes
+            assert info["result"][i] == 0x01010101, hex(int(info["result"][i]))
+            assert info["seen_version"][i, 0] == 2                  # FILL -> 1, user submit -> 2
+        assert np.all(info["seen_version"][[i - 1 for i in ids], 0] == 1)
+        assert st["windows_launched"] == 3                          # engine window, submit lane, engine window
