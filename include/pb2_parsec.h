@@ -148,6 +148,12 @@ int  pb2_mca_device_registration_complete(pb2_context_t* ctx);
 int  pb2_nb_devices(pb2_context_t* ctx);
 pb2_device_module_t* pb2_mca_device_get(pb2_context_t* ctx, int device_index);
 int  pb2_device_get_stats(pb2_device_module_t* dev, pb2_device_stats_t* stats);
+/* parsec_devices_print_statistics (device.c:499-590): one row per device -- kernels run and their share, bytes
+ * required in / moved H2D and D2D (with the percentage of "required"), bytes required out / written back, evictions --
+ * plus the engine's own columns (windows launched, successors released by the device).  Writes a NUL-terminated
+ * table into buf (truncated to cap) and returns the length it would need.  pb2_fini prints it to stdout when the MCA
+ * parameter device_show_statistics is set, like parsec_mca_device_fini does. */
+int  pb2_devices_statistics_string(pb2_context_t* ctx, char* buf, size_t cap);
 int  pb2_device_index(pb2_device_module_t* dev);
 int  pb2_device_type(pb2_device_module_t* dev);
 /* the module entry points, device.h:154-166 (called through the module like the reference does) */

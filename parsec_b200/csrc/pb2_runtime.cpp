@@ -353,6 +353,48 @@ pb2_device_module_t* pb2_mca_device_get(pb2_context_t* ctx, int idx) {
     return (ctx && idx >= 0 && idx < (int)ctx->devices.size()) ? ctx->devices[idx] : nullptr;
 }
 int pb2_device_get_stats(pb2_device_module_t* dev, pb2_device_stats_t* st) { if (!dev || !st) return PB2_ERR_BAD_PARAM; *st = dev->st; return PB2_SUCCESS; }
+static void best_unit(uint64_t bytes, double* v, const char** unit) {       // parsec_compute_best_unit: 1024-based
+    static const char* units[] = {"B", "KB", "MB", "GB", "TB", "PB"};
+    double x = (double)bytes; int u = 0;
+    while (x >= 1024.0 && u < 5) { x /= 1024.0; ++u; }
+    *v = x; *unit = units[u];
+}
+
+int pb2_devices_statistics_string(pb2_context_t* ctx, char* buf, size_t cap) {
+    if (!ctx) return PB2_ERR_BAD_PARAM;
+    std::string out;
+    char line[512];
+    uint64_t total_tasks = 0;
+    for (auto* d : ctx->devices) total_tasks += d->st.executed_tasks;
+    out += "device statistics (bytes moved vs bytes the tasks required)\n";
+    out += " dev | name         |    kernels |      % | required in | moved H2D   (%)    | moved D2D   (%)    | required out | written back (%)  | evictions | windows | released on device\n";
+    struct Tot { uint64_t k = 0, rin = 0, h2d = 0, d2d = 0, rout = 0, out = 0, ev = 0, win = 0, rel = 0; } T;
+    auto row = [&](const char* id, const char* name, uint64_t k, uint64_t rin, uint64_t h2d, uint64_t d2d, uint64_t rout, uint64_t o,
+                   uint64_t ev, uint64_t win, uint64_t rel) {
+        double a, b, c, e, f; const char *ua, *ub, *uc, *ue, *uf;
+        best_unit(rin, &a, &ua); best_unit(h2d, &b, &ub); best_unit(d2d, &c, &uc); best_unit(rout, &e, &ue); best_unit(o, &f, &uf);
+        snprintf(line, sizeof line, " %3s | %-12s | %10llu | %6.2f | %8.2f %-2s | %8.2f %-2s (%6.2f) | %8.2f %-2s (%6.2f) | %9.2f %-2s | %8.2f %-2s (%6.2f) | %9llu | %7llu | %llu\n",
+                 id, name, (unsigned long long)k, total_tasks ? 100.0 * (double)k / (double)total_tasks : 0.0,
+                 a, ua, b, ub, rin ? 100.0 * (double)h2d / (double)rin : 0.0, c, uc, rin ? 100.0 * (double)d2d / (double)rin : 0.0,
+                 e, ue, f, uf, rout ? 100.0 * (double)o / (double)rout : 0.0,
+                 (unsigned long long)ev, (unsigned long long)win, (unsigned long long)rel);
+        out += line;
+    };
+    for (auto* d : ctx->devices) {
+        uint64_t d2d = 0;
+        for (int k = 2; k < PB2_MAX_DEVICES; ++k) d2d += d->st.data_in_from_device[k];
+        char id[8]; snprintf(id, sizeof id, "%d", (int)d->device_index);
+        row(id, d->name.c_str(), d->st.executed_tasks, d->st.required_data_in, d->st.data_in_from_device[0], d2d, d->st.required_data_out,
+            d->st.data_out_to_host, d->st.nb_evictions, d->st.windows_launched, d->st.tasks_released_on_device);
+        T.k += d->st.executed_tasks; T.rin += d->st.required_data_in; T.h2d += d->st.data_in_from_device[0]; T.d2d += d2d;
+        T.rout += d->st.required_data_out; T.out += d->st.data_out_to_host; T.ev += d->st.nb_evictions;
+        T.win += d->st.windows_launched; T.rel += d->st.tasks_released_on_device;
+    }
+    row("all", "", T.k, T.rin, T.h2d, T.d2d, T.rout, T.out, T.ev, T.win, T.rel);
+    if (buf && cap) { const size_t n = out.size() < cap - 1 ? out.size() : cap - 1; memcpy(buf, out.data(), n); buf[n] = 0; }
+    return (int)out.size() + 1;
+}
+
 int pb2_device_index(pb2_device_module_t* dev) { return dev ? dev->device_index : -1; }
 int pb2_device_type(pb2_device_module_t* dev) { return dev ? dev->type : 0; }
 
@@ -1318,6 +1360,11 @@ int pb2_fini(pb2_context_t** pctx) {
     if (!pctx || !*pctx) return PB2_ERR_BAD_PARAM;
     pb2_context_t* ctx = *pctx;
     while (!ctx->taskpools.empty()) pb2_taskpool_free(ctx->taskpools.back());
+    if (ctx->mca["device_show_statistics"]) {                      // parsec_mca_device_fini, device.c:393-398
+        std::vector<char> table((size_t)pb2_devices_statistics_string(ctx, nullptr, 0));
+        pb2_devices_statistics_string(ctx, table.data(), table.size());
+        fputs(table.data(), stdout);
+    }
     for (auto* d : ctx->devices) {
         if (PB2_DEV_IS_GPU(d->type)) {
             for (int l = 1; l <= 2; ++l)

@@ -28,6 +28,7 @@ class DeviceStats(C.Structure):
 PARSEC_SYMBOLS = [
     "pb2_init", "pb2_fini", "pb2_mca_param_set_int", "pb2_mca_param_get_int", "pb2_device_cuda_module_init",
     "pb2_mca_device_registration_complete", "pb2_nb_devices", "pb2_mca_device_get", "pb2_device_get_stats",
+    "pb2_devices_statistics_string",
     "pb2_device_index", "pb2_device_type", "pb2_device_memory_register", "pb2_device_memory_unregister",
     "pb2_device_memory_release", "pb2_device_data_advise", "pb2_device_taskpool_register",
     "pb2_device_taskpool_unregister", "pb2_device_kernel_scheduler", "pb2_device_zone_malloc", "pb2_device_zone_free",
@@ -63,6 +64,7 @@ def lib():
         "pb2_device_cuda_module_init": (C.c_int, [vp, C.c_int, C.c_int, P(vp)]),
         "pb2_mca_device_registration_complete": (C.c_int, [vp]), "pb2_nb_devices": (C.c_int, [vp]),
         "pb2_mca_device_get": (vp, [vp, C.c_int]), "pb2_device_get_stats": (C.c_int, [vp, P(DeviceStats)]),
+        "pb2_devices_statistics_string": (C.c_int, [vp, C.c_char_p, C.c_size_t]),
         "pb2_device_index": (C.c_int, [vp]), "pb2_device_type": (C.c_int, [vp]),
         "pb2_device_memory_register": (C.c_int, [vp, vp, vp, C.c_size_t]),
         "pb2_device_memory_unregister": (C.c_int, [vp, vp, vp]), "pb2_device_memory_release": (C.c_int, [vp]),
@@ -146,6 +148,12 @@ class Context:
 
     def device(self, index):
         return C.c_void_p(self.l.pb2_mca_device_get(self.h, index))
+
+    def statistics_table(self):
+        n = self.l.pb2_devices_statistics_string(self.h, None, 0)
+        buf = C.create_string_buffer(n)
+        self.l.pb2_devices_statistics_string(self.h, buf, n)
+        return buf.value.decode()
 
     def stats(self, dev):
         st = DeviceStats()

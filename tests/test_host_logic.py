@@ -371,3 +371,22 @@ def test_user_submit_tasks_get_their_own_lane():
         pos = {int(task): i for i, task in enumerate(t)}
         for tile in range(3):
             assert pos[3 * tile] < pos[3 * tile + 1] < pos[3 * tile + 2]
+
+
+def test_statistics_table_reports_what_the_devices_did():
+    """parsec_devices_print_statistics (device.c:499-590): per device kernels, required vs moved bytes, evictions."""
+    K, NB, tb = 6, 4, 256
+    host = np.zeros(K * tb // 4, np.int32)
+    with R.Context(cuda_devices=(0,), dry_run=True) as ctx:
+        dc = ctx.block_cyclic(4, tb // 4, 1, K * tb // 4, 1, mat=host)
+        C.c_void_p(ctx.l.pb2_ptg_ex05_broadcast_new(ctx.h, dc, K, NB))
+        ctx.wait()
+        table = ctx.statistics_table()
+    rows = [l for l in table.splitlines() if l.strip().startswith("2 |")]
+    assert len(rows) == 1 and "cuda(0)" in rows[0]
+    cols = [c.strip() for c in rows[0].split("|")]
+    F = NB // 2 + 1
+    assert int(cols[2]) == K * (1 + F)                               # kernels
+    assert cols[4] == "6.00 KB" and cols[5].startswith("1.50 KB") and "25.00" in cols[5]   # each tile H2D once of (1+F) uses
+    assert int(cols[10]) == 1 and int(cols[11]) == K * F
+    assert table.splitlines()[-1].strip().startswith("all")
