@@ -1359,6 +1359,17 @@ int pb2_device_data_advise(pb2_device_module_t* dev, pb2_data_t* data, int advic
 int pb2_fini(pb2_context_t** pctx) {
     if (!pctx || !*pctx) return PB2_ERR_BAD_PARAM;
     pb2_context_t* ctx = *pctx;
+    // windows still in flight (a wait that returned an error): let them finish on the device and drop them before the
+    // tasks they point to go away
+    for (auto* d : ctx->devices)
+        while (!d->inflight.empty()) {
+            InFlight* f = reinterpret_cast<InFlight*>(d->inflight.front());
+            d->inflight.pop_front();
+            if (f->win) pb2_window_destroy(f->win);
+            window_release(d, f->w);
+            for (pb2_gpu_task_t* g : f->taken) delete g;
+            delete f;
+        }
     while (!ctx->taskpools.empty()) pb2_taskpool_free(ctx->taskpools.back());
     if (ctx->mca["device_show_statistics"]) {                      // parsec_mca_device_fini, device.c:393-398
         std::vector<char> table((size_t)pb2_devices_statistics_string(ctx, nullptr, 0));
