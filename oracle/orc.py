@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liboracle.so")
 REF_ZONE_PATH = os.path.join(_HERE, "_ref", "libzone_ref.so")
 REF_DATA_PATH = os.path.join(_HERE, "_ref", "libdata_ref.so")
+REF_TWODBC_PATH = os.path.join(_HERE, "_ref", "libtwodbc_ref.so")
 
 # flow access bits / bodies / flags: same values as include/pb2_engine.h (restated, not imported)
 ACCESS_NONE, ACCESS_READ, ACCESS_WRITE, ACCESS_RW, FLOW_PUSHOUT = 0x00, 0x04, 0x08, 0x0C, 0x40
@@ -214,3 +215,25 @@ def dtd_build(nb_flows, flow_tile, flow_op, ntiles):
         if ne >= 0:
             return src[:ne].copy(), dst[:ne].copy(), fl[:ne].copy(), dep
         cap *= 4
+
+
+_ref_twodbc = None
+
+
+def ref_twodbc():
+    """The reference's own two_dim_rectangle_cyclic.c / grid_2Dcyclic.c / matrix.c, built by Makefile.ref."""
+    global _ref_twodbc
+    if _ref_twodbc is None:
+        L = C.CDLL(REF_TWODBC_PATH)
+        L.ref_twodbc_new.restype = C.c_void_p
+        L.ref_twodbc_new.argtypes = [C.c_int] * 15
+        L.ref_twodbc_free.argtypes = [C.c_void_p]
+        L.ref_twodbc_rank_of.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.ref_twodbc_rank_of.restype = C.c_uint32
+        L.ref_twodbc_key.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.ref_twodbc_key.restype = C.c_uint64
+        L.ref_twodbc_rank_of_key.argtypes = [C.c_void_p, C.c_uint64]
+        L.ref_twodbc_rank_of_key.restype = C.c_uint32
+        L.ref_twodbc_info.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        _ref_twodbc = L
+    return _ref_twodbc

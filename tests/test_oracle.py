@@ -12,6 +12,7 @@ from oracle import orc, orc_dags as dags
 
 HAVE_REF_ZONE = os.path.exists(orc.REF_ZONE_PATH)
 HAVE_REF_DATA = os.path.exists(orc.REF_DATA_PATH)
+HAVE_REF_TWODBC = os.path.exists(orc.REF_TWODBC_PATH)
 
 
 def tiles_for(dag, valid=False):
@@ -169,6 +170,54 @@ def test_twodbc_owner_and_slots(P, Q, kp, kq, ip, jq):
         for m in range(d.mt):
             for n in range(d.nt):
                 assert L.orc_twodbc_rank_of(C.byref(d), m, n) == (m % P) * Q + (n % Q)
+
+
+@pytest.mark.skipif(not HAVE_REF_TWODBC, reason="oracle/_ref/libtwodbc_ref.so not built (needs /root/reference)")
+def test_twodbc_oracle_and_product_equal_reference_build():
+    """The reference's own two_dim_rectangle_cyclic.c (compiled from /root/reference) vs the oracle's restatement vs
+    the product's pb2_matrix_block_cyclic_new: owner, key, derived sizes, for plain, k-cyclic and offset grids, full
+    and sub-matrices, every rank."""
+    from parsec_b200 import runtime as R
+    ref = orc.ref_twodbc()
+    L = orc.lib()
+    rl = R.lib()
+    rng = random.Random(2026)
+    ctxp = C.c_void_p()
+    assert rl.pb2_init(C.byref(ctxp), 1) == 0
+    try:
+        for case in range(60):
+            P, Q = rng.choice([(1, 1), (1, 4), (2, 2), (2, 4), (3, 2), (4, 1)])
+            kp, kq = rng.choice([(1, 1), (1, 1), (2, 1), (2, 3), (3, 2)])
+            ip, jq = rng.randrange(P), rng.randrange(Q)
+            mb, nb = rng.choice([(4, 4), (3, 5), (8, 2)])
+            lm, ln = mb * rng.randrange(3, 14) + rng.randrange(mb), nb * rng.randrange(3, 12) + rng.randrange(nb)
+            i, j = (0, 0) if case % 3 else (rng.randrange(lm // 2), rng.randrange(ln // 2))
+            m, n = lm - i - rng.randrange(0, (lm - i) // 3 + 1), ln - j - rng.randrange(0, (ln - j) // 3 + 1)
+            for rank in range(P * Q):
+                args = (rank, mb, nb, lm, ln, i, j, m, n, P, Q, kp, kq, ip, jq)
+                rd = ref.ref_twodbc_new(*args)
+                od = orc.twodbc(rank, mb, nb, lm, ln, i, j, m, n, P, Q, kp, kq, ip, jq)
+                pd = C.c_void_p(rl.pb2_matrix_block_cyclic_new(ctxp, 4, *args))
+                assert pd.value
+                info = (C.c_int64 * 12)()
+                ref.ref_twodbc_info(rd, info)
+                assert (od.lmt, od.lnt, od.mt, od.nt, od.nb_elem_r, od.nb_elem_c, od.nb_local_tiles, od.bsiz, od.llm, od.lln,
+                        od.rrank, od.crank) == tuple(info), (case, args)
+                pinfo = (C.c_int64 * 8)()
+                assert rl.pb2_dc_info(pd, pinfo) == 0
+                assert tuple(pinfo)[:7] == tuple(info)[:7], (case, args)
+                for mm in range(od.mt):
+                    for nn in range(od.nt):
+                        r_ref = ref.ref_twodbc_rank_of(rd, mm, nn)
+                        assert L.orc_twodbc_rank_of(C.byref(od), mm, nn) == r_ref, (case, args, mm, nn)
+                        assert rl.pb2_dc_rank_of(pd, mm, nn) == r_ref, (case, args, mm, nn)
+                        k_ref = ref.ref_twodbc_key(rd, mm, nn)
+                        assert L.orc_twodbc_key(C.byref(od), mm, nn) == k_ref == rl.pb2_dc_data_key(pd, mm, nn)
+                        assert ref.ref_twodbc_rank_of_key(rd, k_ref) == r_ref
+                rl.pb2_data_collection_free(pd)
+                ref.ref_twodbc_free(rd)
+    finally:
+        rl.pb2_fini(C.byref(ctxp))
 
 
 def test_twodbc_rtt_placement():
