@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "liboracle.so")
 REF_ZONE_PATH = os.path.join(_HERE, "_ref", "libzone_ref.so")
 REF_DATA_PATH = os.path.join(_HERE, "_ref", "libdata_ref.so")
 REF_TWODBC_PATH = os.path.join(_HERE, "_ref", "libtwodbc_ref.so")
+REF_SELECT_PATH = os.path.join(_HERE, "_ref", "libselect_ref.so")
 
 # flow access bits / bodies / flags: same values as include/pb2_engine.h (restated, not imported)
 ACCESS_NONE, ACCESS_READ, ACCESS_WRITE, ACCESS_RW, FLOW_PUSHOUT = 0x00, 0x04, 0x08, 0x0C, 0x40
@@ -237,3 +238,19 @@ def ref_twodbc():
         L.ref_twodbc_info.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         _ref_twodbc = L
     return _ref_twodbc
+
+
+_ref_select = None
+
+
+def ref_select():
+    """The reference's own parsec/mca/device/device.c (parsec_select_best_device), built by Makefile.ref."""
+    global _ref_select
+    if _ref_select is None:
+        L = C.CDLL(REF_SELECT_PATH)
+        L.ref_sel_init.argtypes = [C.c_int, C.c_int]
+        L.ref_sel_add_device.argtypes = [C.c_int, C.c_int64, C.c_int64]
+        L.ref_sel_set_load.argtypes = [C.c_int, C.c_int64, C.c_int64]
+        L.ref_sel_select.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.POINTER(C.c_int64)]
+        _ref_select = L
+    return _ref_select

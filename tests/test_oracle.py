@@ -13,6 +13,7 @@ from oracle import orc, orc_dags as dags
 HAVE_REF_ZONE = os.path.exists(orc.REF_ZONE_PATH)
 HAVE_REF_DATA = os.path.exists(orc.REF_DATA_PATH)
 HAVE_REF_TWODBC = os.path.exists(orc.REF_TWODBC_PATH)
+HAVE_REF_SELECT = os.path.exists(orc.REF_SELECT_PATH)
 
 
 def tiles_for(dag, valid=False):
@@ -258,6 +259,45 @@ def _sel(devs, access, present, pref, owner, skew=20, allow_cpu=0):
     arr = (orc.SelDev * len(devs))(*[orc.SelDev(*d) for d in devs])
     a = [np.array(x, np.int32) for x in (access, present, pref, owner)]
     return orc.lib().orc_select_best_device(arr, len(devs), len(access), *[x.ctypes.data_as(C.c_void_p) for x in a], skew, allow_cpu)
+
+
+@pytest.mark.skipif(not HAVE_REF_SELECT, reason="oracle/_ref/libselect_ref.so not built (needs /root/reference)")
+def test_select_oracle_equals_reference_build():
+    """The reference's own parsec_select_best_device (device.c:100-310, compiled from /root/reference, driven with fake
+    device modules and tasks) vs the oracle: 4000 random tasks over a CPU, the recursive device and four GPUs --
+    affinity by preferred/owner device, ETA with the 20 % skew, taskpool device masks, CPU incarnations with and
+    without load_balance_allow_cpu."""
+    ref = orc.ref_select()
+    CPU, REC, CUDA = 1, 2, 4
+    types = [CPU, REC, CUDA, CUDA, CUDA, CUDA]
+    rng = random.Random(77)
+    ref.ref_sel_init(20, 0)
+    for t in types:
+        assert ref.ref_sel_add_device(t, 0, 1) >= 0
+    for allow_cpu in (0, 1):
+        for skew in (20, 0, 50):
+            ref.ref_sel_init(skew, allow_cpu)
+            for case in range(700):
+                loads = [rng.choice([0, 0, rng.randrange(0, 5000)]) for _ in types]
+                ests = [rng.randrange(1, 400) for _ in types]
+                for d in range(len(types)):
+                    ref.ref_sel_set_load(d, loads[d], ests[d])
+                nb = rng.randrange(1, 5)
+                access = [rng.choice([0x04, 0x08, 0x0C]) for _ in range(nb)]
+                present = [rng.choice([1, 1, 1, 0]) for _ in range(nb)]
+                pref = [rng.choice([-1, -1, -1, 0, 2, 3, 4, 5]) for _ in range(nb)]
+                owner = [rng.choice([-1, 0, 0, 2, 3, 4, 5]) for _ in range(nb)]
+                chore = CUDA | (CPU if rng.random() < 0.4 else 0)
+                mask = rng.choice([0x3f, 0x3f, 0x3d, 0x0f, 0x35, 0x31, 0x03])
+                a = [np.array(x, np.int32) for x in (access, present, pref, owner)]
+                load = C.c_int64()
+                got = ref.ref_sel_select(nb, *[x.ctypes.data_as(C.c_void_p) for x in a], chore, mask, C.byref(load))
+                devs = [(1 if types[d] == CUDA else 0, 1 if types[d] == REC else 0,
+                         1 if ((mask >> d) & 1) and (types[d] & chore) else 0, loads[d], ests[d]) for d in range(len(types))]
+                want = _sel(devs, access, present, pref, owner, skew, allow_cpu)
+                assert got == want, (case, allow_cpu, skew, devs, access, present, pref, owner, chore, hex(mask))
+                if got >= 0:
+                    assert load.value == ests[got]
 
 
 def test_select_best_device_rules():
