@@ -68,10 +68,9 @@ __global__ void pb2_window_reset_kernel(WinDev w, const pb2_tile_t* tiles_init,
 // ---------------------------------------------------------------------------------------------
 // the persistent engine kernel, HBM-bound bodies
 // ---------------------------------------------------------------------------------------------
-// 256 threads, 4 CTAs per SM (<= 64 registers): 1024 threads x 4 x 16 B loads in flight per SM saturate HBM; the
-// cold stage-in / pushout copies may spill, the body loops do not.
 // 64-thread workers, 24 per SM (1536 threads, <= 40 registers): measured best on B200 (sweep in DESIGN.md):
 // many small workers overlap the serial pop / release sections of one task with the streaming of the others.
+// The cold paths (stage-in, sliced stage-in) are out of line so that they do not add to the spills of the body loops.
 #ifndef PB2_HBM_MINB
 #define PB2_HBM_MINB 24
 #endif
