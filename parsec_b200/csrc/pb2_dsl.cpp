@@ -406,10 +406,11 @@ static pb2_taskpool_t* expand(pb2_context_t* ctx, const char* name, std::vector<
     // ---- which datum does each flow carry: follow the input deps back to memory / NEW (iteratively)
     const size_t n = tp->tasks.size();
     std::vector<uint8_t> resolved(n * PB2_MAX_FLOWS, 0);
+    std::vector<std::pair<int32_t, int>> path;
     for (size_t id = 0; id < n; ++id) {
         for (int f = 0; f < tp->tasks[id].nb_flows; ++f) {
             if (resolved[id * PB2_MAX_FLOWS + f]) continue;
-            std::vector<std::pair<int32_t, int>> path;
+            path.clear();
             int32_t cur = (int32_t)id; int cf = f;
             pb2_data_t* found = nullptr;
             for (;;) {
@@ -432,27 +433,32 @@ static pb2_taskpool_t* expand(pb2_context_t* ctx, const char* name, std::vector<
     const double t_2 = expand_now_ms();
     // ---- edges, pushout, startup tasks
     std::vector<std::pair<pb2_data_t*, pb2_data_t*>> finals;
+    // the two emit callbacks are built once (a std::function made from a capturing lambda allocates): they read the
+    // current task / flow through these variables
+    size_t cur_id = 0; int cur_f = 0; pb2_htask_t* cur_t = nullptr;
+    const EmitTask emit_task = [&](int cls, const int32_t* L, int flow) {
+        const int32_t dst = find(cls, L);
+        if (dst < 0) return;
+        pb2i_add_edge(tp, (int32_t)cur_id, dst, flow);
+        // a successor that can only run on the CPU needs the data back on the host (jdf2c.c:6897-6935)
+        if (defs[cls].gpu_body < 0 && (cur_t->access[cur_f] & PB2_FLOW_ACCESS_WRITE)) cur_t->pushout |= (uint8_t)(1 << cur_f);
+    };
+    const EmitMem emit_mem = [&](pb2_data_t* target) {
+        if (target && (cur_t->access[cur_f] & PB2_FLOW_ACCESS_WRITE)) {
+            cur_t->pushout |= (uint8_t)(1 << cur_f);
+            // "-> A(f, k % WS)": the output lands in that collection tile, even when the datum that
+            // travelled along the chain is another one (rtt.jdf:33)
+            if (target != cur_t->data[cur_f] && cur_t->data[cur_f]) finals.emplace_back(cur_t->data[cur_f], target);
+        }
+    };
     for (size_t id = 0; id < n; ++id) {
         pb2_htask_t& t = tp->tasks[id];
         const Key& k = keys[id];
         const ClassDef& cd = defs[k.cls];
+        cur_id = id; cur_t = &t;
         for (int f = 0; f < t.nb_flows; ++f) {
-            cd.out(k.L, f,
-                   [&](int cls, const int32_t* L, int flow) {
-                       const int32_t dst = find(cls, L);
-                       if (dst < 0) return;
-                       pb2i_add_edge(tp, (int32_t)id, dst, flow);
-                       // a successor that can only run on the CPU needs the data back on the host (jdf2c.c:6897-6935)
-                       if (defs[cls].gpu_body < 0 && (t.access[f] & PB2_FLOW_ACCESS_WRITE)) t.pushout |= (uint8_t)(1 << f);
-                   },
-                   [&](pb2_data_t* target) {
-                       if (target && (t.access[f] & PB2_FLOW_ACCESS_WRITE)) {
-                           t.pushout |= (uint8_t)(1 << f);
-                           // "-> A(f, k % WS)": the output lands in that collection tile, even when the datum that
-                           // travelled along the chain is another one (rtt.jdf:33)
-                           if (target != t.data[f] && t.data[f]) finals.emplace_back(t.data[f], target);
-                       }
-                   });
+            cur_f = f;
+            cd.out(k.L, f, emit_task, emit_mem);
             if (t.data[f]) t.data_in[f] = t.data[f]->device_copies[0];
         }
         if (cd.bind) cd.bind(k.L, &t);
