@@ -282,9 +282,20 @@ int pb2_dtd_insert_task_with_task_class(pb2_taskpool_t* tp, pb2_task_class_t* tc
 }
 
 // parsec_dtd_data_flush: bring the newest version of the tile back to its home in host memory
+static void flush_tile_now(pb2_context_t* ctx, pb2_dtd_tile_t* tile);
+
+// the flush itself runs when the pool's inserted tasks have completed (the reference inserts a flush task behind
+// the last user of the tile, insert_function.c:770-860; here the tiles marked for flush are written home at the end
+// of the wait)
+static void arm_flush(pb2_taskpool_t* tp) {
+    pb2_context_t* ctx = tp->ctx;
+    tp->on_complete = [tp, ctx]() { for (auto* t : tp->tile_list) if (t->flushed) flush_tile_now(ctx, t); };
+}
+
 int pb2_dtd_data_flush(pb2_taskpool_t* tp, pb2_dtd_tile_t* tile) {
     if (!tp || !tile) return PB2_ERR_BAD_PARAM;
     tile->flushed = true;
+    arm_flush(tp);
     return PB2_SUCCESS;
 }
 
@@ -308,8 +319,7 @@ static void flush_tile_now(pb2_context_t* ctx, pb2_dtd_tile_t* tile) {
 int pb2_dtd_data_flush_all(pb2_taskpool_t* tp, pb2_data_collection_t* dc) {
     if (!tp || !dc) return PB2_ERR_BAD_PARAM;
     for (auto& kv : tp->tiles) if (kv.first.first == dc) kv.second->flushed = true;
-    pb2_context_t* ctx = tp->ctx;
-    tp->on_complete = [tp, ctx]() { for (auto* t : tp->tile_list) if (t->flushed) flush_tile_now(ctx, t); };
+    arm_flush(tp);
     return PB2_SUCCESS;
 }
 

@@ -747,17 +747,19 @@ int pb2_taskpool_free(pb2_taskpool_t* tp) {
 // gets the replica's version, both become SHARED, the replica moves to the clean LRU).  All the copies of one
 // call travel in ONE kernel launch (pb2_engine_copy_batch) instead of one cudaMemcpyAsync + event per tile.
 static int w2r_flush(pb2_device_module_t* dev, int max_copies) {
-    std::vector<pb2_data_copy_t*> picked;
+    std::vector<pb2_data_copy_t*> picked, stale;
     std::vector<void*> dst; std::vector<const void*> src; std::vector<uint64_t> bytes;
     for (pb2_data_copy_t* c = dev->lru_head[2]; c && (int)picked.size() < max_copies; c = c->lru_next) {
         pb2_data_t* d = c->original;
         pb2_data_copy_t* h = pb2i_host_copy(d);
         if (c->readers != 0 || c->window_tile >= 0 || !h || !h->device_private) continue;
+        if (c->version <= h->version) { stale.push_back(c); continue; }   // another device wrote the tile home since: nothing to save
         void* alias = dev->dry_run ? h->device_private : pb2i_device_visible_host_ptr(dev, d);
         if (!alias) continue;
         picked.push_back(c); dst.push_back(alias); src.push_back(c->device_private); bytes.push_back(d->span);
     }
-    if (picked.empty()) return 0;
+    for (pb2_data_copy_t* c : stale) pb2i_lru_push_back(dev, 1, c);      // not dirty any more: plain eviction candidates
+    if (picked.empty()) return (int)stale.size();
     if (!dev->dry_run) {
         if (pb2_engine_copy_batch(dev->engine, dst.data(), src.data(), bytes.data(), (int32_t)picked.size()) != PB2_SUCCESS) return 0;
         pb2_engine_synchronize(dev->engine);
@@ -771,7 +773,7 @@ static int w2r_flush(pb2_device_module_t* dev, int max_copies) {
         if (d->owner_device == dev->device_index) d->owner_device = -1;
         pb2i_lru_push_back(dev, 1, c);
     }
-    return (int)picked.size();
+    return (int)(picked.size() + stale.size());
 }
 
 // Evict one clean replica not used by the window under construction (reserve_space :1339-1575)
@@ -779,11 +781,16 @@ static bool evict_one(pb2_device_module_t* dev) {
     for (pb2_data_copy_t* c = dev->lru_head[1]; c; c = c->lru_next) {
         if (c->readers != 0 || c->window_tile >= 0) continue;
         pb2_data_t* d = c->original;
+        { const pb2_data_copy_t* h = pb2i_host_copy(d); if (!h || c->version > h->version) continue; }   // never drop the only newest version
         pb2i_lru_remove(dev, c);
         dev->zone.free(c->device_private);
-        d->device_copies[dev->device_index] = nullptr; d->nb_copies--;
+        // The replica object stays attached to its datum, without a slot and INVALID: completed tasks still name it as
+        // their output (data_out) and later consumers as their input (data_in); the reference keeps such objects alive
+        // by reference counting (PARSEC_OBJ_RETAIN in the repo entries).  reserve_space gives it a slot again.
+        c->device_private = nullptr;
+        c->coherency_state = PB2_DATA_COHERENCY_INVALID; c->version = 0; c->readers = 0;
+        c->data_transfer_status = PB2_DATA_STATUS_NOT_TRANSFER;
         if (d->owner_device == dev->device_index) d->owner_device = -1;
-        delete c;
         dev->st.nb_evictions++;
         return true;
     }
@@ -832,6 +839,8 @@ struct Window {
     std::vector<pb2_data_t*> tile_data;
     std::vector<pb2_tile_t> tiles;
     std::vector<pb2_data_copy_t*> tile_src;
+    std::vector<uint8_t> tile_staged;       // the window moves this tile in for its first reader (decided at build, by version)
+    std::vector<pb2_data_copy_t*> src_held; // peer replicas pinned (readers++) as stage-in sources until the window retires
     std::vector<pb2_task_t> tasks;
     std::vector<uint32_t> succ;
     std::vector<int32_t> ready;
@@ -938,11 +947,15 @@ static int build_window(pb2_device_module_t* dev, Window& w, std::vector<pb2_gpu
         const bool valid_here = g->coherency_state != PB2_DATA_COHERENCY_INVALID && g->version >= newest;
         pb2_data_copy_t* src = valid_here ? nullptr : stage_in_source(dev, d);
         w.tile_src[i] = src;
+        // a peer GPU's replica that this window will read from must stay where it is until the window has retired: hold
+        // a reader on it, like the reference does for D2D sources (device_gpu.c:1925-1975, released :2461-2526)
+        if (src && src->device_index >= 2 && src->device_index != dev->device_index) { src->readers++; w.src_held.push_back(src); }
         pb2_data_copy_t* h = pb2i_host_copy(d);
         const bool is_new = (d->dc == nullptr) && h && h->version == 0 && newest == 0;   // NEW: nothing to pull (:2049)
         if (valid_here) { tl.state = PB2_TILE_VALID; tl.version = g->version; }
         else if (is_new) { tl.state = PB2_TILE_VALID; tl.version = 0; w.tile_src[i] = nullptr; }
         else { tl.state = PB2_TILE_INVALID; tl.version = src ? src->version : 0; }
+        w.tile_staged.push_back(tl.state == PB2_TILE_INVALID && src != nullptr);
         tl.src_kind = (src && src->device_index >= 2) ? PB2_SRC_PEER : PB2_SRC_HOST;
         // the home of the tile for pushout is always the host copy; a peer source is only used for stage-in
         void* host_alias = dev->dry_run ? (h ? h->device_private : nullptr) : pb2i_device_visible_host_ptr(dev, d);
@@ -981,6 +994,8 @@ static int build_window(pb2_device_module_t* dev, Window& w, std::vector<pb2_gpu
 }
 
 static void window_release(pb2_device_module_t* dev, Window& w) {
+    for (pb2_data_copy_t* c : w.src_held) c->readers--;
+    w.src_held.clear();
     for (pb2_htask_t* t : w.order) t->window_index = -1;
     for (pb2_data_t* d : w.tile_data) if (d->device_copies[dev->device_index]) {
         d->device_copies[dev->device_index]->window_tile = -1; d->device_copies[dev->device_index]->window_owner = nullptr;
@@ -1000,6 +1015,12 @@ static void retire_task_bookkeeping(pb2_device_module_t* dev, Window& w, pb2_hta
         pb2_data_copy_t* g = d->device_copies[di];
         const uint8_t acc = t->access[f];
         pb2_data_copy_t* in = t->data_in[f] ? t->data_in[f] : pb2i_host_copy(d);
+        // the copy the task was given as input may have been evicted (and written back) since: the bytes then came from
+        // the source chosen when the window was built (stage_in_source: newest valid replica, normally the host copy)
+        if (in->coherency_state == PB2_DATA_COHERENCY_INVALID && in->device_index >= 2) {
+            pb2_data_copy_t* src = w.tile_src[g->window_tile];
+            in = src ? src : pb2i_host_copy(d);
+        }
         dev->st.required_data_in += d->span;                                          // :2055
         if (in == g) {
             // "data already located in the right place" (:1820-1843): no ownership call at all
@@ -1010,6 +1031,18 @@ static void retire_task_bookkeeping(pb2_device_module_t* dev, Window& w, pb2_hta
             pb2_data_copy_t* cand = (!(acc & PB2_FLOW_ACCESS_WRITE) && w.tile_src[g->window_tile]) ? w.tile_src[g->window_tile] : in;
             int from = pb2_data_start_transfer_ownership_to_copy(ctx, d, (uint8_t)di, acc);
             if (d->dc == nullptr && in->device_index == 0 && in->version == 0) from = -1;   // NEW, untouched (:2049-2052)
+            // The window decided by VERSION whether this replica had to be refreshed (build_window: valid_here) and the
+            // kernel moved the bytes for the first reader.  The coherency states alone can say "no transfer": a write to a
+            // replica that is already in place leaves the other GPUs' older replicas SHARED (:1832-1836).  The replay
+            // follows what was done.
+            if ((acc & PB2_FLOW_ACCESS_READ) && w.tile_staged[(size_t)g->window_tile]) {
+                w.tile_staged[(size_t)g->window_tile] = 0;
+                if (w.tile_src[g->window_tile]) cand = w.tile_src[g->window_tile];
+                if (from == -1 && !(d->dc == nullptr && cand->device_index == 0 && cand->version == 0)) {
+                    from = cand->device_index;
+                    g->coherency_state = PB2_DATA_COHERENCY_INVALID;
+                }
+            }
             if (from == -1) {
                 g->data_transfer_status = PB2_DATA_STATUS_COMPLETE_TRANSFER;
                 pb2_data_end_transfer_ownership_to_copy(d, (uint8_t)di, acc);
@@ -1243,7 +1276,12 @@ static int retire_one(pb2_device_module_t* dev) {
     for (pb2_data_t* d : w.tile_data) {
         pb2_data_copy_t* g = d->device_copies[dev->device_index];
         if (!g) continue;
-        pb2i_lru_push_back(dev, g->coherency_state == PB2_DATA_COHERENCY_OWNED ? 2 : 1, g);
+        // dirty = newer than the host copy.  (The reference decides by "a task wrote this flow and did not push it out",
+        // device_gpu.c:3256-3289; the coherency state alone is not enough: a write to a replica that was already in
+        // place leaves it SHARED, :1832-1836, and a SHARED replica on the clean list would be dropped without write-back.)
+        const pb2_data_copy_t* h = pb2i_host_copy(d);
+        const bool dirty = g->coherency_state == PB2_DATA_COHERENCY_OWNED || !h || g->version > h->version;
+        pb2i_lru_push_back(dev, dirty ? 2 : 1, g);
     }
     window_release(dev, w);
     for (pb2_gpu_task_t* g : f->taken) { dev->mutex--; delete g; }    // release_device_task

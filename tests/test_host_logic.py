@@ -390,3 +390,70 @@ def test_statistics_table_reports_what_the_devices_did():
     assert cols[4] == "6.00 KB" and cols[5].startswith("1.50 KB") and "25.00" in cols[5]   # each tile H2D once of (1+F) uses
     assert int(cols[10]) == 1 and int(cols[11]) == K * F
     assert table.splitlines()[-1].strip().startswith("all")
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_dtd_pools_under_pipelining_and_memory_pressure(seed):
+    """Random DTD pools (GPU bodies, CPU bodies, user-submit bodies on shared tiles) on two dry-run GPUs with a device
+    heap far smaller than the working set and windows cut into small pipelined pieces: every task completes exactly
+    once, in an order that respects every RAW / WAW / WAR hazard of the insertion order, and the host copy of every
+    tile ends at version == number of writers after the final flush."""
+    rng = np.random.default_rng(seed)
+    ntiles, ntasks, tb = 10, 120, 1024
+    mca = {"device_cuda_memory_number_of_blocks": 6, "device_cuda_memory_block_size": tb,
+           "device_engine_pipeline": 3, "device_engine_pipeline_min_roots": 2}
+    cpu_hook = R.CPU_HOOK(lambda t, p, ip, fp: 0) if hasattr(R, "CPU_HOOK") else None
+    with R.Context(cuda_devices=(0, 1), dry_run=True, mca=mca) as ctx:
+        tp = C.c_void_p(ctx.l.pb2_dtd_taskpool_new(ctx.h))
+        keep = [R.GPU_SUBMIT(lambda d, g, s: 0)]
+        classes = {}
+        for nf in (1, 2):
+            ops = np.array([R.INOUT] * nf, np.int32)
+            for kind in ("gpu", "user"):
+                tc = C.c_void_p(ctx.l.pb2_dtd_create_task_class(tp, b"k", nf, ops.ctypes.data_as(C.c_void_p)))
+                if kind == "gpu":
+                    assert ctx.l.pb2_dtd_task_class_add_chore(tp, tc, R.DEV_CUDA, L.BODY_NOP, None) == 0
+                else:
+                    assert ctx.l.pb2_dtd_task_class_add_submit(tp, tc, keep[0]) == 0
+                classes[(nf, kind)] = tc
+        tiles = [C.c_void_p(ctx.l.pb2_dtd_tile_new(tp, tb)) for _ in range(ntiles)]
+        uses = []                                              # (task, tile, writes)
+        writers = np.zeros(ntiles, np.int64)
+        for t in range(ntasks):
+            nf = int(rng.integers(1, 3))
+            kind = "user" if rng.random() < 0.15 else "gpu"
+            sel = rng.choice(ntiles, nf, replace=False)
+            ops = [int(rng.choice([R.INPUT, R.INOUT, R.OUTPUT])) for _ in range(nf)]
+            arr = (C.c_void_p * nf)(*[tiles[int(i)] for i in sel])
+            tid = ctx.l.pb2_dtd_insert_task_with_task_class(tp, classes[(nf, kind)], int(rng.integers(0, 4)), R.DEV_CUDA, arr,
+                                                            np.array(ops, np.int32).ctypes.data_as(C.c_void_p), None, 0.0)
+            assert tid == t
+            for i, op in zip(sel, ops):
+                uses.append((t, int(i), op != R.INPUT))
+                writers[int(i)] += op != R.INPUT
+            if t % 37 == 36:
+                ctx.wait()                                      # several rounds: later inserts chain behind completed tasks
+        for tl in tiles:
+            ctx.l.pb2_dtd_data_flush(tp, tl)
+        ctx.wait()
+        order, dev = ctx.trace(tp)
+        assert sorted(order.tolist()) == list(range(ntasks))
+        pos = np.empty(ntasks, np.int64)
+        pos[order] = np.arange(ntasks)
+        last_writer, readers = {}, {}
+        for t, tile, w in uses:                                # hazards of the sequential insertion order
+            if tile in last_writer:
+                assert pos[last_writer[tile]] < pos[t], (seed, "RAW/WAW", last_writer[tile], t, tile)
+            if w:
+                for r in readers.get(tile, []):
+                    if r != t:
+                        assert pos[r] < pos[t], (seed, "WAR", r, t, tile)
+                last_writer[tile] = t; readers[tile] = []
+            else:
+                readers.setdefault(tile, []).append(t)
+        st = [ctx.stats(d) for d in ctx.devices]
+        assert sum(s["executed_tasks"] for s in st) == ntasks
+        assert sum(s["windows_launched"] for s in st) > 3
+        for i, tl in enumerate(tiles):                         # flushed home: the host copy carries the last version
+            hc = ctx.copy_state(C.c_void_p(ctx.l.pb2_dtd_tile_data(tl)), 0)
+            assert hc["version"] == writers[i], (seed, i, hc, int(writers[i]))
