@@ -5,9 +5,9 @@ EXTRA     ?=
 NVCCFLAGS := $(EXTRA) -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v
 CSRC      := parsec_b200/csrc
 LIB       := parsec_b200/libparsec_b200.so
-CU_SRCS   := $(CSRC)/pb2_engine.cu
+CU_SRCS   := $(CSRC)/pb2_engine.cu $(CSRC)/pb2_stream.cu
 CPP_SRCS  := $(wildcard $(CSRC)/*.cpp)
-HDRS      := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) $(wildcard include/*.h)
+HDRS      := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.hpp) $(wildcard include/*.h)
 
 all: $(LIB) oracle
 

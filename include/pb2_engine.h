@@ -127,7 +127,8 @@ typedef struct pb2_engine_params_s {
     int32_t  workers_per_sm;   /* CTAs per SM for HBM-body windows (default 4)                               */
     int32_t  threads;          /* threads per CTA for HBM-body windows (default 256)                         */
     int32_t  max_workers;      /* 0 = all; 1 = single worker => deterministic FIFO order (tests)             */
-    int32_t  stage_mode;       /* 0 = LDG/STG vector copy, 1 = TMA bulk copy through shared memory            */
+    int32_t  stage_mode;       /* tile mover of the HBM-body kernels: 0 = TMA bulk copy (cp.async.bulk through a
+                                * shared-memory ring, default), 1 = SIMT 16-byte LDG/STG loops                      */
     int32_t  queue_policy;     /* 0 = FIFO ring, 1 = successors-first (hot ring before FIFO ring)             */
     int32_t  timeout_ms;       /* device-side watchdog: a window that makes no progress for this long aborts
                                 * (default 20000); a malformed DAG must never hang the GPU                   */

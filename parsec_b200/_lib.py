@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libparsec_b200.so")
+# PB2_LIB_PATH: development aid (sweeps over build variants); the default is the in-tree library
+LIB_PATH = os.environ.get("PB2_LIB_PATH") or os.path.join(_HERE, "libparsec_b200.so")
 
 PB2_SUCCESS = 0
 PB2_ERROR = -1

@@ -21,36 +21,37 @@ namespace pb2 {
 #endif
 constexpr int kUnroll = PB2_UNROLL;
 
-// f(uint4& v, size_t first_elem_index) ; elements are 4-byte lanes x,y,z,w
+// f(uint4& v, uint32_t first_elem_index) ; elements are 4-byte lanes x,y,z,w.  Tiles are below 4 GiB
+// (pb2_tile_t::bytes is 32-bit), so all indices are 32-bit: half the address registers of a size_t loop.
 template <bool READ, bool WRITE, class F>
-__device__ __forceinline__ void cta_vec_loop(void* ptr, size_t bytes, F f) {
+__device__ __forceinline__ void cta_vec_loop(void* ptr, uint32_t bytes, F f) {
     uint4* p = reinterpret_cast<uint4*>(ptr);
-    const size_t nvec = bytes >> 4;
-    const size_t tid = threadIdx.x, nt = blockDim.x;
-    const size_t per_iter = nt * kUnroll;
-    size_t base = 0;
+    const uint32_t nvec = bytes >> 4;
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t per_iter = nt * kUnroll;
+    uint32_t base = 0;
     for (; base + per_iter <= nvec; base += per_iter) {
         uint4 v[kUnroll];
 #pragma unroll
         for (int j = 0; j < kUnroll; ++j) {
-            if (READ) v[j] = ld_stream(p + base + j * nt + tid);
+            if (READ) v[j] = ld_stream(p + (base + j * nt + tid));
             else      v[j] = make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
         for (int j = 0; j < kUnroll; ++j) {
-            f(v[j], (base + j * nt + tid) * 4);
-            if (WRITE) st_stream(p + base + j * nt + tid, v[j]);
+            f(v[j], (base + j * nt + tid) * 4u);
+            if (WRITE) st_stream(p + (base + j * nt + tid), v[j]);
         }
     }
-    for (size_t i = base + tid; i < nvec; i += nt) {
+    for (uint32_t i = base + tid; i < nvec; i += nt) {
         uint4 v = READ ? ld_stream(p + i) : make_uint4(0, 0, 0, 0);
-        f(v, i * 4);
+        f(v, i * 4u);
         if (WRITE) st_stream(p + i, v);
     }
     // scalar 4-byte tail (bytes not a multiple of 16)
-    const size_t nelem = bytes >> 2;
+    const uint32_t nelem = bytes >> 2;
     uint32_t* e = reinterpret_cast<uint32_t*>(ptr);
-    for (size_t i = (nvec << 2) + tid; i < nelem; i += nt) {
+    for (uint32_t i = (nvec << 2) + tid; i < nelem; i += nt) {
         uint4 v = make_uint4(READ ? __ldcg(e + i) : 0u, 0, 0, 0);
         // present the single element in lane x only; f must treat y,z,w as don't-care here
         uint4 w = v;
@@ -64,17 +65,19 @@ __device__ __forceinline__ void cta_vec_loop(void* ptr, size_t bytes, F f) {
 // 4-byte (or 1-byte) aligned, handled by the narrower paths.
 // 'remote' source = host-pinned or peer memory (stage-in), else local HBM.
 template <bool REMOTE_SRC>
-__device__ __forceinline__ void cta_copy(void* dst, const void* src, size_t bytes) {
-    const size_t tid = threadIdx.x, nt = blockDim.x;
+__device__ __forceinline__ void cta_copy_simt(void* dst, const void* src, size_t bytes64) {
+    // callers cut copies into pieces below 4 GiB (tiles are); 32-bit indices keep the register count down
+    const uint32_t bytes = (uint32_t)bytes64;
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
     const uintptr_t al = reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src);
-    size_t done = 0;
+    uint32_t done = 0;
     if ((al & 15) == 0) {
         uint4* d = reinterpret_cast<uint4*>(dst);
         const uint4* s = reinterpret_cast<const uint4*>(src);
-        const size_t nvec = bytes >> 4;
-        constexpr int U = REMOTE_SRC ? 8 : kUnroll;   // more bytes in flight over PCIe / NVLink
-        const size_t per_iter = nt * U;
-        size_t base = 0;
+        const uint32_t nvec = bytes >> 4;
+        constexpr int U = kUnroll;
+        const uint32_t per_iter = nt * U;
+        uint32_t base = 0;
         for (; base + per_iter <= nvec; base += per_iter) {
             uint4 v[U];
 #pragma unroll
@@ -83,16 +86,16 @@ __device__ __forceinline__ void cta_copy(void* dst, const void* src, size_t byte
 #pragma unroll
             for (int j = 0; j < U; ++j) st_stream(d + base + j * nt + tid, v[j]);
         }
-        for (size_t i = base + tid; i < nvec; i += nt)
+        for (uint32_t i = base + tid; i < nvec; i += nt)
             st_stream(d + i, REMOTE_SRC ? ld_remote(s + i) : ld_stream(s + i));
         done = nvec << 4;
     } else if ((al & 3) == 0) {
         uint32_t* d = reinterpret_cast<uint32_t*>(dst);
         const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
-        const size_t n = bytes >> 2;
+        const uint32_t n = bytes >> 2;
         constexpr int U = 8;
-        const size_t per_iter = nt * U;
-        size_t base = 0;
+        const uint32_t per_iter = nt * U;
+        uint32_t base = 0;
         for (; base + per_iter <= n; base += per_iter) {
             uint32_t v[U];
 #pragma unroll
@@ -100,12 +103,29 @@ __device__ __forceinline__ void cta_copy(void* dst, const void* src, size_t byte
 #pragma unroll
             for (int j = 0; j < U; ++j) __stcg(d + base + j * nt + tid, v[j]);
         }
-        for (size_t i = base + tid; i < n; i += nt) __stcg(d + i, __ldcg(s + i));
+        for (uint32_t i = base + tid; i < n; i += nt) __stcg(d + i, __ldcg(s + i));
         done = n << 2;
     }
     const unsigned char* sb = reinterpret_cast<const unsigned char*>(src);
     unsigned char* db = reinterpret_cast<unsigned char*>(dst);
-    for (size_t i = done + tid; i < bytes; i += nt) db[i] = sb[i];
+    for (uint32_t i = done + tid; i < bytes; i += nt) db[i] = sb[i];
+}
+
+// The tile mover.  With a bulk ring (HBM-body kernels) the 16-byte aligned bulk of the copy goes through TMA
+// (cp.async.bulk global -> shared -> global, see pb2_dev_utils.cuh) and only a ragged tail (< 16 bytes) or an
+// unaligned pair of addresses takes the SIMT loops; without one (the GEMM kernels keep their shared memory for
+// operand stages) everything is SIMT.  Ends with a CTA barrier in the bulk case.
+template <bool REMOTE_SRC>
+__device__ __forceinline__ void cta_copy(void* dst, const void* src, size_t bytes, BulkSmem* bulk = nullptr) {
+    const uintptr_t al = reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src);
+    if (bulk != nullptr && (al & 15) == 0 && bytes >= 16) {
+        const size_t body = bytes & ~(size_t)15;
+        cta_bulk_copy(dst, src, body, *bulk);
+        if (bytes != body)
+            cta_copy_simt<REMOTE_SRC>(reinterpret_cast<uint8_t*>(dst) + body, reinterpret_cast<const uint8_t*>(src) + body, bytes - body);
+        return;
+    }
+    cta_copy_simt<REMOTE_SRC>(dst, src, bytes);
 }
 
 // Block-wide sum of a 32-bit count; result valid in thread 0.  smem: >= 32 uint32.
@@ -139,18 +159,18 @@ __device__ __forceinline__ uint64_t run_hbm_body(int body, const BodyArgs& a, ui
         return 0;
     case PB2_BODY_FILL_I32: {
         const uint32_t k = (uint32_t)a.iparam[0];
-        cta_vec_loop<false, true>(a.flow[0], a.bytes[0], [k](uint4& v, size_t) { v = make_uint4(k, k, k, k); });
+        cta_vec_loop<false, true>(a.flow[0], a.bytes[0], [k](uint4& v, uint32_t) { v = make_uint4(k, k, k, k); });
         return 0;
     }
     case PB2_BODY_FILL_F32: {
         const uint32_t k = __float_as_uint(a.fparam);
-        cta_vec_loop<false, true>(a.flow[0], a.bytes[0], [k](uint4& v, size_t) { v = make_uint4(k, k, k, k); });
+        cta_vec_loop<false, true>(a.flow[0], a.bytes[0], [k](uint4& v, uint32_t) { v = make_uint4(k, k, k, k); });
         return 0;
     }
     case PB2_BODY_MEMSET_U8: {
         const uint32_t b = (uint32_t)a.iparam[0] & 0xffu;
         const uint32_t k = b | (b << 8) | (b << 16) | (b << 24);
-        cta_vec_loop<false, true>(a.flow[0], a.bytes[0] & ~3u, [k](uint4& v, size_t) { v = make_uint4(k, k, k, k); });
+        cta_vec_loop<false, true>(a.flow[0], a.bytes[0] & ~3u, [k](uint4& v, uint32_t) { v = make_uint4(k, k, k, k); });
         unsigned char* db = reinterpret_cast<unsigned char*>(a.flow[0]);
         for (size_t i = (a.bytes[0] & ~3u) + threadIdx.x; i < a.bytes[0]; i += blockDim.x) db[i] = (unsigned char)b;
         return 0;
@@ -159,8 +179,8 @@ __device__ __forceinline__ uint64_t run_hbm_body(int body, const BodyArgs& a, ui
     case PB2_BODY_CHECK_F32: {
         const uint32_t k = (body == PB2_BODY_CHECK_I32) ? (uint32_t)a.iparam[0] : __float_as_uint(a.fparam);
         uint32_t bad = 0;
-        const size_t nvec_elems = ((size_t)a.bytes[0] >> 4) << 2;
-        cta_vec_loop<true, false>(a.flow[0], a.bytes[0], [&](uint4& v, size_t i) {
+        const uint32_t nvec_elems = (a.bytes[0] >> 4) << 2;
+        cta_vec_loop<true, false>(a.flow[0], a.bytes[0], [&](uint4& v, uint32_t i) {
             if (i < nvec_elems) bad += (v.x != k) + (v.y != k) + (v.z != k) + (v.w != k);
             else                bad += (v.x != k);
         });
@@ -171,12 +191,12 @@ __device__ __forceinline__ uint64_t run_hbm_body(int body, const BodyArgs& a, ui
     }
     case PB2_BODY_INCR_I32: {
         const uint32_t k = (uint32_t)a.iparam[0];
-        cta_vec_loop<true, true>(a.flow[0], a.bytes[0], [k](uint4& v, size_t) { v.x += k; v.y += k; v.z += k; v.w += k; });
+        cta_vec_loop<true, true>(a.flow[0], a.bytes[0], [k](uint4& v, uint32_t) { v.x += k; v.y += k; v.z += k; v.w += k; });
         return 0;
     }
     case PB2_BODY_SCALE_I32: {
         const int32_t k = a.iparam[0];
-        cta_vec_loop<true, true>(a.flow[0], a.bytes[0], [k](uint4& v, size_t) {
+        cta_vec_loop<true, true>(a.flow[0], a.bytes[0], [k](uint4& v, uint32_t) {
             v.x = (uint32_t)((int32_t)v.x * k); v.y = (uint32_t)((int32_t)v.y * k);
             v.z = (uint32_t)((int32_t)v.z * k); v.w = (uint32_t)((int32_t)v.w * k);
         });
@@ -184,23 +204,23 @@ __device__ __forceinline__ uint64_t run_hbm_body(int body, const BodyArgs& a, ui
     }
     case PB2_BODY_ADD_IOTA_I32: {
         const uint32_t e0 = a.elem0;
-        cta_vec_loop<true, true>(a.flow[0], a.bytes[0], [e0](uint4& v, size_t i) {
-            const uint32_t j = e0 + (uint32_t)i;
+        cta_vec_loop<true, true>(a.flow[0], a.bytes[0], [e0](uint4& v, uint32_t i) {
+            const uint32_t j = e0 + i;
             v.x += j; v.y += j + 1; v.z += j + 2; v.w += j + 3;
         });
         return 0;
     }
     case PB2_BODY_IOTA_I32: {
         const uint32_t e0 = a.elem0;
-        cta_vec_loop<false, true>(a.flow[0], a.bytes[0], [e0](uint4& v, size_t i) {
-            const uint32_t j = e0 + (uint32_t)i;
+        cta_vec_loop<false, true>(a.flow[0], a.bytes[0], [e0](uint4& v, uint32_t i) {
+            const uint32_t j = e0 + i;
             v = make_uint4(j, j + 1, j + 2, j + 3);
         });
         return 0;
     }
     case PB2_BODY_INCR_F32: {
         const float k = a.fparam;
-        cta_vec_loop<true, true>(a.flow[0], a.bytes[0], [k](uint4& v, size_t) {
+        cta_vec_loop<true, true>(a.flow[0], a.bytes[0], [k](uint4& v, uint32_t) {
             v.x = __float_as_uint(__uint_as_float(v.x) + k); v.y = __float_as_uint(__uint_as_float(v.y) + k);
             v.z = __float_as_uint(__uint_as_float(v.z) + k); v.w = __float_as_uint(__uint_as_float(v.w) + k);
         });
@@ -223,9 +243,9 @@ __device__ __forceinline__ uint64_t run_hbm_body(int body, const BodyArgs& a, ui
         const float k = a.fparam;
         const uint4* x = reinterpret_cast<const uint4*>(a.flow[0]);
         const uint32_t* xe = reinterpret_cast<const uint32_t*>(a.flow[0]);
-        const size_t n = a.bytes[0] < a.bytes[1] ? a.bytes[0] : a.bytes[1];
-        const size_t nvec_elems = (n >> 4) << 2;
-        cta_vec_loop<true, true>(a.flow[1], n, [&](uint4& v, size_t i) {
+        const uint32_t n = a.bytes[0] < a.bytes[1] ? a.bytes[0] : a.bytes[1];
+        const uint32_t nvec_elems = (n >> 4) << 2;
+        cta_vec_loop<true, true>(a.flow[1], n, [&](uint4& v, uint32_t i) {
             if (i < nvec_elems) {
                 const uint4 xv = ld_stream(x + (i >> 2));
                 v.x = __float_as_uint(fmaf(k, __uint_as_float(xv.x), __uint_as_float(v.x)));

@@ -27,6 +27,7 @@
 
 #include "../../include/pb2_engine.h"
 #include "pb2_sched.cuh"
+#include "pb2_worker.cuh"
 #include "pb2_gemm.cuh"
 #include "pb2_gemm2.cuh"
 
@@ -70,7 +71,7 @@ __global__ void pb2_window_reset_kernel(WinDev w, const pb2_tile_t* tiles_init,
 // ---------------------------------------------------------------------------------------------
 // 64-thread workers, 24 per SM (1536 threads, <= 40 registers): measured best on B200 (sweep in DESIGN.md):
 // many small workers overlap the serial pop / release sections of one task with the streaming of the others.
-// The cold paths (stage-in, sliced stage-in) are out of line so that they do not add to the spills of the body loops.
+// What one worker does with a task is in pb2_worker.cuh (shared with the streaming kernel of pb2_stream.cu).
 #ifndef PB2_HBM_MINB
 #define PB2_HBM_MINB 24
 #endif
@@ -79,134 +80,54 @@ __global__ void pb2_window_reset_kernel(WinDev w, const pb2_tile_t* tiles_init,
 #endif
 __global__ void __launch_bounds__(PB2_HBM_THREADS, PB2_HBM_MINB)
 pb2_engine_hbm_kernel(WinDev w) {
-    __shared__ __align__(16) pb2_task_t s_task;   // filled with four 16-byte loads
-    __shared__ int32_t    s_id;
-    __shared__ int        s_decide;
-    __shared__ int        s_need;
-    __shared__ int        s_last;
-    __shared__ uint32_t   s_red[32];
+    __shared__ TaskSmem s;
+    __shared__ BulkSmem bulk;
+    if (threadIdx.x == 0) bulk_init(bulk);
+    __syncthreads();
 
     for (;;) {
         if (threadIdx.x == 0) {
             const int32_t e = pop_task(w);
             if (e != kEmpty) __threadfence();   // acquire side: order the tile reads below after the slot read
-            s_id = e;
+            s.entry = e;
         }
         __syncthreads();
-        if (s_id == kEmpty) break;
-        const int32_t id = PB2_ENT_TASK(s_id);
-        const int part = PB2_ENT_PART(s_id);
-        if (threadIdx.x < 4) reinterpret_cast<uint4*>(&s_task)[threadIdx.x] =
+        const int32_t entry = s.entry;
+        if (entry == kEmpty) break;
+        const int32_t id = w.nparts ? PB2_ENT_TASK(entry) : entry;
+        const int part = w.nparts ? PB2_ENT_PART(entry) : 0;
+        if (threadIdx.x < 4) reinterpret_cast<uint4*>(&s.task)[threadIdx.x] =
             __ldg(reinterpret_cast<const uint4*>(&w.tasks[id]) + threadIdx.x);
+        if (threadIdx.x == 0 && part == 0) {
+            w.start_seq[id] = (uint32_t)atomicAdd(&w.ctl->evt.v, 1ull);
+            w.worker[id] = (int32_t)blockIdx.x;
+        }
         __syncthreads();
-        const pb2_task_t& t = s_task;
         const int nparts = task_nparts(w, id);
-
-        // ---- push: reserve + stage in (parsec_device_kernel_push) ----
-        // Thread 0 looks at the tile states once; the resulting mask is CTA-uniform (the states
-        // themselves may change under us, so they must not be re-read per thread around barriers).
-        if (threadIdx.x == 0) {
-            int need = 0;
-            for (int f = 0; f < t.nb_flows; ++f)
-                if (t.tile[f] >= 0 && (t.access[f] & PB2_FLOW_ACCESS_READ) &&
-                    ld_acquire_gpu(&w.tiles[t.tile[f]].state) != PB2_TILE_VALID) need |= 1 << f;
-            s_need = need;
-            if (part == 0) {
-                w.start_seq[id] = (uint32_t)atomicAdd(&w.ctl->evt.v, 1ull);
-                w.worker[id] = (int32_t)blockIdx.x;
-            }
-        }
-        __syncthreads();
-        const int need = s_need;
-        BodyArgs a;
-        a.part = (uint32_t)part; a.elem0 = 0;
-        uint32_t widest = 0;
-        if (nparts > 1)
-            for (int f = 0; f < t.nb_flows; ++f)
-                if (t.tile[f] >= 0 && w.tiles[t.tile[f]].bytes > widest) widest = w.tiles[t.tile[f]].bytes;
-#pragma unroll
-        for (int f = 0; f < PB2_MAX_FLOWS; ++f) {
-            a.flow[f] = nullptr; a.bytes[f] = 0;
-            if (f < t.nb_flows && t.tile[f] >= 0) {
-                pb2_tile_t* tile = &w.tiles[t.tile[f]];
-                // this part's slice: every flow is cut at the same byte offsets (those of the task's widest tile,
-                // 16-byte aligned, the last part takes the remainder), so two-flow bodies pair equal offsets
-                const uint32_t bytes = tile->bytes;
-                const uint32_t per = ((widest / (uint32_t)nparts) + 15u) & ~15u;
-                const uint32_t off = per * (uint32_t)part < bytes ? per * (uint32_t)part : bytes;
-                const uint32_t len = (part == nparts - 1) ? bytes - off : (off + per <= bytes ? per : bytes - off);
-                if ((need >> f) & 1) {
-                    const int ns = tile_slices(w, bytes);
-                    if (ns == 1) stage_in_flow(w, tile, t.access[f], &s_decide);
-                    else if (ns == nparts && bytes == widest) stage_in_slices(w, t.tile[f], ns, part, part + 1, &s_decide);   // my slice only
-                    else {
-                        // the task is cut differently from the tile (its widest flow is another tile)
-                        const uint32_t sper = ((bytes / (uint32_t)ns) + 15u) & ~15u;
-                        int s0 = (int)(off / sper), s1 = (int)((off + len + sper - 1) / sper);
-                        if (s0 > ns - 1) s0 = ns - 1;
-                        if (s1 > ns) s1 = ns;
-                        if (len == 0) s1 = s0;
-                        stage_in_slices(w, t.tile[f], ns, s0, s1, &s_decide);
-                    }
-                }
-                a.flow[f] = reinterpret_cast<uint8_t*>(tile->dev_ptr) + off; a.bytes[f] = len;
-                if (f == 0) a.elem0 = off >> 2;
-                if (threadIdx.x == 0 && part == 0)
-                    w.seen_version[id * PB2_MAX_FLOWS + f] = *reinterpret_cast<volatile uint32_t*>(&tile->version);
-            }
-        }
-        a.iparam[0] = t.iparam[0]; a.iparam[1] = t.iparam[1]; a.iparam[2] = t.iparam[2]; a.fparam = t.fparam;
-
-        // ---- exec: the body (parsec_device_kernel_exec -> submit) ----
-        const unsigned long long r = run_hbm_body(t.body, a, s_red);
-        __syncthreads();
-
-        // ---- pop: pushout + version/coherency epilog (parsec_device_kernel_pop / _epilog) ----
-#pragma unroll
-        for (int f = 0; f < PB2_MAX_FLOWS; ++f) {
-            if (f < t.nb_flows && t.tile[f] >= 0 && (t.access[f] & PB2_FLOW_PUSHOUT) &&
-                (t.access[f] & PB2_FLOW_ACCESS_WRITE)) {
-                pb2_tile_t* tile = &w.tiles[t.tile[f]];
-                const size_t off = reinterpret_cast<uint8_t*>(a.flow[f]) - reinterpret_cast<uint8_t*>(tile->dev_ptr);
-                cta_copy<false>(reinterpret_cast<uint8_t*>(tile->src_ptr) + off, a.flow[f], a.bytes[f]);
-                if (threadIdx.x == 0) atomicAdd(&w.ctl->bytes_d2h.v, (unsigned long long)a.bytes[f]);
-            }
-        }
-        __syncthreads();
+        const unsigned long long r = run_task_part(w, s, &bulk, id, part, nparts);
 
         if (threadIdx.x < 32) {
             __threadfence();   // release side: the body's stores (all threads, ordered by the barrier) become
                                // visible before any successor can observe its dependency word / ring slot
             if (threadIdx.x == 0) {
-                if (r == ~0ull) st_relaxed_gpu(reinterpret_cast<int32_t*>(&w.ctl->done.v), kDoneBadBody);
-                if (t.body == PB2_BODY_CHECK_I32 || t.body == PB2_BODY_CHECK_F32) {
-                    // parts add their mismatch counts; part 0 also carries the tile's first element
-                    if (nparts == 1) w.result[id] = r; else if (r) atomicAdd(&w.result[id], r);
-                    if (r >> 32) atomicAdd(&w.ctl->body_errors.v, r >> 32);
-                } else if (part == 0) w.result[id] = r;
+                const pb2_task_t& t = s.task;
+                store_result(w, t, id, part, nparts, r);
                 // the last part to finish retires the task (fence / RMW chain orders every part's stores before it)
                 int last = 1;
                 if (nparts > 1) { last = atomicSub(&w.parts_left[id], 1) == 1; __threadfence(); }
-                s_last = 0; s_need = last;
+                s.window_done = 0; s.last = last;
                 if (last) {
-                    for (int f = 0; f < t.nb_flows; ++f) {
-                        if (t.tile[f] < 0 || !(t.access[f] & PB2_FLOW_ACCESS_WRITE)) continue;
-                        pb2_tile_t* tile = &w.tiles[t.tile[f]];
-                        // version = candidate->version + 1 for WRITE flows (device_gpu.c:2148-2152)
-                        *reinterpret_cast<volatile uint32_t*>(&tile->version) =
-                            *reinterpret_cast<volatile uint32_t*>(&tile->version) + 1;
-                        if (!(t.access[f] & PB2_FLOW_ACCESS_READ)) st_relaxed_gpu(&tile->state, PB2_TILE_VALID);
-                    }
+                    epilog_written_flows(w, t);
                     w.end_seq[id] = (uint32_t)atomicAdd(&w.ctl->evt.v, 1ull);
                     // the retire log is written before the out-edges are released, so that it is a linear
                     // extension of the DAG's partial order (a successor can only retire after us)
-                    s_last = retire_task(w, id) ? 1 : 0;
+                    s.window_done = retire_task(w, id) ? 1 : 0;
                     __threadfence();
                 }
             }
             __syncwarp();
-            if (s_need) { release_successors_warp(w, t); release_remote_warp(w, id); }
-            if (threadIdx.x == 0 && s_last) {
+            if (s.last) { release_successors_warp(w, s.task); release_remote_warp(w, id); }
+            if (threadIdx.x == 0 && s.window_done) {
                 __threadfence();
                 st_release_gpu(reinterpret_cast<int32_t*>(&w.ctl->done.v), kDoneOK);
             }
@@ -241,24 +162,7 @@ pb2_copy_batch_kernel(const CopyDesc* __restrict__ d, int32_t n) {
 // =============================================================================================
 using namespace pb2;
 
-struct pb2_engine_s {
-    int cuda_device = 0;
-    cudaDeviceProp prop{};
-    pb2_engine_params_t params{};
-    cudaStream_t stream = nullptr;       // where engine work is enqueued
-    cudaStream_t own_stream = nullptr;   // created by the engine
-    cudaStream_t up_stream = nullptr;    // descriptor uploads of the NEXT window: not ordered behind the running one
-    cudaStream_t dma_stream = nullptr;   // pb2_engine_prefetch_h2d
-    cudaEvent_t dma_ev = nullptr;
-    bool dma_pending = false;
-    int nworkers = 0;
-    int nworkers_gemm = 0;
-    std::string last_error;
-    std::mutex mu;
-    bool shared_windows = false;
-    const int32_t* next_rs_begin = nullptr;   // remote out-degree CSR of the next shared window (not owned)
-    std::map<void*, std::pair<size_t, void*>> registered;   // host ptr -> (bytes, device alias)
-};
+#include "pb2_engine_priv.hpp"
 
 struct pb2_window_s {
     pb2_engine_t* e = nullptr;
@@ -282,19 +186,6 @@ struct pb2_window_s {
     std::vector<void*> allocs;
     std::vector<void*> peer_ptrs;
 };
-
-#define PB2_CUDA(e, call)                                                                        \
-    do {                                                                                         \
-        cudaError_t err__ = (call);                                                              \
-        if (err__ != cudaSuccess) {                                                              \
-            char buf__[512];                                                                     \
-            snprintf(buf__, sizeof buf__, "%s:%d %s -> %s", __FILE__, __LINE__, #call,           \
-                     cudaGetErrorString(err__));                                                 \
-            if (e) (e)->last_error = buf__;                                                      \
-            fprintf(stderr, "pb2: CUDA error %s\n", buf__);                                      \
-            return PB2_ERR_DEVICE;                                                               \
-        }                                                                                        \
-    } while (0)
 
 template <class T>
 static int dev_alloc_copy(pb2_window_t* w, T** dptr, const T* host, size_t n) {

@@ -187,7 +187,7 @@ pb2_engine_gemm_kernel(WinDev w, const CUtensorMap* __restrict__ tmaps) {
             for (int f = 0; f < t.nb_flows; ++f) {
                 if (t.tile[f] < 0) continue;
                 pb2_tile_t* tile = &w.tiles[t.tile[f]];
-                if ((need >> f) & 1) stage_in_flow(w, tile, t.access[f], &sh.decide);
+                if ((need >> f) & 1) stage_in_flow(stage_ctx(w), tile, t.access[f], &sh.decide);
                 if (threadIdx.x == 0)
                     w.seen_version[id * PB2_MAX_FLOWS + f] = *reinterpret_cast<volatile uint32_t*>(&tile->version);
             }

@@ -247,8 +247,8 @@ pb2_engine_gemm2_kernel(Win2Dev g) {
                     __syncthreads();
                     if (sh.need) {
                         const int ns = tile_slices(w, tile->bytes);
-                        if (ns == 1) stage_in_flow(w, tile, acc, &sh.decide);
-                        else stage_in_slices(w, tile_id, ns, 0, ns, &sh.decide);     // take what nobody has claimed, wait for the rest
+                        if (ns == 1) stage_in_flow(stage_ctx(w), tile, acc, &sh.decide);
+                        else stage_in_slices(stage_ctx(w), tile_id, ns, 0, ns, &sh.decide);     // take what nobody has claimed, wait for the rest
                         fence_proxy_async();
                     }
                     __syncthreads();
@@ -264,7 +264,7 @@ pb2_engine_gemm2_kernel(Win2Dev g) {
                         pb2_tile_t* tile = &w.tiles[t.tile[f]];
                         if (threadIdx.x == 0) sh.need = ld_acquire_gpu(&tile->state) != PB2_TILE_VALID;
                         __syncthreads();
-                        if (sh.need) { stage_in_flow(w, tile, t.access[f], &sh.decide); fence_proxy_async(); }
+                        if (sh.need) { stage_in_flow(stage_ctx(w), tile, t.access[f], &sh.decide); fence_proxy_async(); }
                         __syncthreads();
                     }
                 }

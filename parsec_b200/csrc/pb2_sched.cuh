@@ -208,8 +208,17 @@ __device__ __forceinline__ bool retire_task(const WinDev& w, int32_t id) {
 // ---------------------------------------------------------------------------------------------
 // stage-in / stage-out of one flow by the whole CTA
 // ---------------------------------------------------------------------------------------------
+// What the out-of-line stage-in helpers need from the window, passed BY VALUE in registers: a reference to the
+// kernel-parameter struct would force a 300-byte local-memory copy of it in every caller.
+struct StageCtx {
+    pb2_tile_t* tiles; Ctl* ctl; uint32_t* slice_claim; uint32_t* slice_done; int32_t use_bulk;
+};
+__device__ __forceinline__ StageCtx stage_ctx(const WinDev& w) {
+    return StageCtx{w.tiles, w.ctl, w.slice_claim, w.slice_done, w.stage_mode == 0 ? 1 : 0};
+}
+
 // Thread 0 decides (s_decide[0]): 1 = this CTA moves the tile, 0 = already valid (possibly after waiting)
-__device__ __noinline__ void stage_in_flow(const WinDev& w, pb2_tile_t* tile, uint8_t access, int* s_decide) {
+static __device__ __noinline__ void stage_in_flow(const StageCtx w, pb2_tile_t* tile, uint8_t access, int* s_decide, BulkSmem* bulk = nullptr) {
     if (threadIdx.x == 0) {
         int decide = 0;
         if (access & PB2_FLOW_ACCESS_READ) {
@@ -227,7 +236,7 @@ __device__ __noinline__ void stage_in_flow(const WinDev& w, pb2_tile_t* tile, ui
     }
     __syncthreads();
     if (*s_decide) {
-        cta_copy<true>(tile->dev_ptr, tile->src_ptr, tile->bytes);
+        cta_copy<true>(tile->dev_ptr, tile->src_ptr, tile->bytes, w.use_bulk ? bulk : nullptr);
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
@@ -253,7 +262,7 @@ __device__ __forceinline__ int tile_slices(const WinDev& w, uint32_t bytes) {
 // bit), so the parts of a wide task -- and the parts of other readers of the same version -- pull the tile in
 // parallel instead of one CTA moving 4 MiB alone; a CTA that finds a slice claimed by someone else only waits
 // for it.  The worker whose slice completes the tile publishes PB2_TILE_VALID.
-__device__ __noinline__ void stage_in_slices(const WinDev& w, int32_t tile_id, int nslices, int s0, int s1, int* s_decide) {
+static __device__ __noinline__ void stage_in_slices(const StageCtx w, int32_t tile_id, int nslices, int s0, int s1, int* s_decide, BulkSmem* bulk = nullptr) {
     pb2_tile_t* tile = &w.tiles[tile_id];
     const uint32_t bytes = tile->bytes;
     const uint32_t sper = ((bytes / (uint32_t)nslices) + 15u) & ~15u;
@@ -266,7 +275,7 @@ __device__ __noinline__ void stage_in_slices(const WinDev& w, int32_t tile_id, i
         if (*s_decide) {
             const uint32_t off = sper * (uint32_t)sl < bytes ? sper * (uint32_t)sl : bytes;
             const uint32_t len = (sl == nslices - 1) ? bytes - off : (off + sper <= bytes ? sper : bytes - off);
-            cta_copy<true>(reinterpret_cast<uint8_t*>(tile->dev_ptr) + off, reinterpret_cast<const uint8_t*>(tile->src_ptr) + off, len);
+            cta_copy<true>(reinterpret_cast<uint8_t*>(tile->dev_ptr) + off, reinterpret_cast<const uint8_t*>(tile->src_ptr) + off, len, w.use_bulk ? bulk : nullptr);
             __syncthreads();
             if (threadIdx.x == 0) {
                 __threadfence();
