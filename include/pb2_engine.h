@@ -207,6 +207,17 @@ int  pb2_engine_copy_batch(pb2_engine_t* engine, void* const* dst, const void* c
 int  pb2_engine_ipc_export(pb2_engine_t* engine, void* dev_ptr, unsigned char handle[64]);
 int  pb2_engine_ipc_open(pb2_engine_t* engine, const unsigned char handle[64], void** dev_ptr);
 int  pb2_engine_ipc_close(pb2_engine_t* engine, void* dev_ptr);
+/* cudaDeviceEnablePeerAccess towards another GPU of this process (parsec_cuda_all_devices_attached,
+ * device_cuda_module.c:144-181): afterwards tile sources may point into that GPU's memory. */
+int  pb2_engine_enable_peer(pb2_engine_t* engine, int peer_cuda_device);
+/* The in-kernel bodies as ONE stand-alone kernel launch on a caller-owned stream: what a BODY [type=CUDA] that names
+ * an engine body enqueues when it runs under a device module that is not the engine's (the reference's stream
+ * engine drives it then, device_gpu.c:2873-2934).  ptrs/bytes: device address and span of each body argument.
+ * CHECK bodies add their mismatch count to a device counter read (and optionally cleared) by
+ * pb2_body_launch_errors. */
+int  pb2_body_launch(void* cuda_stream, int body, int nb_args, void* const* ptrs, const uint64_t* bytes,
+                     const int32_t* iparam3, float fparam);
+int  pb2_body_launch_errors(uint64_t* errors, int reset);
 /* all windows created after this call keep their scheduling arrays in IPC-exportable memory and treat their tasks'
  * dependency goals as counting in-edges from other GPUs too.  next_rs_begin (may be NULL; ntasks+1 entries, must stay
  * valid until the next pb2_window_create returns) is the remote out-edge CSR of the next window: a task with remote

@@ -145,6 +145,35 @@ __global__ void pb2_window2_reset_kernel(Win2Dev g, const int32_t* ready_entries
     if (gid == 0) g.w.ctl->tail.v = (unsigned long long)nentries;
 }
 
+// The same bodies as a stand-alone kernel on a caller's stream: what a BODY [type=CUDA] enqueues when it runs under a
+// device module that is not ours (the reference's stream engine), see pb2_body_launch.
+struct LaunchArgs { void* ptr[PB2_MAX_FLOWS]; unsigned long long bytes[PB2_MAX_FLOWS]; int32_t iparam[3]; float fparam; int32_t body; int32_t nb; };
+__device__ unsigned long long g_body_launch_errors;
+__global__ void __launch_bounds__(256)
+pb2_body_launch_kernel(LaunchArgs la) {
+    __shared__ uint32_t red[32];
+    __shared__ BodyArgs a;
+    // every flow is cut at the same 16-byte aligned offsets, one slice per CTA
+    unsigned long long widest = 0;
+    for (int f = 0; f < la.nb; ++f) widest = la.bytes[f] > widest ? la.bytes[f] : widest;
+    const unsigned long long per = ((widest / gridDim.x) + 15ull) & ~15ull;
+    if (threadIdx.x == 0) {
+        for (int f = 0; f < PB2_MAX_FLOWS; ++f) {
+            const unsigned long long b = f < la.nb ? la.bytes[f] : 0;
+            const unsigned long long off = per * blockIdx.x < b ? per * blockIdx.x : b;
+            const unsigned long long len = (blockIdx.x == gridDim.x - 1) ? b - off : (off + per <= b ? per : b - off);
+            a.flow[f] = f < la.nb ? reinterpret_cast<uint8_t*>(la.ptr[f]) + off : nullptr;
+            a.bytes[f] = (uint32_t)len;
+            if (f == 0) a.elem0 = (uint32_t)(off >> 2);
+        }
+        a.part = blockIdx.x; a.iparam[0] = la.iparam[0]; a.iparam[1] = la.iparam[1]; a.iparam[2] = la.iparam[2]; a.fparam = la.fparam;
+    }
+    __syncthreads();
+    const unsigned long long r = run_hbm_body(la.body, a, red);
+    if (threadIdx.x == 0 && (la.body == PB2_BODY_CHECK_I32 || la.body == PB2_BODY_CHECK_F32) && (r >> 32))
+        atomicAdd(&g_body_launch_errors, r >> 32);
+}
+
 struct CopyDesc { void* dst; const void* src; unsigned long long bytes; };
 
 __global__ void __launch_bounds__(256, 4)
@@ -577,6 +606,50 @@ int pb2_engine_ipc_close(pb2_engine_t* e, void* dev_ptr) {
     PB2_CUDA(e, cudaIpcCloseMemHandle(dev_ptr));
     return PB2_SUCCESS;
 }
+int pb2_engine_enable_peer(pb2_engine_t* e, int peer_cuda_device) {
+    if (!e) return PB2_ERR_BAD_PARAM;
+    if (peer_cuda_device == e->cuda_device) return PB2_SUCCESS;
+    PB2_CUDA(e, cudaSetDevice(e->cuda_device));
+    int can = 0;
+    PB2_CUDA(e, cudaDeviceCanAccessPeer(&can, e->cuda_device, peer_cuda_device));
+    if (!can) return PB2_ERR_NOT_SUPPORTED;
+    cudaError_t err = cudaDeviceEnablePeerAccess(peer_cuda_device, 0);
+    if (err == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return PB2_SUCCESS; }
+    PB2_CUDA(e, err);
+    return PB2_SUCCESS;
+}
+
+int pb2_body_launch(void* cuda_stream, int body, int nb_args, void* const* ptrs, const uint64_t* bytes,
+                    const int32_t* iparam3, float fparam) {
+    if (body < 0 || body >= PB2_BODY_MAX || body == PB2_BODY_GEMM_BF16 || body == PB2_BODY_USER) return PB2_ERR_NOT_SUPPORTED;
+    if (nb_args < 0 || nb_args > PB2_MAX_FLOWS || (nb_args && (!ptrs || !bytes))) return PB2_ERR_BAD_PARAM;
+    LaunchArgs la;
+    memset(&la, 0, sizeof la);
+    unsigned long long widest = 0;
+    for (int f = 0; f < nb_args; ++f) {
+        if (bytes[f] >= (1ull << 32)) return PB2_ERR_VALUE_OUT_OF_BOUNDS;
+        la.ptr[f] = ptrs[f]; la.bytes[f] = bytes[f];
+        widest = bytes[f] > widest ? bytes[f] : widest;
+    }
+    if (iparam3) { la.iparam[0] = iparam3[0]; la.iparam[1] = iparam3[1]; la.iparam[2] = iparam3[2]; }
+    la.fparam = fparam; la.body = body; la.nb = nb_args;
+    if (body == PB2_BODY_NOP) return PB2_SUCCESS;
+    int grid = (int)((widest + 32767) / 32768);             // 32 KiB per CTA
+    if (grid < 1) grid = 1;
+    if (grid > 1184) grid = 1184;
+    if (body == PB2_BODY_ADD_AT_I32) grid = 1;
+    pb2_body_launch_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(la);
+    return cudaGetLastError() == cudaSuccess ? PB2_SUCCESS : PB2_ERR_DEVICE;
+}
+
+int pb2_body_launch_errors(uint64_t* errors, int reset) {
+    unsigned long long v = 0;
+    if (cudaMemcpyFromSymbol(&v, g_body_launch_errors, sizeof v) != cudaSuccess) return PB2_ERR_DEVICE;
+    if (errors) *errors = v;
+    if (reset) { v = 0; if (cudaMemcpyToSymbol(g_body_launch_errors, &v, sizeof v) != cudaSuccess) return PB2_ERR_DEVICE; }
+    return PB2_SUCCESS;
+}
+
 int pb2_engine_set_part_bytes(pb2_engine_t* e, int32_t part_bytes) {
     if (!e) return PB2_ERR_BAD_PARAM;
     e->params.part_bytes = part_bytes == 0 ? 256 * 1024 : part_bytes;

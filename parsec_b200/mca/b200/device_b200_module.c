@@ -1,0 +1,1201 @@
+/*
+ * device_b200_module.c -- one parsec_device_module_t per B200 (parsec/mca/device/device.h:145-189), driven by the
+ * streaming engine of libparsec_b200.so (include/pb2_stream.h): a host-written command ring, ONE persistent sm_100a
+ * kernel per GPU, a retire ring back.
+ *
+ * What is ours and what is PaRSEC's:
+ *   - kernel_scheduler and everything under it (manager election, residency of the flows on the device, the choice of
+ *     a transfer source, eviction and write-back, the run of the body, the epilog and the hand-back to
+ *     __parsec_complete_execution) is this file; it replaces parsec_device_kernel_scheduler and its helpers
+ *     (parsec/mca/device/device_gpu.c:3375-3613, :2592-3292, transfer_gpu.c) for modules of this component;
+ *   - the coherency protocol of parsec_data_t stays PaRSEC's own (parsec_data_start/end_transfer_ownership_to_copy,
+ *     parsec/data.c:313-458): the CPU side of the runtime reads the same states;
+ *   - the device heap is PaRSEC's zone allocator (parsec/utils/zone_malloc.c) through the base-class helpers
+ *     parsec_device_memory_reserve / _release / parsec_device_flush_lru (device_gpu.c:866-1100), exactly like the
+ *     cuda, hip and level_zero components use them.
+ *
+ * Threading (SURVEY.md 8b "Threading"): any worker thread may call kernel_scheduler concurrently.  Callers push their
+ * gpu_task on a lock-free inbox and add one to `owed`; the caller that takes `owed` from 0 to 1 becomes the MANAGER and
+ * keeps driving the device until `owed` is back to 0 (every completed task subtracts one).  Only the manager touches
+ * the LRUs, the command ring and the retire ring, and it completes tasks with its own execution stream.
+ */
+#include "parsec/parsec_config.h"
+#include "parsec/parsec_internal.h"
+#include "parsec/sys/atomic.h"
+#include "parsec/utils/mca_param.h"
+#include "parsec/utils/debug.h"
+#include "parsec/utils/zone_malloc.h"
+#include "parsec/constants.h"
+#include "parsec/data_internal.h"
+#include "parsec/scheduling.h"
+#include "parsec/execution_stream.h"
+#include "parsec/mca/device/device.h"
+#include "parsec/mca/device/device_gpu.h"
+#include "parsec/mca/device/b200/device_b200.h"
+#include "parsec/mca/device/b200/device_b200_internal.h"
+
+#include "pb2_engine.h"
+#include "pb2_stream.h"
+
+#include <cuda_runtime_api.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#include <limits.h>
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* types                                                                                                                */
+/* ------------------------------------------------------------------------------------------------------------------ */
+enum {
+    BT_NEW = 0,        /* popped from the inbox, nothing reserved yet                                   */
+    BT_DMA_IN,         /* copy-engine stage-in of unregistered host memory in progress (event)          */
+    BT_INFLIGHT,       /* descriptor in the command ring / running in the persistent kernel             */
+    BT_LANE,           /* opaque submit body enqueued on the lane stream (event)                        */
+    BT_DMA_OUT,        /* copy-engine pushout in progress (event)                                       */
+    BT_SHADOW          /* look-ahead: runs on the device, the host has not scheduled it yet             */
+};
+
+typedef struct b200_task_s {
+    parsec_list_item_t   item;
+    parsec_gpu_task_t   *gpu_task;        /* NULL while a shadow task waits for the host to schedule it */
+    int32_t              state;
+    int32_t              ticket;          /* pb2_stream ticket, -1 when none */
+    int32_t              body;            /* enum pb2_body_e recorded by parsec_b200_task_body, -1: opaque body */
+    int32_t              nb_args;
+    int32_t              arg_flow[PB2_MAX_FLOWS];
+    int32_t              iparam[3];
+    float                fparam;
+    uint32_t             tile_of_arg[PB2_MAX_FLOWS];
+    uint32_t             peer_src_mask;   /* flows whose source copy on a peer GPU holds a reader for us */
+    parsec_data_copy_t  *peer_src[MAX_PARAM_COUNT];
+    uint32_t             dma_out_mask;    /* pushout flows that need the copy engine (home not device-visible) */
+    uint64_t             result;
+    int32_t              retired;         /* shadow: the device is done with it */
+    cudaEvent_t          ev;
+} b200_task_t;
+
+typedef struct b200_host_range_s { char *base; size_t len; char *alias; } b200_host_range_t;
+
+typedef struct parsec_device_b200_module_s {
+    parsec_device_cuda_module_t super;    /* generated CUDA bodies read cuda_index / the exec stream through this layout */
+    pb2_engine_t        *engine;
+    pb2_stream_t        *stream;
+    int                  dry_run;
+    char                *slab_base;
+    /* inbox + election */
+    parsec_gpu_task_t * volatile inbox;
+    volatile int32_t     owed;
+    volatile int32_t     callers_inside;
+    /* manager-private */
+    parsec_list_t        stalled;         /* b200_task_t waiting for device memory        */
+    parsec_list_t        waiting_event;   /* b200_task_t in BT_DMA_IN / BT_LANE / BT_DMA_OUT, in event order */
+    parsec_list_t        free_bt;
+    b200_task_t         *recording;       /* the task whose submit function is being called in record mode */
+    int32_t              completed_now;   /* completions of the current manager iteration, subtracted from owed at its end */
+    cudaStream_t         dma_stream;
+    parsec_cuda_exec_stream_t *lane;      /* exec_stream[0]: what submit functions receive */
+    parsec_b200_stats_t  st;
+    pb2_retire_t         retbuf[256];
+} parsec_device_b200_module_t;
+
+/* host ranges registered with memory_register: shared by the modules of the component (cudaHostRegisterPortable) */
+static b200_host_range_t *b200_ranges = NULL;
+static int b200_nb_ranges = 0, b200_cap_ranges = 0;
+static parsec_atomic_lock_t b200_ranges_lock = PARSEC_ATOMIC_UNLOCKED;
+
+static int  parsec_b200_submit_is_engine(parsec_advance_task_function_t fn);
+static void parsec_b200_submit_set_engine(parsec_advance_task_function_t fn);
+
+#define B200_DEV(gpu)   ((parsec_device_b200_module_t*)(gpu))
+#define B200_BT(gt)     ((b200_task_t*)(uintptr_t)(gt)->last_data_check_epoch)
+
+#define B200_CUDA(call, what, onerr)                                                              \
+    do { cudaError_t e__ = (call); if( cudaSuccess != e__ ) {                                     \
+        parsec_warning("device_b200: %s: %s", (what), cudaGetErrorString(e__)); onerr; } } while(0)
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* small helpers                                                                                                        */
+/* ------------------------------------------------------------------------------------------------------------------ */
+int parsec_b200_is_b200_device(const parsec_device_module_t *device)
+{
+    return (NULL != device) && (device->component == &parsec_device_b200_component);
+}
+
+int parsec_b200_device_count(void)
+{
+    int n = 0;
+    if( cudaSuccess != cudaGetDeviceCount(&n) ) { (void)cudaGetLastError(); return 0; }
+    return n;
+}
+
+static char *b200_device_visible(const void *host_ptr, size_t len)
+{
+    char *res = NULL;
+    parsec_atomic_lock(&b200_ranges_lock);
+    for( int i = 0; i < b200_nb_ranges; i++ ) {
+        const b200_host_range_t *r = &b200_ranges[i];
+        if( (const char*)host_ptr >= r->base && (const char*)host_ptr + len <= r->base + r->len ) {
+            res = r->alias + ((const char*)host_ptr - r->base);
+            break;
+        }
+    }
+    parsec_atomic_unlock(&b200_ranges_lock);
+    return res;
+}
+
+static b200_task_t *b200_bt_new(parsec_device_b200_module_t *dev, parsec_gpu_task_t *gpu_task)
+{
+    b200_task_t *bt = (b200_task_t*)parsec_list_nolock_pop_front(&dev->free_bt);
+    if( NULL == bt ) {
+        bt = (b200_task_t*)calloc(1, sizeof(b200_task_t));
+        PARSEC_OBJ_CONSTRUCT(&bt->item, parsec_list_item_t);
+        if( !dev->dry_run ) B200_CUDA(cudaEventCreateWithFlags(&bt->ev, cudaEventDisableTiming), "cudaEventCreate", {});
+    }
+    PARSEC_LIST_ITEM_SINGLETON(&bt->item);
+    bt->gpu_task = gpu_task; bt->state = BT_NEW; bt->ticket = -1; bt->body = -1; bt->nb_args = 0;
+    bt->peer_src_mask = 0; bt->dma_out_mask = 0; bt->result = 0; bt->retired = 0;
+    if( NULL != gpu_task ) gpu_task->last_data_check_epoch = (uint64_t)(uintptr_t)bt;
+    return bt;
+}
+
+static void b200_bt_free(parsec_device_b200_module_t *dev, b200_task_t *bt)
+{
+    bt->gpu_task = NULL;
+    parsec_list_nolock_push_front(&dev->free_bt, &bt->item);
+}
+
+static inline int32_t b200_tile_of(const parsec_device_b200_module_t *dev, const parsec_data_copy_t *gpu_copy)
+{
+    return (int32_t)(((char*)gpu_copy->device_private - dev->slab_base) / (ptrdiff_t)dev->super.super.mem_block_size);
+}
+
+/* a reader on a copy that may live on another device: refuse when its owner is reclaiming it (readers < 0) */
+static int b200_copy_acquire_reader(parsec_data_copy_t *copy)
+{
+    int32_t r = copy->readers;
+    while( r >= 0 ) {
+        if( parsec_atomic_cas_int32(&copy->readers, r, r + 1) ) return 1;
+        r = copy->readers;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* eviction and write-back (replaces the tail of parsec_device_data_reserve_space, device_gpu.c:1330-1612, and the     */
+/* W2R pseudo-tasks of transfer_gpu.c:224-362)                                                                         */
+/* ------------------------------------------------------------------------------------------------------------------ */
+static void b200_release_copy_memory(parsec_device_b200_module_t *dev, parsec_data_copy_t *copy)
+{
+    parsec_data_t *original = copy->original;
+    if( NULL != original ) {
+        parsec_atomic_lock(&original->lock);
+        parsec_data_copy_detach(original, copy, dev->super.super.super.device_index);
+        parsec_atomic_unlock(&original->lock);
+    }
+    zone_free(dev->super.super.memory, copy->device_private);
+    copy->device_private = NULL;
+    PARSEC_OBJ_RELEASE(copy);
+    dev->super.super.super.nb_evictions++;
+    dev->st.evictions++;
+}
+
+/* Write the oldest dirty replicas home with the copy engine and move them to the clean LRU.  Blocks the manager for
+ * the duration of the copies (the persistent kernel keeps running beside them). */
+static int b200_write_back_some(parsec_device_b200_module_t *dev, int how_many)
+{
+    parsec_list_item_t *it, *next;
+    int done = 0;
+    if( dev->dry_run ) {
+        for( it = PARSEC_LIST_ITERATOR_FIRST(&dev->super.super.gpu_mem_owned_lru);
+             it != PARSEC_LIST_ITERATOR_END(&dev->super.super.gpu_mem_owned_lru) && done < how_many; it = next ) {
+            parsec_data_copy_t *copy = (parsec_data_copy_t*)it;
+            next = PARSEC_LIST_ITERATOR_NEXT(it);
+            if( 0 != copy->readers ) continue;
+            parsec_data_copy_t *cpu = copy->original->device_copies[0];
+            if( NULL == cpu ) continue;
+            parsec_list_nolock_remove(&dev->super.super.gpu_mem_owned_lru, it);
+            PARSEC_LIST_ITEM_SINGLETON(it);
+            parsec_atomic_lock(&copy->original->lock);
+            cpu->version = copy->version; cpu->coherency_state = PARSEC_DATA_COHERENCY_SHARED;
+            copy->coherency_state = PARSEC_DATA_COHERENCY_SHARED;
+            copy->original->owner_device = 0;
+            parsec_atomic_unlock(&copy->original->lock);
+            parsec_list_nolock_push_back(&dev->super.super.gpu_mem_lru, it);
+            done++;
+        }
+        return done;
+    }
+    parsec_data_copy_t *moved[64];
+    if( how_many > 64 ) how_many = 64;
+    for( it = PARSEC_LIST_ITERATOR_FIRST(&dev->super.super.gpu_mem_owned_lru);
+         it != PARSEC_LIST_ITERATOR_END(&dev->super.super.gpu_mem_owned_lru) && done < how_many; it = next ) {
+        parsec_data_copy_t *copy = (parsec_data_copy_t*)it;
+        next = PARSEC_LIST_ITERATOR_NEXT(it);
+        if( 0 != copy->readers ) continue;
+        parsec_data_copy_t *cpu = copy->original->device_copies[0];
+        if( NULL == cpu || NULL == cpu->device_private ) continue;       /* nowhere to write it: keep it */
+        B200_CUDA(cudaMemcpyAsync(cpu->device_private, copy->device_private, copy->original->span, cudaMemcpyDeviceToHost, dev->dma_stream),
+                  "write-back cudaMemcpyAsync", { continue; });
+        dev->super.super.super.data_out_to_host += copy->original->span;
+        dev->st.bytes_d2h_dma += copy->original->span;
+        moved[done++] = copy;
+    }
+    if( 0 == done ) return 0;
+    B200_CUDA(cudaStreamSynchronize(dev->dma_stream), "write-back synchronize", {});
+    for( int i = 0; i < done; i++ ) {
+        parsec_data_copy_t *copy = moved[i], *cpu = copy->original->device_copies[0];
+        parsec_list_nolock_remove(&dev->super.super.gpu_mem_owned_lru, (parsec_list_item_t*)copy);
+        PARSEC_LIST_ITEM_SINGLETON(copy);
+        parsec_atomic_lock(&copy->original->lock);
+        if( cpu->version < copy->version ) cpu->version = copy->version;
+        cpu->coherency_state = PARSEC_DATA_COHERENCY_SHARED;
+        copy->coherency_state = PARSEC_DATA_COHERENCY_SHARED;
+        if( copy->original->owner_device == (int8_t)dev->super.super.super.device_index ) copy->original->owner_device = 0;
+        parsec_atomic_unlock(&copy->original->lock);
+        parsec_list_nolock_push_back(&dev->super.super.gpu_mem_lru, (parsec_list_item_t*)copy);
+        dev->st.w2r_copies++;
+    }
+    return done;
+}
+
+/* Free one replica nobody uses: oldest clean one first; if every clean replica is busy, write dirty ones home. */
+static int b200_evict_one(parsec_device_b200_module_t *dev)
+{
+    for( int pass = 0; pass < 2; pass++ ) {
+        parsec_list_item_t *it, *next;
+        for( it = PARSEC_LIST_ITERATOR_FIRST(&dev->super.super.gpu_mem_lru);
+             it != PARSEC_LIST_ITERATOR_END(&dev->super.super.gpu_mem_lru); it = next ) {
+            parsec_data_copy_t *copy = (parsec_data_copy_t*)it;
+            next = PARSEC_LIST_ITERATOR_NEXT(it);
+            if( PARSEC_DATA_STATUS_UNDER_TRANSFER == copy->data_transfer_status ) continue;
+            /* tombstone: a peer GPU that wants this replica as a source sees readers < 0 and looks elsewhere */
+            if( !parsec_atomic_cas_int32(&copy->readers, 0, INT_MIN / 2) ) continue;
+            /* never drop the only up-to-date replica */
+            parsec_data_copy_t *cpu = (NULL != copy->original) ? copy->original->device_copies[0] : NULL;
+            if( NULL != copy->original && (NULL == cpu || cpu->version < copy->version) &&
+                copy->original->owner_device == (int8_t)dev->super.super.super.device_index ) {
+                copy->readers = 0;
+                continue;
+            }
+            parsec_list_nolock_remove(&dev->super.super.gpu_mem_lru, it);
+            PARSEC_LIST_ITEM_SINGLETON(it);
+            copy->readers = 0;
+            b200_release_copy_memory(dev, copy);
+            return 1;
+        }
+        if( 0 == b200_write_back_some(dev, 16) ) break;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* residency: every flow gets a replica on this device (parsec_device_data_reserve_space, device_gpu.c:1209)           */
+/* ------------------------------------------------------------------------------------------------------------------ */
+static int b200_reserve(parsec_device_b200_module_t *dev, b200_task_t *bt)
+{
+    parsec_gpu_task_t *gpu_task = bt->gpu_task;
+    parsec_task_t *this_task = gpu_task->ec;
+    const uint8_t my = dev->super.super.super.device_index;
+    parsec_data_copy_t *fresh[MAX_PARAM_COUNT];
+    int nfresh = 0;
+
+    for( uint32_t i = 0; i < gpu_task->nb_flows; i++ ) {
+        const parsec_flow_t *flow = gpu_task->flow_info[i].flow;
+        if( PARSEC_FLOW_ACCESS_NONE == (PARSEC_FLOW_ACCESS_MASK & flow->flow_flags) ) { gpu_task->flow_info[i].flow_span = 0; continue; }
+        parsec_data_copy_t *in = this_task->data[i].data_in;
+        if( NULL == in ) continue;
+        if( in->device_index == my ) { this_task->data[i].data_out = in; continue; }
+        parsec_data_t *master = in->original;
+        parsec_atomic_lock(&master->lock);
+        parsec_data_copy_t *gpu_elem = PARSEC_DATA_GET_COPY(master, my);
+        parsec_atomic_unlock(&master->lock);
+        if( NULL == gpu_elem ) {
+            void *ptr;
+            while( NULL == (ptr = zone_malloc(dev->super.super.memory, gpu_task->flow_info[i].flow_span)) ) {
+                if( !b200_evict_one(dev) ) {
+                    /* nothing can be freed now: undo what this pass allocated and let the task wait for retirements */
+                    for( int k = 0; k < nfresh; k++ ) {
+                        parsec_list_nolock_remove(&dev->super.super.gpu_mem_lru, (parsec_list_item_t*)fresh[k]);
+                        PARSEC_LIST_ITEM_SINGLETON(fresh[k]);
+                        b200_release_copy_memory(dev, fresh[k]);
+                        dev->super.super.super.nb_evictions--; dev->st.evictions--;
+                    }
+                    for( uint32_t k = 0; k < gpu_task->nb_flows; k++ )
+                        if( NULL != this_task->data[k].data_in && this_task->data[k].data_in->device_index != my ) this_task->data[k].data_out = NULL;
+                    return PARSEC_HOOK_RETURN_AGAIN;
+                }
+            }
+            gpu_elem = PARSEC_OBJ_NEW(parsec_data_copy_t);
+            gpu_elem->flags = PARSEC_DATA_FLAG_PARSEC_OWNED | PARSEC_DATA_FLAG_PARSEC_MANAGED;
+            gpu_elem->device_private = ptr;
+            gpu_elem->arena_chunk = (parsec_arena_chunk_t*)dev->super.super.memory;
+            gpu_elem->coherency_state = PARSEC_DATA_COHERENCY_INVALID;
+            gpu_elem->version = 0;
+            gpu_elem->dtt = in->dtt;
+            parsec_atomic_lock(&master->lock);
+            parsec_data_copy_attach(master, gpu_elem, my);
+            parsec_atomic_unlock(&master->lock);
+            /* fresh replicas sit on the clean LRU; a reader or the write detach below protects them */
+            parsec_list_nolock_push_back(&dev->super.super.gpu_mem_lru, (parsec_list_item_t*)gpu_elem);
+            fresh[nfresh++] = gpu_elem;
+        }
+        this_task->data[i].data_out = gpu_elem;
+    }
+    return PARSEC_HOOK_RETURN_DONE;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* stage-in decisions (parsec_device_data_stage_in, device_gpu.c:1799-2165): who is the source, who moves the bytes     */
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* returns 0 ok, 1 when the copy engine was used (the task has to wait for bt->ev), <0 error / retry */
+static int b200_stage_in(parsec_device_b200_module_t *dev, b200_task_t *bt, int for_lane)
+{
+    parsec_gpu_task_t *gpu_task = bt->gpu_task;
+    parsec_task_t *this_task = gpu_task->ec;
+    parsec_device_module_t *mod = &dev->super.super.super;
+    const uint8_t my = mod->device_index;
+    int used_dma = 0;
+
+    for( uint32_t i = 0; i < gpu_task->nb_flows; i++ ) {
+        const parsec_flow_t *flow = gpu_task->flow_info[i].flow;
+        const uint8_t type = (uint8_t)(flow->flow_flags & PARSEC_FLOW_ACCESS_MASK);
+        if( PARSEC_FLOW_ACCESS_NONE == type ) continue;
+        parsec_data_copy_t *in = this_task->data[i].data_in, *out = this_task->data[i].data_out;
+        if( NULL == in || NULL == out ) continue;
+        parsec_data_t *original = in->original;
+        const size_t span = gpu_task->flow_info[i].flow_span;
+        gpu_task->flow_info[i].source = NULL;
+
+        if( in == out ) {      /* the input already is this device's replica */
+            if( PARSEC_FLOW_ACCESS_WRITE & type ) {
+                out->version++;
+                parsec_list_item_ring_chop((parsec_list_item_t*)out); PARSEC_LIST_ITEM_SINGLETON(out);
+                parsec_atomic_lock(&original->lock);
+                original->owner_device = my; out->coherency_state = PARSEC_DATA_COHERENCY_OWNED;
+                parsec_atomic_unlock(&original->lock);
+            }
+            if( PARSEC_FLOW_ACCESS_READ & type ) (void)parsec_atomic_fetch_inc_int32(&out->readers);
+            continue;
+        }
+
+        parsec_atomic_lock(&original->lock);
+        if( PARSEC_FLOW_ACCESS_WRITE & type ) {        /* a written replica leaves the LRUs until the task retires */
+            parsec_list_item_ring_chop((parsec_list_item_t*)out); PARSEC_LIST_ITEM_SINGLETON(out);
+        }
+        /* source: the copy the task was given, unless it is a host copy and a peer GPU we can read holds the same
+         * version (device_gpu.c:1892-1975) */
+        parsec_data_copy_t *src = in;
+        int src_acquired = 0;
+        if( (PARSEC_FLOW_ACCESS_READ & type) ) {
+            if( parsec_mca_device_is_gpu(in->device_index) ) {
+                if( (dev->super.super.peer_access_mask & (1 << in->device_index)) &&
+                    PARSEC_DATA_COHERENCY_INVALID != in->coherency_state && b200_copy_acquire_reader(in) ) src_acquired = 1;
+                else src = original->device_copies[0];
+            } else if( !(PARSEC_FLOW_ACCESS_WRITE & type) ) {
+                for( uint32_t t = 1; t < parsec_nb_devices; t++ ) {
+                    parsec_data_copy_t *cand = original->device_copies[t];
+                    if( t == my || NULL == cand || !(dev->super.super.peer_access_mask & (1 << t)) ) continue;
+                    if( cand->version != in->version || PARSEC_DATA_COHERENCY_INVALID == cand->coherency_state ||
+                        PARSEC_DATA_STATUS_UNDER_TRANSFER == cand->data_transfer_status ) continue;
+                    if( b200_copy_acquire_reader(cand) ) { src = cand; src_acquired = 1; break; }
+                }
+            }
+        }
+        if( NULL == src ) { parsec_atomic_unlock(&original->lock); return PARSEC_HOOK_RETURN_ERROR; }
+
+        int transfer_from = parsec_data_start_transfer_ownership_to_copy(original, my, type);
+        /* what decides is the VERSION: the replica here is current iff it carries the version the task was given */
+        if( -1 != transfer_from && out->version == src->version && PARSEC_DATA_STATUS_COMPLETE_TRANSFER == out->data_transfer_status ) transfer_from = -1;
+        if( NULL == src->device_private ) transfer_from = -1;                /* NEW data nobody wrote yet */
+        if( (NULL == this_task->data[i].source_repo_entry) && (NULL == original->dc) && (0 == in->version) ) transfer_from = -1;
+        if( PARSEC_DATA_STATUS_UNDER_TRANSFER == out->data_transfer_status ) transfer_from = -1;   /* an earlier task brings it */
+        mod->required_data_in += original->span;
+
+        pb2_tile_t tile;
+        memset(&tile, 0, sizeof tile);
+        tile.dev_ptr = out->device_private;
+        tile.bytes = (uint32_t)span;
+        tile.state = PB2_TILE_VALID;
+        tile.src_kind = parsec_mca_device_is_gpu(src->device_index) ? PB2_SRC_PEER : PB2_SRC_HOST;
+        char *home = NULL;              /* where a pushout of this flow goes */
+        if( NULL != original->device_copies[0] && NULL != original->device_copies[0]->device_private )
+            home = b200_device_visible(original->device_copies[0]->device_private, span);
+        tile.src_ptr = home;
+
+        if( -1 == transfer_from ) {
+            if( src_acquired ) { (void)parsec_atomic_fetch_dec_int32(&src->readers); src_acquired = 0; }
+            if( PARSEC_DATA_STATUS_UNDER_TRANSFER != out->data_transfer_status ) {
+                out->data_transfer_status = PARSEC_DATA_STATUS_COMPLETE_TRANSFER;
+                parsec_data_end_transfer_ownership_to_copy(original, my, type);
+            }
+            if( PARSEC_FLOW_ACCESS_WRITE & type ) out->version = src->version + 1;
+        } else {
+            char *visible = (PB2_SRC_PEER == tile.src_kind) ? (char*)src->device_private
+                                                            : b200_device_visible(src->device_private, span);
+            mod->data_in_from_device[src->device_index] += span;
+            mod->nb_data_faults += span;
+            if( NULL != visible && !for_lane && !dev->dry_run ) {
+                /* the persistent kernel pulls it (TMA bulk copy) when the task runs */
+                tile.state = PB2_TILE_INVALID;
+                tile.src_ptr = visible;
+                out->data_transfer_status = PARSEC_DATA_STATUS_UNDER_TRANSFER;
+                if( PB2_SRC_PEER == tile.src_kind ) dev->st.bytes_d2d_kernel += span; else dev->st.bytes_h2d_kernel += span;
+            } else if( !dev->dry_run ) {
+                /* unregistered host memory, or an opaque body that needs the bytes before it is enqueued: copy engine */
+                B200_CUDA(cudaMemcpyAsync(out->device_private, src->device_private, span,
+                                          PB2_SRC_PEER == tile.src_kind ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                          for_lane ? dev->lane->cuda_stream : dev->dma_stream),
+                          "stage-in cudaMemcpyAsync", { parsec_atomic_unlock(&original->lock); return PARSEC_HOOK_RETURN_ERROR; });
+                out->data_transfer_status = PARSEC_DATA_STATUS_UNDER_TRANSFER;
+                dev->st.bytes_h2d_dma += span;
+                used_dma = 1;
+            } else {
+                out->data_transfer_status = PARSEC_DATA_STATUS_UNDER_TRANSFER;
+            }
+            out->version = (PARSEC_FLOW_ACCESS_WRITE & type) ? src->version + 1 : src->version;
+            gpu_task->flow_info[i].source = src_acquired ? src : NULL;
+            if( src_acquired ) { bt->peer_src_mask |= (1u << i); bt->peer_src[i] = src; }
+            /* a pushout of a flow that was pulled from a peer still goes to its host home */
+            if( PB2_SRC_PEER == tile.src_kind && PB2_TILE_INVALID == tile.state && NULL != home && (gpu_task->pushout & (1 << i)) ) {
+                /* the tile has one src_ptr: pull first through the copy engine is not needed -- the kernel stages in
+                 * from src_ptr and pushes out to src_ptr, so a peer-sourced pushout flow uses the DMA pushout below */
+            }
+        }
+        /* the device tile table is rewritten only when what it says changed: the first use of the slot, a new
+         * version to pull, or a new home */
+        tile.version = (PARSEC_FLOW_ACCESS_WRITE & type) ? out->version - 1 : out->version;
+        if( !for_lane ) {
+            const int32_t tid = b200_tile_of(dev, out);
+            if( PB2_SUCCESS != pb2_stream_set_tile(dev->stream, tid, &tile) ) { parsec_atomic_unlock(&original->lock); return PARSEC_HOOK_RETURN_ERROR; }
+        }
+        parsec_atomic_unlock(&original->lock);
+    }
+    return used_dma;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* the body                                                                                                             */
+/* ------------------------------------------------------------------------------------------------------------------ */
+int parsec_b200_task_body(parsec_device_gpu_module_t *gpu_device, parsec_gpu_task_t *gpu_task,
+                          parsec_gpu_exec_stream_t *gpu_stream,
+                          int body, int nb_args, const int *flow_index, const int32_t *iparam, float fparam)
+{
+    if( NULL == gpu_device || NULL == gpu_task || nb_args < 0 || nb_args > PB2_MAX_FLOWS || body < 0 || body >= PB2_BODY_MAX )
+        return PARSEC_HOOK_RETURN_ERROR;
+    for( int a = 0; a < nb_args; a++ )
+        if( flow_index[a] < 0 || (uint32_t)flow_index[a] >= gpu_task->nb_flows ) return PARSEC_HOOK_RETURN_ERROR;
+    if( parsec_b200_is_b200_device(&gpu_device->super) ) {
+        parsec_device_b200_module_t *dev = B200_DEV(gpu_device);
+        b200_task_t *bt = dev->recording;
+        if( NULL == bt || bt->gpu_task != gpu_task ) return PARSEC_HOOK_RETURN_ERROR;
+        bt->body = body; bt->nb_args = nb_args;
+        for( int a = 0; a < nb_args; a++ ) bt->arg_flow[a] = flow_index[a];
+        bt->iparam[0] = iparam ? iparam[0] : 0; bt->iparam[1] = iparam ? iparam[1] : 0; bt->iparam[2] = iparam ? iparam[2] : 0;
+        bt->fparam = fparam;
+        return PARSEC_HOOK_RETURN_DONE;
+    }
+    /* any other GPU module (the reference's stream engine): the same body as a stand-alone kernel on its stream */
+    {
+        void *ptrs[PB2_MAX_FLOWS] = {NULL, NULL, NULL, NULL};
+        uint64_t bytes[PB2_MAX_FLOWS] = {0, 0, 0, 0};
+        int32_t ip[3] = { iparam ? iparam[0] : 0, iparam ? iparam[1] : 0, iparam ? iparam[2] : 0 };
+        for( int a = 0; a < nb_args; a++ ) {
+            ptrs[a] = gpu_task->ec->data[flow_index[a]].data_out->device_private;
+            bytes[a] = gpu_task->flow_info[flow_index[a]].flow_span;
+        }
+        parsec_cuda_exec_stream_t *cs = (parsec_cuda_exec_stream_t*)gpu_stream;
+        return (PB2_SUCCESS == pb2_body_launch((void*)cs->cuda_stream, body, nb_args, ptrs, bytes, ip, fparam))
+               ? PARSEC_HOOK_RETURN_DONE : PARSEC_HOOK_RETURN_ERROR;
+    }
+}
+
+uint64_t parsec_b200_task_result(const parsec_gpu_task_t *gpu_task)
+{
+    const b200_task_t *bt = (const b200_task_t*)(uintptr_t)gpu_task->last_data_check_epoch;
+    return (NULL != bt) ? bt->result : 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* completion: epilog of the flows + hand-back to the runtime (parsec_device_kernel_pop / _epilog, device_gpu.c:2943,  */
+/* :3179, and the complete_task tail of the scheduler, :3562-3590)                                                     */
+/* ------------------------------------------------------------------------------------------------------------------ */
+static void b200_complete(parsec_device_b200_module_t *dev, parsec_execution_stream_t *es, b200_task_t *bt)
+{
+    parsec_gpu_task_t *gpu_task = bt->gpu_task;
+    parsec_task_t *this_task = gpu_task->ec;
+    parsec_device_module_t *mod = &dev->super.super.super;
+
+    for( uint32_t i = 0; i < gpu_task->nb_flows; i++ ) {
+        const parsec_flow_t *flow = gpu_task->flow_info[i].flow;
+        const uint8_t type = (uint8_t)(flow->flow_flags & PARSEC_FLOW_ACCESS_MASK);
+        if( PARSEC_FLOW_ACCESS_NONE == type || NULL == this_task->data[i].data_in ) continue;
+        parsec_data_copy_t *gpu_copy = this_task->data[i].data_out;
+        if( NULL == gpu_copy ) continue;
+        parsec_data_t *original = gpu_copy->original;
+        parsec_atomic_lock(&original->lock);
+        if( PARSEC_DATA_STATUS_UNDER_TRANSFER == gpu_copy->data_transfer_status ) {
+            /* the bytes are here: callback_complete_push (device_gpu.c:2358-2573) */
+            gpu_copy->data_transfer_status = PARSEC_DATA_STATUS_COMPLETE_TRANSFER;
+            parsec_data_end_transfer_ownership_to_copy(original, mod->device_index, type);
+        }
+        if( bt->peer_src_mask & (1u << i) ) (void)parsec_atomic_fetch_dec_int32(&bt->peer_src[i]->readers);
+        if( PARSEC_FLOW_ACCESS_READ & type ) (void)parsec_atomic_fetch_dec_int32(&gpu_copy->readers);
+        if( PARSEC_FLOW_ACCESS_WRITE & type ) {
+            mod->required_data_out += gpu_task->flow_info[i].flow_span;
+            if( gpu_task->pushout & (1 << i) ) {
+                parsec_data_copy_t *cpu_copy = original->device_copies[0];
+                if( NULL != cpu_copy ) {
+                    cpu_copy->version = gpu_copy->version;
+                    cpu_copy->coherency_state = PARSEC_DATA_COHERENCY_SHARED;
+                    gpu_copy->coherency_state = PARSEC_DATA_COHERENCY_SHARED;
+                    cpu_copy->data_transfer_status = PARSEC_DATA_STATUS_COMPLETE_TRANSFER;
+                    mod->data_out_to_host += gpu_task->flow_info[i].flow_span;
+                    if( 0 == (parsec_mpi_allow_gpu_memory_communications & PARSEC_RUNTIME_SEND_GPU_MEMORY) )
+                        this_task->data[i].data_out = cpu_copy;           /* successors consume the host copy */
+                }
+                parsec_list_item_ring_chop((parsec_list_item_t*)gpu_copy); PARSEC_LIST_ITEM_SINGLETON(gpu_copy);
+                parsec_list_nolock_push_back(&dev->super.super.gpu_mem_lru, (parsec_list_item_t*)gpu_copy);
+            } else {
+                gpu_copy->coherency_state = PARSEC_DATA_COHERENCY_OWNED;
+                parsec_list_nolock_push_back(&dev->super.super.gpu_mem_owned_lru, (parsec_list_item_t*)gpu_copy);
+            }
+        } else if( 0 == gpu_copy->readers && 0 != (gpu_copy->flags & PARSEC_DATA_FLAG_PARSEC_OWNED) ) {
+            /* least recently used goes to the front: a replica just read moves to the back of its list */
+            parsec_list_t *l = (PARSEC_DATA_COHERENCY_OWNED == gpu_copy->coherency_state) ? &dev->super.super.gpu_mem_owned_lru
+                                                                                           : &dev->super.super.gpu_mem_lru;
+            parsec_list_item_ring_chop((parsec_list_item_t*)gpu_copy); PARSEC_LIST_ITEM_SINGLETON(gpu_copy);
+            parsec_list_nolock_push_back(l, (parsec_list_item_t*)gpu_copy);
+        }
+        parsec_atomic_unlock(&original->lock);
+    }
+    if( NULL != gpu_task->complete_stage ) {
+        /* the user's completion hook (device_gpu.h:41-43; dtd_test_simple_gemm.c:538) */
+        parsec_gpu_task_t *gt = gpu_task;
+        (void)gpu_task->complete_stage(&dev->super.super, &gt, &dev->lane->super);
+    }
+    __parsec_complete_execution(es, this_task);
+    mod->executed_tasks++;
+    b200_bt_free(dev, bt);
+    gpu_task->last_data_check_epoch = 0;
+    gpu_task->release_device_task(gpu_task);
+    dev->completed_now++;
+}
+
+/* pushout flows whose host home the kernel cannot write (memory that was never registered): copy engine */
+static int b200_dma_pushout(parsec_device_b200_module_t *dev, b200_task_t *bt)
+{
+    parsec_gpu_task_t *gpu_task = bt->gpu_task;
+    int n = 0;
+    if( dev->dry_run ) return 0;
+    for( uint32_t i = 0; i < gpu_task->nb_flows; i++ ) {
+        if( !(bt->dma_out_mask & (1u << i)) ) continue;
+        parsec_data_copy_t *gpu_copy = gpu_task->ec->data[i].data_out;
+        parsec_data_copy_t *cpu_copy = gpu_copy->original->device_copies[0];
+        if( NULL == cpu_copy || NULL == cpu_copy->device_private ) continue;
+        B200_CUDA(cudaMemcpyAsync(cpu_copy->device_private, gpu_copy->device_private, gpu_task->flow_info[i].flow_span,
+                                  cudaMemcpyDeviceToHost, dev->dma_stream), "pushout cudaMemcpyAsync", { continue; });
+        dev->st.bytes_d2h_dma += gpu_task->flow_info[i].flow_span;
+        n++;
+    }
+    if( n ) B200_CUDA(cudaEventRecord(bt->ev, dev->dma_stream), "cudaEventRecord", {});
+    return n;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* one task: from the inbox to the command ring / the lane                                                              */
+/* ------------------------------------------------------------------------------------------------------------------ */
+static int b200_push_engine(parsec_device_b200_module_t *dev, b200_task_t *bt)
+{
+    parsec_gpu_task_t *gpu_task = bt->gpu_task;
+    pb2_task_t t;
+    memset(&t, 0, sizeof t);
+    t.body = (uint8_t)bt->body; t.nb_flows = (uint8_t)bt->nb_args;
+    for( int a = 0; a < PB2_MAX_FLOWS; a++ ) t.tile[a] = -1;
+    for( int a = 0; a < bt->nb_args; a++ ) {
+        const int f = bt->arg_flow[a];
+        const parsec_flow_t *flow = gpu_task->flow_info[f].flow;
+        parsec_data_copy_t *out = gpu_task->ec->data[f].data_out;
+        t.tile[a] = b200_tile_of(dev, out);
+        t.access[a] = (uint8_t)(flow->flow_flags & PARSEC_FLOW_ACCESS_MASK);
+        if( (gpu_task->pushout & (1 << f)) && (PARSEC_FLOW_ACCESS_WRITE & flow->flow_flags) ) {
+            parsec_data_copy_t *cpu = out->original->device_copies[0];
+            if( NULL != cpu && NULL != cpu->device_private && NULL != b200_device_visible(cpu->device_private, gpu_task->flow_info[f].flow_span)
+                && !(bt->peer_src_mask & (1u << f)) )
+                t.access[a] |= PB2_FLOW_PUSHOUT;            /* the worker CTA copies it home */
+            else bt->dma_out_mask |= (1u << f);
+        }
+    }
+    /* pushout flows the body does not name still have to reach the host */
+    for( uint32_t f = 0; f < gpu_task->nb_flows; f++ ) {
+        int named = 0;
+        for( int a = 0; a < bt->nb_args; a++ ) named |= (bt->arg_flow[a] == (int)f);
+        if( !named && (gpu_task->pushout & (1 << f)) && (PARSEC_FLOW_ACCESS_WRITE & gpu_task->flow_info[f].flow->flow_flags) &&
+            NULL != gpu_task->ec->data[f].data_out ) bt->dma_out_mask |= (1u << f);
+    }
+    t.iparam[0] = bt->iparam[0]; t.iparam[1] = bt->iparam[1]; t.iparam[2] = bt->iparam[2]; t.fparam = bt->fparam;
+    t.locals[0] = gpu_task->ec->locals[0].value; t.locals[1] = gpu_task->ec->locals[1].value;
+    int rc = pb2_stream_submit(dev->stream, &t, (uint64_t)(uintptr_t)bt, &bt->ticket);
+    if( PB2_ERR_OUT_OF_RESOURCE == rc ) return PARSEC_HOOK_RETURN_AGAIN;
+    if( PB2_SUCCESS != rc ) { parsec_warning("device_b200: submit failed: %s", pb2_stream_last_error(dev->stream)); return PARSEC_HOOK_RETURN_ERROR; }
+    bt->state = BT_INFLIGHT;
+    dev->st.tasks_engine++;
+    return PARSEC_HOOK_RETURN_DONE;
+}
+
+static int b200_start_task(parsec_device_b200_module_t *dev, parsec_execution_stream_t *es, b200_task_t *bt)
+{
+    parsec_gpu_task_t *gpu_task = bt->gpu_task;
+    int rc;
+    (void)es;
+    if( PARSEC_HOOK_RETURN_DONE != (rc = b200_reserve(dev, bt)) ) return rc;
+
+    /* Which kind of body?  Call the submit function in RECORD mode: a body that names an engine body through
+     * parsec_b200_task_body enqueues nothing and the task goes to the persistent kernel.  A body that did not is an
+     * opaque stream body: it has just enqueued its work on the lane stream, so its inputs must be there first --
+     * such bodies are therefore only probed after a copy-engine stage-in on the same stream. */
+    const int custom_stage = (NULL != gpu_task->stage_in && gpu_task->stage_in != parsec_default_gpu_stage_in) ||
+                             (NULL != gpu_task->stage_out && gpu_task->stage_out != parsec_default_gpu_stage_out);
+    const parsec_task_class_t *tc = gpu_task->ec->task_class;
+    /* engine bodies are recognised by their submit function having been seen naming one (set below, the first time,
+     * after a conservative copy-engine stage-in); dry-run modules never enqueue anything, so they always record */
+    int known_engine = !custom_stage && (dev->dry_run || parsec_b200_submit_is_engine(gpu_task->submit));
+
+    if( known_engine ) {
+        rc = b200_stage_in(dev, bt, 0);
+        if( rc < 0 ) return rc;
+        dev->recording = bt;
+        int src = gpu_task->submit(&dev->super.super, gpu_task, &dev->lane->super);
+        dev->recording = NULL;
+        if( dev->dry_run && bt->body < 0 ) { bt->body = PB2_BODY_NOP; bt->nb_args = 0; }
+        if( src < 0 || bt->body < 0 ) {
+            parsec_warning("device_b200: body of task class %s stopped naming an engine body", tc ? tc->name : "?");
+            return PARSEC_HOOK_RETURN_ERROR;
+        }
+        if( rc > 0 ) {                      /* unregistered host memory: wait for the copy engine, then push */
+            B200_CUDA(cudaEventRecord(bt->ev, dev->dma_stream), "cudaEventRecord", {});
+            bt->state = BT_DMA_IN;
+            parsec_list_nolock_push_back(&dev->waiting_event, &bt->item);
+            return PARSEC_HOOK_RETURN_DONE;
+        }
+        return b200_push_engine(dev, bt);
+    }
+
+    /* stream lane: stage in with the copy engine on the lane stream (or the user's stage_in), run submit, event */
+    rc = b200_stage_in(dev, bt, 1);
+    if( rc < 0 ) return rc;
+    if( custom_stage && NULL != gpu_task->stage_in && gpu_task->stage_in != parsec_default_gpu_stage_in ) {
+        uint32_t mask = 0;
+        for( uint32_t i = 0; i < gpu_task->nb_flows; i++ )
+            if( NULL != gpu_task->ec->data[i].data_out && PARSEC_DATA_STATUS_UNDER_TRANSFER == gpu_task->ec->data[i].data_out->data_transfer_status ) mask |= (1u << i);
+        if( mask && PARSEC_SUCCESS != gpu_task->stage_in(gpu_task, mask, &dev->lane->super) ) return PARSEC_HOOK_RETURN_ERROR;
+    }
+    dev->recording = bt;
+    int src = gpu_task->submit(&dev->super.super, gpu_task, &dev->lane->super);
+    dev->recording = NULL;
+    if( src < 0 && PARSEC_HOOK_RETURN_ASYNC != src ) return PARSEC_HOOK_RETURN_ERROR;
+    if( bt->body >= 0 ) {
+        /* first task of a class whose body names an engine body: remember it, and run THIS one in the kernel too
+         * once its copy-engine stage-in has landed */
+        parsec_b200_submit_set_engine(gpu_task->submit);
+        for( uint32_t i = 0; i < gpu_task->nb_flows; i++ ) {
+            parsec_data_copy_t *out = gpu_task->ec->data[i].data_out;
+            if( NULL == out || NULL == gpu_task->ec->data[i].data_in ) continue;
+            pb2_tile_t tile; memset(&tile, 0, sizeof tile);
+            tile.dev_ptr = out->device_private; tile.bytes = (uint32_t)gpu_task->flow_info[i].flow_span; tile.state = PB2_TILE_VALID;
+            const uint8_t type = (uint8_t)(gpu_task->flow_info[i].flow->flow_flags & PARSEC_FLOW_ACCESS_MASK);
+            tile.version = (PARSEC_FLOW_ACCESS_WRITE & type) ? out->version - 1 : out->version;
+            parsec_data_copy_t *cpu = out->original->device_copies[0];
+            tile.src_ptr = (NULL != cpu && NULL != cpu->device_private) ? b200_device_visible(cpu->device_private, tile.bytes) : NULL;
+            (void)pb2_stream_set_tile(dev->stream, b200_tile_of(dev, out), &tile);
+        }
+        B200_CUDA(cudaEventRecord(bt->ev, dev->lane->cuda_stream), "cudaEventRecord", {});
+        bt->state = BT_DMA_IN;
+        parsec_list_nolock_push_back(&dev->waiting_event, &bt->item);
+        return PARSEC_HOOK_RETURN_DONE;
+    }
+    /* opaque: its kernels are on the lane stream behind the copies; pushouts follow on the same stream */
+    for( uint32_t i = 0; i < gpu_task->nb_flows; i++ )
+        if( (gpu_task->pushout & (1 << i)) && (PARSEC_FLOW_ACCESS_WRITE & gpu_task->flow_info[i].flow->flow_flags) && NULL != gpu_task->ec->data[i].data_out ) {
+            if( NULL != gpu_task->stage_out && gpu_task->stage_out != parsec_default_gpu_stage_out ) {
+                if( PARSEC_SUCCESS != gpu_task->stage_out(gpu_task, 1u << i, &dev->lane->super) ) return PARSEC_HOOK_RETURN_ERROR;
+            } else {
+                parsec_data_copy_t *g = gpu_task->ec->data[i].data_out, *c = g->original->device_copies[0];
+                if( NULL != c && NULL != c->device_private )
+                    B200_CUDA(cudaMemcpyAsync(c->device_private, g->device_private, gpu_task->flow_info[i].flow_span, cudaMemcpyDeviceToHost, dev->lane->cuda_stream),
+                              "lane pushout", { return PARSEC_HOOK_RETURN_ERROR; });
+                dev->st.bytes_d2h_dma += gpu_task->flow_info[i].flow_span;
+            }
+        }
+    B200_CUDA(cudaEventRecord(bt->ev, dev->lane->cuda_stream), "cudaEventRecord", {});
+    bt->state = BT_LANE;
+    dev->st.tasks_lane++;
+    parsec_list_nolock_push_back(&dev->waiting_event, &bt->item);
+    return PARSEC_HOOK_RETURN_DONE;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* submit functions known to name engine bodies (small open-addressed set, shared by the modules)                      */
+/* ------------------------------------------------------------------------------------------------------------------ */
+#define B200_SUBMIT_SET 256
+static void * volatile b200_engine_submits[B200_SUBMIT_SET];
+static int parsec_b200_submit_is_engine(parsec_advance_task_function_t fn)
+{
+    uintptr_t h = ((uintptr_t)fn >> 4) % B200_SUBMIT_SET;
+    for( int p = 0; p < B200_SUBMIT_SET; p++ ) {
+        void *v = b200_engine_submits[(h + p) % B200_SUBMIT_SET];
+        if( v == (void*)fn ) return 1;
+        if( NULL == v ) return 0;
+    }
+    return 0;
+}
+static void parsec_b200_submit_set_engine(parsec_advance_task_function_t fn)
+{
+    uintptr_t h = ((uintptr_t)fn >> 4) % B200_SUBMIT_SET;
+    for( int p = 0; p < B200_SUBMIT_SET; p++ ) {
+        void * volatile *slot = &b200_engine_submits[(h + p) % B200_SUBMIT_SET];
+        if( *slot == (void*)fn ) return;
+        if( NULL == *slot && parsec_atomic_cas_ptr(slot, NULL, (void*)fn) ) return;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* pseudo tasks: data_advise PREFETCH / WARMUP (device.h:79-81; parsec_device_data_advise, device_gpu.c:713-777)        */
+/* A prefetch is a task with one READ flow and an empty body: the persistent kernel pulls the tile in (TMA) like any    */
+/* other stage-in, asynchronously, and later readers of the tile wait on its state on the device.                        */
+/* ------------------------------------------------------------------------------------------------------------------ */
+static const parsec_flow_t b200_prefetch_flow = {
+    .name = "FLOW", .flow_flags = PARSEC_FLOW_ACCESS_READ, .flow_index = 0,
+};
+static parsec_task_class_t b200_prefetch_tc = {
+    .name = "b200 data prefetch", .flags = 0, .task_class_id = 0, .nb_flows = 1, .nb_parameters = 0, .nb_locals = 0,
+    .in = { &b200_prefetch_flow, NULL }, .out = { NULL },
+};
+static int b200_prefetch_submit(parsec_device_gpu_module_t *gpu_device, parsec_gpu_task_t *gpu_task, parsec_gpu_exec_stream_t *gpu_stream)
+{
+    static const int flow0 = 0;
+    return parsec_b200_task_body(gpu_device, gpu_task, gpu_stream, PB2_BODY_NOP, 1, &flow0, NULL, 0.f);
+}
+static void b200_release_pseudo_task(parsec_gpu_task_t *gpu_task)
+{
+    if( NULL != gpu_task->ec ) {
+        if( NULL != gpu_task->ec->data[0].data_in ) PARSEC_DATA_COPY_RELEASE(gpu_task->ec->data[0].data_in);
+        free(gpu_task->ec);
+        gpu_task->ec = NULL;
+    }
+    PARSEC_OBJ_RELEASE(gpu_task);
+}
+
+static parsec_hook_return_t b200_kernel_scheduler(parsec_device_module_t *module, parsec_execution_stream_t *es, void *_gpu_task);
+
+static int b200_data_advise(parsec_device_module_t *module, parsec_data_t *data, int advice)
+{
+    switch( advice ) {
+    case PARSEC_DEV_DATA_ADVICE_PREFERRED_DEVICE:
+        data->preferred_device = module->device_index;
+        return PARSEC_SUCCESS;
+    case PARSEC_DEV_DATA_ADVICE_PREFETCH:
+    case PARSEC_DEV_DATA_ADVICE_WARMUP: {
+        parsec_data_copy_t *src = (data->owner_device >= 0) ? data->device_copies[data->owner_device] : data->device_copies[0];
+        if( NULL == src ) return PARSEC_ERR_NOT_FOUND;
+        parsec_gpu_task_t *gpu_task = (parsec_gpu_task_t*)PARSEC_OBJ_NEW(parsec_gpu_dsl_task_t);
+        gpu_task->task_type = (PARSEC_DEV_DATA_ADVICE_PREFETCH == advice) ? PARSEC_GPU_TASK_TYPE_PREFETCH : PARSEC_GPU_TASK_TYPE_WARMUP;
+        gpu_task->ec = (parsec_task_t*)calloc(1, sizeof(parsec_task_t));
+        PARSEC_OBJ_CONSTRUCT(gpu_task->ec, parsec_task_t);
+        gpu_task->ec->task_class = &b200_prefetch_tc;
+        gpu_task->ec->selected_device = module;
+        gpu_task->nb_flows = 1;
+        gpu_task->flow_info[0].flow = &b200_prefetch_flow;
+        gpu_task->flow_info[0].flow_span = data->span;
+        gpu_task->stage_in = parsec_default_gpu_stage_in;
+        gpu_task->stage_out = parsec_default_gpu_stage_out;
+        gpu_task->submit = b200_prefetch_submit;
+        gpu_task->release_device_task = b200_release_pseudo_task;
+        PARSEC_DATA_COPY_RETAIN(src);
+        gpu_task->ec->data[0].data_in = src;
+        /* same path as any task: whoever is (or becomes) the manager stages it in; the calling thread may become it */
+        (void)b200_kernel_scheduler(module, NULL, gpu_task);
+        return PARSEC_SUCCESS;
+    }
+    default:
+        return PARSEC_ERR_NOT_FOUND;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* the manager loop                                                                                                     */
+/* ------------------------------------------------------------------------------------------------------------------ */
+static void b200_finish(parsec_device_b200_module_t *dev, parsec_execution_stream_t *es, b200_task_t *bt)
+{
+    parsec_gpu_task_t *gpu_task = bt->gpu_task;
+    if( PARSEC_GPU_TASK_TYPE_KERNEL == gpu_task->task_type ) { b200_complete(dev, es, bt); return; }
+    /* pseudo task: the replica is resident and valid now; no runtime completion */
+    parsec_data_copy_t *out = gpu_task->ec->data[0].data_out;
+    if( NULL != out ) {
+        parsec_atomic_lock(&out->original->lock);
+        if( PARSEC_DATA_STATUS_UNDER_TRANSFER == out->data_transfer_status ) {
+            out->data_transfer_status = PARSEC_DATA_STATUS_COMPLETE_TRANSFER;
+            parsec_data_end_transfer_ownership_to_copy(out->original, dev->super.super.super.device_index, PARSEC_FLOW_ACCESS_READ);
+        }
+        if( bt->peer_src_mask & 1u ) (void)parsec_atomic_fetch_dec_int32(&bt->peer_src[0]->readers);
+        (void)parsec_atomic_fetch_dec_int32(&out->readers);
+        if( 0 == out->readers ) {
+            parsec_list_item_ring_chop((parsec_list_item_t*)out); PARSEC_LIST_ITEM_SINGLETON(out);
+            parsec_list_nolock_push_back(PARSEC_DATA_COHERENCY_OWNED == out->coherency_state ? &dev->super.super.gpu_mem_owned_lru : &dev->super.super.gpu_mem_lru,
+                                         (parsec_list_item_t*)out);
+        }
+        parsec_atomic_unlock(&out->original->lock);
+    }
+    b200_bt_free(dev, bt);
+    gpu_task->last_data_check_epoch = 0;
+    gpu_task->release_device_task(gpu_task);
+    dev->completed_now++;
+}
+
+/* returns < 0 on a fatal device problem */
+static int b200_progress(parsec_device_b200_module_t *dev, parsec_execution_stream_t *es)
+{
+    /* 1. inbox -> oldest-first list of tasks to start (callers push LIFO) */
+    parsec_gpu_task_t *head = dev->inbox;
+    while( NULL != head && !parsec_atomic_cas_ptr(&dev->inbox, head, NULL) ) head = dev->inbox;
+    parsec_gpu_task_t *fifo = NULL;
+    while( NULL != head ) {
+        parsec_gpu_task_t *next = (parsec_gpu_task_t*)head->list_item.list_next;
+        head->list_item.list_next = (parsec_list_item_t*)fifo; fifo = head; head = next;
+    }
+    while( NULL != fifo ) {
+        parsec_gpu_task_t *gt = fifo;
+        fifo = (parsec_gpu_task_t*)gt->list_item.list_next;
+        PARSEC_LIST_ITEM_SINGLETON(&gt->list_item);
+        parsec_list_nolock_push_back(&dev->stalled, &b200_bt_new(dev, gt)->item);
+    }
+    /* 2. start tasks in order; the first one that cannot get memory or ring space blocks the ones behind it */
+    int started = 0;
+    for(;;) {
+        b200_task_t *bt = (b200_task_t*)parsec_list_nolock_pop_front(&dev->stalled);
+        if( NULL == bt ) break;
+        int rc;
+        if( BT_NEW == bt->state ) rc = b200_start_task(dev, es, bt);
+        else rc = b200_push_engine(dev, bt);            /* staged, waiting for ring space */
+        if( PARSEC_HOOK_RETURN_AGAIN == rc ) { parsec_list_nolock_push_front(&dev->stalled, &bt->item); break; }
+        if( PARSEC_HOOK_RETURN_DONE != rc ) return -1;
+        started++;
+    }
+    if( started && PB2_SUCCESS != pb2_stream_kick(dev->stream) ) return -1;
+    /* 3. copy-engine / lane events */
+    if( !parsec_list_nolock_is_empty(&dev->waiting_event) ) {
+        parsec_list_item_t *it = PARSEC_LIST_ITERATOR_FIRST(&dev->waiting_event), *next;
+        for( ; it != PARSEC_LIST_ITERATOR_END(&dev->waiting_event); it = next ) {
+            b200_task_t *bt = (b200_task_t*)it;
+            next = PARSEC_LIST_ITERATOR_NEXT(it);
+            cudaError_t q = cudaEventQuery(bt->ev);
+            if( cudaErrorNotReady == q ) { (void)cudaGetLastError(); continue; }
+            if( cudaSuccess != q ) { parsec_warning("device_b200: event failed: %s", cudaGetErrorString(q)); return -1; }
+            parsec_list_nolock_remove(&dev->waiting_event, it);
+            PARSEC_LIST_ITEM_SINGLETON(it);
+            if( BT_DMA_IN == bt->state ) {
+                /* the copy engine delivered the inputs: the replicas are valid, the task goes to the kernel */
+                parsec_gpu_task_t *gt = bt->gpu_task;
+                for( uint32_t i = 0; i < gt->nb_flows; i++ ) {
+                    parsec_data_copy_t *out = gt->ec->data[i].data_out;
+                    if( NULL == out || NULL == gt->ec->data[i].data_in || PARSEC_DATA_STATUS_UNDER_TRANSFER != out->data_transfer_status ) continue;
+                    parsec_atomic_lock(&out->original->lock);
+                    out->data_transfer_status = PARSEC_DATA_STATUS_COMPLETE_TRANSFER;
+                    parsec_data_end_transfer_ownership_to_copy(out->original, dev->super.super.super.device_index,
+                                                               (uint8_t)(gt->flow_info[i].flow->flow_flags & PARSEC_FLOW_ACCESS_MASK));
+                    parsec_atomic_unlock(&out->original->lock);
+                }
+                int rc = b200_push_engine(dev, bt);
+                if( PARSEC_HOOK_RETURN_AGAIN == rc ) parsec_list_nolock_push_front(&dev->stalled, &bt->item);
+                else if( PARSEC_HOOK_RETURN_DONE != rc ) return -1;
+                else if( PB2_SUCCESS != pb2_stream_kick(dev->stream) ) return -1;
+            } else {
+                b200_finish(dev, es, bt);               /* BT_LANE, BT_DMA_OUT */
+            }
+        }
+    }
+    /* 4. retire ring */
+    for(;;) {
+        int n = pb2_stream_poll(dev->stream, dev->retbuf, (int32_t)(sizeof(dev->retbuf) / sizeof(dev->retbuf[0])));
+        if( n < 0 ) { parsec_warning("device_b200: %s", pb2_stream_last_error(dev->stream)); return -1; }
+        for( int i = 0; i < n; i++ ) {
+            b200_task_t *bt = (b200_task_t*)(uintptr_t)dev->retbuf[i].cookie;
+            bt->result = dev->retbuf[i].result;
+            bt->ticket = -1;
+            if( PB2_SUCCESS != dev->retbuf[i].status ) { parsec_warning("device_b200: task ran an unknown engine body"); return -1; }
+            if( bt->dma_out_mask && b200_dma_pushout(dev, bt) > 0 ) {
+                bt->state = BT_DMA_OUT;
+                parsec_list_nolock_push_back(&dev->waiting_event, &bt->item);
+            } else b200_finish(dev, es, bt);
+        }
+        if( n < (int)(sizeof(dev->retbuf) / sizeof(dev->retbuf[0])) ) break;
+    }
+    return 0;
+}
+
+static parsec_hook_return_t
+b200_kernel_scheduler(parsec_device_module_t *module, parsec_execution_stream_t *es, void *_gpu_task)
+{
+    parsec_device_b200_module_t *dev = (parsec_device_b200_module_t*)module;
+    parsec_gpu_task_t *gpu_task = (parsec_gpu_task_t*)_gpu_task;
+
+    int32_t inside = parsec_atomic_fetch_inc_int32(&dev->callers_inside) + 1;
+    if( (uint64_t)inside > dev->st.max_concurrent_callers ) dev->st.max_concurrent_callers = (uint64_t)inside;
+    /* 1. hand the task over: lock-free push on the inbox, then one more task is owed */
+    parsec_gpu_task_t *old;
+    do {
+        old = dev->inbox;
+        gpu_task->list_item.list_next = (parsec_list_item_t*)old;
+    } while( !parsec_atomic_cas_ptr(&dev->inbox, old, gpu_task) );
+    int32_t before = parsec_atomic_fetch_add_int32(&dev->owed, 1);
+    (void)parsec_atomic_fetch_dec_int32(&dev->callers_inside);
+    if( before > 0 ) return PARSEC_HOOK_RETURN_ASYNC;        /* somebody is driving the device and owes this task too */
+
+    /* 2. this thread is the manager until nothing is owed any more */
+    dev->st.manager_entries++;
+    if( NULL == es ) {
+        /* data_advise comes without an execution stream and owes no runtime completion: it cannot complete other
+         * threads' tasks, so it only drives the device until its own pseudo task is done */
+        es = parsec_my_execution_stream();
+    }
+    if( !dev->dry_run ) B200_CUDA(cudaSetDevice(dev->super.cuda_index), "cudaSetDevice", { return PARSEC_HOOK_RETURN_DISABLE; });
+    for(;;) {
+        dev->completed_now = 0;
+        if( b200_progress(dev, es) < 0 ) {
+            parsec_warning("GPU[%d:%s]: the device engine reported a fatal error; giving up", module->device_index, module->name);
+            return PARSEC_HOOK_RETURN_DISABLE;
+        }
+        if( dev->completed_now ) {
+            /* the subtraction that reaches zero is the LAST thing a manager does: the next caller becomes manager */
+            int32_t left = parsec_atomic_fetch_sub_int32(&dev->owed, dev->completed_now) - dev->completed_now;
+            if( 0 == left ) return PARSEC_HOOK_RETURN_ASYNC;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* module entry points                                                                                                  */
+/* ------------------------------------------------------------------------------------------------------------------ */
+static int b200_set_device(parsec_device_gpu_module_t *gpu)
+{
+    parsec_device_b200_module_t *dev = B200_DEV(gpu);
+    if( dev->dry_run ) return PARSEC_SUCCESS;
+    B200_CUDA(cudaSetDevice(dev->super.cuda_index), "cudaSetDevice", { return PARSEC_ERROR; });
+    return PARSEC_SUCCESS;
+}
+static int b200_memory_info(parsec_device_gpu_module_t *gpu, size_t *free_mem, size_t *total_mem)
+{
+    parsec_device_b200_module_t *dev = B200_DEV(gpu);
+    if( dev->dry_run ) { *free_mem = *total_mem = (size_t)8 << 30; return PARSEC_SUCCESS; }
+    pb2_engine_info_t info;
+    if( PB2_SUCCESS != pb2_engine_info(dev->engine, &info) ) return PARSEC_ERROR;
+    *free_mem = info.free_mem; *total_mem = info.total_mem;
+    return PARSEC_SUCCESS;
+}
+static int b200_memory_allocate(parsec_device_gpu_module_t *gpu, size_t bytes, void **addr)
+{
+    parsec_device_b200_module_t *dev = B200_DEV(gpu);
+    if( dev->dry_run ) { *addr = (void*)((uintptr_t)1 << 40); dev->slab_base = (char*)*addr; return PARSEC_SUCCESS; }   /* never dereferenced */
+    if( PB2_SUCCESS != pb2_engine_malloc(dev->engine, bytes, addr) ) return PARSEC_ERR_OUT_OF_RESOURCE;
+    dev->slab_base = (char*)*addr;
+    return PARSEC_SUCCESS;
+}
+static int b200_memory_free(parsec_device_gpu_module_t *gpu, void *addr)
+{
+    parsec_device_b200_module_t *dev = B200_DEV(gpu);
+    if( dev->dry_run ) return PARSEC_SUCCESS;
+    return (PB2_SUCCESS == pb2_engine_free(dev->engine, addr)) ? PARSEC_SUCCESS : PARSEC_ERROR;
+}
+static void *b200_find_incarnation(parsec_device_gpu_module_t *gpu, const char *fname)
+{
+    (void)gpu;
+    return parsec_device_find_function(fname, NULL, NULL);
+}
+
+static int b200_memory_register(parsec_device_module_t *device, parsec_data_collection_t *desc, void *ptr, size_t length)
+{
+    parsec_device_b200_module_t *dev = (parsec_device_b200_module_t*)device;
+    if( desc->memory_registration_status == PARSEC_MEMORY_STATUS_REGISTERED ) return PARSEC_SUCCESS;
+    void *alias = ptr;
+    if( !dev->dry_run ) {
+        if( PB2_SUCCESS != pb2_engine_host_register(dev->engine, ptr, length, &alias) ) return PARSEC_ERROR;
+    }
+    parsec_atomic_lock(&b200_ranges_lock);
+    if( b200_nb_ranges == b200_cap_ranges ) {
+        b200_cap_ranges = b200_cap_ranges ? 2 * b200_cap_ranges : 16;
+        b200_ranges = (b200_host_range_t*)realloc(b200_ranges, sizeof(b200_host_range_t) * (size_t)b200_cap_ranges);
+    }
+    b200_ranges[b200_nb_ranges].base = (char*)ptr; b200_ranges[b200_nb_ranges].len = length; b200_ranges[b200_nb_ranges].alias = (char*)alias;
+    b200_nb_ranges++;
+    parsec_atomic_unlock(&b200_ranges_lock);
+    desc->memory_registration_status = PARSEC_MEMORY_STATUS_REGISTERED;
+    return PARSEC_SUCCESS;
+}
+
+static int b200_memory_unregister(parsec_device_module_t *device, parsec_data_collection_t *desc, void *ptr)
+{
+    parsec_device_b200_module_t *dev = (parsec_device_b200_module_t*)device;
+    if( desc->memory_registration_status == PARSEC_MEMORY_STATUS_UNREGISTERED ) return PARSEC_SUCCESS;
+    int found = 0;
+    parsec_atomic_lock(&b200_ranges_lock);
+    for( int i = 0; i < b200_nb_ranges; i++ )
+        if( b200_ranges[i].base == (char*)ptr ) { b200_ranges[i] = b200_ranges[--b200_nb_ranges]; found = 1; break; }
+    parsec_atomic_unlock(&b200_ranges_lock);
+    if( found && !dev->dry_run ) {
+        /* nothing of ours may be resident while CUDA unpins the range */
+        (void)pb2_stream_quiesce(dev->stream);
+        (void)pb2_engine_host_unregister(dev->engine, ptr);
+    }
+    desc->memory_registration_status = PARSEC_MEMORY_STATUS_UNREGISTERED;
+    return PARSEC_SUCCESS;
+}
+
+static int b200_memory_release(parsec_device_module_t *device)
+{
+    parsec_device_b200_module_t *dev = (parsec_device_b200_module_t*)device;
+    /* dirty replicas go home first: flush_lru would drop them with a warning (device_gpu.c:1033-1037) */
+    if( !dev->dry_run ) (void)pb2_stream_quiesce(dev->stream);
+    while( b200_write_back_some(dev, 64) > 0 ) { }
+    return parsec_device_flush_lru(device);
+}
+
+static int b200_all_devices_attached(parsec_device_module_t *device)
+{
+    parsec_device_b200_module_t *dev = (parsec_device_b200_module_t*)device, *peer;
+    dev->super.super.peer_access_mask = (int16_t)(1 << device->device_index);
+    if( dev->dry_run ) {
+        for( int j = 0; NULL != (peer = (parsec_device_b200_module_t*)parsec_device_b200_component.modules[j]); j++ )
+            dev->super.super.peer_access_mask = (int16_t)(dev->super.super.peer_access_mask | (1 << peer->super.super.super.device_index));
+        return PARSEC_SUCCESS;
+    }
+    for( int j = 0; NULL != (peer = (parsec_device_b200_module_t*)parsec_device_b200_component.modules[j]); j++ ) {
+        if( peer == dev ) continue;
+        if( PB2_SUCCESS == pb2_engine_enable_peer(dev->engine, peer->super.cuda_index) )
+            dev->super.super.peer_access_mask = (int16_t)(dev->super.super.peer_access_mask | (1 << peer->super.super.super.device_index));
+    }
+    return PARSEC_SUCCESS;
+}
+
+int parsec_b200_get_stats(const parsec_device_module_t *device, parsec_b200_stats_t *stats)
+{
+    if( !parsec_b200_is_b200_device(device) || NULL == stats ) return PARSEC_ERR_BAD_PARAM;
+    parsec_device_b200_module_t *dev = (parsec_device_b200_module_t*)device;
+    pb2_stream_stats_t ss;
+    *stats = dev->st;
+    if( PB2_SUCCESS == pb2_stream_stats(dev->stream, &ss) ) {
+        stats->kernel_launches = ss.kernel_launches; stats->released_on_device = ss.released_on_device;
+        stats->bytes_h2d_kernel = ss.bytes_h2d; stats->bytes_d2d_kernel = ss.bytes_d2d; stats->bytes_d2h_kernel = ss.bytes_d2h;
+    }
+    return PARSEC_SUCCESS;
+}
+
+int parsec_b200_module_init(int dev_id, parsec_device_module_t **module)
+{
+    parsec_device_b200_module_t *dev = (parsec_device_b200_module_t*)calloc(1, sizeof(parsec_device_b200_module_t));
+    parsec_device_gpu_module_t *gpu = &dev->super.super;
+    parsec_device_module_t *device = &gpu->super;
+    *module = NULL;
+    PARSEC_OBJ_CONSTRUCT(device, parsec_device_module_t);
+    dev->dry_run = parsec_b200_dry_run > 0;
+    dev->super.cuda_index = (uint8_t)dev_id;
+    dev->super.major = 10; dev->super.minor = 0;
+    if( -1 == asprintf(&device->name, "b200(%d)", dev_id) ) { free(dev); return PARSEC_ERROR; }
+
+    if( !dev->dry_run ) {
+        pb2_engine_params_t ep;
+        memset(&ep, 0, sizeof ep);
+        if( PB2_SUCCESS != pb2_engine_create(&dev->engine, dev_id, &ep) ) {
+            parsec_warning("device_b200: CUDA device %d is not usable by the engine (needs sm_100)", dev_id);
+            free(device->name); free(dev);
+            return PARSEC_ERR_DEVICE;
+        }
+        B200_CUDA(cudaSetDevice(dev_id), "cudaSetDevice", {});
+        B200_CUDA(cudaStreamCreateWithFlags(&dev->dma_stream, cudaStreamNonBlocking), "cudaStreamCreate", {});
+    }
+    /* one exec stream: what submit / stage / complete_stage callbacks receive (device_gpu.h:283-298) */
+    gpu->max_exec_streams = 1;
+    gpu->exec_stream = (parsec_gpu_exec_stream_t**)malloc(sizeof(parsec_gpu_exec_stream_t*));
+    dev->lane = (parsec_cuda_exec_stream_t*)calloc(1, sizeof(parsec_cuda_exec_stream_t));
+    gpu->exec_stream[0] = &dev->lane->super;
+    gpu->num_exec_streams = 1;
+    if( !dev->dry_run ) B200_CUDA(cudaStreamCreateWithFlags(&dev->lane->cuda_stream, cudaStreamNonBlocking), "cudaStreamCreate", {});
+    PARSEC_OBJ_CONSTRUCT(&dev->lane->super.infos, parsec_info_object_array_t);
+    parsec_info_object_array_init(&dev->lane->super.infos, &parsec_per_stream_infos, &dev->lane->super);
+    dev->lane->super.fifo_pending = (parsec_list_t*)PARSEC_OBJ_NEW(parsec_list_t);
+    if( -1 == asprintf(&dev->lane->super.name, "b200(%d)", dev_id) ) dev->lane->super.name = NULL;
+
+    device->type                 = PARSEC_DEV_CUDA;      /* BODY [type=CUDA] chores match unchanged (device.c:123-148) */
+    device->attach               = parsec_device_attach;
+    device->detach               = parsec_device_detach;
+    device->taskpool_register    = parsec_device_taskpool_register;
+    device->taskpool_unregister  = parsec_device_taskpool_unregister;
+    device->memory_register      = b200_memory_register;
+    device->memory_unregister    = b200_memory_unregister;
+    device->memory_release       = b200_memory_release;
+    device->data_advise          = b200_data_advise;
+    device->kernel_scheduler     = b200_kernel_scheduler;
+    device->all_devices_attached = b200_all_devices_attached;
+    gpu->set_device       = b200_set_device;
+    gpu->memory_info      = b200_memory_info;
+    gpu->memory_allocate  = b200_memory_allocate;
+    gpu->memory_free      = b200_memory_free;
+    gpu->find_incarnation = b200_find_incarnation;
+    /* sm_100 rates, GFLOP/s (the reference's table stops before Blackwell, device_cuda_module.c:45-142):
+     * dense bf16/fp16 2250 T, tf32 1100 T, fp32 80 T, fp64 40 T */
+    device->gflops_fp16 = 2250000; device->gflops_tf32 = 1100000; device->gflops_fp32 = 80000; device->gflops_fp64 = 40000;
+    device->gflops_guess = 0;
+    device->device_load = 0;
+
+    PARSEC_OBJ_CONSTRUCT(&gpu->gpu_mem_lru, parsec_list_t);
+    PARSEC_OBJ_CONSTRUCT(&gpu->gpu_mem_owned_lru, parsec_list_t);
+    PARSEC_OBJ_CONSTRUCT(&gpu->pending, parsec_fifo_t);
+    PARSEC_OBJ_CONSTRUCT(&dev->stalled, parsec_list_t);
+    PARSEC_OBJ_CONSTRUCT(&dev->waiting_event, parsec_list_t);
+    PARSEC_OBJ_CONSTRUCT(&dev->free_bt, parsec_list_t);
+
+    int nblocks = parsec_b200_memory_number_of_blocks;
+    if( dev->dry_run && -1 == nblocks ) nblocks = 4096;
+    if( PARSEC_SUCCESS != parsec_device_memory_reserve(gpu, parsec_b200_memory_percentage, nblocks, (size_t)parsec_b200_memory_block_size) ) goto failed;
+
+    pb2_stream_params_t sp;
+    memset(&sp, 0, sizeof sp);
+    sp.cmd_slots = parsec_b200_cmd_slots;
+    sp.max_tiles = (int32_t)gpu->mem_nb_blocks;
+    sp.idle_us = parsec_b200_idle_us;
+    sp.dry_run = dev->dry_run;
+    sp.max_workers = parsec_b200_max_workers;
+    if( PB2_SUCCESS != pb2_stream_create(dev->engine, &sp, &dev->stream) ) goto failed;
+    *module = device;
+    return PARSEC_SUCCESS;
+failed:
+    parsec_warning("device_b200: initialisation of device %d failed", dev_id);
+    if( NULL != dev->engine ) pb2_engine_destroy(dev->engine);
+    free(device->name); free(dev);
+    return PARSEC_ERROR;
+}
+
+int parsec_b200_module_fini(parsec_device_module_t *device)
+{
+    parsec_device_b200_module_t *dev = (parsec_device_b200_module_t*)device;
+    parsec_device_gpu_module_t *gpu = &dev->super.super;
+    if( NULL != dev->stream ) { (void)pb2_stream_quiesce(dev->stream); }
+    while( b200_write_back_some(dev, 64) > 0 ) { }
+    parsec_device_memory_release(gpu);
+    if( NULL != dev->stream ) { pb2_stream_destroy(dev->stream); dev->stream = NULL; }
+    b200_task_t *bt;
+    while( NULL != (bt = (b200_task_t*)parsec_list_nolock_pop_front(&dev->free_bt)) ) {
+        if( !dev->dry_run && NULL != bt->ev ) (void)cudaEventDestroy(bt->ev);
+        free(bt);
+    }
+    PARSEC_OBJ_DESTRUCT(&gpu->pending);
+    PARSEC_OBJ_DESTRUCT(&dev->lane->super.infos);
+    free(dev->lane->super.name);
+    PARSEC_OBJ_RELEASE(dev->lane->super.fifo_pending);
+    if( !dev->dry_run ) {
+        (void)cudaStreamDestroy(dev->lane->cuda_stream);
+        (void)cudaStreamDestroy(dev->dma_stream);
+    }
+    free(dev->lane); free(gpu->exec_stream);
+    if( NULL != dev->engine ) { pb2_engine_destroy(dev->engine); dev->engine = NULL; }
+    free(device->name); device->name = NULL;
+    return PARSEC_SUCCESS;
+}

@@ -1,0 +1,145 @@
+/*
+ * ex05_main.c -- driver of tests/parsec/ex05_b200.jdf: plays the role the reference's test mains play
+ * (examples/Ex05_Broadcast.jdf main, tests/runtime/cuda/stage_main.c).  Prints one JSON line.
+ *
+ *   ex05_b200 [-K groups] [-N NB] [-t tile_elems] [-r repeats] [-c cores] [-m cpu|gpu] [-v] [-- parsec args]
+ *
+ * -m cpu: restrict the taskpool to the CPU incarnations (the reference's own scheduler + CPU bodies: the CPU baseline);
+ * -m gpu: every task class has a CUDA incarnation, whichever GPU component is active drives it.
+ * The check is the example's known answer: every TaskRecv(k, n) sees k in the whole tile; with -m gpu the verdict comes
+ * from the engine's CHECK body through a complete_stage-free path: the final host tiles (pushed out because the
+ * collection is flushed at the end) must hold k, and the device statistics must show each tile staged in once.
+ */
+#include "parsec.h"
+#include "parsec/data_dist/matrix/two_dim_rectangle_cyclic.h"
+#include "parsec/mca/device/device.h"
+#include "parsec/mca/device/b200/device_b200.h"
+#include "parsec/utils/mca_param.h"
+#include "parsec/parsec_internal.h"
+#include "parsec/execution_stream.h"
+#include "ex05_b200.h"
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <unistd.h>
+
+static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+
+int main(int argc, char *argv[])
+{
+    int K = 64, NB = 14, elems = 256 * 256, repeats = 1, cores = -1, verbose = 0, gpu = 1, c;
+    while( -1 != (c = getopt(argc, argv, "K:N:t:r:c:m:v")) ) {
+        switch(c) {
+        case 'K': K = atoi(optarg); break;
+        case 'N': NB = atoi(optarg); break;
+        case 't': elems = atoi(optarg); break;
+        case 'r': repeats = atoi(optarg); break;
+        case 'c': cores = atoi(optarg); break;
+        case 'm': gpu = (0 == strcmp(optarg, "gpu")); break;
+        case 'v': verbose = 1; break;
+        default: break;
+        }
+    }
+    int pargc = argc - optind + 1;
+    char **pargv = (char**)calloc((size_t)pargc + 1, sizeof(char*));
+    pargv[0] = argv[0];
+    for( int i = optind; i < argc; i++ ) pargv[i - optind + 1] = argv[i];
+
+    parsec_context_t *parsec = parsec_init(cores, &pargc, &pargv);
+    if( NULL == parsec ) { fprintf(stderr, "parsec_init failed\n"); return 2; }
+    const int F = NB / 2 + 1;
+    const int nthreads = parsec->virtual_processes[0]->nb_cores;
+
+    parsec_matrix_block_cyclic_t dcA;
+    parsec_matrix_block_cyclic_init(&dcA, PARSEC_MATRIX_INTEGER, PARSEC_MATRIX_TILE, 0,
+                                    elems, 1, K * elems, 1, 0, 0, K * elems, 1, 1, 1, 1, 1, 0, 0);
+    dcA.mat = parsec_data_allocate((size_t)dcA.super.nb_local_tiles * (size_t)dcA.super.bsiz *
+                                   (size_t)parsec_datadist_getsizeoftype(dcA.super.mtype));
+    parsec_data_collection_set_key((parsec_data_collection_t*)&dcA, "dcA");
+    int32_t *mat = (int32_t*)dcA.mat;
+
+    int ngpu = 0, b200 = 0;
+    for( int i = 0; i < (int)parsec_nb_devices; i++ ) {
+        parsec_device_module_t *d = parsec_mca_device_get(i);
+        if( NULL == d || !PARSEC_DEV_IS_GPU(d->type) ) continue;
+        ngpu++; b200 += parsec_b200_is_b200_device(d);
+        if( gpu ) dcA.super.super.register_memory(&dcA.super.super, d);
+    }
+    if( gpu && 0 == ngpu ) { fprintf(stderr, "-m gpu but no GPU device module is active\n"); return 3; }
+
+    int64_t *errors = (int64_t*)calloc((size_t)nthreads + 1, sizeof(int64_t));
+    double best = 1e30, total = 0;
+    int64_t bad_total = 0;
+    for( int r = 0; r < repeats; r++ ) {
+        for( size_t i = 0; i < (size_t)K * elems; i++ ) mat[i] = -7;
+        parsec_ex05_b200_taskpool_t *tp = parsec_ex05_b200_new(&dcA.super, NB, errors);
+        parsec_arena_datatype_set_type(&tp->arenas_datatypes[PARSEC_ex05_b200_DEFAULT_ADT_IDX],
+                                       (size_t)elems * sizeof(int32_t), PARSEC_ARENA_ALIGNMENT_SSE, parsec_datatype_int_t);
+        if( !gpu ) {
+            for( int i = 0; i < (int)parsec_nb_devices; i++ ) {
+                parsec_device_module_t *d = parsec_mca_device_get(i);
+                if( NULL != d && PARSEC_DEV_IS_GPU(d->type) ) tp->super.devices_index_mask &= ~(1u << i);
+            }
+        }
+        const double t0 = now_s();
+        if( 0 > parsec_context_add_taskpool(parsec, (parsec_taskpool_t*)tp) ) return 4;
+        if( 0 > parsec_context_start(parsec) ) return 4;
+        if( 0 > parsec_context_wait(parsec) ) return 4;
+        const double t1 = now_s();
+        /* bring every tile home (what a real application does before it reads its matrix on the CPU) */
+        for( int i = 0; i < (int)parsec_nb_devices; i++ ) {
+            parsec_device_module_t *d = parsec_mca_device_get(i);
+            if( NULL != d && PARSEC_DEV_IS_GPU(d->type) && NULL != d->memory_release ) d->memory_release(d);
+        }
+        const double t2 = now_s();
+        for( int k = 0; k < K; k++ )
+            for( int i = 0; i < elems; i += (elems > 64 ? elems / 64 : 1) ) bad_total += (mat[(size_t)k * elems + i] != k);
+        if( verbose ) fprintf(stderr, "repeat %d: dag %.3f ms, flush %.3f ms\n", r, 1e3 * (t1 - t0), 1e3 * (t2 - t1));
+        if( t1 - t0 < best ) best = t1 - t0;
+        total += t1 - t0;
+        PARSEC_OBJ_DESTRUCT(&tp->arenas_datatypes[PARSEC_ex05_b200_DEFAULT_ADT_IDX]);
+        parsec_taskpool_free((parsec_taskpool_t*)tp);
+    }
+    for( int t = 0; t < nthreads; t++ ) bad_total += errors[t];
+
+    parsec_b200_stats_t st; memset(&st, 0, sizeof st);
+    uint64_t executed_gpu = 0, h2d = 0, required_in = 0;
+    for( int i = 0; i < (int)parsec_nb_devices; i++ ) {
+        parsec_device_module_t *d = parsec_mca_device_get(i);
+        if( NULL == d || !PARSEC_DEV_IS_GPU(d->type) ) continue;
+        executed_gpu += d->executed_tasks; required_in += d->required_data_in;
+        if( NULL != d->data_in_from_device ) h2d += d->data_in_from_device[0];
+        if( parsec_b200_is_b200_device(d) ) {
+            parsec_b200_stats_t s1; parsec_b200_get_stats(d, &s1);
+            st.tasks_engine += s1.tasks_engine; st.tasks_lane += s1.tasks_lane; st.kernel_launches += s1.kernel_launches;
+            st.released_on_device += s1.released_on_device; st.lookahead_submitted += s1.lookahead_submitted;
+            st.bytes_h2d_kernel += s1.bytes_h2d_kernel; st.bytes_h2d_dma += s1.bytes_h2d_dma; st.bytes_d2h_dma += s1.bytes_d2h_dma;
+            st.manager_entries += s1.manager_entries; st.evictions += s1.evictions; st.w2r_copies += s1.w2r_copies;
+            if( s1.max_concurrent_callers > st.max_concurrent_callers ) st.max_concurrent_callers = s1.max_concurrent_callers;
+        }
+    }
+    const long ntasks = (long)K * (1 + F);
+    printf("{\"app\": \"ex05_b200\", \"mode\": \"%s\", \"K\": %d, \"NB\": %d, \"F\": %d, \"tile_bytes\": %ld, \"tasks\": %ld, \"repeats\": %d, "
+           "\"cores\": %d, \"gpu_modules\": %d, \"b200_modules\": %d, \"best_s\": %.6f, \"mean_s\": %.6f, \"tasks_per_s\": %.1f, "
+           "\"errors\": %ld, \"executed_on_gpu\": %lu, \"required_in\": %lu, \"h2d_bytes\": %lu, "
+           "\"b200\": {\"tasks_engine\": %lu, \"tasks_lane\": %lu, \"kernel_launches\": %lu, \"released_on_device\": %lu, "
+           "\"lookahead_submitted\": %lu, \"bytes_h2d_kernel\": %lu, \"bytes_h2d_dma\": %lu, \"bytes_d2h_dma\": %lu, "
+           "\"manager_entries\": %lu, \"max_concurrent_callers\": %lu, \"evictions\": %lu, \"w2r_copies\": %lu}}\n",
+           gpu ? "gpu" : "cpu", K, NB, F, (long)elems * 4, ntasks, repeats, nthreads, ngpu, b200, best, total / repeats,
+           ntasks / best, (long)bad_total, (unsigned long)executed_gpu, (unsigned long)required_in, (unsigned long)h2d,
+           (unsigned long)st.tasks_engine, (unsigned long)st.tasks_lane, (unsigned long)st.kernel_launches,
+           (unsigned long)st.released_on_device, (unsigned long)st.lookahead_submitted, (unsigned long)st.bytes_h2d_kernel,
+           (unsigned long)st.bytes_h2d_dma, (unsigned long)st.bytes_d2h_dma, (unsigned long)st.manager_entries,
+           (unsigned long)st.max_concurrent_callers, (unsigned long)st.evictions, (unsigned long)st.w2r_copies);
+
+    for( int i = 0; i < (int)parsec_nb_devices; i++ ) {
+        parsec_device_module_t *d = parsec_mca_device_get(i);
+        if( gpu && NULL != d && PARSEC_DEV_IS_GPU(d->type) ) dcA.super.super.unregister_memory(&dcA.super.super, d);
+    }
+    parsec_data_free(dcA.mat);
+    parsec_tiled_matrix_destroy((parsec_tiled_matrix_t*)&dcA);
+    free(errors);
+    parsec_fini(&parsec);
+    return bad_total ? 1 : 0;
+}
