@@ -54,6 +54,7 @@ typedef struct parsec_b200_stats_s {
     uint64_t bytes_h2d_kernel, bytes_d2d_kernel, bytes_d2h_kernel;  /* moved by the persistent kernel               */
     uint64_t bytes_h2d_dma, bytes_d2h_dma;                          /* moved by the copy engine (unregistered memory)*/
     uint64_t evictions, w2r_copies;
+    uint64_t check_mismatches;      /* elements the CHECK bodies found different from what they expected             */
     uint64_t manager_entries;       /* how often a worker thread became the manager                                  */
     uint64_t max_concurrent_callers;
 } parsec_b200_stats_t;

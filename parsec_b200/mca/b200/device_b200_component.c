@@ -32,6 +32,7 @@ int parsec_b200_cmd_slots = 65536;
 int parsec_b200_idle_us = 2000;
 int parsec_b200_lookahead = 1;
 int parsec_b200_max_workers = 0;
+int parsec_b200_parallel_completion = 1;
 static int b200_mask = -1;
 
 #if !defined(PARSEC_HAVE_MPI)
@@ -95,6 +96,9 @@ static int device_b200_component_register(void)
     (void)parsec_mca_param_reg_int_name("device_b200", "lookahead",
                                         "Hand single-input successors to the device before the host made them ready (device-side release)",
                                         false, false, 1, &parsec_b200_lookahead);
+    (void)parsec_mca_param_reg_int_name("device_b200", "parallel_completion",
+                                        "Let the worker pool run __parsec_complete_execution of finished GPU tasks instead of the manager thread",
+                                        false, false, 1, &parsec_b200_parallel_completion);
     (void)parsec_mca_param_reg_int_name("device_b200", "max_workers", "Debug: limit the worker CTAs of the persistent kernel (0: all)",
                                         false, false, 0, &parsec_b200_max_workers);
     return (0 == parsec_device_b200_enabled && 0 == parsec_b200_dry_run) ? MCA_ERROR : MCA_SUCCESS;
@@ -116,7 +120,10 @@ static int device_b200_component_open(void)
         if( parsec_device_b200_enabled > 0 && parsec_device_b200_enabled < ndev ) ndev = parsec_device_b200_enabled;
     }
     parsec_device_b200_enabled = ndev;
-    /* both components answer PARSEC_DEV_CUDA chores: never let the reference's stream engine drive the same GPUs */
+    /* both components answer PARSEC_DEV_CUDA chores: never let the reference's stream engine drive the same GPUs.
+     * Components are registered and opened one after the other in list order (mca_repository.c:128-141) and "b200"
+     * sorts before "cuda": its parameters are not registered yet, so the switch is thrown where it will look. */
+    setenv("PARSEC_MCA_device_cuda_enabled", "0", 1);
     {
         int idx = parsec_mca_param_find("device_cuda", NULL, "enabled");
         if( idx >= 0 ) parsec_mca_param_set_int(idx, 0);

@@ -42,12 +42,15 @@
 #include <string.h>
 #include <stdio.h>
 #include <limits.h>
+#include <x86intrin.h>
+#define B200_TSC() __rdtsc()
 
 /* ------------------------------------------------------------------------------------------------------------------ */
 /* types                                                                                                                */
 /* ------------------------------------------------------------------------------------------------------------------ */
 enum {
     BT_NEW = 0,        /* popped from the inbox, nothing reserved yet                                   */
+    BT_STAGED,         /* resident and described to the device, waiting for room in the command ring      */
     BT_DMA_IN,         /* copy-engine stage-in of unregistered host memory in progress (event)          */
     BT_INFLIGHT,       /* descriptor in the command ring / running in the persistent kernel             */
     BT_LANE,           /* opaque submit body enqueued on the lane stream (event)                        */
@@ -71,6 +74,7 @@ typedef struct b200_task_s {
     uint32_t             dma_out_mask;    /* pushout flows that need the copy engine (home not device-visible) */
     uint64_t             result;
     int32_t              retired;         /* shadow: the device is done with it */
+    int32_t              custom_stage;    /* the task brought its own stage_in / stage_out (device_gpu.h:75-91) */
     cudaEvent_t          ev;
 } b200_task_t;
 
@@ -91,10 +95,12 @@ typedef struct parsec_device_b200_module_s {
     parsec_list_t        waiting_event;   /* b200_task_t in BT_DMA_IN / BT_LANE / BT_DMA_OUT, in event order */
     parsec_list_t        free_bt;
     b200_task_t         *recording;       /* the task whose submit function is being called in record mode */
+    parsec_task_t       *completion_ring; /* tasks whose runtime completion is handed to the worker pool */
     int32_t              completed_now;   /* completions of the current manager iteration, subtracted from owed at its end */
     cudaStream_t         dma_stream;
     parsec_cuda_exec_stream_t *lane;      /* exec_stream[0]: what submit functions receive */
     parsec_b200_stats_t  st;
+    uint64_t             tsc[6];          /* manager time by phase (PARSEC_MCA_device_b200_profile): inbox, start, events, poll, finish, idle */
     pb2_retire_t         retbuf[256];
 } parsec_device_b200_module_t;
 
@@ -153,7 +159,7 @@ static b200_task_t *b200_bt_new(parsec_device_b200_module_t *dev, parsec_gpu_tas
     }
     PARSEC_LIST_ITEM_SINGLETON(&bt->item);
     bt->gpu_task = gpu_task; bt->state = BT_NEW; bt->ticket = -1; bt->body = -1; bt->nb_args = 0;
-    bt->peer_src_mask = 0; bt->dma_out_mask = 0; bt->result = 0; bt->retired = 0;
+    bt->peer_src_mask = 0; bt->dma_out_mask = 0; bt->result = 0; bt->retired = 0; bt->custom_stage = 0;
     if( NULL != gpu_task ) gpu_task->last_data_check_epoch = (uint64_t)(uintptr_t)bt;
     return bt;
 }
@@ -189,8 +195,11 @@ static void b200_release_copy_memory(parsec_device_b200_module_t *dev, parsec_da
     parsec_data_t *original = copy->original;
     if( NULL != original ) {
         parsec_atomic_lock(&original->lock);
+        /* the replica holds one reference on its datum: detaching may destroy it, lock included */
+        const int survives = original->super.obj_reference_count != 1;
         parsec_data_copy_detach(original, copy, dev->super.super.super.device_index);
-        parsec_atomic_unlock(&original->lock);
+        parsec_atomic_wmb();
+        if( survives ) parsec_atomic_unlock(&original->lock);
     }
     zone_free(dev->super.super.memory, copy->device_private);
     copy->device_private = NULL;
@@ -259,7 +268,7 @@ static int b200_write_back_some(parsec_device_b200_module_t *dev, int how_many)
 }
 
 /* Free one replica nobody uses: oldest clean one first; if every clean replica is busy, write dirty ones home. */
-static int b200_evict_one(parsec_device_b200_module_t *dev)
+static int b200_evict_one(parsec_device_b200_module_t *dev, const parsec_gpu_task_t *for_task)
 {
     for( int pass = 0; pass < 2; pass++ ) {
         parsec_list_item_t *it, *next;
@@ -268,6 +277,14 @@ static int b200_evict_one(parsec_device_b200_module_t *dev)
             parsec_data_copy_t *copy = (parsec_data_copy_t*)it;
             next = PARSEC_LIST_ITERATOR_NEXT(it);
             if( PARSEC_DATA_STATUS_UNDER_TRANSFER == copy->data_transfer_status ) continue;
+            /* a task that has not run yet was handed this replica as its input (the repo retains it): keep it */
+            if( copy->super.super.obj_reference_count > 1 ) continue;
+            if( NULL != for_task ) {
+                int mine = 0;
+                for( uint32_t f = 0; f < for_task->nb_flows; f++ )
+                    mine |= (for_task->ec->data[f].data_out == copy) || (for_task->ec->data[f].data_in == copy);
+                if( mine ) continue;
+            }
             /* tombstone: a peer GPU that wants this replica as a source sees readers < 0 and looks elsewhere */
             if( !parsec_atomic_cas_int32(&copy->readers, 0, INT_MIN / 2) ) continue;
             /* never drop the only up-to-date replica */
@@ -312,7 +329,7 @@ static int b200_reserve(parsec_device_b200_module_t *dev, b200_task_t *bt)
         if( NULL == gpu_elem ) {
             void *ptr;
             while( NULL == (ptr = zone_malloc(dev->super.super.memory, gpu_task->flow_info[i].flow_span)) ) {
-                if( !b200_evict_one(dev) ) {
+                if( !b200_evict_one(dev, gpu_task) ) {
                     /* nothing can be freed now: undo what this pass allocated and let the task wait for retirements */
                     for( int k = 0; k < nfresh; k++ ) {
                         parsec_list_nolock_remove(&dev->super.super.gpu_mem_lru, (parsec_list_item_t*)fresh[k]);
@@ -347,9 +364,13 @@ static int b200_reserve(parsec_device_b200_module_t *dev, b200_task_t *bt)
 /* ------------------------------------------------------------------------------------------------------------------ */
 /* stage-in decisions (parsec_device_data_stage_in, device_gpu.c:1799-2165): who is the source, who moves the bytes     */
 /* ------------------------------------------------------------------------------------------------------------------ */
-/* returns 0 ok, 1 when the copy engine was used (the task has to wait for bt->ev), <0 error / retry */
-static int b200_stage_in(parsec_device_b200_module_t *dev, b200_task_t *bt, int for_lane)
+/* mode 0: engine task (the kernel pulls device-visible sources, the copy engine the others);
+ * mode 1: lane task, default staging (copy engine on the lane stream); mode 2: lane task with a user stage_in: nothing is
+ * copied here, the flows that need their bytes are left UNDER_TRANSFER for the callback.
+ * returns 0 ok, 1 when a copy was enqueued or is owed (the task has to wait for bt->ev), <0 error / retry */
+static int b200_stage_in(parsec_device_b200_module_t *dev, b200_task_t *bt, int mode)
 {
+    const int for_lane = (0 != mode);
     parsec_gpu_task_t *gpu_task = bt->gpu_task;
     parsec_task_t *this_task = gpu_task->ec;
     parsec_device_module_t *mod = &dev->super.super.super;
@@ -440,6 +461,9 @@ static int b200_stage_in(parsec_device_b200_module_t *dev, b200_task_t *bt, int 
                 tile.src_ptr = visible;
                 out->data_transfer_status = PARSEC_DATA_STATUS_UNDER_TRANSFER;
                 if( PB2_SRC_PEER == tile.src_kind ) dev->st.bytes_d2d_kernel += span; else dev->st.bytes_h2d_kernel += span;
+            } else if( 2 == mode ) {
+                out->data_transfer_status = PARSEC_DATA_STATUS_UNDER_TRANSFER;       /* the user's stage_in moves it */
+                used_dma = 1;
             } else if( !dev->dry_run ) {
                 /* unregistered host memory, or an opaque body that needs the bytes before it is enqueued: copy engine */
                 B200_CUDA(cudaMemcpyAsync(out->device_private, src->device_private, span,
@@ -453,7 +477,7 @@ static int b200_stage_in(parsec_device_b200_module_t *dev, b200_task_t *bt, int 
                 out->data_transfer_status = PARSEC_DATA_STATUS_UNDER_TRANSFER;
             }
             out->version = (PARSEC_FLOW_ACCESS_WRITE & type) ? src->version + 1 : src->version;
-            gpu_task->flow_info[i].source = src_acquired ? src : NULL;
+            gpu_task->flow_info[i].source = src;          /* what a user stage_in reads (stage_custom.jdf:28-60) */
             if( src_acquired ) { bt->peer_src_mask |= (1u << i); bt->peer_src[i] = src; }
             /* a pushout of a flow that was pulled from a peer still goes to its host home */
             if( PB2_SRC_PEER == tile.src_kind && PB2_TILE_INVALID == tile.state && NULL != home && (gpu_task->pushout & (1 << i)) ) {
@@ -573,8 +597,20 @@ static void b200_complete(parsec_device_b200_module_t *dev, parsec_execution_str
         parsec_gpu_task_t *gt = gpu_task;
         (void)gpu_task->complete_stage(&dev->super.super, &gt, &dev->lane->super);
     }
-    __parsec_complete_execution(es, this_task);
     mod->executed_tasks++;
+    if( parsec_b200_parallel_completion ) {
+        /* Hand the runtime-side completion (prepare_output, release_deps of every successor, release_task) to the
+         * worker pool: a task whose status is past HOOK goes straight to __parsec_complete_execution when a worker
+         * dequeues it (scheduling.c:507-545).  It is still called exactly once, by a thread that owns an execution
+         * stream; the manager only keeps the device-side epilog above.  The tasks of one manager iteration are
+         * chained and scheduled with one call at its end. */
+        this_task->status = PARSEC_TASK_STATUS_COMPLETE;
+        PARSEC_LIST_ITEM_SINGLETON(this_task);
+        if( NULL == dev->completion_ring ) dev->completion_ring = this_task;
+        else parsec_list_item_ring_push((parsec_list_item_t*)dev->completion_ring, (parsec_list_item_t*)this_task);
+    } else {
+        __parsec_complete_execution(es, this_task);
+    }
     b200_bt_free(dev, bt);
     gpu_task->last_data_check_epoch = 0;
     gpu_task->release_device_task(gpu_task);
@@ -587,6 +623,12 @@ static int b200_dma_pushout(parsec_device_b200_module_t *dev, b200_task_t *bt)
     parsec_gpu_task_t *gpu_task = bt->gpu_task;
     int n = 0;
     if( dev->dry_run ) return 0;
+    if( NULL != gpu_task->stage_out && gpu_task->stage_out != parsec_default_gpu_stage_out ) {
+        /* the user's stage_out enqueues the copies on the stream it is given (stage_custom.jdf:62-95) */
+        if( PARSEC_SUCCESS != gpu_task->stage_out(gpu_task, bt->dma_out_mask, &dev->lane->super) ) return 0;
+        B200_CUDA(cudaEventRecord(bt->ev, dev->lane->cuda_stream), "cudaEventRecord", {});
+        return 1;
+    }
     for( uint32_t i = 0; i < gpu_task->nb_flows; i++ ) {
         if( !(bt->dma_out_mask & (1u << i)) ) continue;
         parsec_data_copy_t *gpu_copy = gpu_task->ec->data[i].data_out;
@@ -619,8 +661,8 @@ static int b200_push_engine(parsec_device_b200_module_t *dev, b200_task_t *bt)
         t.access[a] = (uint8_t)(flow->flow_flags & PARSEC_FLOW_ACCESS_MASK);
         if( (gpu_task->pushout & (1 << f)) && (PARSEC_FLOW_ACCESS_WRITE & flow->flow_flags) ) {
             parsec_data_copy_t *cpu = out->original->device_copies[0];
-            if( NULL != cpu && NULL != cpu->device_private && NULL != b200_device_visible(cpu->device_private, gpu_task->flow_info[f].flow_span)
-                && !(bt->peer_src_mask & (1u << f)) )
+            if( !bt->custom_stage && NULL != cpu && NULL != cpu->device_private &&
+                NULL != b200_device_visible(cpu->device_private, gpu_task->flow_info[f].flow_span) && !(bt->peer_src_mask & (1u << f)) )
                 t.access[a] |= PB2_FLOW_PUSHOUT;            /* the worker CTA copies it home */
             else bt->dma_out_mask |= (1u << f);
         }
@@ -656,9 +698,10 @@ static int b200_start_task(parsec_device_b200_module_t *dev, parsec_execution_st
     const int custom_stage = (NULL != gpu_task->stage_in && gpu_task->stage_in != parsec_default_gpu_stage_in) ||
                              (NULL != gpu_task->stage_out && gpu_task->stage_out != parsec_default_gpu_stage_out);
     const parsec_task_class_t *tc = gpu_task->ec->task_class;
+    bt->custom_stage = custom_stage;
     /* engine bodies are recognised by their submit function having been seen naming one (set below, the first time,
      * after a conservative copy-engine stage-in); dry-run modules never enqueue anything, so they always record */
-    int known_engine = !custom_stage && (dev->dry_run || parsec_b200_submit_is_engine(gpu_task->submit));
+    int known_engine = dev->dry_run || (!custom_stage && parsec_b200_submit_is_engine(gpu_task->submit));
 
     if( known_engine ) {
         rc = b200_stage_in(dev, bt, 0);
@@ -677,13 +720,15 @@ static int b200_start_task(parsec_device_b200_module_t *dev, parsec_execution_st
             parsec_list_nolock_push_back(&dev->waiting_event, &bt->item);
             return PARSEC_HOOK_RETURN_DONE;
         }
+        bt->state = BT_STAGED;
         return b200_push_engine(dev, bt);
     }
 
     /* stream lane: stage in with the copy engine on the lane stream (or the user's stage_in), run submit, event */
-    rc = b200_stage_in(dev, bt, 1);
+    const int user_in = (NULL != gpu_task->stage_in && gpu_task->stage_in != parsec_default_gpu_stage_in);
+    rc = b200_stage_in(dev, bt, user_in ? 2 : 1);
     if( rc < 0 ) return rc;
-    if( custom_stage && NULL != gpu_task->stage_in && gpu_task->stage_in != parsec_default_gpu_stage_in ) {
+    if( user_in ) {
         uint32_t mask = 0;
         for( uint32_t i = 0; i < gpu_task->nb_flows; i++ )
             if( NULL != gpu_task->ec->data[i].data_out && PARSEC_DATA_STATUS_UNDER_TRANSFER == gpu_task->ec->data[i].data_out->data_transfer_status ) mask |= (1u << i);
@@ -854,6 +899,7 @@ static void b200_finish(parsec_device_b200_module_t *dev, parsec_execution_strea
 /* returns < 0 on a fatal device problem */
 static int b200_progress(parsec_device_b200_module_t *dev, parsec_execution_stream_t *es)
 {
+    uint64_t t0 = B200_TSC(), t1;
     /* 1. inbox -> oldest-first list of tasks to start (callers push LIFO) */
     parsec_gpu_task_t *head = dev->inbox;
     while( NULL != head && !parsec_atomic_cas_ptr(&dev->inbox, head, NULL) ) head = dev->inbox;
@@ -866,21 +912,39 @@ static int b200_progress(parsec_device_b200_module_t *dev, parsec_execution_stre
         parsec_gpu_task_t *gt = fifo;
         fifo = (parsec_gpu_task_t*)gt->list_item.list_next;
         PARSEC_LIST_ITEM_SINGLETON(&gt->list_item);
+        if( UINT64_MAX != gt->last_data_check_epoch ) { parsec_warning("device_b200: gpu_task %p seen twice in the inbox (epoch %lx)", (void*)gt, (unsigned long)gt->last_data_check_epoch); abort(); }
         parsec_list_nolock_push_back(&dev->stalled, &b200_bt_new(dev, gt)->item);
     }
-    /* 2. start tasks in order; the first one that cannot get memory or ring space blocks the ones behind it */
+    t1 = B200_TSC(); dev->tsc[0] += t1 - t0; t0 = t1;
+    /* 2. start tasks, oldest first.  A task that cannot get device memory yet stays where it is and the ones behind it
+     *    are tried: their inputs may be resident already (they hold references that keep replicas from being evicted),
+     *    and their retirement is what frees memory.  A full command ring stops the pass. */
     int started = 0;
-    for(;;) {
-        b200_task_t *bt = (b200_task_t*)parsec_list_nolock_pop_front(&dev->stalled);
-        if( NULL == bt ) break;
-        int rc;
-        if( BT_NEW == bt->state ) rc = b200_start_task(dev, es, bt);
-        else rc = b200_push_engine(dev, bt);            /* staged, waiting for ring space */
-        if( PARSEC_HOOK_RETURN_AGAIN == rc ) { parsec_list_nolock_push_front(&dev->stalled, &bt->item); break; }
-        if( PARSEC_HOOK_RETURN_DONE != rc ) return -1;
-        started++;
+    {
+        parsec_list_item_t *it = PARSEC_LIST_ITERATOR_FIRST(&dev->stalled), *next;
+        int misses = 0;
+        for( ; it != PARSEC_LIST_ITERATOR_END(&dev->stalled) && misses < 64; it = next ) {
+            b200_task_t *bt = (b200_task_t*)it;
+            next = PARSEC_LIST_ITERATOR_NEXT(it);
+            int rc;
+            parsec_list_nolock_remove(&dev->stalled, it);
+            PARSEC_LIST_ITEM_SINGLETON(it);
+            if( BT_NEW == bt->state ) rc = b200_start_task(dev, es, bt);
+            else rc = b200_push_engine(dev, bt);            /* staged, waiting for ring space */
+            if( PARSEC_HOOK_RETURN_AGAIN == rc ) {
+                /* back where it was */
+                if( next == PARSEC_LIST_ITERATOR_END(&dev->stalled) ) parsec_list_nolock_push_back(&dev->stalled, it);
+                else parsec_list_nolock_add_before(&dev->stalled, next, it);
+                if( BT_NEW != bt->state ) break;            /* ring full */
+                misses++;
+                continue;
+            }
+            if( PARSEC_HOOK_RETURN_DONE != rc ) return -1;
+            started++;
+        }
     }
     if( started && PB2_SUCCESS != pb2_stream_kick(dev->stream) ) return -1;
+    t1 = B200_TSC(); dev->tsc[1] += t1 - t0; t0 = t1;
     /* 3. copy-engine / lane events */
     if( !parsec_list_nolock_is_empty(&dev->waiting_event) ) {
         parsec_list_item_t *it = PARSEC_LIST_ITERATOR_FIRST(&dev->waiting_event), *next;
@@ -904,6 +968,7 @@ static int b200_progress(parsec_device_b200_module_t *dev, parsec_execution_stre
                                                                (uint8_t)(gt->flow_info[i].flow->flow_flags & PARSEC_FLOW_ACCESS_MASK));
                     parsec_atomic_unlock(&out->original->lock);
                 }
+                bt->state = BT_STAGED;
                 int rc = b200_push_engine(dev, bt);
                 if( PARSEC_HOOK_RETURN_AGAIN == rc ) parsec_list_nolock_push_front(&dev->stalled, &bt->item);
                 else if( PARSEC_HOOK_RETURN_DONE != rc ) return -1;
@@ -913,13 +978,21 @@ static int b200_progress(parsec_device_b200_module_t *dev, parsec_execution_stre
             }
         }
     }
+    t1 = B200_TSC(); dev->tsc[2] += t1 - t0; t0 = t1;
     /* 4. retire ring */
     for(;;) {
         int n = pb2_stream_poll(dev->stream, dev->retbuf, (int32_t)(sizeof(dev->retbuf) / sizeof(dev->retbuf[0])));
         if( n < 0 ) { parsec_warning("device_b200: %s", pb2_stream_last_error(dev->stream)); return -1; }
+        t1 = B200_TSC(); dev->tsc[n ? 3 : 5] += t1 - t0; t0 = t1;
         for( int i = 0; i < n; i++ ) {
             b200_task_t *bt = (b200_task_t*)(uintptr_t)dev->retbuf[i].cookie;
+            if( NULL == bt->gpu_task || BT_INFLIGHT != bt->state ) {
+                parsec_warning("device_b200: retire record %d/%d for a task that is not in flight (bt %p state %d ticket %d/%d gpu_task %p)",
+                               i, n, (void*)bt, bt->state, bt->ticket, dev->retbuf[i].ticket, (void*)bt->gpu_task);
+                return -1;
+            }
             bt->result = dev->retbuf[i].result;
+            if( PB2_BODY_CHECK_I32 == bt->body || PB2_BODY_CHECK_F32 == bt->body ) dev->st.check_mismatches += bt->result >> 32;
             bt->ticket = -1;
             if( PB2_SUCCESS != dev->retbuf[i].status ) { parsec_warning("device_b200: task ran an unknown engine body"); return -1; }
             if( bt->dma_out_mask && b200_dma_pushout(dev, bt) > 0 ) {
@@ -927,6 +1000,7 @@ static int b200_progress(parsec_device_b200_module_t *dev, parsec_execution_stre
                 parsec_list_nolock_push_back(&dev->waiting_event, &bt->item);
             } else b200_finish(dev, es, bt);
         }
+        t1 = B200_TSC(); dev->tsc[4] += t1 - t0; t0 = t1;
         if( n < (int)(sizeof(dev->retbuf) / sizeof(dev->retbuf[0])) ) break;
     }
     return 0;
@@ -940,13 +1014,15 @@ b200_kernel_scheduler(parsec_device_module_t *module, parsec_execution_stream_t 
 
     int32_t inside = parsec_atomic_fetch_inc_int32(&dev->callers_inside) + 1;
     if( (uint64_t)inside > dev->st.max_concurrent_callers ) dev->st.max_concurrent_callers = (uint64_t)inside;
-    /* 1. hand the task over: lock-free push on the inbox, then one more task is owed */
+    /* 1. one more task is owed, THEN it is handed over (lock-free push on the inbox).  In this order the manager can
+     *    never complete a task whose debt has not been booked yet: booking first keeps `owed` from dropping to zero --
+     *    and a second manager from being elected -- while a task is on its way into the inbox. */
+    int32_t before = parsec_atomic_fetch_add_int32(&dev->owed, 1);
     parsec_gpu_task_t *old;
     do {
         old = dev->inbox;
         gpu_task->list_item.list_next = (parsec_list_item_t*)old;
     } while( !parsec_atomic_cas_ptr(&dev->inbox, old, gpu_task) );
-    int32_t before = parsec_atomic_fetch_add_int32(&dev->owed, 1);
     (void)parsec_atomic_fetch_dec_int32(&dev->callers_inside);
     if( before > 0 ) return PARSEC_HOOK_RETURN_ASYNC;        /* somebody is driving the device and owes this task too */
 
@@ -958,16 +1034,38 @@ b200_kernel_scheduler(parsec_device_module_t *module, parsec_execution_stream_t 
         es = parsec_my_execution_stream();
     }
     if( !dev->dry_run ) B200_CUDA(cudaSetDevice(dev->super.cuda_index), "cudaSetDevice", { return PARSEC_HOOK_RETURN_DISABLE; });
+    uint64_t idle_spins = 0;
     for(;;) {
         dev->completed_now = 0;
+        if( 0 == (++idle_spins & 0x3ffffff) && NULL != getenv("PARSEC_B200_DEBUG") ) {
+            int ns = 0, nw = 0;
+            parsec_list_item_t *it;
+            for( it = PARSEC_LIST_ITERATOR_FIRST(&dev->stalled); it != PARSEC_LIST_ITERATOR_END(&dev->stalled); it = PARSEC_LIST_ITERATOR_NEXT(it) ) ns++;
+            for( it = PARSEC_LIST_ITERATOR_FIRST(&dev->waiting_event); it != PARSEC_LIST_ITERATOR_END(&dev->waiting_event); it = PARSEC_LIST_ITERATOR_NEXT(it) ) nw++;
+            fprintf(stderr, "b200 manager stuck? owed %d inbox %p stalled %d waiting_event %d stream inflight %d executed %lu\n",
+                    dev->owed, (void*)dev->inbox, ns, nw, pb2_stream_inflight(dev->stream), (unsigned long)module->executed_tasks);
+        }
         if( b200_progress(dev, es) < 0 ) {
             parsec_warning("GPU[%d:%s]: the device engine reported a fatal error; giving up", module->device_index, module->name);
             return PARSEC_HOOK_RETURN_DISABLE;
         }
-        if( dev->completed_now ) {
-            /* the subtraction that reaches zero is the LAST thing a manager does: the next caller becomes manager */
-            int32_t left = parsec_atomic_fetch_sub_int32(&dev->owed, dev->completed_now) - dev->completed_now;
+        if( NULL != dev->completion_ring ) {
+            parsec_task_t *ring = dev->completion_ring;
+            dev->completion_ring = NULL;
+            __parsec_schedule(es, ring, 0);
+        }
+        /* `completed_now` belongs to the manager: take a private copy BEFORE the subtraction -- the instant `owed`
+         * reaches zero another thread may become the manager and reset the field */
+        const int32_t done_now = dev->completed_now;
+        if( done_now ) {
+            idle_spins = 0;
+            /* the subtraction that reaches zero is the LAST thing a manager does with the device */
+            const int32_t left = parsec_atomic_fetch_sub_int32(&dev->owed, done_now) - done_now;
             if( 0 == left ) return PARSEC_HOOK_RETURN_ASYNC;
+            if( left < 0 ) {
+                parsec_warning("GPU[%d:%s]: more tasks completed than were handed over (%d)", module->device_index, module->name, left);
+                return PARSEC_HOOK_RETURN_DISABLE;
+            }
         }
     }
 }
@@ -1178,6 +1276,12 @@ int parsec_b200_module_fini(parsec_device_module_t *device)
     parsec_device_b200_module_t *dev = (parsec_device_b200_module_t*)device;
     parsec_device_gpu_module_t *gpu = &dev->super.super;
     if( NULL != dev->stream ) { (void)pb2_stream_quiesce(dev->stream); }
+    if( NULL != getenv("PARSEC_B200_PROFILE") ) {
+        uint64_t tot = 0; for( int i = 0; i < 6; i++ ) tot += dev->tsc[i];
+        fprintf(stderr, "b200 manager cycles: inbox %.1f%% start %.1f%% events %.1f%% poll %.1f%% finish %.1f%% idle-poll %.1f%% (total %.1f Mcycles, %lu tasks)\n",
+                100.0 * dev->tsc[0] / (tot + 1), 100.0 * dev->tsc[1] / (tot + 1), 100.0 * dev->tsc[2] / (tot + 1), 100.0 * dev->tsc[3] / (tot + 1),
+                100.0 * dev->tsc[4] / (tot + 1), 100.0 * dev->tsc[5] / (tot + 1), tot * 1e-6, (unsigned long)device->executed_tasks);
+    }
     while( b200_write_back_some(dev, 64) > 0 ) { }
     parsec_device_memory_release(gpu);
     if( NULL != dev->stream ) { pb2_stream_destroy(dev->stream); dev->stream = NULL; }

@@ -1,0 +1,113 @@
+"""The real drop-in boundary: parsec/mca/device/b200 compiled INTO the reference runtime (oracle/build_ref_runtime.sh),
+driven by task pools the reference's own parsec-ptgpp generated from .jdf files with BODY [type=CUDA] incarnations
+(tests/parsec/*.jdf).  CPU tests: the reference runtime alone (CPU bodies: the oracle), and the component in dry-run mode
+(scheduling, ownership hand-over, concurrent callers; no bodies run).  GPU tests: the same binaries on a B200, and the
+reference's own cuda component on the same task pools as a cross-check."""
+import json
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "oracle", "_ref", "bin")
+
+
+def run(app, args, env=None, timeout=300):
+    exe = os.path.join(BIN, app)
+    if not os.path.exists(exe):
+        pytest.fail(f"{exe} is missing: run __graft_entry__.build() where /root/reference is mounted "
+                    "(oracle/build_ref_runtime.sh + make -C tests/parsec)")
+    e = dict(os.environ)
+    e.pop("PARSEC_MCA_device_b200_enabled", None)
+    e.pop("PARSEC_MCA_device_b200_dry_run", None)
+    e.update(env or {})
+    p = subprocess.run([exe] + [str(a) for a in args], env=e, cwd="/tmp", capture_output=True, text=True, timeout=timeout)
+    lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    assert lines, f"no JSON line from {app}: rc={p.returncode}\n{p.stdout[-2000:]}\n{p.stderr[-2000:]}"
+    return p.returncode, json.loads(lines[-1]), p.stderr
+
+
+CPU_ENV = {"PARSEC_MCA_device_cuda_enabled": "0"}
+
+
+def test_reference_runtime_cpu_bodies_known_answer():
+    """The reference's scheduler + dependency engine + the CPU incarnations: every TaskRecv(k, n) sees k."""
+    rc, d, _ = run("ex05_b200", ["-K", 128, "-t", 1024, "-m", "cpu", "-c", 4, "-w"], CPU_ENV)
+    assert rc == 0 and d["errors"] == 0 and d["tasks"] == 128 * 9 and d["executed_on_gpu"] == 0
+    rc, d, _ = run("stage_b200", ["-m", "cpu"], CPU_ENV)
+    assert rc == 0 and d["check_errors"] == 0 and d["host_errors"] == 0
+
+
+@pytest.mark.parametrize("ndev,cores", [(1, 8), (2, 8), (4, 3)])
+def test_component_dry_run_schedules_generated_taskpool(ndev, cores):
+    """kernel_scheduler takes every parsec_gpu_task_t the generated hooks build, from concurrent worker threads, and
+    completes each task exactly once (the taskpool terminates, executed_tasks adds up)."""
+    K, rep = 1024, 3
+    rc, d, err = run("ex05_b200", ["-K", K, "-t", 64, "-m", "gpu", "-c", cores, "-r", rep],
+                     {"PARSEC_MCA_device_b200_dry_run": str(ndev)})
+    assert d["b200_modules"] == ndev and d["gpu_modules"] == ndev, err[-500:]
+    assert d["executed_on_gpu"] == K * 9 * rep
+    assert d["b200"]["tasks_engine"] == K * 9 * rep and d["b200"]["tasks_lane"] == 0
+    assert d["b200"]["manager_entries"] >= 1
+    if cores >= 8:
+        assert d["b200"]["max_concurrent_callers"] >= 2, "no two worker threads were ever inside kernel_scheduler together"
+    # dry-run bodies do not run: the host tiles keep their initial value, every sampled element is 'wrong'
+    assert d["errors"] > 0
+
+
+def test_component_dry_run_memory_pressure_evicts_and_writes_back():
+    """A heap of 64 blocks for 256 tiles: clean replicas are evicted, dirty ones written back first."""
+    rc, d, err = run("ex05_b200", ["-K", 256, "-t", 131072, "-m", "gpu", "-c", 4],
+                     {"PARSEC_MCA_device_b200_dry_run": "1", "PARSEC_MCA_device_b200_memory_number_of_blocks": "64"})
+    assert d["executed_on_gpu"] == 256 * 9, err[-500:]
+    assert d["b200"]["evictions"] >= 256 - 64
+    assert d["b200"]["w2r_copies"] > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("wb", [False, True])
+def test_component_gpu_ex05_known_answer(wb):
+    K, rep = 512, 2
+    args = ["-K", K, "-t", 65536, "-m", "gpu", "-c", 8, "-r", rep] + (["-w"] if wb else [])
+    rc, d, err = run("ex05_b200", args, {"PARSEC_MCA_device_b200_enabled": "1"})
+    assert rc == 0, err[-1000:]
+    assert d["b200_modules"] == 1 and d["gpu_modules"] == 1
+    assert d["errors"] == 0 and d["b200"]["check_mismatches"] == 0
+    assert d["executed_on_gpu"] == K * 9 * rep and d["b200"]["tasks_engine"] == K * 9 * rep
+    assert d["b200"]["kernel_launches"] >= 1
+    # each tile is staged in exactly once per pass that finds it invalid: required == moved (device.c:545-590)
+    moved = d["b200"]["bytes_h2d_kernel"] + d["b200"]["bytes_h2d_dma"]
+    assert moved == d["h2d_bytes"]
+    assert d["h2d_bytes"] == K * 262144 * (1 if wb else rep)
+
+
+@pytest.mark.gpu
+def test_component_gpu_memory_pressure():
+    """256 tiles of 256 KiB through a 96-block heap: eviction + write-back on the real device, results still right."""
+    rc, d, err = run("ex05_b200", ["-K", 256, "-t", 65536, "-m", "gpu", "-c", 8],
+                     {"PARSEC_MCA_device_b200_enabled": "1", "PARSEC_MCA_device_b200_memory_number_of_blocks": "96"})
+    assert rc == 0 and d["errors"] == 0 and d["b200"]["check_mismatches"] == 0, err[-1000:]
+    assert d["b200"]["evictions"] > 0
+
+
+@pytest.mark.gpu
+def test_component_gpu_stage_callbacks_and_opaque_bodies():
+    """Golden vector 'stage' (stage_custom.jdf:266-279): default staging == user stage_in/stage_out == opaque stream body."""
+    rc, d, err = run("stage_b200", ["-m", "gpu", "-c", 4], {"PARSEC_MCA_device_b200_enabled": "1"})
+    assert rc == 0, err[-1000:]
+    assert d["check_errors"] == 0 and d["host_errors"] == 0
+    assert d["executed_on_gpu"] == 3 * d["tiles"]
+    assert d["tasks_lane"] >= d["tiles"]                    # the opaque bodies ran on the stream lane
+    assert d["complete_stage_calls"] == d["tiles"]
+    assert d["bytes_h2d_dma"] > 0 and d["bytes_d2h_dma"] > 0  # C is pageable, B is strided: copy engine
+
+
+@pytest.mark.gpu
+def test_reference_cuda_component_agrees_on_the_same_taskpools():
+    """The same binaries under the reference's own stream engine (device_cuda): same known answers."""
+    env = {"PARSEC_MCA_device_cuda_enabled": "1"}
+    rc, d, err = run("ex05_b200", ["-K", 256, "-t", 65536, "-m", "gpu", "-c", 8, "-w"], env)
+    assert rc == 0 and d["errors"] == 0 and d["b200_modules"] == 0 and d["gpu_modules"] == 1, err[-1000:]
+    rc, d, err = run("stage_b200", ["-m", "gpu", "-c", 4], env)
+    assert rc == 0 and d["check_errors"] == 0 and d["host_errors"] == 0, err[-1000:]
