@@ -230,6 +230,7 @@ static int b200_write_back_some(parsec_device_b200_module_t *dev, int how_many)
             copy->original->owner_device = 0;
             parsec_atomic_unlock(&copy->original->lock);
             parsec_list_nolock_push_back(&dev->super.super.gpu_mem_lru, it);
+            dev->st.w2r_copies++;
             done++;
         }
         return done;
@@ -359,6 +360,20 @@ static int b200_reserve(parsec_device_b200_module_t *dev, b200_task_t *bt)
         this_task->data[i].data_out = gpu_elem;
     }
     return PARSEC_HOOK_RETURN_DONE;
+}
+
+/* does starting this task require a fresh allocation on the device? */
+static int b200_needs_memory(const parsec_device_b200_module_t *dev, const parsec_gpu_task_t *gpu_task)
+{
+    const uint8_t my = dev->super.super.super.device_index;
+    for( uint32_t i = 0; i < gpu_task->nb_flows; i++ ) {
+        const parsec_flow_t *flow = gpu_task->flow_info[i].flow;
+        if( PARSEC_FLOW_ACCESS_NONE == (PARSEC_FLOW_ACCESS_MASK & flow->flow_flags) ) continue;
+        const parsec_data_copy_t *in = gpu_task->ec->data[i].data_in;
+        if( NULL == in || in->device_index == my ) continue;
+        if( NULL == PARSEC_DATA_GET_COPY(in->original, my) ) return 1;
+    }
+    return 0;
 }
 
 /* ------------------------------------------------------------------------------------------------------------------ */
@@ -540,6 +555,57 @@ uint64_t parsec_b200_task_result(const parsec_gpu_task_t *gpu_task)
 }
 
 /* ------------------------------------------------------------------------------------------------------------------ */
+/* runtime-side completion on the worker pool                                                                           */
+/* The manager keeps the device-side epilog; prepare_output / release_deps / release_task of a finished task -- the      */
+/* expensive part, proportional to its number of successors -- is run by whichever worker dequeues a small PROXY task.   */
+/* The proxy is an ordinary parsec_task_t of a private class with one CPU incarnation; its hook calls                     */
+/* __parsec_complete_execution on the real task (exactly once, with the worker's own execution stream) and returns        */
+/* ASYNC, so the runtime never tries to complete the proxy itself.  Until that hook has run, successors have not taken    */
+/* their references on the task's output replicas yet: the replicas stay PINNED (a reader each) so that eviction cannot     */
+/* take them away in between.                                                                                             */
+/* ------------------------------------------------------------------------------------------------------------------ */
+typedef struct b200_proxy_s {
+    parsec_task_t        task;
+    parsec_task_t       *original;
+    int                  npins;
+    parsec_data_copy_t  *pins[MAX_PARAM_COUNT];
+    struct b200_proxy_s * volatile next_free;
+} b200_proxy_t;
+static b200_proxy_t * volatile b200_proxy_free = NULL;      /* LIFO shared by the modules and the workers */
+static parsec_atomic_lock_t b200_proxy_lock = PARSEC_ATOMIC_UNLOCKED;
+
+static parsec_hook_return_t b200_completion_hook(parsec_execution_stream_t *es, parsec_task_t *task)
+{
+    b200_proxy_t *px = (b200_proxy_t*)task;
+    (void)__parsec_complete_execution(es, px->original);
+    for( int i = 0; i < px->npins; i++ ) (void)parsec_atomic_fetch_dec_int32(&px->pins[i]->readers);
+    parsec_atomic_lock(&b200_proxy_lock);
+    px->next_free = b200_proxy_free; b200_proxy_free = px;
+    parsec_atomic_unlock(&b200_proxy_lock);
+    return PARSEC_HOOK_RETURN_ASYNC;      /* nothing of the proxy is left for the runtime to complete */
+}
+static const __parsec_chore_t b200_completion_chores[] = {
+    { .type = PARSEC_DEV_CPU, .evaluate = NULL, .hook = b200_completion_hook, .dyld = NULL, .dyld_fn = NULL },
+    { .type = PARSEC_DEV_NONE, .evaluate = NULL, .hook = NULL, .dyld = NULL, .dyld_fn = NULL },
+};
+static const parsec_task_class_t b200_completion_tc = {
+    .name = "b200 completion", .flags = 0, .task_class_id = 0, .nb_flows = 0, .nb_parameters = 0, .nb_locals = 0,
+    .incarnations = b200_completion_chores,
+};
+static b200_proxy_t *b200_proxy_get(void)
+{
+    b200_proxy_t *px;
+    parsec_atomic_lock(&b200_proxy_lock);
+    if( NULL != (px = b200_proxy_free) ) b200_proxy_free = px->next_free;
+    parsec_atomic_unlock(&b200_proxy_lock);
+    if( NULL == px ) {
+        px = (b200_proxy_t*)calloc(1, sizeof(b200_proxy_t));
+        PARSEC_OBJ_CONSTRUCT(&px->task, parsec_task_t);
+    }
+    return px;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
 /* completion: epilog of the flows + hand-back to the runtime (parsec_device_kernel_pop / _epilog, device_gpu.c:2943,  */
 /* :3179, and the complete_task tail of the scheduler, :3562-3590)                                                     */
 /* ------------------------------------------------------------------------------------------------------------------ */
@@ -599,15 +665,27 @@ static void b200_complete(parsec_device_b200_module_t *dev, parsec_execution_str
     }
     mod->executed_tasks++;
     if( parsec_b200_parallel_completion ) {
-        /* Hand the runtime-side completion (prepare_output, release_deps of every successor, release_task) to the
-         * worker pool: a task whose status is past HOOK goes straight to __parsec_complete_execution when a worker
-         * dequeues it (scheduling.c:507-545).  It is still called exactly once, by a thread that owns an execution
-         * stream; the manager only keeps the device-side epilog above.  The tasks of one manager iteration are
-         * chained and scheduled with one call at its end. */
-        this_task->status = PARSEC_TASK_STATUS_COMPLETE;
-        PARSEC_LIST_ITEM_SINGLETON(this_task);
-        if( NULL == dev->completion_ring ) dev->completion_ring = this_task;
-        else parsec_list_item_ring_push((parsec_list_item_t*)dev->completion_ring, (parsec_list_item_t*)this_task);
+        b200_proxy_t *px = b200_proxy_get();
+        px->original = this_task;
+        px->npins = 0;
+        for( uint32_t i = 0; i < gpu_task->nb_flows; i++ ) {
+            parsec_data_copy_t *o = this_task->data[i].data_out;
+            if( NULL == o || o->device_index != mod->device_index ) continue;
+            (void)parsec_atomic_fetch_inc_int32(&o->readers);          /* pinned until release_deps has run */
+            px->pins[px->npins++] = o;
+        }
+        PARSEC_LIST_ITEM_SINGLETON(&px->task);
+        px->task.taskpool = this_task->taskpool;
+        px->task.task_class = &b200_completion_tc;
+        px->task.priority = INT32_MAX;                                 /* completions first: they release work */
+        px->task.status = PARSEC_TASK_STATUS_HOOK;                     /* no prepare_input */
+        px->task.chore_mask = 1;
+        px->task.selected_device = parsec_mca_device_get(0);
+        px->task.selected_chore = 0;
+        px->task.load = 0;
+        px->task.repo_entry = NULL;
+        if( NULL == dev->completion_ring ) dev->completion_ring = &px->task;
+        else parsec_list_item_ring_push((parsec_list_item_t*)dev->completion_ring, (parsec_list_item_t*)&px->task);
     } else {
         __parsec_complete_execution(es, this_task);
     }
@@ -922,11 +1000,13 @@ static int b200_progress(parsec_device_b200_module_t *dev, parsec_execution_stre
     int started = 0;
     {
         parsec_list_item_t *it = PARSEC_LIST_ITERATOR_FIRST(&dev->stalled), *next;
-        int misses = 0;
-        for( ; it != PARSEC_LIST_ITERATOR_END(&dev->stalled) && misses < 64; it = next ) {
+        int mem_blocked = 0;
+        for( ; it != PARSEC_LIST_ITERATOR_END(&dev->stalled); it = next ) {
             b200_task_t *bt = (b200_task_t*)it;
             next = PARSEC_LIST_ITERATOR_NEXT(it);
             int rc;
+            /* once a task has failed to get memory in this pass, only tasks that need none are tried */
+            if( mem_blocked && BT_NEW == bt->state && b200_needs_memory(dev, bt->gpu_task) ) continue;
             parsec_list_nolock_remove(&dev->stalled, it);
             PARSEC_LIST_ITEM_SINGLETON(it);
             if( BT_NEW == bt->state ) rc = b200_start_task(dev, es, bt);
@@ -936,7 +1016,7 @@ static int b200_progress(parsec_device_b200_module_t *dev, parsec_execution_stre
                 if( next == PARSEC_LIST_ITERATOR_END(&dev->stalled) ) parsec_list_nolock_push_back(&dev->stalled, it);
                 else parsec_list_nolock_add_before(&dev->stalled, next, it);
                 if( BT_NEW != bt->state ) break;            /* ring full */
-                misses++;
+                mem_blocked = 1;
                 continue;
             }
             if( PARSEC_HOOK_RETURN_DONE != rc ) return -1;
