@@ -180,6 +180,8 @@ pb2_data_t* pb2_data_new_temporary(pb2_context_t* ctx, size_t size);   /* arena 
 int  pb2_data_start_transfer_ownership_to_copy(pb2_context_t* ctx, pb2_data_t* data, uint8_t device, uint8_t access);
 void pb2_data_end_transfer_ownership_to_copy(pb2_data_t* data, uint8_t device, uint8_t access);
 pb2_data_copy_t* pb2_data_get_copy(pb2_data_t* data, int device);
+/* parsec_data_copy_attach, data.c:174-196: a fresh INVALID replica on `device` (NULL when the datum already has one) */
+pb2_data_copy_t* pb2_data_copy_attach(pb2_data_t* data, int device);
 /* out[6] = present, coherency_state, data_transfer_status, readers, version, flags */
 int  pb2_data_copy_state(pb2_data_t* data, int device, int32_t* out);
 int  pb2_data_owner_device(pb2_data_t* data);

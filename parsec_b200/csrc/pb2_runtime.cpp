@@ -148,58 +148,65 @@ static void data_destroy(pb2_data_t* d) {
     delete d;
 }
 
+// The coherency protocol of a datum when device `device` is about to access it (behaviour of parsec/data.c:334-458,
+// checked transition by transition against the reference's own build of that file in tests/test_oracle.py).
+// Stated as data: what the DESTINATION replica's state says about fetching, then what the access does to the others.
+extern "C++" {
+namespace {
+enum class Fetch : uint8_t { never, always, if_owner_is_newer };
+// indexed by PB2_DATA_COHERENCY_* (INVALID 0, OWNED 1, EXCLUSIVE 2, SHARED 4)
+constexpr Fetch kFetchRule[5] = { Fetch::always, Fetch::never, Fetch::never, Fetch::never, Fetch::if_owner_is_newer };
+
+template <class F> inline void for_each_other_valid(pb2_data_t* d, int nb, int skip, F f) {
+    for (int i = 0; i < nb; ++i) {
+        pb2_data_copy_t* c = d->device_copies[i];
+        if (i != skip && c && c->coherency_state != PB2_DATA_COHERENCY_INVALID) f(i, c);
+    }
+}
+}  // namespace
+}  // extern "C++"
+
 int pb2_data_start_transfer_ownership_to_copy(pb2_context_t* ctx, pb2_data_t* data, uint8_t device, uint8_t access_mode) {
     const int nb = ctx ? (int)ctx->devices.size() : PB2_MAX_DEVICES;
-    int transfer_required = 0;
-    int valid_copy = data->owner_device;
-    pb2_data_copy_t* copy = data->device_copies[device];
-    if (!copy) return PB2_ERR_NOT_FOUND - 100;
-    if (valid_copy == device) goto bookkeeping;
-    switch (copy->coherency_state) {
-    case PB2_DATA_COHERENCY_INVALID:
-        transfer_required = 1;
-        if (-1 == valid_copy) {
-            for (int i = 0; i < nb; i++) {
-                if (!data->device_copies[i] || PB2_DATA_COHERENCY_INVALID == data->device_copies[i]->coherency_state) continue;
-                valid_copy = i;
-            }
+    pb2_data_copy_t* const dst = data->device_copies[device];
+    if (!dst) return PB2_ERR_NOT_FOUND - 100;
+    const bool reads = (access_mode & PB2_FLOW_ACCESS_READ) != 0, writes = (access_mode & PB2_FLOW_ACCESS_WRITE) != 0;
+    int source = data->owner_device;
+    bool fetch = false;
+
+    if (source != device) {                      // a device that owns the datum changes nothing but the book-keeping
+        // 1. does the destination need bytes, and from whom?
+        switch (kFetchRule[dst->coherency_state & 7]) {
+        case Fetch::always:
+            fetch = true;
+            if (source < 0) for_each_other_valid(data, nb, -1, [&](int i, pb2_data_copy_t*) { source = i; });   // last valid replica
+            break;
+        case Fetch::if_owner_is_newer:
+            for_each_other_valid(data, nb, -1, [&](int, pb2_data_copy_t* c) {
+                fetch |= (c->coherency_state == PB2_DATA_COHERENCY_OWNED && c->version > dst->version); });
+            break;
+        case Fetch::never: break;
         }
-        break;
-    case PB2_DATA_COHERENCY_SHARED:
-        for (int i = 0; i < nb; i++) {
-            if (!data->device_copies[i]) continue;
-            if (PB2_DATA_COHERENCY_OWNED == data->device_copies[i]->coherency_state &&
-                data->device_copies[i]->version > copy->version) transfer_required = 1;
+        // 2. what the access does to the other replicas
+        if (reads) {
+            const bool owner_turns_reader = dst->coherency_state == PB2_DATA_COHERENCY_OWNED && !writes;
+            for_each_other_valid(data, nb, device, [&](int, pb2_data_copy_t* c) {
+                if (owner_turns_reader) {        // the dirty replica is read in place: older replicas die, nobody owns
+                    if (c->version < dst->version) c->coherency_state = PB2_DATA_COHERENCY_INVALID;
+                    data->owner_device = -1;
+                }
+                if (c->coherency_state == PB2_DATA_COHERENCY_EXCLUSIVE) c->coherency_state = PB2_DATA_COHERENCY_SHARED;
+            });
+        } else {
+            fetch = false;                       // write-only: the old bytes are not needed
         }
-        break;
-    default: break;
+        if (writes) for_each_other_valid(data, nb, -1, [](int, pb2_data_copy_t* c) { c->coherency_state = PB2_DATA_COHERENCY_SHARED; });
     }
-    if (PB2_FLOW_ACCESS_READ & access_mode) {
-        for (int i = 0; i < nb; i++) {
-            pb2_data_copy_t* o = data->device_copies[i];
-            if (device == i || !o || PB2_DATA_COHERENCY_INVALID == o->coherency_state) continue;
-            if (PB2_DATA_COHERENCY_OWNED == copy->coherency_state && !(PB2_FLOW_ACCESS_WRITE & access_mode)) {
-                if (o->version < copy->version) o->coherency_state = PB2_DATA_COHERENCY_INVALID;
-                data->owner_device = -1;
-            }
-            if (PB2_DATA_COHERENCY_EXCLUSIVE == o->coherency_state) o->coherency_state = PB2_DATA_COHERENCY_SHARED;
-        }
-    } else {
-        transfer_required = 0;    /* finally we'll just overwrite w/o read */
-    }
-    if (PB2_FLOW_ACCESS_WRITE & access_mode) {
-        for (int i = 0; i < nb; i++) {
-            pb2_data_copy_t* o = data->device_copies[i];
-            if (!o || PB2_DATA_COHERENCY_INVALID == o->coherency_state) continue;
-            o->coherency_state = PB2_DATA_COHERENCY_SHARED;
-        }
-    }
-bookkeeping:
-    if (PB2_FLOW_ACCESS_READ & access_mode) copy->readers++;
-    if (PB2_FLOW_ACCESS_WRITE & access_mode) data->owner_device = (int8_t)device;
-    if (!transfer_required) return -1;
-    copy->coherency_state = PB2_DATA_COHERENCY_INVALID;
-    return valid_copy;
+    if (reads) dst->readers++;
+    if (writes) data->owner_device = (int8_t)device;
+    if (!fetch) return -1;
+    dst->coherency_state = PB2_DATA_COHERENCY_INVALID;   // until pb2_data_end_transfer_ownership_to_copy
+    return source;
 }
 
 void pb2_data_end_transfer_ownership_to_copy(pb2_data_t* data, uint8_t device, uint8_t access_mode) {
@@ -207,6 +214,12 @@ void pb2_data_end_transfer_ownership_to_copy(pb2_data_t* data, uint8_t device, u
     if (!copy) return;
     if (PB2_FLOW_ACCESS_READ & access_mode) copy->coherency_state = PB2_DATA_COHERENCY_SHARED;
     if (PB2_FLOW_ACCESS_WRITE & access_mode) copy->coherency_state = PB2_DATA_COHERENCY_OWNED;
+}
+
+/* parsec_data_copy_attach (data.c:174-196): a new, INVALID replica of the datum on `device`; NULL if one exists */
+pb2_data_copy_t* pb2_data_copy_attach(pb2_data_t* data, int device) {
+    if (!data || device < 0 || device >= PB2_MAX_DEVICES || data->device_copies[device]) return nullptr;
+    return new_copy(data, device, PB2_DATA_FLAG_PARSEC_MANAGED);
 }
 
 pb2_data_copy_t* pb2_data_get_copy(pb2_data_t* data, int device) {
@@ -589,15 +602,27 @@ static int run_cpu_task(pb2_context_t* ctx, pb2_htask_t* t) {
         if (!d) continue;
         pb2_data_copy_t* h = pb2i_host_copy(d);
         if (!h) return PB2_ERROR;
-        // newest version must already be on the host (pushout by the producing GPU task); if a GPU still owns a
-        // newer one (no pushout requested), fetch it now: the reference would have forced the pushout.
-        if (d->owner_device >= 2 && d->device_copies[d->owner_device] &&
-            d->device_copies[d->owner_device]->version > h->version && (t->access[f] & PB2_FLOW_ACCESS_READ)) {
-            pb2_device_module_t* od = ctx->devices[d->owner_device];
-            pb2_data_copy_t* g = d->device_copies[d->owner_device];
-            if (!od->dry_run) { pb2_engine_memcpy_d2h(od->engine, h->device_private, g->device_private, d->span); }
-            od->st.data_out_to_host += d->span;
-            h->version = g->version; g->coherency_state = PB2_DATA_COHERENCY_SHARED;
+        // The newest version must be on the host before a CPU body reads it.  A producing GPU task normally pushed it
+        // out; when it did not (no pushout requested, or an in-place write that left the coherency states untouched,
+        // device_gpu.c:1832-1836) the decision is taken by VERSION, like every other one that moves bytes here: fetch
+        // from the valid replica with the highest version whenever it is newer than the host copy.
+        if (t->access[f] & PB2_FLOW_ACCESS_READ) {
+            pb2_data_copy_t* newest = nullptr;
+            for (int i = 2; i < (int)ctx->devices.size(); ++i) {
+                pb2_data_copy_t* c = d->device_copies[i];
+                if (c && c->device_private && c->coherency_state != PB2_DATA_COHERENCY_INVALID && c->version > h->version &&
+                    (!newest || c->version > newest->version)) newest = c;
+            }
+            if (newest) {
+                pb2_device_module_t* od = ctx->devices[newest->device_index];
+                // the task that wrote this version has been retired (that is why this task is ready): the bytes are final;
+                // the copy is ordered behind whatever the engine stream still runs
+                if (!od->dry_run) { pb2_engine_memcpy_d2h(od->engine, h->device_private, newest->device_private, d->span); }
+                od->st.data_out_to_host += d->span;
+                h->version = newest->version;
+                h->coherency_state = PB2_DATA_COHERENCY_SHARED; newest->coherency_state = PB2_DATA_COHERENCY_SHARED;
+                d->owner_device = 0;
+            }
         }
         pb2_data_start_transfer_ownership_to_copy(ctx, d, 0, t->access[f]);
         pb2_data_end_transfer_ownership_to_copy(d, 0, t->access[f]);
@@ -612,9 +637,22 @@ static int run_cpu_task(pb2_context_t* ctx, pb2_htask_t* t) {
         pb2_data_copy_t* h = pb2i_host_copy(d);
         if (t->access[f] & PB2_FLOW_ACCESS_READ) h->readers--;
         if (t->access[f] & PB2_FLOW_ACCESS_WRITE) {
-            h->version++;
-            for (int i = 1; i < PB2_MAX_DEVICES; ++i)            // stale replicas
-                if (d->device_copies[i] && d->device_copies[i]->version < h->version) d->device_copies[i]->coherency_state = PB2_DATA_COHERENCY_INVALID;
+            // the CPU result supersedes EVERY replica, including GPU ones that are newer than the host copy was
+            // (write-only flow after GPU writes without pushout): version = newest + 1, all the others stale
+            uint32_t newest = h->version;
+            for (int i = 1; i < PB2_MAX_DEVICES; ++i)
+                if (d->device_copies[i] && d->device_copies[i]->version > newest) newest = d->device_copies[i]->version;
+            h->version = newest + 1;
+            h->coherency_state = PB2_DATA_COHERENCY_OWNED; d->owner_device = 0;
+            for (int i = 1; i < PB2_MAX_DEVICES; ++i) {
+                pb2_data_copy_t* c = d->device_copies[i];
+                if (!c) continue;
+                c->coherency_state = PB2_DATA_COHERENCY_INVALID;
+                if (i >= 2 && c->lru_list == 2 && c->readers == 0) {          // nothing left to write back
+                    pb2_device_module_t* od = ctx->devices[i];
+                    pb2i_lru_remove(od, c); pb2i_lru_push_back(od, 1, c);
+                }
+            }
         }
     }
     ctx->devices[0]->st.executed_tasks++;
@@ -906,7 +944,11 @@ static int build_window(pb2_device_module_t* dev, Window& w, std::vector<pb2_gpu
         if (!ok) {
             // no room: this task (and everything behind it) waits for the next window (HOOK_RETURN_AGAIN)
             full = true;
-            for (pb2_data_copy_t* g : fresh) { g->window_tile = -1; g->window_owner = nullptr; w.tile_data.pop_back(); }
+            for (pb2_data_copy_t* g : fresh) {
+                g->window_tile = -1; g->window_owner = nullptr; w.tile_data.pop_back();
+                // a slot reserve_space has just allocated for this task is on no list yet: put it where eviction finds it
+                if (g->lru_list == 0) pb2i_lru_push_back(dev, (g->coherency_state == PB2_DATA_COHERENCY_OWNED && g->version > 0) ? 2 : 1, g);
+            }
             continue;
         }
         t->window_index = (int32_t)w.order.size();
@@ -940,6 +982,7 @@ static int build_window(pb2_device_module_t* dev, Window& w, std::vector<pb2_gpu
         pb2_tile_t& tl = w.tiles[i];
         memset(&tl, 0, sizeof tl);
         tl.dev_ptr = g->device_private;
+        if (d->span > 0xffffffffull) { dev->ctx->last_error = "tile larger than 4 GiB (pb2_tile_t::bytes is 32-bit)"; return PB2_ERR_VALUE_OUT_OF_BOUNDS; }
         tl.bytes = (uint32_t)d->span;
         uint32_t newest = 0;
         for (int k = 0; k < PB2_MAX_DEVICES; ++k)
@@ -1024,7 +1067,15 @@ static void retire_task_bookkeeping(pb2_device_module_t* dev, Window& w, pb2_hta
         dev->st.required_data_in += d->span;                                          // :2055
         if (in == g) {
             // "data already located in the right place" (:1820-1843): no ownership call at all
-            if (acc & PB2_FLOW_ACCESS_WRITE) g->version++;
+            if (acc & PB2_FLOW_ACCESS_WRITE) {
+                // in-place write: this replica is now THE valid one -- say so in the protocol's own terms, so that
+                // nobody (CPU bodies, other GPUs, the write-back) has to infer it from the version alone
+                g->version++;
+                g->coherency_state = PB2_DATA_COHERENCY_OWNED; d->owner_device = (int8_t)di;
+                for (int i = 0; i < PB2_MAX_DEVICES; ++i)
+                    if (i != di && d->device_copies[i] && d->device_copies[i]->coherency_state != PB2_DATA_COHERENCY_INVALID)
+                        d->device_copies[i]->coherency_state = PB2_DATA_COHERENCY_SHARED;
+            }
             if (acc & PB2_FLOW_ACCESS_READ) g->readers++;
         } else {
             // read-only flows may have been given a peer replica as source at build time (:1888-2008)

@@ -34,7 +34,7 @@ PARSEC_SYMBOLS = [
     "pb2_device_taskpool_unregister", "pb2_device_kernel_scheduler", "pb2_device_zone_malloc", "pb2_device_zone_free",
     "pb2_device_zone_in_use", "pb2_device_lru_sizes", "pb2_select_best_device", "pb2_data_create",
     "pb2_data_new_temporary", "pb2_data_start_transfer_ownership_to_copy", "pb2_data_end_transfer_ownership_to_copy",
-    "pb2_data_get_copy", "pb2_data_copy_state", "pb2_data_owner_device", "pb2_data_preferred_device",
+    "pb2_data_get_copy", "pb2_data_copy_attach", "pb2_data_copy_state", "pb2_data_owner_device", "pb2_data_preferred_device",
     "pb2_matrix_block_cyclic_new", "pb2_data_collection_free", "pb2_data_collection_set_mat", "pb2_dc_rank_of",
     "pb2_dc_data_of", "pb2_dc_data_key", "pb2_dc_position", "pb2_dc_info", "pb2_dc_register_memory",
     "pb2_dc_distribute_on_devices", "pb2_dc_host_write_all", "pb2_context_add_taskpool", "pb2_context_start", "pb2_context_wait",
@@ -77,7 +77,7 @@ def lib():
         "pb2_data_create": (vp, [vp, C.c_uint64, vp, C.c_size_t]), "pb2_data_new_temporary": (vp, [vp, C.c_size_t]),
         "pb2_data_start_transfer_ownership_to_copy": (C.c_int, [vp, vp, C.c_uint8, C.c_uint8]),
         "pb2_data_end_transfer_ownership_to_copy": (None, [vp, C.c_uint8, C.c_uint8]),
-        "pb2_data_get_copy": (vp, [vp, C.c_int]), "pb2_data_copy_state": (C.c_int, [vp, C.c_int, P(i32)]),
+        "pb2_data_get_copy": (vp, [vp, C.c_int]), "pb2_data_copy_attach": (vp, [vp, C.c_int]), "pb2_data_copy_state": (C.c_int, [vp, C.c_int, P(i32)]),
         "pb2_data_owner_device": (C.c_int, [vp]), "pb2_data_preferred_device": (C.c_int, [vp]),
         "pb2_matrix_block_cyclic_new": (vp, [vp] + [C.c_int] * 16),
         "pb2_data_collection_free": (C.c_int, [vp]), "pb2_data_collection_set_mat": (C.c_int, [vp, vp]),
@@ -115,6 +115,8 @@ def lib():
 
 # pb2_gpu_submit_t: int submit(pb2_device_module_t* dev, pb2_gpu_task_t* gpu_task, void* cuda_stream)
 GPU_SUBMIT = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p)
+# pb2_cpu_hook_t: int hook(pb2_htask_t* task, void** flow_ptrs, const int32_t* iparam, float fparam)
+CPU_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_float)
 
 
 def _chk(rc, what):

@@ -16,14 +16,15 @@ def test_library_exports_every_declared_symbol():
     """The C-ABI library loads without a GPU and exports every symbol include/*.h declares."""
     lib = L.load()
     declared = set()
-    for hdr in ("include/pb2_engine.h", "include/pb2_parsec.h"):
+    for hdr in ("include/pb2_engine.h", "include/pb2_parsec.h", "include/pb2_stream.h"):
         txt = open(hdr).read()
         declared |= set(re.findall(r"\b(pb2_[a-z0-9_]+)\s*\(", txt))
     declared -= {"pb2_cpu_hook_t"}
     assert declared, "no declarations found"
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
     assert not missing, missing
-    assert set(L.ENGINE_SYMBOLS) | set(R.PARSEC_SYMBOLS) >= declared
+    from parsec_b200.stream import STREAM_SYMBOLS
+    assert set(L.ENGINE_SYMBOLS) | set(R.PARSEC_SYMBOLS) | set(STREAM_SYMBOLS) >= declared
 
 
 def test_no_gpu_means_loud_failure():
@@ -392,7 +393,7 @@ def test_statistics_table_reports_what_the_devices_did():
     assert table.splitlines()[-1].strip().startswith("all")
 
 
-@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("seed", range(16))
 def test_random_dtd_pools_under_pipelining_and_memory_pressure(seed):
     """Random DTD pools (GPU bodies, CPU bodies, user-submit bodies on shared tiles) on two dry-run GPUs with a device
     heap far smaller than the working set and windows cut into small pipelined pieces: every task completes exactly
@@ -402,7 +403,7 @@ def test_random_dtd_pools_under_pipelining_and_memory_pressure(seed):
     ntiles, ntasks, tb = 10, 120, 1024
     mca = {"device_cuda_memory_number_of_blocks": 6, "device_cuda_memory_block_size": tb,
            "device_engine_pipeline": 3, "device_engine_pipeline_min_roots": 2}
-    cpu_hook = R.CPU_HOOK(lambda t, p, ip, fp: 0) if hasattr(R, "CPU_HOOK") else None
+    cpu_hook = R.CPU_HOOK(lambda t, p, ip, fp: 0)
     with R.Context(cuda_devices=(0, 1), dry_run=True, mca=mca) as ctx:
         tp = C.c_void_p(ctx.l.pb2_dtd_taskpool_new(ctx.h))
         keep = [R.GPU_SUBMIT(lambda d, g, s: 0)]
@@ -416,20 +417,31 @@ def test_random_dtd_pools_under_pipelining_and_memory_pressure(seed):
                 else:
                     assert ctx.l.pb2_dtd_task_class_add_submit(tp, tc, keep[0]) == 0
                 classes[(nf, kind)] = tc
+            # CPU-only classes: GPU -> CPU hand-over without pushout, CPU writes between GPU uses
+            tc = C.c_void_p(ctx.l.pb2_dtd_create_task_class(tp, b"c", nf, ops.ctypes.data_as(C.c_void_p)))
+            assert ctx.l.pb2_dtd_task_class_add_chore(tp, tc, R.DEV_CPU, 0, C.cast(cpu_hook, C.c_void_p)) == 0
+            classes[(nf, "cpu")] = tc
         tiles = [C.c_void_p(ctx.l.pb2_dtd_tile_new(tp, tb)) for _ in range(ntiles)]
         uses = []                                              # (task, tile, writes)
+        kinds, expect_seen, uses_of = [], {}, []
+        uses_reads = lambda op: op != R.OUTPUT
         writers = np.zeros(ntiles, np.int64)
         for t in range(ntasks):
             nf = int(rng.integers(1, 3))
-            kind = "user" if rng.random() < 0.15 else "gpu"
+            u = rng.random()
+            kind = "user" if u < 0.12 else ("cpu" if u < 0.32 else "gpu")
+            kinds.append(kind)
             sel = rng.choice(ntiles, nf, replace=False)
             ops = [int(rng.choice([R.INPUT, R.INOUT, R.OUTPUT])) for _ in range(nf)]
+            uses_of.append(ops)
             arr = (C.c_void_p * nf)(*[tiles[int(i)] for i in sel])
-            tid = ctx.l.pb2_dtd_insert_task_with_task_class(tp, classes[(nf, kind)], int(rng.integers(0, 4)), R.DEV_CUDA, arr,
+            tid = ctx.l.pb2_dtd_insert_task_with_task_class(tp, classes[(nf, kind)], int(rng.integers(0, 4)),
+                                                            R.DEV_CPU if kind == "cpu" else R.DEV_CUDA, arr,
                                                             np.array(ops, np.int32).ctypes.data_as(C.c_void_p), None, 0.0)
             assert tid == t
-            for i, op in zip(sel, ops):
+            for f, (i, op) in enumerate(zip(sel, ops)):
                 uses.append((t, int(i), op != R.INPUT))
+                expect_seen[(t, f)] = int(writers[int(i)])      # version a reader must see: writers inserted before it
                 writers[int(i)] += op != R.INPUT
             if t % 37 == 36:
                 ctx.wait()                                      # several rounds: later inserts chain behind completed tasks
@@ -451,9 +463,63 @@ def test_random_dtd_pools_under_pipelining_and_memory_pressure(seed):
                 last_writer[tile] = t; readers[tile] = []
             else:
                 readers.setdefault(tile, []).append(t)
-        st = [ctx.stats(d) for d in ctx.devices]
+        # a CPU body reads the newest version wherever it was produced (GPU in-place writes leave no pushout behind)
+        info = ctx.task_info(tp)
+        for (t, f), v in expect_seen.items():
+            if kinds[t] == "cpu" and uses_reads(uses_of[t][f]):
+                assert info["seen_version"][t, f] == v, (seed, t, f, kinds[t], int(info["seen_version"][t, f]), v)
+        st = [ctx.stats(d) for d in ctx.devices] + [ctx.stats(ctx.l.pb2_mca_device_get(ctx.h, 0))]
         assert sum(s["executed_tasks"] for s in st) == ntasks
         assert sum(s["windows_launched"] for s in st) > 3
         for i, tl in enumerate(tiles):                         # flushed home: the host copy carries the last version
             hc = ctx.copy_state(C.c_void_p(ctx.l.pb2_dtd_tile_data(tl)), 0)
             assert hc["version"] == writers[i], (seed, i, hc, int(writers[i]))
+
+
+def test_product_coherency_protocol_equals_oracle_on_random_sequences():
+    """pb2_data_start/end_transfer_ownership_to_copy (the product's own statement of parsec/data.c:313-458) against the
+    oracle, which tests/test_oracle.py pins to the reference's own build of data.c: same return value, owner, states,
+    readers and versions after every step of 300 random access sequences."""
+    import random
+    from oracle import orc
+
+    class Copy(C.Structure):            # include/pb2_parsec.h: struct pb2_data_copy_s (public part)
+        _fields_ = [("device_index", C.c_int8), ("flags", C.c_uint8), ("coherency_state", C.c_uint8),
+                    ("data_transfer_status", C.c_uint8), ("readers", C.c_int32), ("version", C.c_uint32)]
+
+    l = R.lib()
+    O = orc.lib()
+    NDEV = 6
+    Rd, Wr = 0x04, 0x08
+    buf = np.zeros(16, np.int32)
+    for seed in range(300):
+        rnd = random.Random(1000 + seed)
+        pd = C.c_void_p(l.pb2_data_create(None, seed, buf.ctypes.data_as(C.c_void_p), buf.nbytes))
+        od = orc.OrcData()
+        O.orc_data_create(C.byref(od), NDEV, 0)
+        for step in range(14):
+            dev = rnd.randrange(1, NDEV)
+            acc = rnd.choice([Rd, Wr, Rd | Wr, Rd, Rd | Wr])
+            if not od.copy[dev].present:
+                assert l.pb2_data_copy_attach(pd, dev)
+                od.copy[dev].present = 1
+            if od.copy[dev].coherency_state == 0x1 and od.owner_device != dev:
+                continue                                    # two owners: a sane program never asks for this
+            r_p = l.pb2_data_start_transfer_ownership_to_copy(None, pd, dev, acc)
+            r_o = O.orc_data_start_transfer_ownership(C.byref(od), dev, acc)
+            assert r_p == r_o, (seed, step, dev, acc)
+            l.pb2_data_end_transfer_ownership_to_copy(pd, dev, acc)
+            O.orc_data_end_transfer_ownership(C.byref(od), dev, acc)
+            pc = C.cast(l.pb2_data_get_copy(pd, dev), C.POINTER(Copy)).contents
+            if acc & Wr:
+                src = r_o if r_o >= 0 else dev
+                pc.version = od.copy[dev].version = od.copy[src].version + 1
+            elif r_o >= 0:
+                pc.version = od.copy[dev].version = od.copy[r_o].version
+            assert l.pb2_data_owner_device(pd) == od.owner_device, (seed, step)
+            for d in range(NDEV):
+                cp = l.pb2_data_get_copy(pd, d)
+                assert bool(cp) == bool(od.copy[d].present)
+                if cp:
+                    c = C.cast(cp, C.POINTER(Copy)).contents
+                    assert (c.coherency_state, c.readers, c.version) == (od.copy[d].coherency_state, od.copy[d].readers, od.copy[d].version), (seed, step, d)
