@@ -226,6 +226,9 @@ int  pb2_engine_set_shared_windows(pb2_engine_t* engine, int on, const int32_t* 
 /* part size for the windows created from now on (a serial chain of large tiles wants small parts: a 64-thread
  * worker keeps only 4 KiB in flight; wide DAGs want one part per tile) */
 int  pb2_engine_set_part_bytes(pb2_engine_t* engine, int32_t part_bytes);
+/* granularity of cooperative stage-in (default 64 KiB, <= 0: whole tiles): a tile that has to be staged in is cut into
+ * slices of this size and every worker that needs the tile pulls the slices nobody has claimed yet */
+int  pb2_engine_set_stage_slice_bytes(pb2_engine_t* engine, int32_t bytes);
 
 /* --- one window of the DAG ---
  * tasks[ntasks], succ[nsucc] (CSR via succ_begin/succ_count), tiles[ntiles] and the ids of

@@ -73,7 +73,7 @@ __global__ void pb2_window_reset_kernel(WinDev w, const pb2_tile_t* tiles_init,
 // many small workers overlap the serial pop / release sections of one task with the streaming of the others.
 // What one worker does with a task is in pb2_worker.cuh (shared with the streaming kernel of pb2_stream.cu).
 #ifndef PB2_HBM_MINB
-#define PB2_HBM_MINB 24
+#define PB2_HBM_MINB 20
 #endif
 #ifndef PB2_HBM_THREADS
 #define PB2_HBM_THREADS 64
@@ -440,6 +440,7 @@ int pb2_engine_create(pb2_engine_t** engine, int cuda_device, const pb2_engine_p
     if (p.timeout_ms <= 0) p.timeout_ms = 20000;
     if (p.part_bytes == 0) p.part_bytes = 256 * 1024;
     e->params = p;
+    if (const char* sl = getenv("PB2_STAGE_SLICE_BYTES")) e->stage_slice_bytes = atoi(sl);
     PB2_CUDA(e, cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
     PB2_CUDA(e, cudaStreamCreateWithFlags(&e->up_stream, cudaStreamNonBlocking));
     PB2_CUDA(e, cudaStreamCreateWithFlags(&e->dma_stream, cudaStreamNonBlocking));
@@ -650,6 +651,11 @@ int pb2_body_launch_errors(uint64_t* errors, int reset) {
     return PB2_SUCCESS;
 }
 
+int pb2_engine_set_stage_slice_bytes(pb2_engine_t* e, int32_t bytes) {
+    if (!e) return PB2_ERR_BAD_PARAM;
+    e->stage_slice_bytes = bytes;
+    return PB2_SUCCESS;
+}
 int pb2_engine_set_part_bytes(pb2_engine_t* e, int32_t part_bytes) {
     if (!e) return PB2_ERR_BAD_PARAM;
     e->params.part_bytes = part_bytes == 0 ? 256 * 1024 : part_bytes;
@@ -760,8 +766,21 @@ int pb2_window_create(pb2_engine_t* e, pb2_window_t** window, int kind,
         TRY(dev_alloc_copy(w, &d_np, nparts.data(), (size_t)ntasks));
         d.nparts = d_np;
         TRY(dev_alloc_copy(w, &d.parts_left, (const int32_t*)nullptr, (size_t)ntasks));
-        TRY(dev_alloc_copy(w, &d.slice_claim, (const uint32_t*)nullptr, (size_t)ntiles * PB2_SLICE_WORDS));
-        TRY(dev_alloc_copy(w, &d.slice_done, (const uint32_t*)nullptr, (size_t)ntiles * (PB2_SLICE_WORDS + 1)));
+    }
+    if (kind == 0) {
+        // Stage-in is cut finer than tasks are: a tile that has to come from the host or a peer GPU is pulled in slices
+        // of stage_slice_bytes by EVERY worker that needs it (claim bit per slice), so the readers of a tile share the
+        // transfer instead of one moving it while the others wait.
+        int32_t slice = e->stage_slice_bytes > 0 ? e->stage_slice_bytes : 0;
+        if (e->params.part_bytes > 0 && (slice == 0 || e->params.part_bytes < slice)) slice = e->params.part_bytes;
+        bool sliced = false;
+        for (int32_t i = 0; i < ntiles && !sliced; ++i)
+            sliced = slice > 0 && tiles[i].state != PB2_TILE_VALID && tiles[i].bytes > (uint32_t)slice;
+        if (sliced || extra_parts) {
+            d.part_bytes = slice > 0 ? slice : e->params.part_bytes;
+            TRY(dev_alloc_copy(w, &d.slice_claim, (const uint32_t*)nullptr, (size_t)ntiles * PB2_SLICE_WORDS));
+            TRY(dev_alloc_copy(w, &d.slice_done, (const uint32_t*)nullptr, (size_t)ntiles * (PB2_SLICE_WORDS + 1)));
+        }
     }
     if (kind == 1 && w->v2) {
         // operand tiles that have to be staged in (host or peer GPU) are pulled in 64 KiB slices by every CTA pair

@@ -20,6 +20,7 @@ struct pb2_engine_s {
     cudaEvent_t dma_ev = nullptr;
     bool dma_pending = false;
     int nworkers = 0;
+    int32_t stage_slice_bytes = 64 * 1024;   // stage-in granularity: every CTA that needs a tile pulls the slices nobody has claimed
     int nworkers_gemm = 0;
     std::string last_error;
     std::mutex mu;

@@ -211,10 +211,10 @@ __device__ __forceinline__ bool retire_task(const WinDev& w, int32_t id) {
 // What the out-of-line stage-in helpers need from the window, passed BY VALUE in registers: a reference to the
 // kernel-parameter struct would force a 300-byte local-memory copy of it in every caller.
 struct StageCtx {
-    pb2_tile_t* tiles; Ctl* ctl; uint32_t* slice_claim; uint32_t* slice_done; int32_t use_bulk;
+    pb2_tile_t* tiles; Ctl* ctl; uint32_t* slice_claim; uint32_t* slice_done; int32_t use_bulk; int32_t part_bytes;
 };
 __device__ __forceinline__ StageCtx stage_ctx(const WinDev& w) {
-    return StageCtx{w.tiles, w.ctl, w.slice_claim, w.slice_done, w.stage_mode == 0 ? 1 : 0};
+    return StageCtx{w.tiles, w.ctl, w.slice_claim, w.slice_done, w.stage_mode == 0 ? 1 : 0, w.part_bytes};
 }
 
 // Thread 0 decides (s_decide[0]): 1 = this CTA moves the tile, 0 = already valid (possibly after waiting)
@@ -252,11 +252,12 @@ static __device__ __noinline__ void stage_in_flow(const StageCtx w, pb2_tile_t* 
 
 // Number of stage-in slices of a tile: the same rule pb2_window_create uses for the parts of a wide task.
 #define PB2_SLICE_WORDS (PB2_MAX_PARTS / 32)
-__device__ __forceinline__ int tile_slices(const WinDev& w, uint32_t bytes) {
-    if (w.part_bytes <= 0 || !w.slice_claim) return 1;
-    const uint32_t n = (bytes + (uint32_t)w.part_bytes - 1) / (uint32_t)w.part_bytes;
+__device__ __forceinline__ int tile_slices_of(int32_t part_bytes, const uint32_t* slice_claim, uint32_t bytes) {
+    if (part_bytes <= 0 || !slice_claim) return 1;
+    const uint32_t n = (bytes + (uint32_t)part_bytes - 1) / (uint32_t)part_bytes;
     return n > PB2_MAX_PARTS ? PB2_MAX_PARTS : (n < 1 ? 1 : (int)n);
 }
+__device__ __forceinline__ int tile_slices(const WinDev& w, uint32_t bytes) { return tile_slices_of(w.part_bytes, w.slice_claim, bytes); }
 
 // Stage in the slices [s0, s1) of a tile larger than part_bytes.  Every slice is moved by exactly one CTA (claim
 // bit), so the parts of a wide task -- and the parts of other readers of the same version -- pull the tile in

@@ -25,6 +25,31 @@ struct alignas(16) TaskSmem {
     uint32_t   red[32];
 };
 
+// All threads (uniform): stage in every flow whose bit is set in s.need.  One CTA-wide call per task at most.
+static __device__ __noinline__ void stage_in_needed_flows(const StageCtx c, TaskSmem* sp, BulkSmem* bulk) {
+    TaskSmem& s = *sp;
+    const int need = s.need;
+#pragma unroll 1
+    for (int f = 0; f < PB2_MAX_FLOWS; ++f) {
+        if (!((need >> f) & 1)) continue;
+        const int32_t tid = s.task.tile[f];
+        const uint32_t bytes = s.tbytes[f];
+        const int ns = tile_slices_of(c.part_bytes, c.slice_claim, bytes);
+        if (ns == 1) stage_in_flow(c, &c.tiles[tid], s.task.access[f], &s.decide, bulk);
+        else {
+            // slices [s0, s1) of the tile cover this part's bytes (the task may be cut differently from the tile
+            // when its widest flow is another tile)
+            const uint32_t sper = ((bytes / (uint32_t)ns) + 15u) & ~15u;
+            const uint32_t off = s.off[f], len = s.args.bytes[f];
+            int s0 = (int)(off / sper), s1 = (int)((off + len + sper - 1) / sper);
+            if (s0 > ns - 1) s0 = ns - 1;
+            if (s1 > ns) s1 = ns;
+            if (len == 0) s1 = s0;
+            stage_in_slices(c, tid, ns, s0, s1, &s.decide, bulk);
+        }
+    }
+}
+
 // All threads.  On entry s.task holds the descriptor (published by a barrier).  Returns the body result (thread 0).
 __device__ __forceinline__ unsigned long long
 run_task_part(const WinDev& w, TaskSmem& s, BulkSmem* bulk, int32_t id, int part, int nparts) {
@@ -61,28 +86,9 @@ run_task_part(const WinDev& w, TaskSmem& s, BulkSmem* bulk, int32_t id, int part
         }
     }
     __syncthreads();
-    const int need = s.need;
-    if (need) {
-#pragma unroll
-        for (int f = 0; f < PB2_MAX_FLOWS; ++f) {
-            if (!((need >> f) & 1)) continue;
-            const int32_t tid = t.tile[f];
-            const uint32_t bytes = s.tbytes[f];
-            const int ns = tile_slices(w, bytes);
-            if (ns == 1) stage_in_flow(stage_ctx(w), &w.tiles[tid], t.access[f], &s.decide, bulk);
-            else {
-                // slices [s0, s1) of the tile cover this part's bytes (the task may be cut differently from the tile
-                // when its widest flow is another tile)
-                const uint32_t sper = ((bytes / (uint32_t)ns) + 15u) & ~15u;
-                const uint32_t off = s.off[f], len = s.args.bytes[f];
-                int s0 = (int)(off / sper), s1 = (int)((off + len + sper - 1) / sper);
-                if (s0 > ns - 1) s0 = ns - 1;
-                if (s1 > ns) s1 = ns;
-                if (len == 0) s1 = s0;
-                stage_in_slices(stage_ctx(w), tid, ns, s0, s1, &s.decide, bulk);
-            }
-        }
-    }
+    // the cold path, out of line and called once: everything it needs is in shared memory, nothing of the caller's
+    // has to survive the call in registers
+    if (s.need) stage_in_needed_flows(stage_ctx(w), &s, bulk);
 
     // ---- exec: the body (parsec_device_kernel_exec -> submit) ----
     const unsigned long long r = run_hbm_body(t.body, s.args, s.red);

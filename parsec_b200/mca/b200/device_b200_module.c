@@ -75,6 +75,7 @@ typedef struct b200_task_s {
     uint64_t             result;
     int32_t              retired;         /* shadow: the device is done with it */
     int32_t              custom_stage;    /* the task brought its own stage_in / stage_out (device_gpu.h:75-91) */
+    uint64_t             cold_bytes;      /* bytes this task stages in over PCIe / NVLink (throttle, see b200_start_task) */
     cudaEvent_t          ev;
 } b200_task_t;
 
@@ -94,13 +95,14 @@ typedef struct parsec_device_b200_module_s {
     parsec_list_t        stalled;         /* b200_task_t waiting for device memory        */
     parsec_list_t        waiting_event;   /* b200_task_t in BT_DMA_IN / BT_LANE / BT_DMA_OUT, in event order */
     parsec_list_t        free_bt;
+    uint64_t             cold_inflight;   /* bytes of stage-in handed to the device and not retired yet */
     b200_task_t         *recording;       /* the task whose submit function is being called in record mode */
     parsec_task_t       *completion_ring; /* tasks whose runtime completion is handed to the worker pool */
     int32_t              completed_now;   /* completions of the current manager iteration, subtracted from owed at its end */
     cudaStream_t         dma_stream;
     parsec_cuda_exec_stream_t *lane;      /* exec_stream[0]: what submit functions receive */
     parsec_b200_stats_t  st;
-    uint64_t             tsc[6];          /* manager time by phase (PARSEC_MCA_device_b200_profile): inbox, start, events, poll, finish, idle */
+    uint64_t             tsc[8];          /* manager time by phase (PARSEC_MCA_device_b200_profile): inbox, start, events, poll, finish, idle */
     pb2_retire_t         retbuf[256];
 } parsec_device_b200_module_t;
 
@@ -159,7 +161,7 @@ static b200_task_t *b200_bt_new(parsec_device_b200_module_t *dev, parsec_gpu_tas
     }
     PARSEC_LIST_ITEM_SINGLETON(&bt->item);
     bt->gpu_task = gpu_task; bt->state = BT_NEW; bt->ticket = -1; bt->body = -1; bt->nb_args = 0;
-    bt->peer_src_mask = 0; bt->dma_out_mask = 0; bt->result = 0; bt->retired = 0; bt->custom_stage = 0;
+    bt->peer_src_mask = 0; bt->dma_out_mask = 0; bt->result = 0; bt->retired = 0; bt->custom_stage = 0; bt->cold_bytes = 0;
     if( NULL != gpu_task ) gpu_task->last_data_check_epoch = (uint64_t)(uintptr_t)bt;
     return bt;
 }
@@ -470,6 +472,7 @@ static int b200_stage_in(parsec_device_b200_module_t *dev, b200_task_t *bt, int 
                                                             : b200_device_visible(src->device_private, span);
             mod->data_in_from_device[src->device_index] += span;
             mod->nb_data_faults += span;
+            bt->cold_bytes += span;
             if( NULL != visible && !for_lane && !dev->dry_run ) {
                 /* the persistent kernel pulls it (TMA bulk copy) when the task runs */
                 tile.state = PB2_TILE_INVALID;
@@ -767,6 +770,11 @@ static int b200_start_task(parsec_device_b200_module_t *dev, parsec_execution_st
     parsec_gpu_task_t *gpu_task = bt->gpu_task;
     int rc;
     (void)es;
+    /* Stage-in window.  The worker CTAs of the persistent kernel would happily start thousands of PCIe pulls at once;
+     * they would then all finish together, tens of milliseconds later, and their successors with them.  Keeping only a
+     * few link round-trips worth of cold bytes in flight makes tasks retire as a steady stream: the host side (this
+     * manager, the workers that release successors) and the transfers overlap instead of alternating in bursts. */
+    if( dev->cold_inflight >= (uint64_t)parsec_b200_stage_window && b200_needs_memory(dev, gpu_task) ) return PARSEC_HOOK_RETURN_AGAIN;
     if( PARSEC_HOOK_RETURN_DONE != (rc = b200_reserve(dev, bt)) ) return rc;
 
     /* Which kind of body?  Call the submit function in RECORD mode: a body that names an engine body through
@@ -784,6 +792,7 @@ static int b200_start_task(parsec_device_b200_module_t *dev, parsec_execution_st
     if( known_engine ) {
         rc = b200_stage_in(dev, bt, 0);
         if( rc < 0 ) return rc;
+        dev->cold_inflight += bt->cold_bytes;
         dev->recording = bt;
         int src = gpu_task->submit(&dev->super.super, gpu_task, &dev->lane->super);
         dev->recording = NULL;
@@ -806,6 +815,7 @@ static int b200_start_task(parsec_device_b200_module_t *dev, parsec_execution_st
     const int user_in = (NULL != gpu_task->stage_in && gpu_task->stage_in != parsec_default_gpu_stage_in);
     rc = b200_stage_in(dev, bt, user_in ? 2 : 1);
     if( rc < 0 ) return rc;
+    dev->cold_inflight += bt->cold_bytes;
     if( user_in ) {
         uint32_t mask = 0;
         for( uint32_t i = 0; i < gpu_task->nb_flows; i++ )
@@ -950,6 +960,7 @@ static int b200_data_advise(parsec_device_module_t *module, parsec_data_t *data,
 static void b200_finish(parsec_device_b200_module_t *dev, parsec_execution_stream_t *es, b200_task_t *bt)
 {
     parsec_gpu_task_t *gpu_task = bt->gpu_task;
+    dev->cold_inflight -= bt->cold_bytes; bt->cold_bytes = 0;
     if( PARSEC_GPU_TASK_TYPE_KERNEL == gpu_task->task_type ) { b200_complete(dev, es, bt); return; }
     /* pseudo task: the replica is resident and valid now; no runtime completion */
     parsec_data_copy_t *out = gpu_task->ec->data[0].data_out;
@@ -1001,7 +1012,7 @@ static int b200_progress(parsec_device_b200_module_t *dev, parsec_execution_stre
     {
         parsec_list_item_t *it = PARSEC_LIST_ITERATOR_FIRST(&dev->stalled), *next;
         int mem_blocked = 0;
-        for( ; it != PARSEC_LIST_ITERATOR_END(&dev->stalled); it = next ) {
+        for( ; it != PARSEC_LIST_ITERATOR_END(&dev->stalled) && started < 256; it = next ) {     /* then look at the retire ring again */
             b200_task_t *bt = (b200_task_t*)it;
             next = PARSEC_LIST_ITERATOR_NEXT(it);
             int rc;
@@ -1112,6 +1123,7 @@ b200_kernel_scheduler(parsec_device_module_t *module, parsec_execution_stream_t 
         /* data_advise comes without an execution stream and owes no runtime completion: it cannot complete other
          * threads' tasks, so it only drives the device until its own pseudo task is done */
         es = parsec_my_execution_stream();
+        if( NULL == es && NULL != module->context ) es = module->context->virtual_processes[0]->execution_streams[0];
     }
     if( !dev->dry_run ) B200_CUDA(cudaSetDevice(dev->super.cuda_index), "cudaSetDevice", { return PARSEC_HOOK_RETURN_DISABLE; });
     uint64_t idle_spins = 0;
@@ -1132,7 +1144,9 @@ b200_kernel_scheduler(parsec_device_module_t *module, parsec_execution_stream_t 
         if( NULL != dev->completion_ring ) {
             parsec_task_t *ring = dev->completion_ring;
             dev->completion_ring = NULL;
+            const uint64_t ts0 = B200_TSC();
             __parsec_schedule(es, ring, 0);
+            dev->tsc[6] += B200_TSC() - ts0;
         }
         /* `completed_now` belongs to the manager: take a private copy BEFORE the subtraction -- the instant `owed`
          * reaches zero another thread may become the manager and reset the field */
@@ -1357,10 +1371,10 @@ int parsec_b200_module_fini(parsec_device_module_t *device)
     parsec_device_gpu_module_t *gpu = &dev->super.super;
     if( NULL != dev->stream ) { (void)pb2_stream_quiesce(dev->stream); }
     if( NULL != getenv("PARSEC_B200_PROFILE") ) {
-        uint64_t tot = 0; for( int i = 0; i < 6; i++ ) tot += dev->tsc[i];
-        fprintf(stderr, "b200 manager cycles: inbox %.1f%% start %.1f%% events %.1f%% poll %.1f%% finish %.1f%% idle-poll %.1f%% (total %.1f Mcycles, %lu tasks)\n",
-                100.0 * dev->tsc[0] / (tot + 1), 100.0 * dev->tsc[1] / (tot + 1), 100.0 * dev->tsc[2] / (tot + 1), 100.0 * dev->tsc[3] / (tot + 1),
-                100.0 * dev->tsc[4] / (tot + 1), 100.0 * dev->tsc[5] / (tot + 1), tot * 1e-6, (unsigned long)device->executed_tasks);
+        uint64_t tot = 0; for( int i = 0; i < 7; i++ ) tot += dev->tsc[i];
+        fprintf(stderr, "b200 manager Mcycles: inbox %.1f start %.1f events %.1f poll %.1f finish %.1f idle-poll %.1f schedule %.1f (total %.1f, %lu tasks, %lu manager entries)\n",
+                dev->tsc[0] * 1e-6, dev->tsc[1] * 1e-6, dev->tsc[2] * 1e-6, dev->tsc[3] * 1e-6, dev->tsc[4] * 1e-6, dev->tsc[5] * 1e-6, dev->tsc[6] * 1e-6,
+                tot * 1e-6, (unsigned long)device->executed_tasks, (unsigned long)dev->st.manager_entries);
     }
     while( b200_write_back_some(dev, 64) > 0 ) { }
     parsec_device_memory_release(gpu);

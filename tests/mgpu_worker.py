@@ -72,24 +72,17 @@ def cholesky(case, rank, world, local, torch, dist, orc, M, L, Engine):
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     tot = torch.tensor([d2d, nremote], device="cuda")
     dist.all_reduce(tot)
-    if rank == 0:
-        print(json.dumps({"ok": bool(flag.item()), "world": world, "case": case, "bytes_d2d": int(tot[0].item()),
-                          "remote_edges": int(tot[1].item()), "max_abs": big, "exact_range": big < 2.0 ** 23}))
-    dist.destroy_process_group()
+    return {"ok": bool(flag.item()), "world": world, "case": case, "bytes_d2d": int(tot[0].item()),
+            "remote_edges": int(tot[1].item()), "max_abs": big, "exact_range": big < 2.0 ** 23}
 
 
-def main():
-    import torch
-    import torch.distributed as dist
+def run_case(case, rank, world, local, torch, dist):
+    """One parity case on an initialised process group (tests run it through main(), bench.py calls it in-run).
+    Returns the verdict (identical on every rank)."""
     from oracle import orc
     from parsec_b200 import multigpu as M
     from parsec_b200 import _lib as L
     from parsec_b200.engine import Engine
-
-    case = sys.argv[1]
-    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     g = None
     if case == "ex05":
         g = M.ex05_global(64 * world, 14, world, 65536)
@@ -101,8 +94,7 @@ def main():
         full = T.random_dtd(400, 6, world, 4242, tile_bytes=4096)
         g = T.drop_cross_rank_control_edges(full)
     if case.startswith("cholesky"):
-        cholesky(case, rank, world, local, torch, dist, orc, M, L, Engine)
-        return
+        return cholesky(case, rank, world, local, torch, dist, orc, M, L, Engine)
     tasks, succ, tiles, ready, task_rank, tile_rank = g
     glob = orc.run_window(*(full if case == "random_dtd" else g)[:4])
     assert glob["rc"] == 0
@@ -159,9 +151,19 @@ def main():
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     tot = torch.tensor([d2d, len(run.p["rs_rank"])], device="cuda")
     dist.all_reduce(tot)
+    return {"ok": bool(flag.item()), "world": world, "case": case, "bytes_d2d": int(tot[0].item()), "remote_edges": int(tot[1].item())}
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    case = sys.argv[1]
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    out = run_case(case, rank, world, local, torch, dist)
     if rank == 0:
-        print(json.dumps({"ok": bool(flag.item()), "world": world, "case": case, "bytes_d2d": int(tot[0].item()),
-                          "remote_edges": int(tot[1].item())}))
+        print(json.dumps(out))
     dist.destroy_process_group()
 
 

@@ -33,8 +33,8 @@ static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &
 
 int main(int argc, char *argv[])
 {
-    int K = 64, NB = 14, elems = 256 * 256, repeats = 1, cores = -1, verbose = 0, gpu = 1, wb = 0, c;
-    while( -1 != (c = getopt(argc, argv, "K:N:t:r:c:m:vw")) ) {
+    int K = 64, NB = 14, elems = 256 * 256, repeats = 1, cores = -1, verbose = 0, gpu = 1, wb = 0, prefetch = 0, c;
+    while( -1 != (c = getopt(argc, argv, "K:N:t:r:c:m:vwp")) ) {
         switch(c) {
         case 'K': K = atoi(optarg); break;
         case 'N': NB = atoi(optarg); break;
@@ -44,6 +44,7 @@ int main(int argc, char *argv[])
         case 'm': gpu = (0 == strcmp(optarg, "gpu")); break;
         case 'v': verbose = 1; break;
         case 'w': wb = 1; break;
+        case 'p': prefetch = 1; break;
         default: break;
         }
     }
@@ -75,8 +76,24 @@ int main(int argc, char *argv[])
     }
     if( gpu && 0 == ngpu ) { fprintf(stderr, "-m gpu but no GPU device module is active\n"); return 3; }
 
+    /* -p: PARSEC_DEV_DATA_ADVICE_PREFETCH (device.h:79-81) for every tile before the first task pool is handed over */
+    uint64_t h2d_prefetch = 0;
+    if( gpu && prefetch ) {
+        int gdev = -1;
+        for( int i = 0; i < (int)parsec_nb_devices && gdev < 0; i++ ) {
+            parsec_device_module_t *d = parsec_mca_device_get(i);
+            if( NULL != d && PARSEC_DEV_IS_GPU(d->type) ) gdev = i;
+        }
+        for( int k = 0; k < K; k++ ) {
+            parsec_data_t *dta = dcA.super.super.data_of(&dcA.super.super, k, 0);
+            if( PARSEC_SUCCESS != parsec_advise_data_on_device(dta, gdev, PARSEC_DEV_DATA_ADVICE_PREFETCH) ) return 5;
+        }
+        parsec_device_module_t *d = parsec_mca_device_get(gdev);
+        if( NULL != d->data_in_from_device ) h2d_prefetch = d->data_in_from_device[0];
+    }
     int64_t *errors = (int64_t*)calloc((size_t)nthreads + 1, sizeof(int64_t));
     double best = 1e30, total = 0;
+    char times[4096]; int tl = 0; times[0] = 0;
     int64_t bad_total = 0;
     for( int r = 0; r < repeats; r++ ) {
         for( size_t i = 0; i < (size_t)K * elems; i++ ) mat[i] = -7;
@@ -106,6 +123,7 @@ int main(int argc, char *argv[])
             for( int k = 0; k < K; k++ )
                 for( int i = 0; i < elems; i += (elems > 64 ? elems / 64 : 1) ) bad_total += (mat[(size_t)k * elems + i] != k);
         if( verbose ) fprintf(stderr, "repeat %d: dag %.3f ms, flush %.3f ms\n", r, 1e3 * (t1 - t0), 1e3 * (t2 - t1));
+        if( tl < 4000 ) tl += snprintf(times + tl, sizeof(times) - (size_t)tl, "%s%.6f", r ? ", " : "", t1 - t0);
         if( t1 - t0 < best ) best = t1 - t0;
         total += t1 - t0;
         PARSEC_OBJ_DESTRUCT(&tp->arenas_datatypes[PARSEC_ex05_b200_DEFAULT_ADT_IDX]);
@@ -137,13 +155,13 @@ int main(int argc, char *argv[])
     bad_total += (int64_t)st.check_mismatches;
     const long ntasks = (long)K * (1 + F);
     printf("{\"app\": \"ex05_b200\", \"mode\": \"%s\", \"wb\": %d, \"K\": %d, \"NB\": %d, \"F\": %d, \"tile_bytes\": %ld, \"tasks\": %ld, \"repeats\": %d, "
-           "\"cores\": %d, \"gpu_modules\": %d, \"b200_modules\": %d, \"best_s\": %.6f, \"mean_s\": %.6f, \"tasks_per_s\": %.1f, "
-           "\"errors\": %ld, \"executed_on_gpu\": %lu, \"required_in\": %lu, \"h2d_bytes\": %lu, "
+           "\"cores\": %d, \"gpu_modules\": %d, \"b200_modules\": %d, \"best_s\": %.6f, \"mean_s\": %.6f, \"times_s\": [%s], \"tasks_per_s\": %.1f, "
+           "\"errors\": %ld, \"executed_on_gpu\": %lu, \"required_in\": %lu, \"h2d_bytes\": %lu, \"h2d_prefetch_bytes\": %lu, "
            "\"b200\": {\"tasks_engine\": %lu, \"tasks_lane\": %lu, \"kernel_launches\": %lu, \"released_on_device\": %lu, "
            "\"lookahead_submitted\": %lu, \"bytes_h2d_kernel\": %lu, \"bytes_h2d_dma\": %lu, \"bytes_d2h_dma\": %lu, "
            "\"check_mismatches\": %lu, \"manager_entries\": %lu, \"max_concurrent_callers\": %lu, \"evictions\": %lu, \"w2r_copies\": %lu}}\n",
-           gpu ? "gpu" : "cpu", wb, K, NB, F, (long)elems * 4, ntasks, repeats, nthreads, ngpu, b200, best, total / repeats,
-           ntasks / best, (long)bad_total, (unsigned long)executed_gpu, (unsigned long)required_in, (unsigned long)h2d,
+           gpu ? "gpu" : "cpu", wb, K, NB, F, (long)elems * 4, ntasks, repeats, nthreads, ngpu, b200, best, total / repeats, times,
+           ntasks / best, (long)bad_total, (unsigned long)executed_gpu, (unsigned long)required_in, (unsigned long)h2d, (unsigned long)h2d_prefetch,
            (unsigned long)st.tasks_engine, (unsigned long)st.tasks_lane, (unsigned long)st.kernel_launches,
            (unsigned long)st.released_on_device, (unsigned long)st.lookahead_submitted, (unsigned long)st.bytes_h2d_kernel,
            (unsigned long)st.bytes_h2d_dma, (unsigned long)st.bytes_d2h_dma, (unsigned long)st.check_mismatches, (unsigned long)st.manager_entries,

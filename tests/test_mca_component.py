@@ -111,3 +111,20 @@ def test_reference_cuda_component_agrees_on_the_same_taskpools():
     assert rc == 0 and d["errors"] == 0 and d["b200_modules"] == 0 and d["gpu_modules"] == 1, err[-1000:]
     rc, d, err = run("stage_b200", ["-m", "gpu", "-c", 4], env)
     assert rc == 0 and d["check_errors"] == 0 and d["host_errors"] == 0, err[-1000:]
+
+
+def test_component_dry_run_prefetch_advice():
+    """PARSEC_DEV_DATA_ADVICE_PREFETCH on every tile before the pool: the DAG itself stages nothing in."""
+    rc, d, err = run("ex05_b200", ["-K", 64, "-t", 1024, "-m", "gpu", "-c", 4, "-p"], {"PARSEC_MCA_device_b200_dry_run": "1"})
+    assert d["h2d_prefetch_bytes"] == 64 * 4096 and d["h2d_bytes"] == 64 * 4096, err[-500:]
+    assert d["executed_on_gpu"] == 64 * 9
+
+
+@pytest.mark.gpu
+def test_component_gpu_prefetch_advice_is_asynchronous_and_valid():
+    """The prefetch is an engine task (empty body, one READ flow): the persistent kernel pulls the tiles in; the tasks of
+    the pool then find them resident (no second transfer) and the known answer still holds."""
+    rc, d, err = run("ex05_b200", ["-K", 256, "-t", 65536, "-m", "gpu", "-c", 8, "-p"], {"PARSEC_MCA_device_b200_enabled": "1"})
+    assert rc == 0 and d["errors"] == 0 and d["b200"]["check_mismatches"] == 0, err[-1000:]
+    assert d["h2d_prefetch_bytes"] == 256 * 262144 and d["h2d_bytes"] == 256 * 262144
+    assert d["b200"]["tasks_engine"] == 256 * 9 + 256           # the 256 prefetch tasks ran in the kernel too
