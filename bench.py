@@ -410,7 +410,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device; parsec_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
 
     def barrier():
         if world > 1:
@@ -520,8 +521,15 @@ def main():
         step()
     finish()
     t_wait = time.perf_counter()
-    while rank == 0 and not sampler.rows and time.perf_counter() - t_wait < 2.0:
-        step(); finish()                                          # keep the GPU under load until the sampler reports
+    while True:                                                   # keep the GPUs under load until the sampler reports
+        go = 1.0 if (rank == 0 and not sampler.rows and time.perf_counter() - t_wait < 2.0) else 0.0
+        if world > 1:                                             # every rank takes the same number of steps
+            flag = torch.tensor([go], dtype=torch.float64, device="cuda")
+            dist.broadcast(flag, src=0)
+            go = float(flag.item())
+        if go == 0.0:
+            break
+        step(); finish()
     barrier()
     if rank == 0:
         sampler.rows.clear()                                      # keep only samples of the timed region

@@ -87,6 +87,7 @@ typedef struct parsec_device_b200_module_s {
     pb2_stream_t        *stream;
     int                  dry_run;
     char                *slab_base;
+    uint8_t             *tile_described;  /* per heap block: the device tile table entry of the replica that starts here is current */
     /* inbox + election */
     parsec_gpu_task_t * volatile inbox;
     volatile int32_t     owed;
@@ -203,6 +204,7 @@ static void b200_release_copy_memory(parsec_device_b200_module_t *dev, parsec_da
         parsec_atomic_wmb();
         if( survives ) parsec_atomic_unlock(&original->lock);
     }
+    if( NULL != dev->tile_described ) dev->tile_described[b200_tile_of(dev, copy)] = 0;
     zone_free(dev->super.super.memory, copy->device_private);
     copy->device_private = NULL;
     PARSEC_OBJ_RELEASE(copy);
@@ -393,6 +395,20 @@ static int b200_stage_in(parsec_device_b200_module_t *dev, b200_task_t *bt, int 
     parsec_device_module_t *mod = &dev->super.super.super;
     const uint8_t my = mod->device_index;
     int used_dma = 0;
+    uint32_t pre_acquired = 0;
+
+    /* A task that was handed another GPU's replica needs that replica to stay: take the readers first, all or none,
+     * before anything of the task's own state changes (a replica its owner is reclaiming makes the task wait) */
+    for( uint32_t i = 0; i < gpu_task->nb_flows; i++ ) {
+        const parsec_flow_t *flow = gpu_task->flow_info[i].flow;
+        parsec_data_copy_t *in = this_task->data[i].data_in;
+        if( NULL == in || NULL == this_task->data[i].data_out || in == this_task->data[i].data_out ) continue;
+        if( !(PARSEC_FLOW_ACCESS_READ & flow->flow_flags) || !parsec_mca_device_is_gpu(in->device_index) ) continue;
+        if( b200_copy_acquire_reader(in) ) { pre_acquired |= (1u << i); continue; }
+        for( uint32_t k = 0; k < i; k++ )
+            if( pre_acquired & (1u << k) ) (void)parsec_atomic_fetch_dec_int32(&this_task->data[k].data_in->readers);
+        return PARSEC_HOOK_RETURN_AGAIN;
+    }
 
     for( uint32_t i = 0; i < gpu_task->nb_flows; i++ ) {
         const parsec_flow_t *flow = gpu_task->flow_info[i].flow;
@@ -413,6 +429,17 @@ static int b200_stage_in(parsec_device_b200_module_t *dev, b200_task_t *bt, int 
                 parsec_atomic_unlock(&original->lock);
             }
             if( PARSEC_FLOW_ACCESS_READ & type ) (void)parsec_atomic_fetch_inc_int32(&out->readers);
+            if( !for_lane && !dev->tile_described[b200_tile_of(dev, out)] ) {
+                /* the replica was filled on the stream lane (copy engine, opaque body): the kernel has not met it yet */
+                pb2_tile_t tile;
+                memset(&tile, 0, sizeof tile);
+                tile.dev_ptr = out->device_private; tile.bytes = (uint32_t)span; tile.state = PB2_TILE_VALID;
+                tile.version = (PARSEC_FLOW_ACCESS_WRITE & type) ? out->version - 1 : out->version;
+                if( NULL != original->device_copies[0] && NULL != original->device_copies[0]->device_private )
+                    tile.src_ptr = b200_device_visible(original->device_copies[0]->device_private, span);
+                if( PB2_SUCCESS != pb2_stream_set_tile(dev->stream, b200_tile_of(dev, out), &tile) ) return PARSEC_HOOK_RETURN_ERROR;
+                dev->tile_described[b200_tile_of(dev, out)] = 1;
+            }
             continue;
         }
 
@@ -423,12 +450,14 @@ static int b200_stage_in(parsec_device_b200_module_t *dev, b200_task_t *bt, int 
         /* source: the copy the task was given, unless it is a host copy and a peer GPU we can read holds the same
          * version (device_gpu.c:1892-1975) */
         parsec_data_copy_t *src = in;
-        int src_acquired = 0;
+        int src_acquired = 0, src_detour = 0;
         if( (PARSEC_FLOW_ACCESS_READ & type) ) {
             if( parsec_mca_device_is_gpu(in->device_index) ) {
-                if( (dev->super.super.peer_access_mask & (1 << in->device_index)) &&
-                    PARSEC_DATA_COHERENCY_INVALID != in->coherency_state && b200_copy_acquire_reader(in) ) src_acquired = 1;
-                else src = original->device_copies[0];
+                /* the task was handed another GPU's replica: it IS the newest version (no pushout was asked for), so
+                 * the bytes have to come from there -- in place over NVLink when this GPU can address it, through
+                 * the copy engine otherwise; a replica its owner is reclaiming right now is retried later */
+                src_acquired = (pre_acquired >> i) & 1;            /* taken above */
+                src_detour = !(dev->super.super.peer_access_mask & (1 << in->device_index));
             } else if( !(PARSEC_FLOW_ACCESS_WRITE & type) ) {
                 for( uint32_t t = 1; t < parsec_nb_devices; t++ ) {
                     parsec_data_copy_t *cand = original->device_copies[t];
@@ -473,7 +502,8 @@ static int b200_stage_in(parsec_device_b200_module_t *dev, b200_task_t *bt, int 
             mod->data_in_from_device[src->device_index] += span;
             mod->nb_data_faults += span;
             bt->cold_bytes += span;
-            if( NULL != visible && !for_lane && !dev->dry_run ) {
+            if( PB2_SRC_PEER == tile.src_kind ) { if( src_detour ) dev->st.peer_detours++; else dev->st.peer_pulls++; }
+            if( NULL != visible && !src_detour && !for_lane && !dev->dry_run ) {
                 /* the persistent kernel pulls it (TMA bulk copy) when the task runs */
                 tile.state = PB2_TILE_INVALID;
                 tile.src_ptr = visible;
@@ -507,8 +537,14 @@ static int b200_stage_in(parsec_device_b200_module_t *dev, b200_task_t *bt, int 
          * version to pull, or a new home */
         tile.version = (PARSEC_FLOW_ACCESS_WRITE & type) ? out->version - 1 : out->version;
         if( !for_lane ) {
+            /* The entry is written when the replica is new to the device or when a new pull has just been decided -- and
+             * ONLY then: a second reader that arrives while the first one's pull is still running must find the entry as
+             * the kernel left it (STAGING), not a fresh "VALID" from the host. */
             const int32_t tid = b200_tile_of(dev, out);
-            if( PB2_SUCCESS != pb2_stream_set_tile(dev->stream, tid, &tile) ) { parsec_atomic_unlock(&original->lock); return PARSEC_HOOK_RETURN_ERROR; }
+            if( -1 != transfer_from || !dev->tile_described[tid] ) {
+                if( PB2_SUCCESS != pb2_stream_set_tile(dev->stream, tid, &tile) ) { parsec_atomic_unlock(&original->lock); return PARSEC_HOOK_RETURN_ERROR; }
+                dev->tile_described[tid] = 1;
+            }
         }
         parsec_atomic_unlock(&original->lock);
     }
@@ -840,6 +876,7 @@ static int b200_start_task(parsec_device_b200_module_t *dev, parsec_execution_st
             parsec_data_copy_t *cpu = out->original->device_copies[0];
             tile.src_ptr = (NULL != cpu && NULL != cpu->device_private) ? b200_device_visible(cpu->device_private, tile.bytes) : NULL;
             (void)pb2_stream_set_tile(dev->stream, b200_tile_of(dev, out), &tile);
+            dev->tile_described[b200_tile_of(dev, out)] = 1;
         }
         B200_CUDA(cudaEventRecord(bt->ev, dev->lane->cuda_stream), "cudaEventRecord", {});
         bt->state = BT_DMA_IN;
@@ -1247,7 +1284,9 @@ static int b200_memory_release(parsec_device_module_t *device)
     /* dirty replicas go home first: flush_lru would drop them with a warning (device_gpu.c:1033-1037) */
     if( !dev->dry_run ) (void)pb2_stream_quiesce(dev->stream);
     while( b200_write_back_some(dev, 64) > 0 ) { }
-    return parsec_device_flush_lru(device);
+    const int rc = parsec_device_flush_lru(device);
+    if( NULL != dev->tile_described ) memset(dev->tile_described, 0, (size_t)dev->super.super.mem_nb_blocks);
+    return rc;
 }
 
 static int b200_all_devices_attached(parsec_device_module_t *device)
@@ -1263,6 +1302,8 @@ static int b200_all_devices_attached(parsec_device_module_t *device)
         if( peer == dev ) continue;
         if( PB2_SUCCESS == pb2_engine_enable_peer(dev->engine, peer->super.cuda_index) )
             dev->super.super.peer_access_mask = (int16_t)(dev->super.super.peer_access_mask | (1 << peer->super.super.super.device_index));
+        else parsec_warning("GPU[%d:%s]: no peer access to %s: its replicas will be fetched through the copy engine",
+                            device->device_index, device->name, peer->super.super.super.name);
     }
     return PARSEC_SUCCESS;
 }
@@ -1348,6 +1389,7 @@ int parsec_b200_module_init(int dev_id, parsec_device_module_t **module)
     if( dev->dry_run && -1 == nblocks ) nblocks = 4096;
     if( PARSEC_SUCCESS != parsec_device_memory_reserve(gpu, parsec_b200_memory_percentage, nblocks, (size_t)parsec_b200_memory_block_size) ) goto failed;
 
+    dev->tile_described = (uint8_t*)calloc((size_t)gpu->mem_nb_blocks + 1, 1);
     pb2_stream_params_t sp;
     memset(&sp, 0, sizeof sp);
     sp.cmd_slots = parsec_b200_cmd_slots;
@@ -1392,6 +1434,7 @@ int parsec_b200_module_fini(parsec_device_module_t *device)
         (void)cudaStreamDestroy(dev->lane->cuda_stream);
         (void)cudaStreamDestroy(dev->dma_stream);
     }
+    free(dev->tile_described);
     free(dev->lane); free(gpu->exec_stream);
     if( NULL != dev->engine ) { pb2_engine_destroy(dev->engine); dev->engine = NULL; }
     free(device->name); device->name = NULL;

@@ -144,7 +144,7 @@ int main(int argc, char *argv[])
             st.released_on_device += s1.released_on_device; st.lookahead_submitted += s1.lookahead_submitted;
             st.bytes_h2d_kernel += s1.bytes_h2d_kernel; st.bytes_h2d_dma += s1.bytes_h2d_dma; st.bytes_d2h_dma += s1.bytes_d2h_dma;
             st.manager_entries += s1.manager_entries; st.evictions += s1.evictions; st.w2r_copies += s1.w2r_copies;
-            st.check_mismatches += s1.check_mismatches;
+            st.check_mismatches += s1.check_mismatches; st.peer_pulls += s1.peer_pulls; st.peer_detours += s1.peer_detours;
             if( s1.max_concurrent_callers > st.max_concurrent_callers ) st.max_concurrent_callers = s1.max_concurrent_callers;
         }
     }
@@ -159,13 +159,13 @@ int main(int argc, char *argv[])
            "\"errors\": %ld, \"executed_on_gpu\": %lu, \"required_in\": %lu, \"h2d_bytes\": %lu, \"h2d_prefetch_bytes\": %lu, "
            "\"b200\": {\"tasks_engine\": %lu, \"tasks_lane\": %lu, \"kernel_launches\": %lu, \"released_on_device\": %lu, "
            "\"lookahead_submitted\": %lu, \"bytes_h2d_kernel\": %lu, \"bytes_h2d_dma\": %lu, \"bytes_d2h_dma\": %lu, "
-           "\"check_mismatches\": %lu, \"manager_entries\": %lu, \"max_concurrent_callers\": %lu, \"evictions\": %lu, \"w2r_copies\": %lu}}\n",
+           "\"check_mismatches\": %lu, \"manager_entries\": %lu, \"max_concurrent_callers\": %lu, \"evictions\": %lu, \"w2r_copies\": %lu, \"peer_pulls\": %lu, \"peer_detours\": %lu}}\n",
            gpu ? "gpu" : "cpu", wb, K, NB, F, (long)elems * 4, ntasks, repeats, nthreads, ngpu, b200, best, total / repeats, times,
            ntasks / best, (long)bad_total, (unsigned long)executed_gpu, (unsigned long)required_in, (unsigned long)h2d, (unsigned long)h2d_prefetch,
            (unsigned long)st.tasks_engine, (unsigned long)st.tasks_lane, (unsigned long)st.kernel_launches,
            (unsigned long)st.released_on_device, (unsigned long)st.lookahead_submitted, (unsigned long)st.bytes_h2d_kernel,
            (unsigned long)st.bytes_h2d_dma, (unsigned long)st.bytes_d2h_dma, (unsigned long)st.check_mismatches, (unsigned long)st.manager_entries,
-           (unsigned long)st.max_concurrent_callers, (unsigned long)st.evictions, (unsigned long)st.w2r_copies);
+           (unsigned long)st.max_concurrent_callers, (unsigned long)st.evictions, (unsigned long)st.w2r_copies, (unsigned long)st.peer_pulls, (unsigned long)st.peer_detours);
 
     for( int i = 0; i < (int)parsec_nb_devices; i++ ) {
         parsec_device_module_t *d = parsec_mca_device_get(i);

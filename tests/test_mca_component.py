@@ -128,3 +128,18 @@ def test_component_gpu_prefetch_advice_is_asynchronous_and_valid():
     assert rc == 0 and d["errors"] == 0 and d["b200"]["check_mismatches"] == 0, err[-1000:]
     assert d["h2d_prefetch_bytes"] == 256 * 262144 and d["h2d_bytes"] == 256 * 262144
     assert d["b200"]["tasks_engine"] == 256 * 9 + 256           # the 256 prefetch tasks ran in the kernel too
+
+
+@pytest.mark.gpu
+def test_component_two_gpus_in_one_process_peer_pulls():
+    """The reference's own multi-GPU model: one process, two device modules.  Readers placed on the other GPU pull the
+    producer's replica over NVLink (several readers of one tile arrive together: only the first one's pull may describe
+    the tile to the device); the known answer holds and nothing detours through the host."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    rc, d, err = run("ex05_b200", ["-K", 1024, "-t", 65536, "-m", "gpu", "-c", 16, "-r", 2], {"PARSEC_MCA_device_b200_enabled": "2"})
+    assert rc == 0 and d["errors"] == 0 and d["b200"]["check_mismatches"] == 0, err[-1000:]
+    assert d["b200_modules"] == 2 and d["b200"]["peer_pulls"] > 0 and d["b200"]["peer_detours"] == 0
+    rc, d, err = run("stage_b200", ["-m", "gpu", "-c", 4], {"PARSEC_MCA_device_b200_enabled": "2"})
+    assert rc == 0 and d["check_errors"] == 0 and d["host_errors"] == 0, err[-1000:]
