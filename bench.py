@@ -283,8 +283,8 @@ def secondary_rtt(rank, world, local, torch, dist):
     rec = {"config": "rtt ring, 1024x1024 fp32 tiles, NT=1024, %d GPUs (configs[3])" % world, "runs": []}
     for frags in (1, 16):
         g = M.rtt_global(nt, world, tile, frags)
-        part = M.Partition(*g, nranks=world)
-        eng = Engine(local, timeout_ms=20000)
+        part = M.Partition(*g, nranks=world, part_bytes=32768)
+        eng = Engine(local, timeout_ms=20000, part_bytes=32768)     # a serial chain of 4 MiB tiles wants many small parts
         eng.use_stream(M.work_stream(torch))
         run = M.SharedRun(eng, part, rank, world, dist, torch)
         for _ in range(2):
@@ -305,7 +305,7 @@ def secondary_rtt(rank, world, local, torch, dist):
             slab = np.zeros(run.slab_bytes // 4, np.int32)
             eng.d2h(slab, run.slab); eng.synchronize()
             k0 = ((nt - 1) // world) * world
-            ok = bool(np.all(slab[: frags * tile // 4] == (2 + steps) * (k0 + 1) + nt))
+            ok = bool(np.all(slab[: frags * tile // 4] == (1 + steps) * (k0 + 1) + nt))   # 2 warm-up runs + `steps` runs
         flag = torch.tensor([1 if ok else 0], device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         t = float(ms.item()) / 1e3
@@ -429,7 +429,7 @@ def main():
     # One process drives all N GPUs, the way the reference does: same path at every N.  Run first, before this process
     # takes its own device memory.
     e2e = None
-    if rank == 0:
+    if rank == 0 and args.e2e_steps > 0:     # --e2e-steps 0: profiler runs (a persistent kernel fed by the host cannot run under ncu's serialised launches)
         try:
             e2e = e2e_mca(K * world, world, args.e2e_steps, args.e2e_cores)
         except Exception as exc:
@@ -453,7 +453,7 @@ def main():
 
     # ---------------------------------------------------------------- e2e through this repository's own host runtime
     e2e_standalone = None
-    if world == 1:
+    if world == 1 and args.e2e_steps > 0:
         tsplit = {"new": 0.0, "wait": 0.0, "read": 0.0}
 
         def e2e_step():

@@ -54,6 +54,8 @@ typedef struct parsec_b200_stats_s {
     uint64_t bytes_h2d_kernel, bytes_d2d_kernel, bytes_d2h_kernel;  /* moved by the persistent kernel               */
     uint64_t bytes_h2d_dma, bytes_d2h_dma;                          /* moved by the copy engine (unregistered memory)*/
     uint64_t evictions, w2r_copies;
+    uint64_t registration_hits;             /* memory_register calls served by the registration cache */
+    uint64_t first_entry_ns, first_task_ns, last_done_ns;   /* CLOCK_MONOTONIC of the first hand-over / last completion since the last memory_release */
     uint64_t peer_pulls;            /* stage-ins whose source was another GPU's replica, read over NVLink           */
     uint64_t peer_detours;          /* GPU sources that could not be read in place (no peer access): copy engine      */
     uint64_t check_mismatches;      /* elements the CHECK bodies found different from what they expected             */

@@ -34,6 +34,7 @@ int parsec_b200_lookahead = 1;
 int parsec_b200_max_workers = 0;
 int parsec_b200_parallel_completion = 1;
 int parsec_b200_stage_window = 32 * 1024 * 1024;
+int parsec_b200_registration_cache = 1;
 static int b200_mask = -1;
 
 #if !defined(PARSEC_HAVE_MPI)
@@ -103,6 +104,9 @@ static int device_b200_component_register(void)
     (void)parsec_mca_param_reg_int_name("device_b200", "stage_window",
                                         "Bytes of stage-in (host or peer to device) allowed in flight before further cold tasks wait",
                                         false, false, 32 * 1024 * 1024, &parsec_b200_stage_window);
+    (void)parsec_mca_param_reg_int_name("device_b200", "registration_cache",
+                                        "Keep host ranges pinned after memory_unregister and revive them at the next registration of the same range",
+                                        false, false, 1, &parsec_b200_registration_cache);
     (void)parsec_mca_param_reg_int_name("device_b200", "max_workers", "Debug: limit the worker CTAs of the persistent kernel (0: all)",
                                         false, false, 0, &parsec_b200_max_workers);
     return (0 == parsec_device_b200_enabled && 0 == parsec_b200_dry_run) ? MCA_ERROR : MCA_SUCCESS;

@@ -42,6 +42,8 @@
 #include <string.h>
 #include <stdio.h>
 #include <limits.h>
+#include <time.h>
+static inline uint64_t b200_now_ns(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec; }
 #include <x86intrin.h>
 #define B200_TSC() __rdtsc()
 
@@ -79,7 +81,7 @@ typedef struct b200_task_s {
     cudaEvent_t          ev;
 } b200_task_t;
 
-typedef struct b200_host_range_s { char *base; size_t len; char *alias; } b200_host_range_t;
+typedef struct b200_host_range_s { char *base; size_t len; char *alias; int lazy; } b200_host_range_t;   /* lazy: unregistered by its owner, still pinned (registration cache) */
 
 typedef struct parsec_device_b200_module_s {
     parsec_device_cuda_module_t super;    /* generated CUDA bodies read cuda_index / the exec stream through this layout */
@@ -1140,6 +1142,7 @@ b200_kernel_scheduler(parsec_device_module_t *module, parsec_execution_stream_t 
     parsec_device_b200_module_t *dev = (parsec_device_b200_module_t*)module;
     parsec_gpu_task_t *gpu_task = (parsec_gpu_task_t*)_gpu_task;
 
+    if( 0 == dev->st.first_entry_ns ) dev->st.first_entry_ns = b200_now_ns();
     int32_t inside = parsec_atomic_fetch_inc_int32(&dev->callers_inside) + 1;
     if( (uint64_t)inside > dev->st.max_concurrent_callers ) dev->st.max_concurrent_callers = (uint64_t)inside;
     /* 1. one more task is owed, THEN it is handed over (lock-free push on the inbox).  In this order the manager can
@@ -1156,6 +1159,7 @@ b200_kernel_scheduler(parsec_device_module_t *module, parsec_execution_stream_t 
 
     /* 2. this thread is the manager until nothing is owed any more */
     dev->st.manager_entries++;
+    if( 0 == dev->st.first_task_ns ) dev->st.first_task_ns = b200_now_ns();
     if( NULL == es ) {
         /* data_advise comes without an execution stream and owes no runtime completion: it cannot complete other
          * threads' tasks, so it only drives the device until its own pseudo task is done */
@@ -1192,7 +1196,7 @@ b200_kernel_scheduler(parsec_device_module_t *module, parsec_execution_stream_t 
             idle_spins = 0;
             /* the subtraction that reaches zero is the LAST thing a manager does with the device */
             const int32_t left = parsec_atomic_fetch_sub_int32(&dev->owed, done_now) - done_now;
-            if( 0 == left ) return PARSEC_HOOK_RETURN_ASYNC;
+            if( 0 == left ) { dev->st.last_done_ns = b200_now_ns(); return PARSEC_HOOK_RETURN_ASYNC; }
             if( left < 0 ) {
                 parsec_warning("GPU[%d:%s]: more tasks completed than were handed over (%d)", module->device_index, module->name, left);
                 return PARSEC_HOOK_RETURN_DISABLE;
@@ -1244,7 +1248,27 @@ static int b200_memory_register(parsec_device_module_t *device, parsec_data_coll
 {
     parsec_device_b200_module_t *dev = (parsec_device_b200_module_t*)device;
     if( desc->memory_registration_status == PARSEC_MEMORY_STATUS_REGISTERED ) return PARSEC_SUCCESS;
+    /* Registration cache.  ptgpp-generated pools register their collections in the startup hook and unregister them in
+     * the destructor (jdf2c.c: "Register all the data"), so an application that runs one pool after another over the
+     * same matrix pays cudaHostRegister -- 40 to 400 ms per GiB on this host -- inside every parsec_context_add_taskpool.
+     * Ranges given back with memory_unregister stay pinned (lazy) and are revived by the next registration of the same
+     * range; a registration that merely overlaps a lazy range retires it first.  device_b200_registration_cache = 0
+     * restores eager unpinning. */
     void *alias = ptr;
+    int revived = 0;
+    parsec_atomic_lock(&b200_ranges_lock);
+    for( int i = 0; i < b200_nb_ranges; i++ ) {
+        b200_host_range_t *r = &b200_ranges[i];
+        if( !r->lazy ) continue;
+        if( r->base == (char*)ptr && r->len >= length ) { r->lazy = 0; revived = 1; break; }
+        if( (char*)ptr < r->base + r->len && r->base < (char*)ptr + length ) {      /* overlap: the old pinning goes */
+            char *old = r->base;
+            *r = b200_ranges[--b200_nb_ranges]; i--;
+            if( !dev->dry_run ) { (void)pb2_stream_quiesce(dev->stream); (void)pb2_engine_host_unregister(dev->engine, old); }
+        }
+    }
+    parsec_atomic_unlock(&b200_ranges_lock);
+    if( revived ) { dev->st.registration_hits++; desc->memory_registration_status = PARSEC_MEMORY_STATUS_REGISTERED; return PARSEC_SUCCESS; }
     if( !dev->dry_run ) {
         if( PB2_SUCCESS != pb2_engine_host_register(dev->engine, ptr, length, &alias) ) return PARSEC_ERROR;
     }
@@ -1254,6 +1278,7 @@ static int b200_memory_register(parsec_device_module_t *device, parsec_data_coll
         b200_ranges = (b200_host_range_t*)realloc(b200_ranges, sizeof(b200_host_range_t) * (size_t)b200_cap_ranges);
     }
     b200_ranges[b200_nb_ranges].base = (char*)ptr; b200_ranges[b200_nb_ranges].len = length; b200_ranges[b200_nb_ranges].alias = (char*)alias;
+    b200_ranges[b200_nb_ranges].lazy = 0;
     b200_nb_ranges++;
     parsec_atomic_unlock(&b200_ranges_lock);
     desc->memory_registration_status = PARSEC_MEMORY_STATUS_REGISTERED;
@@ -1266,8 +1291,12 @@ static int b200_memory_unregister(parsec_device_module_t *device, parsec_data_co
     if( desc->memory_registration_status == PARSEC_MEMORY_STATUS_UNREGISTERED ) return PARSEC_SUCCESS;
     int found = 0;
     parsec_atomic_lock(&b200_ranges_lock);
-    for( int i = 0; i < b200_nb_ranges; i++ )
-        if( b200_ranges[i].base == (char*)ptr ) { b200_ranges[i] = b200_ranges[--b200_nb_ranges]; found = 1; break; }
+    for( int i = 0; i < b200_nb_ranges; i++ ) {
+        if( b200_ranges[i].base != (char*)ptr || b200_ranges[i].lazy ) continue;
+        if( parsec_b200_registration_cache ) b200_ranges[i].lazy = 1;
+        else { b200_ranges[i] = b200_ranges[--b200_nb_ranges]; found = 1; }
+        break;
+    }
     parsec_atomic_unlock(&b200_ranges_lock);
     if( found && !dev->dry_run ) {
         /* nothing of ours may be resident while CUDA unpins the range */
@@ -1278,9 +1307,33 @@ static int b200_memory_unregister(parsec_device_module_t *device, parsec_data_co
     return PARSEC_SUCCESS;
 }
 
+/* module_fini: whatever the cache still pins is given back */
+static void b200_registration_cache_drop(parsec_device_b200_module_t *dev)
+{
+    parsec_atomic_lock(&b200_ranges_lock);
+    for( int i = 0; i < b200_nb_ranges; i++ ) {
+        if( !b200_ranges[i].lazy ) continue;
+        if( !dev->dry_run ) (void)pb2_engine_host_unregister(dev->engine, b200_ranges[i].base);
+        b200_ranges[i] = b200_ranges[--b200_nb_ranges]; i--;
+    }
+    parsec_atomic_unlock(&b200_ranges_lock);
+}
+
+static void b200_profile_print(parsec_device_b200_module_t *dev)
+{
+    if( NULL == getenv("PARSEC_B200_PROFILE") ) return;
+    uint64_t tot = 0; for( int i = 0; i < 7; i++ ) tot += dev->tsc[i];
+    fprintf(stderr, "b200 manager Mcycles: inbox %.1f start %.1f events %.1f poll %.1f finish %.1f idle-poll %.1f schedule %.1f (total %.1f, %lu tasks so far, %lu manager entries)\n",
+            dev->tsc[0] * 1e-6, dev->tsc[1] * 1e-6, dev->tsc[2] * 1e-6, dev->tsc[3] * 1e-6, dev->tsc[4] * 1e-6, dev->tsc[5] * 1e-6, dev->tsc[6] * 1e-6,
+            tot * 1e-6, (unsigned long)dev->super.super.super.executed_tasks, (unsigned long)dev->st.manager_entries);
+    memset(dev->tsc, 0, sizeof dev->tsc);
+}
+
 static int b200_memory_release(parsec_device_module_t *device)
 {
     parsec_device_b200_module_t *dev = (parsec_device_b200_module_t*)device;
+    b200_profile_print(dev);
+    dev->st.first_task_ns = dev->st.first_entry_ns = 0;
     /* dirty replicas go home first: flush_lru would drop them with a warning (device_gpu.c:1033-1037) */
     if( !dev->dry_run ) (void)pb2_stream_quiesce(dev->stream);
     while( b200_write_back_some(dev, 64) > 0 ) { }
@@ -1412,14 +1465,10 @@ int parsec_b200_module_fini(parsec_device_module_t *device)
     parsec_device_b200_module_t *dev = (parsec_device_b200_module_t*)device;
     parsec_device_gpu_module_t *gpu = &dev->super.super;
     if( NULL != dev->stream ) { (void)pb2_stream_quiesce(dev->stream); }
-    if( NULL != getenv("PARSEC_B200_PROFILE") ) {
-        uint64_t tot = 0; for( int i = 0; i < 7; i++ ) tot += dev->tsc[i];
-        fprintf(stderr, "b200 manager Mcycles: inbox %.1f start %.1f events %.1f poll %.1f finish %.1f idle-poll %.1f schedule %.1f (total %.1f, %lu tasks, %lu manager entries)\n",
-                dev->tsc[0] * 1e-6, dev->tsc[1] * 1e-6, dev->tsc[2] * 1e-6, dev->tsc[3] * 1e-6, dev->tsc[4] * 1e-6, dev->tsc[5] * 1e-6, dev->tsc[6] * 1e-6,
-                tot * 1e-6, (unsigned long)device->executed_tasks, (unsigned long)dev->st.manager_entries);
-    }
+    b200_profile_print(dev);
     while( b200_write_back_some(dev, 64) > 0 ) { }
     parsec_device_memory_release(gpu);
+    b200_registration_cache_drop(dev);
     if( NULL != dev->stream ) { pb2_stream_destroy(dev->stream); dev->stream = NULL; }
     b200_task_t *bt;
     while( NULL != (bt = (b200_task_t*)parsec_list_nolock_pop_front(&dev->free_bt)) ) {

@@ -106,11 +106,25 @@ int main(int argc, char *argv[])
                 if( NULL != d && PARSEC_DEV_IS_GPU(d->type) ) tp->super.devices_index_mask &= ~(1u << i);
             }
         }
+        struct timespec ts0, ts1; clock_gettime(CLOCK_MONOTONIC, &ts0);
         const double t0 = now_s();
         if( 0 > parsec_context_add_taskpool(parsec, (parsec_taskpool_t*)tp) ) return 4;
+        const double ta = now_s();
         if( 0 > parsec_context_start(parsec) ) return 4;
+        const double tst = now_s();
         if( 0 > parsec_context_wait(parsec) ) return 4;
         const double t1 = now_s();
+        clock_gettime(CLOCK_MONOTONIC, &ts1);
+        if( verbose ) {
+            const double m0 = ts0.tv_sec * 1e3 + ts0.tv_nsec * 1e-6, m1 = ts1.tv_sec * 1e3 + ts1.tv_nsec * 1e-6;
+            for( int i = 0; i < (int)parsec_nb_devices; i++ ) {
+                parsec_device_module_t *d = parsec_mca_device_get(i);
+                parsec_b200_stats_t s1;
+                if( NULL != d && parsec_b200_is_b200_device(d) && 0 == parsec_b200_get_stats(d, &s1) )
+                    fprintf(stderr, "  dev %d: add_taskpool %.3f ms, start %.3f ms, first kernel_scheduler entry at %.3f ms, manager at %.3f ms, last completion %.3f ms before wait returned\n", i,
+                            1e3 * (ta - t0), 1e3 * (tst - ta), s1.first_entry_ns * 1e-6 - m0, s1.first_task_ns * 1e-6 - m0, m1 - s1.last_done_ns * 1e-6);
+            }
+        }
         /* bring every tile home (what a real application does before it reads its matrix on the CPU) */
         for( int i = 0; i < (int)parsec_nb_devices; i++ ) {
             parsec_device_module_t *d = parsec_mca_device_get(i);
