@@ -565,7 +565,7 @@ def main():
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32",
            "data": "synthetic", "config": cfg, "tile_gbs": world * algo_bytes / (ms_per_step / 1e3) / 1e9,
            "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
-           "engine": {"hbm_worker": "64 threads x 20 per SM, TMA bulk tile mover", "gemm_worker": "CTA pair, cta_group::2, fused k-chains"}}
+           "engine": {"hbm_worker": "64 threads x 12 per SM (80 registers, no spills), 16 x 16-byte loads per thread in flight in read-only bodies, TMA bulk tile mover", "gemm_worker": "CTA pair, cta_group::2, fused k-chains"}}
     if world == 1:
         peak, how = measured("hbm_gbs", 6650.0)
         ach = algo_bytes / (only_kernel_ms / 1e3) / 1e9

@@ -129,7 +129,7 @@ __device__ __forceinline__ void cta_copy(void* dst, const void* src, size_t byte
 }
 
 #ifndef PB2_CHECK_UNROLL
-#define PB2_CHECK_UNROLL 4
+#define PB2_CHECK_UNROLL 16
 #endif
 // OR over the slice of (element ^ k): zero iff every 4-byte element equals k.  Read-only, 16-byte loads,
 // PB2_CHECK_UNROLL independent requests per thread in flight.

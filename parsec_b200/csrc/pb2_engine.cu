@@ -69,11 +69,13 @@ __global__ void pb2_window_reset_kernel(WinDev w, const pb2_tile_t* tiles_init,
 // ---------------------------------------------------------------------------------------------
 // the persistent engine kernel, HBM-bound bodies
 // ---------------------------------------------------------------------------------------------
-// 64-thread workers, 24 per SM (1536 threads, <= 40 registers): measured best on B200 (sweep in DESIGN.md):
-// many small workers overlap the serial pop / release sections of one task with the streaming of the others.
+// 64-thread workers, 12 per SM (<= 80 registers, no spills): a worker keeps PB2_CHECK_UNROLL = 16 (read-only bodies) or
+// PB2_UNROLL = 4 (read-modify-write bodies) 16-byte requests per thread in flight -- bytes in flight per SM are what
+// the L2-bound Ex05 window responds to (r02 sweep in DESIGN.md: 20 x 4 requests 0.76 ms, 20 x 6 0.62 ms, 12 x 16 0.60 ms),
+// while many small workers still overlap the serial pop / release sections of one task with the streaming of the others.
 // What one worker does with a task is in pb2_worker.cuh (shared with the streaming kernel of pb2_stream.cu).
 #ifndef PB2_HBM_MINB
-#define PB2_HBM_MINB 20
+#define PB2_HBM_MINB 12
 #endif
 #ifndef PB2_HBM_THREADS
 #define PB2_HBM_THREADS 64

@@ -260,7 +260,7 @@ __device__ __forceinline__ void dispatcher_warp(const StreamDev& sd) {
 // the persistent streaming kernel
 // ---------------------------------------------------------------------------------------------
 #ifndef PB2_STREAM_MINB
-#define PB2_STREAM_MINB 20
+#define PB2_STREAM_MINB 12
 #endif
 __global__ void __launch_bounds__(64, PB2_STREAM_MINB)
 pb2_stream_kernel(StreamDev sd) {

@@ -101,6 +101,7 @@ typedef struct parsec_device_b200_module_s {
     uint64_t             cold_inflight;   /* bytes of stage-in handed to the device and not retired yet */
     b200_task_t         *recording;       /* the task whose submit function is being called in record mode */
     parsec_task_t       *completion_ring; /* tasks whose runtime completion is handed to the worker pool */
+    void * volatile      proxy_free;      /* b200_proxy_t LIFO: workers push, this module's manager pops */
     int32_t              completed_now;   /* completions of the current manager iteration, subtracted from owed at its end */
     cudaStream_t         dma_stream;
     parsec_cuda_exec_stream_t *lane;      /* exec_stream[0]: what submit functions receive */
@@ -173,6 +174,46 @@ static void b200_bt_free(parsec_device_b200_module_t *dev, b200_task_t *bt)
 {
     bt->gpu_task = NULL;
     parsec_list_nolock_push_front(&dev->free_bt, &bt->item);
+}
+
+/* The manager walks objects other cores wrote a moment ago (gpu_task, parsec_task_t, data copies, parsec_data_t): every
+ * first touch is a cache-to-cache transfer of 100+ ns, and one task touches half a dozen of them one after the other.
+ * Both manager loops therefore run a four-deep software prefetch ahead of the task they work on, one pointer level
+ * per step (each level needs the line the previous step asked for). */
+#define B200_PF(p) __builtin_prefetch((const void*)(p), 0, 3)
+static inline void b200_pf1(const b200_task_t *bt)
+{
+    const char *g = (const char*)bt->gpu_task;
+    if( NULL != g ) { B200_PF(g); B200_PF(g + 64); B200_PF(g + 128); }
+}
+static inline void b200_pf2(const b200_task_t *bt)
+{
+    const parsec_gpu_task_t *g = bt->gpu_task;
+    if( NULL == g || NULL == g->ec ) return;
+    const parsec_task_t *t = g->ec;
+    B200_PF(t); B200_PF((const char*)t + 64);
+    B200_PF(&t->data[0]); B200_PF((const char*)&t->data[0] + 64);
+    B200_PF(g->flow_info);
+}
+static inline void b200_pf3(const b200_task_t *bt)
+{
+    const parsec_gpu_task_t *g = bt->gpu_task;
+    if( NULL == g || NULL == g->ec ) return;
+    const uint32_t n = g->nb_flows < 4 ? g->nb_flows : 4;
+    for( uint32_t i = 0; i < n; i++ ) {
+        if( NULL != g->ec->data[i].data_in ) B200_PF(g->ec->data[i].data_in);
+        if( NULL != g->ec->data[i].data_out ) B200_PF(g->ec->data[i].data_out);
+    }
+}
+static inline void b200_pf4(const b200_task_t *bt)
+{
+    const parsec_gpu_task_t *g = bt->gpu_task;
+    if( NULL == g || NULL == g->ec ) return;
+    const uint32_t n = g->nb_flows < 4 ? g->nb_flows : 4;
+    for( uint32_t i = 0; i < n; i++ ) {
+        const parsec_data_copy_t *c = (NULL != g->ec->data[i].data_in) ? g->ec->data[i].data_in : g->ec->data[i].data_out;
+        if( NULL != c && NULL != c->original ) { B200_PF(c->original); B200_PF((const char*)c->original + 64); }
+    }
 }
 
 static inline int32_t b200_tile_of(const parsec_device_b200_module_t *dev, const parsec_data_copy_t *gpu_copy)
@@ -610,19 +651,23 @@ typedef struct b200_proxy_s {
     parsec_task_t       *original;
     int                  npins;
     parsec_data_copy_t  *pins[MAX_PARAM_COUNT];
+    parsec_gpu_task_t   *gpu_task;       /* given back by the worker too: free() of another thread's allocation is not cheap */
+    struct b200_proxy_s * volatile *home; /* free list of the module that made it */
     struct b200_proxy_s * volatile next_free;
 } b200_proxy_t;
-static b200_proxy_t * volatile b200_proxy_free = NULL;      /* LIFO shared by the modules and the workers */
-static parsec_atomic_lock_t b200_proxy_lock = PARSEC_ATOMIC_UNLOCKED;
 
 static parsec_hook_return_t b200_completion_hook(parsec_execution_stream_t *es, parsec_task_t *task)
 {
     b200_proxy_t *px = (b200_proxy_t*)task;
     (void)__parsec_complete_execution(es, px->original);
     for( int i = 0; i < px->npins; i++ ) (void)parsec_atomic_fetch_dec_int32(&px->pins[i]->readers);
-    parsec_atomic_lock(&b200_proxy_lock);
-    px->next_free = b200_proxy_free; b200_proxy_free = px;
-    parsec_atomic_unlock(&b200_proxy_lock);
+    if( NULL != px->gpu_task ) { px->gpu_task->release_device_task(px->gpu_task); px->gpu_task = NULL; }
+    /* lock-free push; the module's manager is the only thread that pops, so the list has no ABA problem */
+    b200_proxy_t *old;
+    do {
+        old = *px->home;
+        px->next_free = old;
+    } while( !parsec_atomic_cas_ptr(px->home, old, px) );
     return PARSEC_HOOK_RETURN_ASYNC;      /* nothing of the proxy is left for the runtime to complete */
 }
 static const __parsec_chore_t b200_completion_chores[] = {
@@ -633,15 +678,18 @@ static const parsec_task_class_t b200_completion_tc = {
     .name = "b200 completion", .flags = 0, .task_class_id = 0, .nb_flows = 0, .nb_parameters = 0, .nb_locals = 0,
     .incarnations = b200_completion_chores,
 };
-static b200_proxy_t *b200_proxy_get(void)
+/* manager only */
+static b200_proxy_t *b200_proxy_get(b200_proxy_t * volatile *home)
 {
     b200_proxy_t *px;
-    parsec_atomic_lock(&b200_proxy_lock);
-    if( NULL != (px = b200_proxy_free) ) b200_proxy_free = px->next_free;
-    parsec_atomic_unlock(&b200_proxy_lock);
+    do {
+        px = *home;
+        if( NULL == px ) break;
+    } while( !parsec_atomic_cas_ptr(home, px, px->next_free) );
     if( NULL == px ) {
         px = (b200_proxy_t*)calloc(1, sizeof(b200_proxy_t));
         PARSEC_OBJ_CONSTRUCT(&px->task, parsec_task_t);
+        px->home = home;
     }
     return px;
 }
@@ -706,8 +754,9 @@ static void b200_complete(parsec_device_b200_module_t *dev, parsec_execution_str
     }
     mod->executed_tasks++;
     if( parsec_b200_parallel_completion ) {
-        b200_proxy_t *px = b200_proxy_get();
+        b200_proxy_t *px = b200_proxy_get((b200_proxy_t * volatile *)&dev->proxy_free);
         px->original = this_task;
+        px->gpu_task = gpu_task;
         px->npins = 0;
         for( uint32_t i = 0; i < gpu_task->nb_flows; i++ ) {
             parsec_data_copy_t *o = this_task->data[i].data_out;
@@ -732,7 +781,7 @@ static void b200_complete(parsec_device_b200_module_t *dev, parsec_execution_str
     }
     b200_bt_free(dev, bt);
     gpu_task->last_data_check_epoch = 0;
-    gpu_task->release_device_task(gpu_task);
+    if( !parsec_b200_parallel_completion ) gpu_task->release_device_task(gpu_task);
     dev->completed_now++;
 }
 
@@ -1055,6 +1104,13 @@ static int b200_progress(parsec_device_b200_module_t *dev, parsec_execution_stre
             b200_task_t *bt = (b200_task_t*)it;
             next = PARSEC_LIST_ITERATOR_NEXT(it);
             int rc;
+            {   /* look-ahead prefetch, one pointer level per position */
+                parsec_list_item_t *la = next;
+                if( la != PARSEC_LIST_ITERATOR_END(&dev->stalled) ) { b200_pf4((b200_task_t*)la); la = PARSEC_LIST_ITERATOR_NEXT(la);
+                if( la != PARSEC_LIST_ITERATOR_END(&dev->stalled) ) { b200_pf3((b200_task_t*)la); la = PARSEC_LIST_ITERATOR_NEXT(la);
+                if( la != PARSEC_LIST_ITERATOR_END(&dev->stalled) ) { b200_pf2((b200_task_t*)la); la = PARSEC_LIST_ITERATOR_NEXT(la);
+                if( la != PARSEC_LIST_ITERATOR_END(&dev->stalled) ) { b200_pf1((b200_task_t*)la); } } } }
+            }
             /* once a task has failed to get memory in this pass, only tasks that need none are tried */
             if( mem_blocked && BT_NEW == bt->state && b200_needs_memory(dev, bt->gpu_task) ) continue;
             parsec_list_nolock_remove(&dev->stalled, it);
@@ -1116,6 +1172,10 @@ static int b200_progress(parsec_device_b200_module_t *dev, parsec_execution_stre
         t1 = B200_TSC(); dev->tsc[n ? 3 : 5] += t1 - t0; t0 = t1;
         for( int i = 0; i < n; i++ ) {
             b200_task_t *bt = (b200_task_t*)(uintptr_t)dev->retbuf[i].cookie;
+            if( i + 1 < n ) b200_pf4((const b200_task_t*)(uintptr_t)dev->retbuf[i + 1].cookie);
+            if( i + 2 < n ) b200_pf3((const b200_task_t*)(uintptr_t)dev->retbuf[i + 2].cookie);
+            if( i + 3 < n ) b200_pf2((const b200_task_t*)(uintptr_t)dev->retbuf[i + 3].cookie);
+            if( i + 4 < n ) b200_pf1((const b200_task_t*)(uintptr_t)dev->retbuf[i + 4].cookie);
             if( NULL == bt->gpu_task || BT_INFLIGHT != bt->state ) {
                 parsec_warning("device_b200: retire record %d/%d for a task that is not in flight (bt %p state %d ticket %d/%d gpu_task %p)",
                                i, n, (void*)bt, bt->state, bt->ticket, dev->retbuf[i].ticket, (void*)bt->gpu_task);
@@ -1470,6 +1530,8 @@ int parsec_b200_module_fini(parsec_device_module_t *device)
     parsec_device_memory_release(gpu);
     b200_registration_cache_drop(dev);
     if( NULL != dev->stream ) { pb2_stream_destroy(dev->stream); dev->stream = NULL; }
+    for( b200_proxy_t *px = (b200_proxy_t*)dev->proxy_free, *nx; NULL != px; px = nx ) { nx = px->next_free; free(px); }
+    dev->proxy_free = NULL;
     b200_task_t *bt;
     while( NULL != (bt = (b200_task_t*)parsec_list_nolock_pop_front(&dev->free_bt)) ) {
         if( !dev->dry_run && NULL != bt->ev ) (void)cudaEventDestroy(bt->ev);
