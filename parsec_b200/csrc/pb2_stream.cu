@@ -15,6 +15,7 @@
 #include <string.h>
 #include <atomic>
 #include <deque>
+#include <mutex>
 #include <vector>
 
 #include "../../include/pb2_stream.h"
@@ -59,7 +60,9 @@ struct HostCtl {            // pinned host memory, written by both sides
     volatile uint32_t stop_req;     // host -> device: park as soon as nothing is in flight
     volatile uint32_t error;        // kDone* code when state == HS_ERROR
     volatile uint32_t pad;
-    volatile unsigned long long cmd_consumed;   // device -> host: commands the dispatcher has taken
+    char pad0[48];                  // `state` changes a few times per run and is read at every kick: its own line
+    volatile unsigned long long cmd_consumed;   // device -> host: commands the dispatcher has taken (rewritten all the time)
+    char pad1[56];
 };
 
 struct SCtl {               // device memory
@@ -360,15 +363,28 @@ struct pb2_stream_s {
     std::vector<void*> dev_allocs;
     cudaStream_t kstream = nullptr;
     int nworkers = 0;
-    // host bookkeeping
-    unsigned long long cmd_written = 0, ret_read = 0;
+    // Host bookkeeping, in two halves that two different threads may drive at the same time (include/pb2_stream.h):
+    //   SUBMIT side (set_tile / submit / add_edge / kick): cmd_written, consumed_seen, free_tickets, the per-ticket arrays
+    //   POLL side   (poll):                                ret_read
+    // Tickets travel back from the poll side through a single-producer single-consumer ring; the in-flight counters are
+    // atomics; per-ticket arrays are written before the command is published and read after its retire record arrived.
+    unsigned long long cmd_written = 0;
+    unsigned long long consumed_seen = 0;    // last value read from h_ctl->cmd_consumed (the device rewrites that line all the time)
     std::vector<int32_t> free_tickets, free_nodes;
     std::vector<uint64_t> cookie;            // per ticket
     std::vector<uint16_t> tk_parts;          // per ticket
     std::vector<std::vector<int32_t>> tk_nodes;   // per ticket: edge nodes that die with it
     std::vector<uint8_t> tk_live;
-    uint64_t entries_inflight = 0;
-    int64_t inflight = 0;
+    alignas(64) unsigned long long ret_read = 0;
+    std::vector<int32_t> freed;              // SPSC ring of tickets given back by poll, capacity `slots`
+    alignas(64) std::atomic<uint64_t> freed_tail{0};   // written by poll
+    alignas(64) std::atomic<uint64_t> freed_head{0};   // written by submit
+    alignas(64) std::atomic<int64_t> entries_inflight{0};
+    std::atomic<int64_t> inflight{0};
+    std::atomic<uint64_t> n_submitted{0}, n_retired{0};
+    std::mutex launch_mu;                    // (re)launch of the persistent kernel: either side may find it parked
+    std::mutex nodes_mu;                     // free_nodes: add_edge takes, poll gives back (look-ahead edges only)
+    std::mutex dry_mu;                       // dry run: the emulated device is shared by both sides
     pb2_stream_stats_t st{};
     // dry run
     std::vector<DryTask> dry_tasks;
@@ -429,6 +445,7 @@ int pb2_stream_create(pb2_engine_t* e, const pb2_stream_params_t* params, pb2_st
     for (int32_t i = (int32_t)s->slots - 1; i >= 0; --i) { s->free_tickets.push_back(i); s->free_nodes.push_back(i); }
     s->tile_bytes.assign((size_t)p.max_tiles, 0);
     s->cookie.assign(s->slots, 0); s->tk_parts.assign(s->slots, 1); s->tk_nodes.resize(s->slots); s->tk_live.assign(s->slots, 0);
+    s->freed.assign(s->slots, -1);
     if (s->dry) {
         s->dry_tasks.resize(s->slots);
         s->dry_tiles.resize((size_t)p.max_tiles);
@@ -507,7 +524,11 @@ int pb2_stream_destroy(pb2_stream_t* s) {
 static int stream_launch_if_parked(pb2_stream_t* s) {
     if (s->dry) return PB2_SUCCESS;
     std::atomic_thread_fence(std::memory_order_seq_cst);
-    const uint32_t st = s->h_ctl->state;
+    uint32_t st = s->h_ctl->state;
+    if (st == HS_RUNNING) return PB2_SUCCESS;
+    if (st == HS_ERROR) { s->last_error = "streaming kernel aborted (watchdog or unknown body)"; return PB2_ERR_DEVICE; }
+    std::lock_guard<std::mutex> guard(s->launch_mu);
+    st = s->h_ctl->state;                       // the other side may have relaunched it meanwhile
     if (st == HS_RUNNING) return PB2_SUCCESS;
     if (st == HS_ERROR) { s->last_error = "streaming kernel aborted (watchdog or unknown body)"; return PB2_ERR_DEVICE; }
     STREAM_CUDA(s, cudaSetDevice(s->e->cuda_device));
@@ -522,7 +543,9 @@ static int stream_launch_if_parked(pb2_stream_t* s) {
 
 // reserve the next command slot (waits for the dispatcher when the ring is full)
 static int stream_cmd_slot(pb2_stream_t* s, Cmd** out) {
-    if (s->cmd_written - s->h_ctl->cmd_consumed >= (unsigned long long)s->slots) {
+    // flow control reads the device-written counter only when the last value seen says the ring could be full
+    if (s->cmd_written - s->consumed_seen >= (unsigned long long)s->slots) s->consumed_seen = s->h_ctl->cmd_consumed;
+    if (s->cmd_written - s->consumed_seen >= (unsigned long long)s->slots) {
         int rc = stream_launch_if_parked(s);
         if (rc != PB2_SUCCESS) return rc;
         unsigned long long spins = 0;
@@ -530,8 +553,11 @@ static int stream_cmd_slot(pb2_stream_t* s, Cmd** out) {
             if (s->h_ctl->state == HS_ERROR) { s->last_error = "streaming kernel aborted"; return PB2_ERR_DEVICE; }
             if ((++spins & 0xfffff) == 0 && s->h_ctl->state == HS_STOPPED) { rc = stream_launch_if_parked(s); if (rc != PB2_SUCCESS) return rc; }
         }
+        s->consumed_seen = s->h_ctl->cmd_consumed;
     }
     *out = &s->h_cmd[s->cmd_written & (s->slots - 1)];
+    // the slots a few commands ahead: last read by the device a lap ago, nowhere near this core's cache
+    __builtin_prefetch(&s->h_cmd[(s->cmd_written + 6) & (s->slots - 1)], 1, 3);
     return PB2_SUCCESS;
 }
 static void stream_cmd_publish(pb2_stream_t* s, Cmd* c) {
@@ -565,7 +591,13 @@ int pb2_stream_submit(pb2_stream_t* s, const pb2_task_t* task, uint64_t cookie, 
     if (task->dep_goal < 0 || task->dep_goal > 0xffff) return PB2_ERR_VALUE_OUT_OF_BOUNDS;
     for (int f = 0; f < task->nb_flows; ++f)
         if (task->tile[f] >= s->p.max_tiles) { s->last_error = "tile id out of bounds"; return PB2_ERR_VALUE_OUT_OF_BOUNDS; }
-    if (s->free_tickets.empty()) return PB2_ERR_OUT_OF_RESOURCE;
+    if (s->free_tickets.empty()) {              // take back what the poll side has retired
+        uint64_t h = s->freed_head.load(std::memory_order_relaxed);
+        const uint64_t t = s->freed_tail.load(std::memory_order_acquire);
+        for (; h != t; ++h) s->free_tickets.push_back(s->freed[h & (s->slots - 1)]);
+        s->freed_head.store(h, std::memory_order_release);
+        if (s->free_tickets.empty()) return PB2_ERR_OUT_OF_RESOURCE;
+    }
     // parts: ceil(widest tile / part_bytes), the rule the device applies to the slices of a tile (tile_slices)
     uint32_t np = 1;
     if (s->p.part_bytes > 0 && task->body != PB2_BODY_NOP) {
@@ -576,10 +608,15 @@ int pb2_stream_submit(pb2_stream_t* s, const pb2_task_t* task, uint64_t cookie, 
         if (np > PB2_MAX_PARTS) np = PB2_MAX_PARTS;
         if (np < 1) np = 1;
     }
-    if (s->entries_inflight + np + 64 > (uint64_t)s->ring_cap / 2) return PB2_ERR_OUT_OF_RESOURCE;
+    if ((uint64_t)s->entries_inflight.load(std::memory_order_relaxed) + np + 64 > (uint64_t)s->ring_cap / 2) return PB2_ERR_OUT_OF_RESOURCE;
     const int32_t tk = s->free_tickets.back();
     if (s->dry) {
+        std::lock_guard<std::mutex> guard(s->dry_mu);
         s->free_tickets.pop_back();
+        s->cookie[(size_t)tk] = cookie; s->tk_parts[(size_t)tk] = (uint16_t)np; s->tk_live[(size_t)tk] = 1;
+        s->entries_inflight.fetch_add(np, std::memory_order_relaxed); s->inflight.fetch_add(1, std::memory_order_relaxed);
+        s->n_submitted.fetch_add(1, std::memory_order_relaxed);
+        if (ticket) *ticket = tk;
         DryTask& dt = s->dry_tasks[(size_t)tk];
         dt.t = *task; dt.dep = task->dep_goal; dt.succ.clear(); dt.done = false;
         if (dt.dep == 0) s->dry_ready.push_back(tk);
@@ -588,6 +625,7 @@ int pb2_stream_submit(pb2_stream_t* s, const pb2_task_t* task, uint64_t cookie, 
         int rc = stream_cmd_slot(s, &c);
         if (rc != PB2_SUCCESS) return rc;
         s->free_tickets.pop_back();
+        s->cookie[(size_t)tk] = cookie; s->tk_parts[(size_t)tk] = (uint16_t)np; s->tk_live[(size_t)tk] = 1;
         memset(c, 0, 60);
         c->op = CMD_TASK; c->body = task->body; c->nb_flows = task->nb_flows; c->flags = task->flags;
         c->nparts = (uint16_t)np; c->dep_goal = (uint16_t)task->dep_goal;
@@ -595,11 +633,11 @@ int pb2_stream_submit(pb2_stream_t* s, const pb2_task_t* task, uint64_t cookie, 
         for (int f = 0; f < PB2_MAX_FLOWS; ++f) { c->u.task.tile[f] = f < task->nb_flows ? task->tile[f] : -1; c->u.task.access[f] = task->access[f]; }
         c->u.task.iparam[0] = task->iparam[0]; c->u.task.iparam[1] = task->iparam[1]; c->u.task.iparam[2] = task->iparam[2];
         c->u.task.fparam = task->fparam; c->u.task.locals[0] = task->locals[0]; c->u.task.locals[1] = task->locals[1];
+        s->entries_inflight.fetch_add(np, std::memory_order_relaxed); s->inflight.fetch_add(1, std::memory_order_relaxed);
+        s->n_submitted.fetch_add(1, std::memory_order_relaxed);
+        if (ticket) *ticket = tk;               // before the command is visible: the caller's record may be recycled right after
         stream_cmd_publish(s, c);
     }
-    s->cookie[(size_t)tk] = cookie; s->tk_parts[(size_t)tk] = (uint16_t)np; s->tk_live[(size_t)tk] = 1;
-    s->entries_inflight += np; s->inflight++; s->st.submitted++;
-    if (ticket) *ticket = tk;
     return PB2_SUCCESS;
 }
 
@@ -608,17 +646,22 @@ int pb2_stream_add_edge(pb2_stream_t* s, int32_t pred, int32_t succ) {
     if (!s->tk_live[(size_t)pred] || !s->tk_live[(size_t)succ]) { s->last_error = "edge names a ticket that is not in flight"; return PB2_ERR_BAD_PARAM; }
     s->st.edges++;
     if (s->dry) {
+        std::lock_guard<std::mutex> guard(s->dry_mu);
         DryTask& p = s->dry_tasks[(size_t)pred];
         if (p.done) { if (--s->dry_tasks[(size_t)succ].dep == 0) s->dry_ready.push_back(succ); }
         else p.succ.push_back(succ);
         return PB2_SUCCESS;
     }
-    if (s->free_nodes.empty()) return PB2_ERR_OUT_OF_RESOURCE;
     Cmd* c;
     int rc = stream_cmd_slot(s, &c);
     if (rc != PB2_SUCCESS) return rc;
-    const int32_t node = s->free_nodes.back(); s->free_nodes.pop_back();
-    s->tk_nodes[(size_t)pred].push_back(node);
+    int32_t node;
+    {
+        std::lock_guard<std::mutex> guard(s->nodes_mu);
+        if (s->free_nodes.empty()) return PB2_ERR_OUT_OF_RESOURCE;
+        node = s->free_nodes.back(); s->free_nodes.pop_back();
+        s->tk_nodes[(size_t)pred].push_back(node);
+    }
     memset(c, 0, 60);
     c->op = CMD_EDGE; c->u.edge.pred = pred; c->u.edge.succ = succ; c->u.edge.node = node;
     stream_cmd_publish(s, c);
@@ -628,14 +671,14 @@ int pb2_stream_add_edge(pb2_stream_t* s, int32_t pred, int32_t succ) {
 int pb2_stream_kick(pb2_stream_t* s) {
     if (!s) return PB2_ERR_BAD_PARAM;
     if (s->dry || s->cmd_written == 0) return PB2_SUCCESS;
-    if (s->h_ctl->cmd_consumed == s->cmd_written && s->inflight == 0) return PB2_SUCCESS;
-    return stream_launch_if_parked(s);
+    return stream_launch_if_parked(s);          // a fence and one read of a line that changes a few times per run
 }
 
 int pb2_stream_poll(pb2_stream_t* s, pb2_retire_t* out, int32_t max) {
     if (!s || (max > 0 && !out)) return PB2_ERR_BAD_PARAM;
     int n = 0;
     if (s->dry) {
+        std::lock_guard<std::mutex> guard(s->dry_mu);
         while (n < max && !s->dry_ready.empty()) {
             const int32_t tk = s->dry_ready.front(); s->dry_ready.pop_front();
             DryTask& dt = s->dry_tasks[(size_t)tk];
@@ -652,8 +695,12 @@ int pb2_stream_poll(pb2_stream_t* s, pb2_retire_t* out, int32_t max) {
             }
             for (int32_t sc : dt.succ) if (--s->dry_tasks[(size_t)sc].dep == 0) s->dry_ready.push_back(sc);
             dt.succ.clear();
-            s->tk_live[(size_t)tk] = 0; s->free_tickets.push_back(tk);
-            s->entries_inflight -= s->tk_parts[(size_t)tk]; s->inflight--; s->st.retired++;
+            s->tk_live[(size_t)tk] = 0;
+            const uint64_t ft = s->freed_tail.load(std::memory_order_relaxed);
+            s->freed[ft & (s->slots - 1)] = tk;
+            s->freed_tail.store(ft + 1, std::memory_order_release);
+            s->entries_inflight.fetch_sub(s->tk_parts[(size_t)tk], std::memory_order_relaxed); s->inflight.fetch_sub(1, std::memory_order_relaxed);
+            s->n_retired.fetch_add(1, std::memory_order_relaxed);
         }
         return n;
     }
@@ -662,7 +709,7 @@ int pb2_stream_poll(pb2_stream_t* s, pb2_retire_t* out, int32_t max) {
                                                                   : "streaming kernel ran a task with an unknown body id";
         return s->h_ctl->error == (uint32_t)kDoneTimeout ? PB2_ERR_DEVICE : PB2_ERR_BAD_PARAM;
     }
-    if (s->h_ctl->state == HS_STOPPED && (s->inflight > 0 || s->cmd_written != s->h_ctl->cmd_consumed)) {
+    if (s->h_ctl->state == HS_STOPPED && s->inflight.load(std::memory_order_relaxed) > 0) {
         // nobody kicked: every retire record already written is in the ring; anything else needs the kernel
         const Retire* nxt = &s->h_ret[s->ret_read & (s->slots - 1)];
         const uint32_t g = ((uint32_t)(s->ret_read / (unsigned long long)s->slots) + 1u) & 0x7fffffffu;
@@ -673,6 +720,7 @@ int pb2_stream_poll(pb2_stream_t* s, pb2_retire_t* out, int32_t max) {
     }
     while (n < max) {
         const Retire* rec = &s->h_ret[s->ret_read & (s->slots - 1)];
+        __builtin_prefetch(&s->h_ret[(s->ret_read + 8) & (s->slots - 1)], 0, 3);
         const uint32_t gen = ((uint32_t)(s->ret_read / (unsigned long long)s->slots) + 1u) & 0x7fffffffu;
         const uint32_t stamp = *reinterpret_cast<const volatile uint32_t*>(&rec->stamp);
         if ((stamp & 0x7fffffffu) != gen) break;
@@ -682,10 +730,17 @@ int pb2_stream_poll(pb2_stream_t* s, pb2_retire_t* out, int32_t max) {
         r.cookie = s->cookie[(size_t)tk]; r.result = *reinterpret_cast<const volatile uint64_t*>(&rec->result);
         for (int f = 0; f < PB2_MAX_FLOWS; ++f) r.seen_version[f] = *reinterpret_cast<const volatile uint32_t*>(&rec->seen[f]);
         r.ticket = tk; r.status = (stamp & 0x80000000u) ? PB2_ERR_BAD_PARAM : PB2_SUCCESS;
-        for (int32_t nd : s->tk_nodes[(size_t)tk]) s->free_nodes.push_back(nd);
-        s->tk_nodes[(size_t)tk].clear();
-        s->tk_live[(size_t)tk] = 0; s->free_tickets.push_back(tk);
-        s->entries_inflight -= s->tk_parts[(size_t)tk]; s->inflight--; s->st.retired++;
+        if (!s->tk_nodes[(size_t)tk].empty()) {
+            std::lock_guard<std::mutex> guard(s->nodes_mu);
+            for (int32_t nd : s->tk_nodes[(size_t)tk]) s->free_nodes.push_back(nd);
+            s->tk_nodes[(size_t)tk].clear();
+        }
+        s->tk_live[(size_t)tk] = 0;
+        const uint64_t ft = s->freed_tail.load(std::memory_order_relaxed);
+        s->freed[ft & (s->slots - 1)] = tk;
+        s->freed_tail.store(ft + 1, std::memory_order_release);
+        s->entries_inflight.fetch_sub(s->tk_parts[(size_t)tk], std::memory_order_relaxed); s->inflight.fetch_sub(1, std::memory_order_relaxed);
+        s->n_retired.fetch_add(1, std::memory_order_relaxed);
         s->ret_read++;
     }
     return n;
@@ -706,7 +761,7 @@ int pb2_stream_quiesce(pb2_stream_t* s) {
     return PB2_SUCCESS;
 }
 
-int pb2_stream_inflight(pb2_stream_t* s) { return s ? (int)s->inflight : 0; }
+int pb2_stream_inflight(pb2_stream_t* s) { return s ? (int)s->inflight.load() : 0; }
 
 int pb2_stream_stats(pb2_stream_t* s, pb2_stream_stats_t* out) {
     if (!s || !out) return PB2_ERR_BAD_PARAM;
@@ -721,6 +776,7 @@ int pb2_stream_stats(pb2_stream_t* s, pb2_stream_stats_t* out) {
         s->st.stage_ins = c.stage_ins.v; s->st.body_errors = c.body_errors.v;
         s->st.edges_late = sc.edges_late.v; s->st.released_on_device = sc.released.v;
     }
+    s->st.submitted = s->n_submitted.load(); s->st.retired = s->n_retired.load();
     *out = s->st;
     return PB2_SUCCESS;
 }

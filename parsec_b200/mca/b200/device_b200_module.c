@@ -38,6 +38,7 @@
 #include "pb2_stream.h"
 
 #include <cuda_runtime_api.h>
+#include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
 #include <stdio.h>
@@ -50,6 +51,23 @@ static inline uint64_t b200_now_ns(void) { struct timespec ts; clock_gettime(CLO
 /* ------------------------------------------------------------------------------------------------------------------ */
 /* types                                                                                                                */
 /* ------------------------------------------------------------------------------------------------------------------ */
+/* The two locks of a module are taken once or twice per task by every worker thread.  parsec_atomic_lock backs off with
+ * nanosleep(): right for the rarely contended locks of the runtime, a 50 us stall here.  A ticket lock instead: FIFO
+ * hand-over, waiters spin on a line only the holder writes. */
+typedef struct b200_lock_s {
+    volatile uint32_t next;    char pad0[60];
+    volatile uint32_t serving; char pad1[60];
+} b200_lock_t;
+static inline void b200_lock(b200_lock_t *l)
+{
+    const uint32_t t = __atomic_fetch_add(&l->next, 1, __ATOMIC_RELAXED);
+    while( __atomic_load_n(&l->serving, __ATOMIC_ACQUIRE) != t ) _mm_pause();
+}
+static inline void b200_unlock(b200_lock_t *l)
+{
+    __atomic_store_n(&l->serving, l->serving + 1, __ATOMIC_RELEASE);
+}
+
 enum {
     BT_NEW = 0,        /* popped from the inbox, nothing reserved yet                                   */
     BT_STAGED,         /* resident and described to the device, waiting for room in the command ring      */
@@ -60,12 +78,25 @@ enum {
     BT_SHADOW          /* look-ahead: runs on the device, the host has not scheduled it yet             */
 };
 
+/* One record per task handed to the device.  Laid out by who touches what: the manager's hot path (inbox, submit,
+ * retire) reads the first two lines and `cmd`, the worker that runs the epilog reads `proxy` and the task itself. */
 typedef struct b200_task_s {
     parsec_list_item_t   item;
     parsec_gpu_task_t   *gpu_task;        /* NULL while a shadow task waits for the host to schedule it */
     int32_t              state;
     int32_t              ticket;          /* pb2_stream ticket, -1 when none */
     int32_t              body;            /* enum pb2_body_e recorded by parsec_b200_task_body, -1: opaque body */
+    int32_t              prepared;        /* the caller found every flow resident: residency, readers and versions are settled */
+    int32_t              cmd_built;       /* `cmd` is ready for pb2_stream_submit */
+    int32_t              recorded;        /* the caller of kernel_scheduler already ran the submit function in record mode */
+    int32_t              has_complete_stage;
+    uint32_t             dma_out_mask;    /* pushout flows that need the copy engine (home not device-visible) */
+    uint64_t             result;
+    uint64_t             cold_bytes;      /* bytes this task stages in over PCIe / NVLink (throttle, see b200_start_task) */
+    struct parsec_device_b200_module_s *dev;
+    pb2_task_t           cmd __attribute__((aligned(64)));   /* the engine command of this task (built by whoever settles its flows) */
+    parsec_task_t        proxy __attribute__((aligned(64))); /* the completion task the worker pool runs for this one (b200_epilog_hook) */
+    /* start path of tasks the manager has to look at, lane / copy-engine paths */
     int32_t              nb_args;
     int32_t              arg_flow[PB2_MAX_FLOWS];
     int32_t              iparam[3];
@@ -73,12 +104,11 @@ typedef struct b200_task_s {
     uint32_t             tile_of_arg[PB2_MAX_FLOWS];
     uint32_t             peer_src_mask;   /* flows whose source copy on a peer GPU holds a reader for us */
     parsec_data_copy_t  *peer_src[MAX_PARAM_COUNT];
-    uint32_t             dma_out_mask;    /* pushout flows that need the copy engine (home not device-visible) */
-    uint64_t             result;
     int32_t              retired;         /* shadow: the device is done with it */
     int32_t              custom_stage;    /* the task brought its own stage_in / stage_out (device_gpu.h:75-91) */
-    uint64_t             cold_bytes;      /* bytes this task stages in over PCIe / NVLink (throttle, see b200_start_task) */
-    cudaEvent_t          ev;
+    cudaEvent_t          ev;              /* created the first time a copy-engine / lane path needs it */
+    int32_t              ev_dev;          /* CUDA device the event belongs to, -1: none */
+    struct b200_task_s  *next_free;       /* per-thread free list */
 } b200_task_t;
 
 typedef struct b200_host_range_s { char *base; size_t len; char *alias; int lazy; } b200_host_range_t;   /* lazy: unregistered by its owner, still pinned (registration cache) */
@@ -90,18 +120,30 @@ typedef struct parsec_device_b200_module_s {
     int                  dry_run;
     char                *slab_base;
     uint8_t             *tile_described;  /* per heap block: the device tile table entry of the replica that starts here is current */
-    /* inbox + election */
-    parsec_gpu_task_t * volatile inbox;
+    /* inbox + election: callers take a slot index with one fetch-and-add and store their task record there; the
+     * manager reads the slots in order (pointers side by side: it can prefetch the records well ahead) */
+    b200_task_t * volatile *inbox_ring;
+    volatile int64_t     inbox_tail;      /* next slot a caller takes */
+    char                 pad0_[56];
+    volatile int64_t     inbox_head;      /* slots the manager has emptied (written by the manager only) */
     volatile int32_t     owed;
     volatile int32_t     callers_inside;
+    volatile int64_t     epilogs_done;    /* epilogs the worker threads have ended (their own cache line: the manager never writes it) */
+    char                 pad_[56];
+    b200_lock_t          lru_lock;        /* gpu_mem_lru / gpu_mem_owned_lru: the manager and the workers' epilogs */
     /* manager-private */
-    parsec_list_t        stalled;         /* b200_task_t waiting for device memory        */
+    parsec_list_t        stalled;         /* b200_task_t not started yet: new ones, and ones waiting for memory or ring space */
+    parsec_list_t        settled;         /* ... whose flows the caller settled (b200_prepare_resident): they only need ring space */
+    int32_t              nb_settled;
     parsec_list_t        waiting_event;   /* b200_task_t in BT_DMA_IN / BT_LANE / BT_DMA_OUT, in event order */
-    parsec_list_t        free_bt;
-    uint64_t             cold_inflight;   /* bytes of stage-in handed to the device and not retired yet */
-    b200_task_t         *recording;       /* the task whose submit function is being called in record mode */
-    parsec_task_t       *completion_ring; /* tasks whose runtime completion is handed to the worker pool */
-    void * volatile      proxy_free;      /* b200_proxy_t LIFO: workers push, this module's manager pops */
+    int64_t              cold_inflight;   /* bytes of stage-in handed to the device and not retired yet */
+    int32_t              nb_stalled;
+    int32_t              again_window;    /* the last AGAIN of b200_start_task came from the stage-in window, not from memory */
+    volatile int32_t     retry_stalled;   /* something happened that may let a waiting task start (a retirement, a newcomer, the end of an epilog) */
+    int32_t              blocked_spins;   /* manager iterations since the last attempt to start a waiting task */
+    parsec_task_t       *completion_ring; /* proxies of finished tasks, handed to the worker pool once per iteration */
+    int64_t              epilogs_started; /* finished tasks handed to the worker pool */
+    uint64_t             tsc_start[4];    /* start phase by step: reserve, stage-in decisions, record, command */
     int32_t              completed_now;   /* completions of the current manager iteration, subtracted from owed at its end */
     cudaStream_t         dma_stream;
     parsec_cuda_exec_stream_t *lane;      /* exec_stream[0]: what submit functions receive */
@@ -155,25 +197,110 @@ static char *b200_device_visible(const void *host_ptr, size_t len)
     return res;
 }
 
+#define B200_INBOX_SLOTS (1 << 16)
+/* Task records live on PER-THREAD free lists: the worker that calls kernel_scheduler takes one, the worker that runs the
+ * task's epilog gives it back -- both are threads of the same pool, so the lists stay balanced without any atomic. */
+#define B200_TL_CACHE    8192
+#define B200_FLAG_WRITER ((parsec_data_flag_t)1 << 4)   /* a task that writes this replica is in flight: the replica is on no LRU */
+static __thread b200_task_t *b200_tl_free = NULL;
+static __thread int          b200_tl_nfree = 0;
+static __thread b200_task_t *b200_tl_recording = NULL;   /* the task whose submit function this thread is calling in record mode */
+
+static parsec_hook_return_t b200_epilog_hook(parsec_execution_stream_t *es, parsec_task_t *task);
+static const __parsec_chore_t b200_completion_chores[] = {
+    { .type = PARSEC_DEV_CPU, .evaluate = NULL, .hook = b200_epilog_hook, .dyld = NULL, .dyld_fn = NULL },
+    { .type = PARSEC_DEV_NONE, .evaluate = NULL, .hook = NULL, .dyld = NULL, .dyld_fn = NULL },
+};
+static const parsec_task_class_t b200_completion_tc = {
+    .name = "b200 completion", .flags = 0, .task_class_id = 0, .nb_flows = 0, .nb_parameters = 0, .nb_locals = 0,
+    .incarnations = b200_completion_chores,
+};
+
 static b200_task_t *b200_bt_new(parsec_device_b200_module_t *dev, parsec_gpu_task_t *gpu_task)
 {
-    b200_task_t *bt = (b200_task_t*)parsec_list_nolock_pop_front(&dev->free_bt);
-    if( NULL == bt ) {
-        bt = (b200_task_t*)calloc(1, sizeof(b200_task_t));
+    b200_task_t *bt = b200_tl_free;
+    if( NULL != bt ) { b200_tl_free = bt->next_free; b200_tl_nfree--; }
+    else {
+        if( 0 != posix_memalign((void**)&bt, 64, sizeof(b200_task_t)) ) abort();
+        memset(bt, 0, sizeof(b200_task_t));
         PARSEC_OBJ_CONSTRUCT(&bt->item, parsec_list_item_t);
-        if( !dev->dry_run ) B200_CUDA(cudaEventCreateWithFlags(&bt->ev, cudaEventDisableTiming), "cudaEventCreate", {});
+        PARSEC_OBJ_CONSTRUCT(&bt->proxy, parsec_task_t);
+        bt->proxy.task_class = &b200_completion_tc;
+        bt->proxy.priority = INT32_MAX;                 /* completions first: they release work */
+        bt->proxy.status = PARSEC_TASK_STATUS_HOOK;     /* no prepare_input */
+        bt->proxy.chore_mask = 1;
+        bt->proxy.selected_chore = 0;
+        bt->proxy.selected_device = parsec_mca_device_get(0);
+        bt->proxy.load = 0;
+        bt->proxy.repo_entry = NULL;
+        bt->ev_dev = -1;
     }
     PARSEC_LIST_ITEM_SINGLETON(&bt->item);
+    bt->dev = dev;
     bt->gpu_task = gpu_task; bt->state = BT_NEW; bt->ticket = -1; bt->body = -1; bt->nb_args = 0;
     bt->peer_src_mask = 0; bt->dma_out_mask = 0; bt->result = 0; bt->retired = 0; bt->custom_stage = 0; bt->cold_bytes = 0;
+    bt->recorded = 0; bt->has_complete_stage = 0; bt->prepared = 0; bt->cmd_built = 0;
     if( NULL != gpu_task ) gpu_task->last_data_check_epoch = (uint64_t)(uintptr_t)bt;
     return bt;
 }
 
-static void b200_bt_free(parsec_device_b200_module_t *dev, b200_task_t *bt)
+static void b200_bt_free(b200_task_t *bt)
 {
     bt->gpu_task = NULL;
-    parsec_list_nolock_push_front(&dev->free_bt, &bt->item);
+    if( b200_tl_nfree < B200_TL_CACHE ) { bt->next_free = b200_tl_free; b200_tl_free = bt; b200_tl_nfree++; return; }
+    if( bt->ev_dev >= 0 ) (void)cudaEventDestroy(bt->ev);
+    free(bt);
+}
+
+/* CUDA calls are issued by whichever thread starts or finishes the task: make the module's GPU current first (only the
+ * copy-engine / lane paths come here, never the engine fast path) */
+static inline void b200_cuda_here(parsec_device_b200_module_t *dev)
+{
+    if( !dev->dry_run ) B200_CUDA(cudaSetDevice(dev->super.cuda_index), "cudaSetDevice", {});
+}
+
+/* the event of a task that takes a copy-engine / lane path (made on first use, remade when the record moves to another GPU) */
+static cudaEvent_t b200_bt_event(parsec_device_b200_module_t *dev, b200_task_t *bt)
+{
+    if( bt->ev_dev != (int32_t)dev->super.cuda_index ) {
+        if( bt->ev_dev >= 0 ) (void)cudaEventDestroy(bt->ev);
+        bt->ev_dev = -1;
+        b200_cuda_here(dev);
+        B200_CUDA(cudaEventCreateWithFlags(&bt->ev, cudaEventDisableTiming), "cudaEventCreate", { return bt->ev; });
+        bt->ev_dev = (int32_t)dev->super.cuda_index;
+    }
+    return bt->ev;
+}
+
+/* Every insertion into an LRU list first takes the replica off whatever list it is on (a no-op for a singleton): a
+ * replica can never be linked twice, whatever order epilogs and starts interleave in. */
+static inline void b200_lru_put(parsec_device_b200_module_t *dev, parsec_list_t *list, parsec_data_copy_t *copy)
+{
+    b200_lock(&dev->lru_lock);
+    copy->flags &= (parsec_data_flag_t)~B200_FLAG_WRITER;
+    parsec_list_item_ring_chop((parsec_list_item_t*)copy); PARSEC_LIST_ITEM_SINGLETON(copy);
+    parsec_list_nolock_push_back(list, (parsec_list_item_t*)copy);
+    b200_unlock(&dev->lru_lock);
+}
+/* off the lists; `for_writer`: until the writing task's epilog puts it back */
+static inline void b200_lru_take(parsec_device_b200_module_t *dev, parsec_data_copy_t *copy, int for_writer)
+{
+    b200_lock(&dev->lru_lock);
+    if( for_writer ) copy->flags |= B200_FLAG_WRITER;
+    parsec_list_item_ring_chop((parsec_list_item_t*)copy); PARSEC_LIST_ITEM_SINGLETON(copy);
+    b200_unlock(&dev->lru_lock);
+}
+/* a replica that was just read moves to the back of its list -- unless a writer has taken it off the lists meanwhile */
+static inline void b200_lru_touch(parsec_device_b200_module_t *dev, parsec_data_copy_t *copy)
+{
+    b200_lock(&dev->lru_lock);
+    if( !(copy->flags & B200_FLAG_WRITER) ) {
+        parsec_list_t *l = (PARSEC_DATA_COHERENCY_OWNED == copy->coherency_state) ? &dev->super.super.gpu_mem_owned_lru
+                                                                                  : &dev->super.super.gpu_mem_lru;
+        parsec_list_item_ring_chop((parsec_list_item_t*)copy); PARSEC_LIST_ITEM_SINGLETON(copy);
+        parsec_list_nolock_push_back(l, (parsec_list_item_t*)copy);
+    }
+    b200_unlock(&dev->lru_lock);
 }
 
 /* The manager walks objects other cores wrote a moment ago (gpu_task, parsec_task_t, data copies, parsec_data_t): every
@@ -181,6 +308,7 @@ static void b200_bt_free(parsec_device_b200_module_t *dev, b200_task_t *bt)
  * Both manager loops therefore run a four-deep software prefetch ahead of the task they work on, one pointer level
  * per step (each level needs the line the previous step asked for). */
 #define B200_PF(p) __builtin_prefetch((const void*)(p), 0, 3)
+#define B200_PFW(p) __builtin_prefetch((const void*)(p), 1, 3)
 static inline void b200_pf1(const b200_task_t *bt)
 {
     const char *g = (const char*)bt->gpu_task;
@@ -256,63 +384,55 @@ static void b200_release_copy_memory(parsec_device_b200_module_t *dev, parsec_da
 }
 
 /* Write the oldest dirty replicas home with the copy engine and move them to the clean LRU.  Blocks the manager for
- * the duration of the copies (the persistent kernel keeps running beside them). */
+ * the duration of the copies (the persistent kernel keeps running beside them).  The replicas are off every list while
+ * their bytes travel; the LRU lock is held for the list work only, never across the copies. */
 static int b200_write_back_some(parsec_device_b200_module_t *dev, int how_many)
 {
     parsec_list_item_t *it, *next;
-    int done = 0;
-    if( dev->dry_run ) {
-        for( it = PARSEC_LIST_ITERATOR_FIRST(&dev->super.super.gpu_mem_owned_lru);
-             it != PARSEC_LIST_ITERATOR_END(&dev->super.super.gpu_mem_owned_lru) && done < how_many; it = next ) {
-            parsec_data_copy_t *copy = (parsec_data_copy_t*)it;
-            next = PARSEC_LIST_ITERATOR_NEXT(it);
-            if( 0 != copy->readers ) continue;
-            parsec_data_copy_t *cpu = copy->original->device_copies[0];
-            if( NULL == cpu ) continue;
-            parsec_list_nolock_remove(&dev->super.super.gpu_mem_owned_lru, it);
-            PARSEC_LIST_ITEM_SINGLETON(it);
-            parsec_atomic_lock(&copy->original->lock);
-            cpu->version = copy->version; cpu->coherency_state = PARSEC_DATA_COHERENCY_SHARED;
-            copy->coherency_state = PARSEC_DATA_COHERENCY_SHARED;
-            copy->original->owner_device = 0;
-            parsec_atomic_unlock(&copy->original->lock);
-            parsec_list_nolock_push_back(&dev->super.super.gpu_mem_lru, it);
-            dev->st.w2r_copies++;
-            done++;
-        }
-        return done;
-    }
     parsec_data_copy_t *moved[64];
+    int done = 0;
     if( how_many > 64 ) how_many = 64;
+    b200_lock(&dev->lru_lock);
     for( it = PARSEC_LIST_ITERATOR_FIRST(&dev->super.super.gpu_mem_owned_lru);
          it != PARSEC_LIST_ITERATOR_END(&dev->super.super.gpu_mem_owned_lru) && done < how_many; it = next ) {
         parsec_data_copy_t *copy = (parsec_data_copy_t*)it;
         next = PARSEC_LIST_ITERATOR_NEXT(it);
-        if( 0 != copy->readers ) continue;
+        if( 0 != copy->readers || (copy->flags & B200_FLAG_WRITER) ) continue;
         parsec_data_copy_t *cpu = copy->original->device_copies[0];
-        if( NULL == cpu || NULL == cpu->device_private ) continue;       /* nowhere to write it: keep it */
-        B200_CUDA(cudaMemcpyAsync(cpu->device_private, copy->device_private, copy->original->span, cudaMemcpyDeviceToHost, dev->dma_stream),
-                  "write-back cudaMemcpyAsync", { continue; });
-        dev->super.super.super.data_out_to_host += copy->original->span;
-        dev->st.bytes_d2h_dma += copy->original->span;
+        if( NULL == cpu || (!dev->dry_run && NULL == cpu->device_private) ) continue;       /* nowhere to write it: keep it */
+        parsec_list_nolock_remove(&dev->super.super.gpu_mem_owned_lru, it);
+        PARSEC_LIST_ITEM_SINGLETON(it);
         moved[done++] = copy;
     }
+    b200_unlock(&dev->lru_lock);
     if( 0 == done ) return 0;
-    B200_CUDA(cudaStreamSynchronize(dev->dma_stream), "write-back synchronize", {});
+    if( !dev->dry_run ) {
+        b200_cuda_here(dev);
+        for( int i = 0; i < done; i++ ) {
+            parsec_data_copy_t *copy = moved[i], *cpu = copy->original->device_copies[0];
+            B200_CUDA(cudaMemcpyAsync(cpu->device_private, copy->device_private, copy->original->span, cudaMemcpyDeviceToHost, dev->dma_stream),
+                      "write-back cudaMemcpyAsync", { moved[i] = NULL; b200_lru_put(dev, &dev->super.super.gpu_mem_owned_lru, copy); continue; });
+            (void)parsec_atomic_fetch_add_int64((volatile int64_t*)&dev->super.super.super.data_out_to_host, (int64_t)copy->original->span);
+            dev->st.bytes_d2h_dma += copy->original->span;
+        }
+        B200_CUDA(cudaStreamSynchronize(dev->dma_stream), "write-back synchronize", {});
+    }
+    int n = 0;
     for( int i = 0; i < done; i++ ) {
-        parsec_data_copy_t *copy = moved[i], *cpu = copy->original->device_copies[0];
-        parsec_list_nolock_remove(&dev->super.super.gpu_mem_owned_lru, (parsec_list_item_t*)copy);
-        PARSEC_LIST_ITEM_SINGLETON(copy);
+        parsec_data_copy_t *copy = moved[i];
+        if( NULL == copy ) continue;
+        parsec_data_copy_t *cpu = copy->original->device_copies[0];
         parsec_atomic_lock(&copy->original->lock);
         if( cpu->version < copy->version ) cpu->version = copy->version;
         cpu->coherency_state = PARSEC_DATA_COHERENCY_SHARED;
         copy->coherency_state = PARSEC_DATA_COHERENCY_SHARED;
         if( copy->original->owner_device == (int8_t)dev->super.super.super.device_index ) copy->original->owner_device = 0;
         parsec_atomic_unlock(&copy->original->lock);
-        parsec_list_nolock_push_back(&dev->super.super.gpu_mem_lru, (parsec_list_item_t*)copy);
+        b200_lru_put(dev, &dev->super.super.gpu_mem_lru, copy);
         dev->st.w2r_copies++;
+        n++;
     }
-    return done;
+    return n;
 }
 
 /* Free one replica nobody uses: oldest clean one first; if every clean replica is busy, write dirty ones home. */
@@ -320,11 +440,13 @@ static int b200_evict_one(parsec_device_b200_module_t *dev, const parsec_gpu_tas
 {
     for( int pass = 0; pass < 2; pass++ ) {
         parsec_list_item_t *it, *next;
+        parsec_data_copy_t *victim = NULL;
+        b200_lock(&dev->lru_lock);
         for( it = PARSEC_LIST_ITERATOR_FIRST(&dev->super.super.gpu_mem_lru);
              it != PARSEC_LIST_ITERATOR_END(&dev->super.super.gpu_mem_lru); it = next ) {
             parsec_data_copy_t *copy = (parsec_data_copy_t*)it;
             next = PARSEC_LIST_ITERATOR_NEXT(it);
-            if( PARSEC_DATA_STATUS_UNDER_TRANSFER == copy->data_transfer_status ) continue;
+            if( PARSEC_DATA_STATUS_UNDER_TRANSFER == copy->data_transfer_status || (copy->flags & B200_FLAG_WRITER) ) continue;
             /* a task that has not run yet was handed this replica as its input (the repo retains it): keep it */
             if( copy->super.super.obj_reference_count > 1 ) continue;
             if( NULL != for_task ) {
@@ -344,8 +466,13 @@ static int b200_evict_one(parsec_device_b200_module_t *dev, const parsec_gpu_tas
             }
             parsec_list_nolock_remove(&dev->super.super.gpu_mem_lru, it);
             PARSEC_LIST_ITEM_SINGLETON(it);
-            copy->readers = 0;
-            b200_release_copy_memory(dev, copy);
+            victim = copy;
+            break;
+        }
+        b200_unlock(&dev->lru_lock);
+        if( NULL != victim ) {
+            victim->readers = 0;
+            b200_release_copy_memory(dev, victim);
             return 1;
         }
         if( 0 == b200_write_back_some(dev, 16) ) break;
@@ -380,8 +507,7 @@ static int b200_reserve(parsec_device_b200_module_t *dev, b200_task_t *bt)
                 if( !b200_evict_one(dev, gpu_task) ) {
                     /* nothing can be freed now: undo what this pass allocated and let the task wait for retirements */
                     for( int k = 0; k < nfresh; k++ ) {
-                        parsec_list_nolock_remove(&dev->super.super.gpu_mem_lru, (parsec_list_item_t*)fresh[k]);
-                        PARSEC_LIST_ITEM_SINGLETON(fresh[k]);
+                        b200_lru_take(dev, fresh[k], 0);
                         b200_release_copy_memory(dev, fresh[k]);
                         dev->super.super.super.nb_evictions--; dev->st.evictions--;
                     }
@@ -401,7 +527,7 @@ static int b200_reserve(parsec_device_b200_module_t *dev, b200_task_t *bt)
             parsec_data_copy_attach(master, gpu_elem, my);
             parsec_atomic_unlock(&master->lock);
             /* fresh replicas sit on the clean LRU; a reader or the write detach below protects them */
-            parsec_list_nolock_push_back(&dev->super.super.gpu_mem_lru, (parsec_list_item_t*)gpu_elem);
+            b200_lru_put(dev, &dev->super.super.gpu_mem_lru, gpu_elem);
             fresh[nfresh++] = gpu_elem;
         }
         this_task->data[i].data_out = gpu_elem;
@@ -466,7 +592,7 @@ static int b200_stage_in(parsec_device_b200_module_t *dev, b200_task_t *bt, int 
         if( in == out ) {      /* the input already is this device's replica */
             if( PARSEC_FLOW_ACCESS_WRITE & type ) {
                 out->version++;
-                parsec_list_item_ring_chop((parsec_list_item_t*)out); PARSEC_LIST_ITEM_SINGLETON(out);
+                b200_lru_take(dev, out, 1);
                 parsec_atomic_lock(&original->lock);
                 original->owner_device = my; out->coherency_state = PARSEC_DATA_COHERENCY_OWNED;
                 parsec_atomic_unlock(&original->lock);
@@ -488,7 +614,7 @@ static int b200_stage_in(parsec_device_b200_module_t *dev, b200_task_t *bt, int 
 
         parsec_atomic_lock(&original->lock);
         if( PARSEC_FLOW_ACCESS_WRITE & type ) {        /* a written replica leaves the LRUs until the task retires */
-            parsec_list_item_ring_chop((parsec_list_item_t*)out); PARSEC_LIST_ITEM_SINGLETON(out);
+            b200_lru_take(dev, out, 1);
         }
         /* source: the copy the task was given, unless it is a host copy and a peer GPU we can read holds the same
          * version (device_gpu.c:1892-1975) */
@@ -557,6 +683,7 @@ static int b200_stage_in(parsec_device_b200_module_t *dev, b200_task_t *bt, int 
                 used_dma = 1;
             } else if( !dev->dry_run ) {
                 /* unregistered host memory, or an opaque body that needs the bytes before it is enqueued: copy engine */
+                b200_cuda_here(dev);
                 B200_CUDA(cudaMemcpyAsync(out->device_private, src->device_private, span,
                                           PB2_SRC_PEER == tile.src_kind ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                                           for_lane ? dev->lane->cuda_stream : dev->dma_stream),
@@ -606,8 +733,7 @@ int parsec_b200_task_body(parsec_device_gpu_module_t *gpu_device, parsec_gpu_tas
     for( int a = 0; a < nb_args; a++ )
         if( flow_index[a] < 0 || (uint32_t)flow_index[a] >= gpu_task->nb_flows ) return PARSEC_HOOK_RETURN_ERROR;
     if( parsec_b200_is_b200_device(&gpu_device->super) ) {
-        parsec_device_b200_module_t *dev = B200_DEV(gpu_device);
-        b200_task_t *bt = dev->recording;
+        b200_task_t *bt = b200_tl_recording;
         if( NULL == bt || bt->gpu_task != gpu_task ) return PARSEC_HOOK_RETURN_ERROR;
         bt->body = body; bt->nb_args = nb_args;
         for( int a = 0; a < nb_args; a++ ) bt->arg_flow[a] = flow_index[a];
@@ -637,72 +763,30 @@ uint64_t parsec_b200_task_result(const parsec_gpu_task_t *gpu_task)
 }
 
 /* ------------------------------------------------------------------------------------------------------------------ */
-/* runtime-side completion on the worker pool                                                                           */
-/* The manager keeps the device-side epilog; prepare_output / release_deps / release_task of a finished task -- the      */
-/* expensive part, proportional to its number of successors -- is run by whichever worker dequeues a small PROXY task.   */
-/* The proxy is an ordinary parsec_task_t of a private class with one CPU incarnation; its hook calls                     */
-/* __parsec_complete_execution on the real task (exactly once, with the worker's own execution stream) and returns        */
-/* ASYNC, so the runtime never tries to complete the proxy itself.  Until that hook has run, successors have not taken    */
-/* their references on the task's output replicas yet: the replicas stay PINNED (a reader each) so that eviction cannot     */
-/* take them away in between.                                                                                             */
-/* ------------------------------------------------------------------------------------------------------------------ */
-typedef struct b200_proxy_s {
-    parsec_task_t        task;
-    parsec_task_t       *original;
-    int                  npins;
-    parsec_data_copy_t  *pins[MAX_PARAM_COUNT];
-    parsec_gpu_task_t   *gpu_task;       /* given back by the worker too: free() of another thread's allocation is not cheap */
-    struct b200_proxy_s * volatile *home; /* free list of the module that made it */
-    struct b200_proxy_s * volatile next_free;
-} b200_proxy_t;
-
-static parsec_hook_return_t b200_completion_hook(parsec_execution_stream_t *es, parsec_task_t *task)
-{
-    b200_proxy_t *px = (b200_proxy_t*)task;
-    (void)__parsec_complete_execution(es, px->original);
-    for( int i = 0; i < px->npins; i++ ) (void)parsec_atomic_fetch_dec_int32(&px->pins[i]->readers);
-    if( NULL != px->gpu_task ) { px->gpu_task->release_device_task(px->gpu_task); px->gpu_task = NULL; }
-    /* lock-free push; the module's manager is the only thread that pops, so the list has no ABA problem */
-    b200_proxy_t *old;
-    do {
-        old = *px->home;
-        px->next_free = old;
-    } while( !parsec_atomic_cas_ptr(px->home, old, px) );
-    return PARSEC_HOOK_RETURN_ASYNC;      /* nothing of the proxy is left for the runtime to complete */
-}
-static const __parsec_chore_t b200_completion_chores[] = {
-    { .type = PARSEC_DEV_CPU, .evaluate = NULL, .hook = b200_completion_hook, .dyld = NULL, .dyld_fn = NULL },
-    { .type = PARSEC_DEV_NONE, .evaluate = NULL, .hook = NULL, .dyld = NULL, .dyld_fn = NULL },
-};
-static const parsec_task_class_t b200_completion_tc = {
-    .name = "b200 completion", .flags = 0, .task_class_id = 0, .nb_flows = 0, .nb_parameters = 0, .nb_locals = 0,
-    .incarnations = b200_completion_chores,
-};
-/* manager only */
-static b200_proxy_t *b200_proxy_get(b200_proxy_t * volatile *home)
-{
-    b200_proxy_t *px;
-    do {
-        px = *home;
-        if( NULL == px ) break;
-    } while( !parsec_atomic_cas_ptr(home, px, px->next_free) );
-    if( NULL == px ) {
-        px = (b200_proxy_t*)calloc(1, sizeof(b200_proxy_t));
-        PARSEC_OBJ_CONSTRUCT(&px->task, parsec_task_t);
-        px->home = home;
-    }
-    return px;
-}
-
-/* ------------------------------------------------------------------------------------------------------------------ */
 /* completion: epilog of the flows + hand-back to the runtime (parsec_device_kernel_pop / _epilog, device_gpu.c:2943,  */
 /* :3179, and the complete_task tail of the scheduler, :3562-3590)                                                     */
+/*                                                                                                                      */
+/* The manager is one thread and every task passes through it twice; what it does per task decides the task rate of     */
+/* the device.  The whole epilog -- coherency of every flow, LRU position, prepare_output / release_deps /               */
+/* release_task -- therefore runs on the WORKER POOL: the manager only links the task record's embedded proxy task      */
+/* (an ordinary parsec_task_t of a private class with one CPU incarnation) into a ring it schedules once per iteration. */
+/* The proxy's hook does the epilog, calls __parsec_complete_execution on the real task (exactly once, with that         */
+/* worker's execution stream) and returns ASYNC, so the runtime never tries to complete the proxy itself.  Every replica */
+/* of the task keeps one reader until release_deps has given the successors their references: eviction cannot take it   */
+/* away in between.                                                                                                      */
 /* ------------------------------------------------------------------------------------------------------------------ */
-static void b200_complete(parsec_device_b200_module_t *dev, parsec_execution_stream_t *es, b200_task_t *bt)
+static inline void b200_stat_add(uint64_t *counter, uint64_t v)
+{
+    (void)parsec_atomic_fetch_add_int64((volatile int64_t*)counter, (int64_t)v);
+}
+
+/* the flows of a finished task; fills held[] with the replicas that keep a reader until the caller lets them go */
+static int b200_epilog_flows(parsec_device_b200_module_t *dev, b200_task_t *bt, parsec_data_copy_t **held)
 {
     parsec_gpu_task_t *gpu_task = bt->gpu_task;
     parsec_task_t *this_task = gpu_task->ec;
     parsec_device_module_t *mod = &dev->super.super.super;
+    int nheld = 0;
 
     for( uint32_t i = 0; i < gpu_task->nb_flows; i++ ) {
         const parsec_flow_t *flow = gpu_task->flow_info[i].flow;
@@ -711,16 +795,22 @@ static void b200_complete(parsec_device_b200_module_t *dev, parsec_execution_str
         parsec_data_copy_t *gpu_copy = this_task->data[i].data_out;
         if( NULL == gpu_copy ) continue;
         parsec_data_t *original = gpu_copy->original;
-        parsec_atomic_lock(&original->lock);
+        /* The datum's lock (parsec_atomic_lock: nanosleep under contention) is taken when something of the protocol
+         * changes -- the end of a transfer, a write.  The other readers of a replica that is simply there only move its
+         * LRU position and let go of their reader: eight of them finishing together must not queue up on it. */
+        const int locked = (PARSEC_FLOW_ACCESS_WRITE & type) || PARSEC_DATA_STATUS_UNDER_TRANSFER == gpu_copy->data_transfer_status;
+        if( locked ) parsec_atomic_lock(&original->lock);
         if( PARSEC_DATA_STATUS_UNDER_TRANSFER == gpu_copy->data_transfer_status ) {
             /* the bytes are here: callback_complete_push (device_gpu.c:2358-2573) */
             gpu_copy->data_transfer_status = PARSEC_DATA_STATUS_COMPLETE_TRANSFER;
             parsec_data_end_transfer_ownership_to_copy(original, mod->device_index, type);
         }
         if( bt->peer_src_mask & (1u << i) ) (void)parsec_atomic_fetch_dec_int32(&bt->peer_src[i]->readers);
-        if( PARSEC_FLOW_ACCESS_READ & type ) (void)parsec_atomic_fetch_dec_int32(&gpu_copy->readers);
+        /* READ flows took their reader when the task started; a write-only flow takes one now */
+        if( !(PARSEC_FLOW_ACCESS_READ & type) ) (void)parsec_atomic_fetch_inc_int32(&gpu_copy->readers);
+        held[nheld++] = gpu_copy;
         if( PARSEC_FLOW_ACCESS_WRITE & type ) {
-            mod->required_data_out += gpu_task->flow_info[i].flow_span;
+            b200_stat_add(&mod->required_data_out, gpu_task->flow_info[i].flow_span);
             if( gpu_task->pushout & (1 << i) ) {
                 parsec_data_copy_t *cpu_copy = original->device_copies[0];
                 if( NULL != cpu_copy ) {
@@ -728,61 +818,69 @@ static void b200_complete(parsec_device_b200_module_t *dev, parsec_execution_str
                     cpu_copy->coherency_state = PARSEC_DATA_COHERENCY_SHARED;
                     gpu_copy->coherency_state = PARSEC_DATA_COHERENCY_SHARED;
                     cpu_copy->data_transfer_status = PARSEC_DATA_STATUS_COMPLETE_TRANSFER;
-                    mod->data_out_to_host += gpu_task->flow_info[i].flow_span;
+                    b200_stat_add(&mod->data_out_to_host, gpu_task->flow_info[i].flow_span);
                     if( 0 == (parsec_mpi_allow_gpu_memory_communications & PARSEC_RUNTIME_SEND_GPU_MEMORY) )
                         this_task->data[i].data_out = cpu_copy;           /* successors consume the host copy */
                 }
-                parsec_list_item_ring_chop((parsec_list_item_t*)gpu_copy); PARSEC_LIST_ITEM_SINGLETON(gpu_copy);
-                parsec_list_nolock_push_back(&dev->super.super.gpu_mem_lru, (parsec_list_item_t*)gpu_copy);
+                b200_lru_put(dev, &dev->super.super.gpu_mem_lru, gpu_copy);
             } else {
                 gpu_copy->coherency_state = PARSEC_DATA_COHERENCY_OWNED;
-                parsec_list_nolock_push_back(&dev->super.super.gpu_mem_owned_lru, (parsec_list_item_t*)gpu_copy);
+                b200_lru_put(dev, &dev->super.super.gpu_mem_owned_lru, gpu_copy);
             }
-        } else if( 0 == gpu_copy->readers && 0 != (gpu_copy->flags & PARSEC_DATA_FLAG_PARSEC_OWNED) ) {
-            /* least recently used goes to the front: a replica just read moves to the back of its list */
-            parsec_list_t *l = (PARSEC_DATA_COHERENCY_OWNED == gpu_copy->coherency_state) ? &dev->super.super.gpu_mem_owned_lru
-                                                                                           : &dev->super.super.gpu_mem_lru;
-            parsec_list_item_ring_chop((parsec_list_item_t*)gpu_copy); PARSEC_LIST_ITEM_SINGLETON(gpu_copy);
-            parsec_list_nolock_push_back(l, (parsec_list_item_t*)gpu_copy);
+        } else if( 1 == gpu_copy->readers && 0 != (gpu_copy->flags & PARSEC_DATA_FLAG_PARSEC_OWNED) ) {
+            /* least recently used goes to the front: the last reader of a replica moves it to the back of its list */
+            b200_lru_touch(dev, gpu_copy);
         }
-        parsec_atomic_unlock(&original->lock);
+        if( locked ) parsec_atomic_unlock(&original->lock);
     }
+    return nheld;
+}
+
+static parsec_hook_return_t b200_epilog_hook(parsec_execution_stream_t *es, parsec_task_t *task)
+{
+    b200_task_t *bt = (b200_task_t*)((char*)task - offsetof(b200_task_t, proxy));
+    parsec_device_b200_module_t *dev = bt->dev;
+    parsec_gpu_task_t *gpu_task = bt->gpu_task;
+    parsec_data_copy_t *held[MAX_PARAM_COUNT];
+    const int nheld = b200_epilog_flows(dev, bt, held);
+    (void)__parsec_complete_execution(es, gpu_task->ec);
+    for( int i = 0; i < nheld; i++ ) (void)parsec_atomic_fetch_dec_int32(&held[i]->readers);
+    gpu_task->last_data_check_epoch = 0;
+    gpu_task->release_device_task(gpu_task);
+    b200_bt_free(bt);          /* the proxy lives in the record: nothing of it is touched after this hook returns ASYNC */
+    if( dev->nb_stalled > 0 ) dev->retry_stalled = 1;      /* the readers just dropped may be what a waiting task needs evicted */
+    parsec_atomic_wmb();
+    (void)parsec_atomic_fetch_add_int64(&dev->epilogs_done, 1);
+    return PARSEC_HOOK_RETURN_ASYNC;
+}
+
+/* manager side of a finished kernel task */
+static void b200_complete(parsec_device_b200_module_t *dev, parsec_execution_stream_t *es, b200_task_t *bt)
+{
+    parsec_gpu_task_t *gpu_task = bt->gpu_task;
+    dev->super.super.super.executed_tasks++;
+    dev->completed_now++;
+    if( parsec_b200_parallel_completion && !bt->has_complete_stage ) {
+        /* nothing of the task but its record is touched here */
+        dev->epilogs_started++;
+        PARSEC_LIST_ITEM_SINGLETON(&bt->proxy);
+        if( NULL == dev->completion_ring ) dev->completion_ring = &bt->proxy;
+        else parsec_list_item_ring_push((parsec_list_item_t*)dev->completion_ring, (parsec_list_item_t*)&bt->proxy);
+        return;
+    }
+    /* in line: a user completion hook (device_gpu.h:41-43; dtd_test_simple_gemm.c:538) is called by the thread that
+     * drives the device, like the reference does, and device_b200_parallel_completion = 0 asks for it */
+    parsec_data_copy_t *held[MAX_PARAM_COUNT];
+    const int nheld = b200_epilog_flows(dev, bt, held);
     if( NULL != gpu_task->complete_stage ) {
-        /* the user's completion hook (device_gpu.h:41-43; dtd_test_simple_gemm.c:538) */
         parsec_gpu_task_t *gt = gpu_task;
         (void)gpu_task->complete_stage(&dev->super.super, &gt, &dev->lane->super);
     }
-    mod->executed_tasks++;
-    if( parsec_b200_parallel_completion ) {
-        b200_proxy_t *px = b200_proxy_get((b200_proxy_t * volatile *)&dev->proxy_free);
-        px->original = this_task;
-        px->gpu_task = gpu_task;
-        px->npins = 0;
-        for( uint32_t i = 0; i < gpu_task->nb_flows; i++ ) {
-            parsec_data_copy_t *o = this_task->data[i].data_out;
-            if( NULL == o || o->device_index != mod->device_index ) continue;
-            (void)parsec_atomic_fetch_inc_int32(&o->readers);          /* pinned until release_deps has run */
-            px->pins[px->npins++] = o;
-        }
-        PARSEC_LIST_ITEM_SINGLETON(&px->task);
-        px->task.taskpool = this_task->taskpool;
-        px->task.task_class = &b200_completion_tc;
-        px->task.priority = INT32_MAX;                                 /* completions first: they release work */
-        px->task.status = PARSEC_TASK_STATUS_HOOK;                     /* no prepare_input */
-        px->task.chore_mask = 1;
-        px->task.selected_device = parsec_mca_device_get(0);
-        px->task.selected_chore = 0;
-        px->task.load = 0;
-        px->task.repo_entry = NULL;
-        if( NULL == dev->completion_ring ) dev->completion_ring = &px->task;
-        else parsec_list_item_ring_push((parsec_list_item_t*)dev->completion_ring, (parsec_list_item_t*)&px->task);
-    } else {
-        __parsec_complete_execution(es, this_task);
-    }
-    b200_bt_free(dev, bt);
+    __parsec_complete_execution(es, gpu_task->ec);
+    for( int i = 0; i < nheld; i++ ) (void)parsec_atomic_fetch_dec_int32(&held[i]->readers);
     gpu_task->last_data_check_epoch = 0;
-    if( !parsec_b200_parallel_completion ) gpu_task->release_device_task(gpu_task);
-    dev->completed_now++;
+    gpu_task->release_device_task(gpu_task);
+    b200_bt_free(bt);
 }
 
 /* pushout flows whose host home the kernel cannot write (memory that was never registered): copy engine */
@@ -791,10 +889,11 @@ static int b200_dma_pushout(parsec_device_b200_module_t *dev, b200_task_t *bt)
     parsec_gpu_task_t *gpu_task = bt->gpu_task;
     int n = 0;
     if( dev->dry_run ) return 0;
+    b200_cuda_here(dev);
     if( NULL != gpu_task->stage_out && gpu_task->stage_out != parsec_default_gpu_stage_out ) {
         /* the user's stage_out enqueues the copies on the stream it is given (stage_custom.jdf:62-95) */
         if( PARSEC_SUCCESS != gpu_task->stage_out(gpu_task, bt->dma_out_mask, &dev->lane->super) ) return 0;
-        B200_CUDA(cudaEventRecord(bt->ev, dev->lane->cuda_stream), "cudaEventRecord", {});
+        B200_CUDA(cudaEventRecord(b200_bt_event(dev, bt), dev->lane->cuda_stream), "cudaEventRecord", {});
         return 1;
     }
     for( uint32_t i = 0; i < gpu_task->nb_flows; i++ ) {
@@ -807,31 +906,33 @@ static int b200_dma_pushout(parsec_device_b200_module_t *dev, b200_task_t *bt)
         dev->st.bytes_d2h_dma += gpu_task->flow_info[i].flow_span;
         n++;
     }
-    if( n ) B200_CUDA(cudaEventRecord(bt->ev, dev->dma_stream), "cudaEventRecord", {});
+    if( n ) B200_CUDA(cudaEventRecord(b200_bt_event(dev, bt), dev->dma_stream), "cudaEventRecord", {});
     return n;
 }
 
 /* ------------------------------------------------------------------------------------------------------------------ */
 /* one task: from the inbox to the command ring / the lane                                                              */
 /* ------------------------------------------------------------------------------------------------------------------ */
-static int b200_push_engine(parsec_device_b200_module_t *dev, b200_task_t *bt)
+/* The engine command of a task whose flows all have their replica (data_out): tile ids, access modes, where a pushout
+ * goes.  Touches nothing of the device: built by whoever settled the flows -- the calling worker for resident tasks. */
+static void b200_build_cmd(parsec_device_b200_module_t *dev, b200_task_t *bt)
 {
     parsec_gpu_task_t *gpu_task = bt->gpu_task;
-    pb2_task_t t;
-    memset(&t, 0, sizeof t);
-    t.body = (uint8_t)bt->body; t.nb_flows = (uint8_t)bt->nb_args;
-    for( int a = 0; a < PB2_MAX_FLOWS; a++ ) t.tile[a] = -1;
+    pb2_task_t *t = &bt->cmd;
+    memset(t, 0, sizeof *t);
+    t->body = (uint8_t)bt->body; t->nb_flows = (uint8_t)bt->nb_args;
+    for( int a = 0; a < PB2_MAX_FLOWS; a++ ) t->tile[a] = -1;
     for( int a = 0; a < bt->nb_args; a++ ) {
         const int f = bt->arg_flow[a];
         const parsec_flow_t *flow = gpu_task->flow_info[f].flow;
         parsec_data_copy_t *out = gpu_task->ec->data[f].data_out;
-        t.tile[a] = b200_tile_of(dev, out);
-        t.access[a] = (uint8_t)(flow->flow_flags & PARSEC_FLOW_ACCESS_MASK);
+        t->tile[a] = b200_tile_of(dev, out);
+        t->access[a] = (uint8_t)(flow->flow_flags & PARSEC_FLOW_ACCESS_MASK);
         if( (gpu_task->pushout & (1 << f)) && (PARSEC_FLOW_ACCESS_WRITE & flow->flow_flags) ) {
             parsec_data_copy_t *cpu = out->original->device_copies[0];
             if( !bt->custom_stage && NULL != cpu && NULL != cpu->device_private &&
                 NULL != b200_device_visible(cpu->device_private, gpu_task->flow_info[f].flow_span) && !(bt->peer_src_mask & (1u << f)) )
-                t.access[a] |= PB2_FLOW_PUSHOUT;            /* the worker CTA copies it home */
+                t->access[a] |= PB2_FLOW_PUSHOUT;            /* the worker CTA copies it home */
             else bt->dma_out_mask |= (1u << f);
         }
     }
@@ -842,14 +943,68 @@ static int b200_push_engine(parsec_device_b200_module_t *dev, b200_task_t *bt)
         if( !named && (gpu_task->pushout & (1 << f)) && (PARSEC_FLOW_ACCESS_WRITE & gpu_task->flow_info[f].flow->flow_flags) &&
             NULL != gpu_task->ec->data[f].data_out ) bt->dma_out_mask |= (1u << f);
     }
-    t.iparam[0] = bt->iparam[0]; t.iparam[1] = bt->iparam[1]; t.iparam[2] = bt->iparam[2]; t.fparam = bt->fparam;
-    t.locals[0] = gpu_task->ec->locals[0].value; t.locals[1] = gpu_task->ec->locals[1].value;
-    int rc = pb2_stream_submit(dev->stream, &t, (uint64_t)(uintptr_t)bt, &bt->ticket);
-    if( PB2_ERR_OUT_OF_RESOURCE == rc ) return PARSEC_HOOK_RETURN_AGAIN;
-    if( PB2_SUCCESS != rc ) { parsec_warning("device_b200: submit failed: %s", pb2_stream_last_error(dev->stream)); return PARSEC_HOOK_RETURN_ERROR; }
+    t->iparam[0] = bt->iparam[0]; t->iparam[1] = bt->iparam[1]; t->iparam[2] = bt->iparam[2]; t->fparam = bt->fparam;
+    t->locals[0] = gpu_task->ec->locals[0].value; t->locals[1] = gpu_task->ec->locals[1].value;
+    bt->cmd_built = 1;
+}
+
+/* manager only */
+static int b200_push_engine(parsec_device_b200_module_t *dev, b200_task_t *bt)
+{
+    if( !bt->cmd_built ) b200_build_cmd(dev, bt);
+    /* The instant the command is published the task may run and retire: the record is final BEFORE the submit. */
+    const int32_t state_before = bt->state;
     bt->state = BT_INFLIGHT;
+    int rc = pb2_stream_submit(dev->stream, &bt->cmd, (uint64_t)(uintptr_t)bt, &bt->ticket);
+    if( PB2_SUCCESS != rc ) {
+        bt->state = state_before;
+        if( PB2_ERR_OUT_OF_RESOURCE == rc ) return PARSEC_HOOK_RETURN_AGAIN;
+        parsec_warning("device_b200: submit failed: %s", pb2_stream_last_error(dev->stream));
+        return PARSEC_HOOK_RETURN_ERROR;
+    }
     dev->st.tasks_engine++;
     return PARSEC_HOOK_RETURN_DONE;
+}
+
+/* Called by the worker thread that hands the task over, BEFORE the hand-over.  A task whose every input already is this
+ * device's replica (the data came from a task that ran here) needs no decision of the manager: nothing is allocated,
+ * nothing moves.  The caller -- the thread that has the task, its flows and the replicas in its cache -- takes the
+ * readers, bumps the versions of the written flows and builds the engine command; the manager only submits it.
+ * returns 1 when the task is settled, 0 when the manager has to look at it (nothing was changed then). */
+static int b200_prepare_resident(parsec_device_b200_module_t *dev, b200_task_t *bt)
+{
+    parsec_gpu_task_t *gpu_task = bt->gpu_task;
+    parsec_task_t *this_task = gpu_task->ec;
+    const uint8_t my = dev->super.super.super.device_index;
+    if( NULL == dev->tile_described ) return 0;
+    for( uint32_t i = 0; i < gpu_task->nb_flows; i++ ) {
+        const parsec_flow_t *flow = gpu_task->flow_info[i].flow;
+        if( PARSEC_FLOW_ACCESS_NONE == (PARSEC_FLOW_ACCESS_MASK & flow->flow_flags) ) continue;
+        const parsec_data_copy_t *in = this_task->data[i].data_in;
+        if( NULL == in ) continue;
+        if( in->device_index != my || NULL == in->device_private || NULL == in->original ) return 0;
+        if( !dev->tile_described[b200_tile_of(dev, in)] ) return 0;      /* filled on the stream lane: the kernel has not met it */
+    }
+    for( uint32_t i = 0; i < gpu_task->nb_flows; i++ ) {
+        const parsec_flow_t *flow = gpu_task->flow_info[i].flow;
+        const uint8_t type = (uint8_t)(flow->flow_flags & PARSEC_FLOW_ACCESS_MASK);
+        if( PARSEC_FLOW_ACCESS_NONE == type ) { gpu_task->flow_info[i].flow_span = 0; continue; }
+        parsec_data_copy_t *in = this_task->data[i].data_in;
+        if( NULL == in ) continue;
+        this_task->data[i].data_out = in;
+        gpu_task->flow_info[i].source = NULL;
+        if( PARSEC_FLOW_ACCESS_WRITE & type ) {
+            in->version++;
+            b200_lru_take(dev, in, 1);
+            parsec_atomic_lock(&in->original->lock);
+            in->original->owner_device = my; in->coherency_state = PARSEC_DATA_COHERENCY_OWNED;
+            parsec_atomic_unlock(&in->original->lock);
+        }
+        if( PARSEC_FLOW_ACCESS_READ & type ) (void)parsec_atomic_fetch_inc_int32(&in->readers);
+    }
+    b200_build_cmd(dev, bt);
+    bt->prepared = 1;
+    return 1;
 }
 
 static int b200_start_task(parsec_device_b200_module_t *dev, parsec_execution_stream_t *es, b200_task_t *bt)
@@ -861,8 +1016,12 @@ static int b200_start_task(parsec_device_b200_module_t *dev, parsec_execution_st
      * they would then all finish together, tens of milliseconds later, and their successors with them.  Keeping only a
      * few link round-trips worth of cold bytes in flight makes tasks retire as a steady stream: the host side (this
      * manager, the workers that release successors) and the transfers overlap instead of alternating in bursts. */
-    if( dev->cold_inflight >= (uint64_t)parsec_b200_stage_window && b200_needs_memory(dev, gpu_task) ) return PARSEC_HOOK_RETURN_AGAIN;
+    dev->again_window = 0;
+    if( bt->prepared ) { bt->state = BT_STAGED; return b200_push_engine(dev, bt); }
+    if( dev->cold_inflight >= (int64_t)parsec_b200_stage_window && b200_needs_memory(dev, gpu_task) ) { dev->again_window = 1; return PARSEC_HOOK_RETURN_AGAIN; }
+    uint64_t c0 = B200_TSC(), c1;
     if( PARSEC_HOOK_RETURN_DONE != (rc = b200_reserve(dev, bt)) ) return rc;
+    c1 = B200_TSC(); dev->tsc_start[0] += c1 - c0; c0 = c1;
 
     /* Which kind of body?  Call the submit function in RECORD mode: a body that names an engine body through
      * parsec_b200_task_body enqueues nothing and the task goes to the persistent kernel.  A body that did not is an
@@ -874,44 +1033,55 @@ static int b200_start_task(parsec_device_b200_module_t *dev, parsec_execution_st
     bt->custom_stage = custom_stage;
     /* engine bodies are recognised by their submit function having been seen naming one (set below, the first time,
      * after a conservative copy-engine stage-in); dry-run modules never enqueue anything, so they always record */
-    int known_engine = dev->dry_run || (!custom_stage && parsec_b200_submit_is_engine(gpu_task->submit));
+    int known_engine = bt->recorded || dev->dry_run || (!custom_stage && parsec_b200_submit_is_engine(gpu_task->submit));
 
     if( known_engine ) {
         rc = b200_stage_in(dev, bt, 0);
         if( rc < 0 ) return rc;
-        dev->cold_inflight += bt->cold_bytes;
-        dev->recording = bt;
-        int src = gpu_task->submit(&dev->super.super, gpu_task, &dev->lane->super);
-        dev->recording = NULL;
+        c1 = B200_TSC(); dev->tsc_start[1] += c1 - c0; c0 = c1;
+        dev->cold_inflight += (int64_t)bt->cold_bytes;
+        int src = 0;
+        if( !bt->recorded ) {             /* normally done by the thread that called kernel_scheduler */
+            b200_tl_recording = bt;
+            src = gpu_task->submit(&dev->super.super, gpu_task, &dev->lane->super);
+            b200_tl_recording = NULL;
+            bt->recorded = 1;
+            bt->has_complete_stage = (NULL != gpu_task->complete_stage);
+        }
         if( dev->dry_run && bt->body < 0 ) { bt->body = PB2_BODY_NOP; bt->nb_args = 0; }
         if( src < 0 || bt->body < 0 ) {
             parsec_warning("device_b200: body of task class %s stopped naming an engine body", tc ? tc->name : "?");
             return PARSEC_HOOK_RETURN_ERROR;
         }
         if( rc > 0 ) {                      /* unregistered host memory: wait for the copy engine, then push */
-            B200_CUDA(cudaEventRecord(bt->ev, dev->dma_stream), "cudaEventRecord", {});
+            B200_CUDA(cudaEventRecord(b200_bt_event(dev, bt), dev->dma_stream), "cudaEventRecord", {});
             bt->state = BT_DMA_IN;
             parsec_list_nolock_push_back(&dev->waiting_event, &bt->item);
             return PARSEC_HOOK_RETURN_DONE;
         }
         bt->state = BT_STAGED;
-        return b200_push_engine(dev, bt);
+        c1 = B200_TSC(); dev->tsc_start[2] += c1 - c0; c0 = c1;
+        rc = b200_push_engine(dev, bt);
+        dev->tsc_start[3] += B200_TSC() - c0;
+        return rc;
     }
 
     /* stream lane: stage in with the copy engine on the lane stream (or the user's stage_in), run submit, event */
+    b200_cuda_here(dev);
     const int user_in = (NULL != gpu_task->stage_in && gpu_task->stage_in != parsec_default_gpu_stage_in);
     rc = b200_stage_in(dev, bt, user_in ? 2 : 1);
     if( rc < 0 ) return rc;
-    dev->cold_inflight += bt->cold_bytes;
+    dev->cold_inflight += (int64_t)bt->cold_bytes;
     if( user_in ) {
         uint32_t mask = 0;
         for( uint32_t i = 0; i < gpu_task->nb_flows; i++ )
             if( NULL != gpu_task->ec->data[i].data_out && PARSEC_DATA_STATUS_UNDER_TRANSFER == gpu_task->ec->data[i].data_out->data_transfer_status ) mask |= (1u << i);
         if( mask && PARSEC_SUCCESS != gpu_task->stage_in(gpu_task, mask, &dev->lane->super) ) return PARSEC_HOOK_RETURN_ERROR;
     }
-    dev->recording = bt;
+    b200_tl_recording = bt;
     int src = gpu_task->submit(&dev->super.super, gpu_task, &dev->lane->super);
-    dev->recording = NULL;
+    b200_tl_recording = NULL;
+    bt->has_complete_stage = (NULL != gpu_task->complete_stage);     /* a body may install one (dtd_test_simple_gemm.c:538) */
     if( src < 0 && PARSEC_HOOK_RETURN_ASYNC != src ) return PARSEC_HOOK_RETURN_ERROR;
     if( bt->body >= 0 ) {
         /* first task of a class whose body names an engine body: remember it, and run THIS one in the kernel too
@@ -929,7 +1099,7 @@ static int b200_start_task(parsec_device_b200_module_t *dev, parsec_execution_st
             (void)pb2_stream_set_tile(dev->stream, b200_tile_of(dev, out), &tile);
             dev->tile_described[b200_tile_of(dev, out)] = 1;
         }
-        B200_CUDA(cudaEventRecord(bt->ev, dev->lane->cuda_stream), "cudaEventRecord", {});
+        B200_CUDA(cudaEventRecord(b200_bt_event(dev, bt), dev->lane->cuda_stream), "cudaEventRecord", {});
         bt->state = BT_DMA_IN;
         parsec_list_nolock_push_back(&dev->waiting_event, &bt->item);
         return PARSEC_HOOK_RETURN_DONE;
@@ -947,7 +1117,7 @@ static int b200_start_task(parsec_device_b200_module_t *dev, parsec_execution_st
                 dev->st.bytes_d2h_dma += gpu_task->flow_info[i].flow_span;
             }
         }
-    B200_CUDA(cudaEventRecord(bt->ev, dev->lane->cuda_stream), "cudaEventRecord", {});
+    B200_CUDA(cudaEventRecord(b200_bt_event(dev, bt), dev->lane->cuda_stream), "cudaEventRecord", {});
     bt->state = BT_LANE;
     dev->st.tasks_lane++;
     parsec_list_nolock_push_back(&dev->waiting_event, &bt->item);
@@ -1048,7 +1218,8 @@ static int b200_data_advise(parsec_device_module_t *module, parsec_data_t *data,
 static void b200_finish(parsec_device_b200_module_t *dev, parsec_execution_stream_t *es, b200_task_t *bt)
 {
     parsec_gpu_task_t *gpu_task = bt->gpu_task;
-    dev->cold_inflight -= bt->cold_bytes; bt->cold_bytes = 0;
+    dev->cold_inflight -= (int64_t)bt->cold_bytes; bt->cold_bytes = 0;
+    dev->retry_stalled = 1;           /* a retirement frees ring space, reopens the stage-in window, unpins replicas */
     if( PARSEC_GPU_TASK_TYPE_KERNEL == gpu_task->task_type ) { b200_complete(dev, es, bt); return; }
     /* pseudo task: the replica is resident and valid now; no runtime completion */
     parsec_data_copy_t *out = gpu_task->ec->data[0].data_out;
@@ -1059,59 +1230,87 @@ static void b200_finish(parsec_device_b200_module_t *dev, parsec_execution_strea
             parsec_data_end_transfer_ownership_to_copy(out->original, dev->super.super.super.device_index, PARSEC_FLOW_ACCESS_READ);
         }
         if( bt->peer_src_mask & 1u ) (void)parsec_atomic_fetch_dec_int32(&bt->peer_src[0]->readers);
+        if( 1 == out->readers ) b200_lru_touch(dev, out);
         (void)parsec_atomic_fetch_dec_int32(&out->readers);
-        if( 0 == out->readers ) {
-            parsec_list_item_ring_chop((parsec_list_item_t*)out); PARSEC_LIST_ITEM_SINGLETON(out);
-            parsec_list_nolock_push_back(PARSEC_DATA_COHERENCY_OWNED == out->coherency_state ? &dev->super.super.gpu_mem_owned_lru : &dev->super.super.gpu_mem_lru,
-                                         (parsec_list_item_t*)out);
-        }
         parsec_atomic_unlock(&out->original->lock);
     }
-    b200_bt_free(dev, bt);
+    b200_bt_free(bt);
     gpu_task->last_data_check_epoch = 0;
     gpu_task->release_device_task(gpu_task);
     dev->completed_now++;
 }
 
-/* returns < 0 on a fatal device problem */
+/* The manager: inbox, starts, events of the copy-engine / lane paths, retire ring.
+ * returns < 0 on a fatal device problem */
 static int b200_progress(parsec_device_b200_module_t *dev, parsec_execution_stream_t *es)
 {
     uint64_t t0 = B200_TSC(), t1;
-    /* 1. inbox -> oldest-first list of tasks to start (callers push LIFO) */
-    parsec_gpu_task_t *head = dev->inbox;
-    while( NULL != head && !parsec_atomic_cas_ptr(&dev->inbox, head, NULL) ) head = dev->inbox;
-    parsec_gpu_task_t *fifo = NULL;
-    while( NULL != head ) {
-        parsec_gpu_task_t *next = (parsec_gpu_task_t*)head->list_item.list_next;
-        head->list_item.list_next = (parsec_list_item_t*)fifo; fifo = head; head = next;
-    }
-    while( NULL != fifo ) {
-        parsec_gpu_task_t *gt = fifo;
-        fifo = (parsec_gpu_task_t*)gt->list_item.list_next;
-        PARSEC_LIST_ITEM_SINGLETON(&gt->list_item);
-        if( UINT64_MAX != gt->last_data_check_epoch ) { parsec_warning("device_b200: gpu_task %p seen twice in the inbox (epoch %lx)", (void*)gt, (unsigned long)gt->last_data_check_epoch); abort(); }
-        parsec_list_nolock_push_back(&dev->stalled, &b200_bt_new(dev, gt)->item);
+    /* 1. inbox -> list of tasks to start, in slot order.  A slot whose index has been taken but whose pointer is not
+     *    there yet ends the pass: its caller is a few instructions away from storing it. */
+    {
+        int64_t head = dev->inbox_head;
+        const int64_t head0 = head;
+        for(;;) {
+            b200_task_t * volatile *slot = &dev->inbox_ring[head & (B200_INBOX_SLOTS - 1)];
+            b200_task_t *bt = *slot;
+            if( NULL == bt ) break;
+            parsec_atomic_rmb();
+            *slot = NULL;
+            head++;
+            {   /* the records a few slots further on: written by other cores a moment ago */
+                const char *la = (const char*)dev->inbox_ring[(head + 6) & (B200_INBOX_SLOTS - 1)];
+                if( NULL != la ) { B200_PFW(la); B200_PFW(la + 64); B200_PF(la + offsetof(b200_task_t, cmd)); }
+            }
+            if( bt->prepared ) { parsec_list_nolock_push_back(&dev->settled, &bt->item); dev->nb_settled++; }
+            else { parsec_list_nolock_push_back(&dev->stalled, &bt->item); dev->nb_stalled++; }
+        }
+        if( head != head0 ) { dev->inbox_head = head; dev->retry_stalled = 1; }
     }
     t1 = B200_TSC(); dev->tsc[0] += t1 - t0; t0 = t1;
-    /* 2. start tasks, oldest first.  A task that cannot get device memory yet stays where it is and the ones behind it
-     *    are tried: their inputs may be resident already (they hold references that keep replicas from being evicted),
-     *    and their retirement is what frees memory.  A full command ring stops the pass. */
+    /* 2. start tasks.  Settled tasks first (they only need a slot in the command ring; the stage-ins in flight are for
+     *    them), then the others, oldest first.  A task that cannot get device memory stays where it is and the
+     *    ones behind it are tried: their inputs may be resident already (they hold references that keep
+     *    replicas from being evicted), and their retirement is what frees memory.  A full command ring stops the pass,
+     *    and so does the stage-in window (a throttle, not a shortage: retirements reopen it). */
     int started = 0;
-    {
+    /* references that keep a replica from being evicted are also dropped where nobody tells the device (the data
+     * repositories of the runtime): a blocked task is retried every so often whatever happened */
+    if( (dev->nb_settled > 0 || dev->nb_stalled > 0) && !dev->retry_stalled && ++dev->blocked_spins >= 1024 ) dev->retry_stalled = 1;
+    if( dev->retry_stalled && (dev->nb_settled > 0 || dev->nb_stalled > 0) ) {
+        int ring_full = 0, cut = 0;
+        dev->retry_stalled = 0; dev->blocked_spins = 0;
+        while( dev->nb_settled > 0 ) {
+            if( started >= 512 ) { cut = 1; break; }            /* then look at the retire ring again */
+            b200_task_t *bt = (b200_task_t*)PARSEC_LIST_ITERATOR_FIRST(&dev->settled);
+            parsec_list_item_t *la = PARSEC_LIST_ITERATOR_NEXT(&bt->item);
+            if( la != PARSEC_LIST_ITERATOR_END(&dev->settled) ) { la = PARSEC_LIST_ITERATOR_NEXT(la);
+                if( la != PARSEC_LIST_ITERATOR_END(&dev->settled) ) { B200_PF(la); B200_PF((const char*)la + offsetof(b200_task_t, cmd)); } }
+            parsec_list_nolock_remove(&dev->settled, &bt->item);
+            PARSEC_LIST_ITEM_SINGLETON(&bt->item);
+            if( BT_NEW == bt->state ) bt->state = BT_STAGED;
+            const int rc = b200_push_engine(dev, bt);
+            if( PARSEC_HOOK_RETURN_AGAIN == rc ) { parsec_list_nolock_push_front(&dev->settled, &bt->item); ring_full = 1; break; }
+            if( PARSEC_HOOK_RETURN_DONE != rc ) return -1;
+            dev->nb_settled--;
+            started++;
+        }
         parsec_list_item_t *it = PARSEC_LIST_ITERATOR_FIRST(&dev->stalled), *next;
         int mem_blocked = 0;
-        for( ; it != PARSEC_LIST_ITERATOR_END(&dev->stalled) && started < 256; it = next ) {     /* then look at the retire ring again */
+        for( ; !ring_full && !cut && it != PARSEC_LIST_ITERATOR_END(&dev->stalled); it = next ) {
             b200_task_t *bt = (b200_task_t*)it;
             next = PARSEC_LIST_ITERATOR_NEXT(it);
             int rc;
-            {   /* look-ahead prefetch, one pointer level per position */
+            if( started >= 512 ) { cut = 1; break; }
+            if( next != PARSEC_LIST_ITERATOR_END(&dev->stalled) ) {
+                /* look-ahead prefetch of what the full start path reads, one pointer level per position */
                 parsec_list_item_t *la = next;
-                if( la != PARSEC_LIST_ITERATOR_END(&dev->stalled) ) { b200_pf4((b200_task_t*)la); la = PARSEC_LIST_ITERATOR_NEXT(la);
+                b200_pf4((b200_task_t*)la); la = PARSEC_LIST_ITERATOR_NEXT(la);
                 if( la != PARSEC_LIST_ITERATOR_END(&dev->stalled) ) { b200_pf3((b200_task_t*)la); la = PARSEC_LIST_ITERATOR_NEXT(la);
                 if( la != PARSEC_LIST_ITERATOR_END(&dev->stalled) ) { b200_pf2((b200_task_t*)la); la = PARSEC_LIST_ITERATOR_NEXT(la);
-                if( la != PARSEC_LIST_ITERATOR_END(&dev->stalled) ) { b200_pf1((b200_task_t*)la); } } } }
+                if( la != PARSEC_LIST_ITERATOR_END(&dev->stalled) ) { b200_pf1((b200_task_t*)la); } } }
             }
-            /* once a task has failed to get memory in this pass, only tasks that need none are tried */
+            /* once a task has failed to get memory in this pass, only tasks that need none are tried -- all of them:
+             * the task whose retirement frees memory may be anywhere behind */
             if( mem_blocked && BT_NEW == bt->state && b200_needs_memory(dev, bt->gpu_task) ) continue;
             parsec_list_nolock_remove(&dev->stalled, it);
             PARSEC_LIST_ITEM_SINGLETON(it);
@@ -1122,12 +1321,15 @@ static int b200_progress(parsec_device_b200_module_t *dev, parsec_execution_stre
                 if( next == PARSEC_LIST_ITERATOR_END(&dev->stalled) ) parsec_list_nolock_push_back(&dev->stalled, it);
                 else parsec_list_nolock_add_before(&dev->stalled, next, it);
                 if( BT_NEW != bt->state ) break;            /* ring full */
+                if( dev->again_window ) break;              /* throttled: every cold task behind this one is, too */
                 mem_blocked = 1;
                 continue;
             }
             if( PARSEC_HOOK_RETURN_DONE != rc ) return -1;
+            dev->nb_stalled--;
             started++;
         }
+        if( cut ) dev->retry_stalled = 1;
     }
     if( started && PB2_SUCCESS != pb2_stream_kick(dev->stream) ) return -1;
     t1 = B200_TSC(); dev->tsc[1] += t1 - t0; t0 = t1;
@@ -1156,7 +1358,7 @@ static int b200_progress(parsec_device_b200_module_t *dev, parsec_execution_stre
                 }
                 bt->state = BT_STAGED;
                 int rc = b200_push_engine(dev, bt);
-                if( PARSEC_HOOK_RETURN_AGAIN == rc ) parsec_list_nolock_push_front(&dev->stalled, &bt->item);
+                if( PARSEC_HOOK_RETURN_AGAIN == rc ) { parsec_list_nolock_push_front(&dev->stalled, &bt->item); dev->nb_stalled++; dev->retry_stalled = 1; }
                 else if( PARSEC_HOOK_RETURN_DONE != rc ) return -1;
                 else if( PB2_SUCCESS != pb2_stream_kick(dev->stream) ) return -1;
             } else {
@@ -1172,10 +1374,7 @@ static int b200_progress(parsec_device_b200_module_t *dev, parsec_execution_stre
         t1 = B200_TSC(); dev->tsc[n ? 3 : 5] += t1 - t0; t0 = t1;
         for( int i = 0; i < n; i++ ) {
             b200_task_t *bt = (b200_task_t*)(uintptr_t)dev->retbuf[i].cookie;
-            if( i + 1 < n ) b200_pf4((const b200_task_t*)(uintptr_t)dev->retbuf[i + 1].cookie);
-            if( i + 2 < n ) b200_pf3((const b200_task_t*)(uintptr_t)dev->retbuf[i + 2].cookie);
-            if( i + 3 < n ) b200_pf2((const b200_task_t*)(uintptr_t)dev->retbuf[i + 3].cookie);
-            if( i + 4 < n ) b200_pf1((const b200_task_t*)(uintptr_t)dev->retbuf[i + 4].cookie);
+            if( i + 5 < n ) { const char *la = (const char*)(uintptr_t)dev->retbuf[i + 5].cookie; B200_PFW(la); B200_PFW(la + 64); B200_PFW(la + offsetof(b200_task_t, proxy)); }
             if( NULL == bt->gpu_task || BT_INFLIGHT != bt->state ) {
                 parsec_warning("device_b200: retire record %d/%d for a task that is not in flight (bt %p state %d ticket %d/%d gpu_task %p)",
                                i, n, (void*)bt, bt->state, bt->ticket, dev->retbuf[i].ticket, (void*)bt->gpu_task);
@@ -1205,15 +1404,42 @@ b200_kernel_scheduler(parsec_device_module_t *module, parsec_execution_stream_t 
     if( 0 == dev->st.first_entry_ns ) dev->st.first_entry_ns = b200_now_ns();
     int32_t inside = parsec_atomic_fetch_inc_int32(&dev->callers_inside) + 1;
     if( (uint64_t)inside > dev->st.max_concurrent_callers ) dev->st.max_concurrent_callers = (uint64_t)inside;
-    /* 1. one more task is owed, THEN it is handed over (lock-free push on the inbox).  In this order the manager can
-     *    never complete a task whose debt has not been booked yet: booking first keeps `owed` from dropping to zero --
-     *    and a second manager from being elected -- while a task is on its way into the inbox. */
+    /* 0. What does not need a decision of the manager is done here, by the calling thread, in parallel with every other
+     *    caller -- it built the gpu_task a moment ago and ran prepare_input on the task: every line is in its cache,
+     *    while the manager would have to pull each of them from here, and one thread paying a dozen cache-to-cache
+     *    transfers per task is what bounds the task rate of a device.
+     *      - the task record;
+     *      - the RECORDING of the body: a submit function known to name an engine body is a pure function of the task
+     *        (it enqueues nothing), so it can run before the flows are resident;
+     *      - for a task whose inputs all are this device's replicas already: readers, versions, the engine command. */
+    if( UINT64_MAX != gpu_task->last_data_check_epoch ) {
+        parsec_warning("device_b200: gpu_task %p handed to kernel_scheduler twice (epoch %lx)", (void*)gpu_task, (unsigned long)gpu_task->last_data_check_epoch);
+        abort();
+    }
+    b200_task_t *bt = b200_bt_new(dev, gpu_task);
+    bt->proxy.taskpool = (NULL != gpu_task->ec) ? gpu_task->ec->taskpool : NULL;
+    bt->custom_stage = (NULL != gpu_task->stage_in && gpu_task->stage_in != parsec_default_gpu_stage_in) ||
+                       (NULL != gpu_task->stage_out && gpu_task->stage_out != parsec_default_gpu_stage_out);
+    if( !bt->custom_stage && NULL != gpu_task->submit && (dev->dry_run || parsec_b200_submit_is_engine(gpu_task->submit)) ) {
+        b200_tl_recording = bt;
+        const int src = gpu_task->submit(&dev->super.super, gpu_task, &dev->lane->super);
+        b200_tl_recording = NULL;
+        if( src >= 0 && bt->body >= 0 ) bt->recorded = 1;
+        else if( !dev->dry_run ) bt->body = -1;        /* the manager will say what is wrong with it */
+        else { bt->recorded = 1; bt->body = PB2_BODY_NOP; bt->nb_args = 0; }   /* dry run: an opaque body is a no-op */
+    }
+    bt->has_complete_stage = (NULL != gpu_task->complete_stage);     /* a body may install one (dtd_test_simple_gemm.c:538) */
+    if( bt->recorded && PARSEC_GPU_TASK_TYPE_KERNEL == gpu_task->task_type ) (void)b200_prepare_resident(dev, bt);
+    /* 1. one more task is owed, THEN it is handed over.  In this order the manager can never complete a task whose debt
+     *    has not been booked yet: booking first keeps `owed` from dropping to zero -- and a second manager from being
+     *    elected -- while a task is on its way into the inbox. */
     int32_t before = parsec_atomic_fetch_add_int32(&dev->owed, 1);
-    parsec_gpu_task_t *old;
-    do {
-        old = dev->inbox;
-        gpu_task->list_item.list_next = (parsec_list_item_t*)old;
-    } while( !parsec_atomic_cas_ptr(&dev->inbox, old, gpu_task) );
+    {
+        const int64_t idx = parsec_atomic_fetch_add_int64(&dev->inbox_tail, 1);
+        while( idx - dev->inbox_head >= B200_INBOX_SLOTS ) { _mm_pause(); }   /* ring full: the manager is draining it */
+        parsec_atomic_wmb();
+        dev->inbox_ring[idx & (B200_INBOX_SLOTS - 1)] = bt;
+    }
     (void)parsec_atomic_fetch_dec_int32(&dev->callers_inside);
     if( before > 0 ) return PARSEC_HOOK_RETURN_ASYNC;        /* somebody is driving the device and owes this task too */
 
@@ -1226,17 +1452,13 @@ b200_kernel_scheduler(parsec_device_module_t *module, parsec_execution_stream_t 
         es = parsec_my_execution_stream();
         if( NULL == es && NULL != module->context ) es = module->context->virtual_processes[0]->execution_streams[0];
     }
-    if( !dev->dry_run ) B200_CUDA(cudaSetDevice(dev->super.cuda_index), "cudaSetDevice", { return PARSEC_HOOK_RETURN_DISABLE; });
+    b200_cuda_here(dev);
     uint64_t idle_spins = 0;
     for(;;) {
         dev->completed_now = 0;
         if( 0 == (++idle_spins & 0x3ffffff) && NULL != getenv("PARSEC_B200_DEBUG") ) {
-            int ns = 0, nw = 0;
-            parsec_list_item_t *it;
-            for( it = PARSEC_LIST_ITERATOR_FIRST(&dev->stalled); it != PARSEC_LIST_ITERATOR_END(&dev->stalled); it = PARSEC_LIST_ITERATOR_NEXT(it) ) ns++;
-            for( it = PARSEC_LIST_ITERATOR_FIRST(&dev->waiting_event); it != PARSEC_LIST_ITERATOR_END(&dev->waiting_event); it = PARSEC_LIST_ITERATOR_NEXT(it) ) nw++;
-            fprintf(stderr, "b200 manager stuck? owed %d inbox %p stalled %d waiting_event %d stream inflight %d executed %lu\n",
-                    dev->owed, (void*)dev->inbox, ns, nw, pb2_stream_inflight(dev->stream), (unsigned long)module->executed_tasks);
+            fprintf(stderr, "b200 manager stuck? owed %d inbox %ld stalled %d stream inflight %d executed %lu\n",
+                    dev->owed, (long)(dev->inbox_tail - dev->inbox_head), dev->nb_stalled, pb2_stream_inflight(dev->stream), (unsigned long)module->executed_tasks);
         }
         if( b200_progress(dev, es) < 0 ) {
             parsec_warning("GPU[%d:%s]: the device engine reported a fatal error; giving up", module->device_index, module->name);
@@ -1386,7 +1608,9 @@ static void b200_profile_print(parsec_device_b200_module_t *dev)
     fprintf(stderr, "b200 manager Mcycles: inbox %.1f start %.1f events %.1f poll %.1f finish %.1f idle-poll %.1f schedule %.1f (total %.1f, %lu tasks so far, %lu manager entries)\n",
             dev->tsc[0] * 1e-6, dev->tsc[1] * 1e-6, dev->tsc[2] * 1e-6, dev->tsc[3] * 1e-6, dev->tsc[4] * 1e-6, dev->tsc[5] * 1e-6, dev->tsc[6] * 1e-6,
             tot * 1e-6, (unsigned long)dev->super.super.super.executed_tasks, (unsigned long)dev->st.manager_entries);
-    memset(dev->tsc, 0, sizeof dev->tsc);
+    fprintf(stderr, "b200 manager start Mcycles: reserve %.1f stage-in %.1f record %.1f command %.1f\n",
+            dev->tsc_start[0] * 1e-6, dev->tsc_start[1] * 1e-6, dev->tsc_start[2] * 1e-6, dev->tsc_start[3] * 1e-6);
+    memset(dev->tsc, 0, sizeof dev->tsc); memset(dev->tsc_start, 0, sizeof dev->tsc_start);
 }
 
 static int b200_memory_release(parsec_device_module_t *device)
@@ -1394,6 +1618,8 @@ static int b200_memory_release(parsec_device_module_t *device)
     parsec_device_b200_module_t *dev = (parsec_device_b200_module_t*)device;
     b200_profile_print(dev);
     dev->st.first_task_ns = dev->st.first_entry_ns = 0;
+    /* the tail of an epilog (letting go of the readers it held) may still be running on a worker thread */
+    while( dev->epilogs_done < dev->epilogs_started ) { parsec_atomic_rmb(); }
     /* dirty replicas go home first: flush_lru would drop them with a warning (device_gpu.c:1033-1037) */
     if( !dev->dry_run ) (void)pb2_stream_quiesce(dev->stream);
     while( b200_write_back_some(dev, 64) > 0 ) { }
@@ -1495,8 +1721,10 @@ int parsec_b200_module_init(int dev_id, parsec_device_module_t **module)
     PARSEC_OBJ_CONSTRUCT(&gpu->gpu_mem_owned_lru, parsec_list_t);
     PARSEC_OBJ_CONSTRUCT(&gpu->pending, parsec_fifo_t);
     PARSEC_OBJ_CONSTRUCT(&dev->stalled, parsec_list_t);
+    PARSEC_OBJ_CONSTRUCT(&dev->settled, parsec_list_t);
     PARSEC_OBJ_CONSTRUCT(&dev->waiting_event, parsec_list_t);
-    PARSEC_OBJ_CONSTRUCT(&dev->free_bt, parsec_list_t);
+    memset(&dev->lru_lock, 0, sizeof dev->lru_lock);
+    dev->inbox_ring = (b200_task_t * volatile *)calloc(B200_INBOX_SLOTS, sizeof(b200_task_t*));
 
     int nblocks = parsec_b200_memory_number_of_blocks;
     if( dev->dry_run && -1 == nblocks ) nblocks = 4096;
@@ -1526,17 +1754,12 @@ int parsec_b200_module_fini(parsec_device_module_t *device)
     parsec_device_gpu_module_t *gpu = &dev->super.super;
     if( NULL != dev->stream ) { (void)pb2_stream_quiesce(dev->stream); }
     b200_profile_print(dev);
+    while( dev->epilogs_done < dev->epilogs_started ) { parsec_atomic_rmb(); }
     while( b200_write_back_some(dev, 64) > 0 ) { }
     parsec_device_memory_release(gpu);
     b200_registration_cache_drop(dev);
     if( NULL != dev->stream ) { pb2_stream_destroy(dev->stream); dev->stream = NULL; }
-    for( b200_proxy_t *px = (b200_proxy_t*)dev->proxy_free, *nx; NULL != px; px = nx ) { nx = px->next_free; free(px); }
-    dev->proxy_free = NULL;
-    b200_task_t *bt;
-    while( NULL != (bt = (b200_task_t*)parsec_list_nolock_pop_front(&dev->free_bt)) ) {
-        if( !dev->dry_run && NULL != bt->ev ) (void)cudaEventDestroy(bt->ev);
-        free(bt);
-    }
+    free((void*)dev->inbox_ring); dev->inbox_ring = NULL;
     PARSEC_OBJ_DESTRUCT(&gpu->pending);
     PARSEC_OBJ_DESTRUCT(&dev->lane->super.infos);
     free(dev->lane->super.name);
