@@ -151,7 +151,7 @@ def e2e_mca(K, ngpus, steps, cores):
            # the bench process keeps its own slabs on the same GPUs: give the component's heap what the workload needs
            "PARSEC_MCA_device_b200_memory_number_of_blocks": str(max(2 * K // max(ngpus, 1), 1024) + 1024)}
     warm = 2
-    d = run_app("ex05_b200", ["-m", "gpu", "-K", K, "-t", TILE // 4, "-r", steps + warm, "-c", cores], env)
+    d = run_app("ex05_b200", ["-m", "gpu", "-K", K, "-t", TILE // 4, "-r", steps + warm, "-c", cores], env, timeout=240)
     if d is None:
         return None
     assert d["errors"] == 0 and d["b200"]["check_mismatches"] == 0, "e2e run: wrong values"
@@ -244,7 +244,14 @@ def secondary_gemm(clock_index):
             worst = max(worst, float(err.max()))
             checked.append([i, j])
         sampler = ClockSampler(clock_index).start()
-        ms = sorted(w.run()["kernel_ms"] for _ in range(7))
+        t_wait = time.perf_counter()
+        while not sampler.rows and time.perf_counter() - t_wait < 3.0:      # nvidia-smi needs ~100 ms before its first sample
+            w.run()
+        sampler.rows.clear()
+        ms = []
+        while len(ms) < 7 or (len(sampler.rows) < 2 and len(ms) < 60):      # the timed runs, under the sampler
+            ms.append(w.run()["kernel_ms"])
+        ms.sort()
         clocks = sampler.stop()
         w.close()
     med = ms[len(ms) // 2]
@@ -300,18 +307,26 @@ def secondary_rtt(rank, world, local, torch, dist):
         st = run.wait()
         ms = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda", dtype=torch.float64)
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        ok = True
+        ok, seen = True, [0, 0]
+        k0 = ((nt - 1) // world) * world
+        # rank 0's slot enters run r holding (r-1)*(k0+1) (its last writer of the previous run is PING(k0)); the chain adds
+        # nt to that: after the 2 warm-up runs and the `steps` timed ones the last hop's rank holds this value
+        want = (1 + steps) * (k0 + 1) + nt
         if (nt - 1) % world == rank:                       # the rank that ran the last hop holds the final version
             slab = np.zeros(run.slab_bytes // 4, np.int32)
             eng.d2h(slab, run.slab); eng.synchronize()
-            k0 = ((nt - 1) // world) * world
-            ok = bool(np.all(slab[: frags * tile // 4] == (1 + steps) * (k0 + 1) + nt))   # 2 warm-up runs + `steps` runs
-        flag = torch.tensor([1 if ok else 0], device="cuda")
+            got = slab[: frags * tile // 4]
+            seen = [int(got.min()), int(got.max())]
+            ok = bool(np.all(got == want))
+        flag = torch.tensor([1 if ok else 0, seen[0], seen[1]], device="cuda")
+        mx = flag.clone()
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         t = float(ms.item()) / 1e3
         rec["runs"].append({"FRAGS": frags, "ms_per_run": t * 1e3, "us_per_hop": t / (nt - 1) * 1e6,
                             "tile_GBs": (nt - 1) * frags * tile / t / 1e9, "nvlink_frac": (nt - 1) * frags * tile / t / 1e9 / NVLINK_GBS / max(min(frags, world), 1),
-                            "parity_ok": bool(flag.item()), "retired": st["tasks_retired"]})
+                            "parity_ok": bool(flag[0].item()), "expected_value": want, "seen_min_max": [int(mx[1].item()), int(mx[2].item())],
+                            "retired": st["tasks_retired"]})
         del run
         eng.close()
     return rec
@@ -368,7 +383,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--groups", type=int, default=K_GROUPS, help="broadcast groups per GPU (config value: 4096)")
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--e2e-cores", type=int, default=16, help="worker threads of the reference runtime in the e2e run")
+    ap.add_argument("--e2e-cores", type=int, default=32, help="worker threads of the reference runtime in the e2e run")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary records of the other BASELINE configs")
     ap.add_argument("--mgpu", default="direct", choices=["direct", "exchange"],
                     help="N>1: device-released cross-GPU edges (default) or two windows + one NCCL exchange")
@@ -426,14 +441,19 @@ def main():
         return float(t.item())
 
     # ---------------------------------------------------------------- e2e through the reference-facing plug-in (rank 0)
-    # One process drives all N GPUs, the way the reference does: same path at every N.  Run first, before this process
-    # takes its own device memory.
-    e2e = None
-    if rank == 0 and args.e2e_steps > 0:     # --e2e-steps 0: profiler runs (a persistent kernel fed by the host cannot run under ncu's serialised launches)
+    # One process drives all N GPUs, the way the reference does: same path at every N.  At N = 1 it runs first, before this
+    # process takes its own device memory; at N > 1 it runs LAST, after the process group is gone, so that no rank ever sits
+    # in a collective while rank 0 drives a separate application (an NCCL watchdog would kill the whole job).
+    def run_e2e():
         try:
-            e2e = e2e_mca(K * world, world, args.e2e_steps, args.e2e_cores)
+            return e2e_mca(K * world, world, args.e2e_steps, args.e2e_cores)
         except Exception as exc:
             print("bench.py: e2e through the MCA component failed: %r" % (exc,), file=sys.stderr)
+            return {"unavailable": "e2e run through the MCA component failed: %r" % (exc,)}
+
+    e2e = None
+    if rank == 0 and world == 1 and args.e2e_steps > 0:     # --e2e-steps 0: profiler runs (a persistent kernel fed by the host cannot run under ncu's serialised launches)
+        e2e = run_e2e()
     barrier()
 
     secondary = {}
@@ -603,15 +623,24 @@ def main():
         out["roofline"] = {"bound": "nvlink", "achieved": ingress / (ms_per_step / 1e3) / 1e9, "peak": NVLINK_GBS, "unit": "GB/s",
                            "frac": ingress / (ms_per_step / 1e3) / 1e9 / NVLINK_GBS, "traffic": ingress,
                            "note": "bytes the busiest rank pulls from its peers per step (counted by the kernel) over 900 GB/s per direction; the step cannot be shorter than traffic / peak"}
-    out["e2e"] = e2e if e2e is not None else (e2e_standalone or {"unavailable": "oracle/_ref/bin/ex05_b200 missing"})
     if e2e_standalone is not None:
         out["e2e_standalone"] = e2e_standalone
     if secondary:
         out["secondary"] = secondary
+    if world > 1:
+        barrier()
+        dist.destroy_process_group()
+        if rank == 0 and args.e2e_steps > 0:
+            try:                                             # this process' own slabs go first
+                del run, step, finish
+                import gc; gc.collect(); torch.cuda.empty_cache()
+            except Exception:
+                pass
+            time.sleep(1.0)                                  # the other ranks are exiting: their device memory comes back
+            e2e = run_e2e()
+    out["e2e"] = e2e if e2e is not None else (e2e_standalone or {"unavailable": "oracle/_ref/bin/ex05_b200 missing or e2e skipped"})
     if rank == 0:
         print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -379,9 +379,12 @@ struct pb2_stream_s {
     std::vector<int32_t> freed;              // SPSC ring of tickets given back by poll, capacity `slots`
     alignas(64) std::atomic<uint64_t> freed_tail{0};   // written by poll
     alignas(64) std::atomic<uint64_t> freed_head{0};   // written by submit
-    alignas(64) std::atomic<int64_t> entries_inflight{0};
-    std::atomic<int64_t> inflight{0};
-    std::atomic<uint64_t> n_submitted{0}, n_retired{0};
+    // counters: each side writes its own line; the other side reads it only when its last view is not good enough
+    alignas(64) std::atomic<uint64_t> sub_tasks{0};     // submit side: tasks / ring entries handed to the device
+    std::atomic<uint64_t> sub_entries{0};
+    uint64_t ret_entries_seen = 0;                      // submit side's last view of ret_entries
+    alignas(64) std::atomic<uint64_t> ret_tasks{0};     // poll side: tasks / ring entries whose record was read
+    std::atomic<uint64_t> ret_entries{0};
     std::mutex launch_mu;                    // (re)launch of the persistent kernel: either side may find it parked
     std::mutex nodes_mu;                     // free_nodes: add_edge takes, poll gives back (look-ahead edges only)
     std::mutex dry_mu;                       // dry run: the emulated device is shared by both sides
@@ -608,14 +611,20 @@ int pb2_stream_submit(pb2_stream_t* s, const pb2_task_t* task, uint64_t cookie, 
         if (np > PB2_MAX_PARTS) np = PB2_MAX_PARTS;
         if (np < 1) np = 1;
     }
-    if ((uint64_t)s->entries_inflight.load(std::memory_order_relaxed) + np + 64 > (uint64_t)s->ring_cap / 2) return PB2_ERR_OUT_OF_RESOURCE;
+    {   // ready-ring capacity: entries in flight, with a view of the poll side's counter that is refreshed only when needed
+        const uint64_t sub = s->sub_entries.load(std::memory_order_relaxed);
+        if (sub - s->ret_entries_seen + np + 64 > (uint64_t)s->ring_cap / 2) {
+            s->ret_entries_seen = s->ret_entries.load(std::memory_order_acquire);
+            if (sub - s->ret_entries_seen + np + 64 > (uint64_t)s->ring_cap / 2) return PB2_ERR_OUT_OF_RESOURCE;
+        }
+    }
     const int32_t tk = s->free_tickets.back();
     if (s->dry) {
         std::lock_guard<std::mutex> guard(s->dry_mu);
         s->free_tickets.pop_back();
         s->cookie[(size_t)tk] = cookie; s->tk_parts[(size_t)tk] = (uint16_t)np; s->tk_live[(size_t)tk] = 1;
-        s->entries_inflight.fetch_add(np, std::memory_order_relaxed); s->inflight.fetch_add(1, std::memory_order_relaxed);
-        s->n_submitted.fetch_add(1, std::memory_order_relaxed);
+        s->sub_entries.store(s->sub_entries.load(std::memory_order_relaxed) + np, std::memory_order_relaxed);
+        s->sub_tasks.store(s->sub_tasks.load(std::memory_order_relaxed) + 1, std::memory_order_release);
         if (ticket) *ticket = tk;
         DryTask& dt = s->dry_tasks[(size_t)tk];
         dt.t = *task; dt.dep = task->dep_goal; dt.succ.clear(); dt.done = false;
@@ -633,8 +642,8 @@ int pb2_stream_submit(pb2_stream_t* s, const pb2_task_t* task, uint64_t cookie, 
         for (int f = 0; f < PB2_MAX_FLOWS; ++f) { c->u.task.tile[f] = f < task->nb_flows ? task->tile[f] : -1; c->u.task.access[f] = task->access[f]; }
         c->u.task.iparam[0] = task->iparam[0]; c->u.task.iparam[1] = task->iparam[1]; c->u.task.iparam[2] = task->iparam[2];
         c->u.task.fparam = task->fparam; c->u.task.locals[0] = task->locals[0]; c->u.task.locals[1] = task->locals[1];
-        s->entries_inflight.fetch_add(np, std::memory_order_relaxed); s->inflight.fetch_add(1, std::memory_order_relaxed);
-        s->n_submitted.fetch_add(1, std::memory_order_relaxed);
+        s->sub_entries.store(s->sub_entries.load(std::memory_order_relaxed) + np, std::memory_order_relaxed);
+        s->sub_tasks.store(s->sub_tasks.load(std::memory_order_relaxed) + 1, std::memory_order_release);
         if (ticket) *ticket = tk;               // before the command is visible: the caller's record may be recycled right after
         stream_cmd_publish(s, c);
     }
@@ -699,8 +708,8 @@ int pb2_stream_poll(pb2_stream_t* s, pb2_retire_t* out, int32_t max) {
             const uint64_t ft = s->freed_tail.load(std::memory_order_relaxed);
             s->freed[ft & (s->slots - 1)] = tk;
             s->freed_tail.store(ft + 1, std::memory_order_release);
-            s->entries_inflight.fetch_sub(s->tk_parts[(size_t)tk], std::memory_order_relaxed); s->inflight.fetch_sub(1, std::memory_order_relaxed);
-            s->n_retired.fetch_add(1, std::memory_order_relaxed);
+            s->ret_entries.store(s->ret_entries.load(std::memory_order_relaxed) + s->tk_parts[(size_t)tk], std::memory_order_release);
+            s->ret_tasks.store(s->ret_tasks.load(std::memory_order_relaxed) + 1, std::memory_order_release);
         }
         return n;
     }
@@ -709,7 +718,7 @@ int pb2_stream_poll(pb2_stream_t* s, pb2_retire_t* out, int32_t max) {
                                                                   : "streaming kernel ran a task with an unknown body id";
         return s->h_ctl->error == (uint32_t)kDoneTimeout ? PB2_ERR_DEVICE : PB2_ERR_BAD_PARAM;
     }
-    if (s->h_ctl->state == HS_STOPPED && s->inflight.load(std::memory_order_relaxed) > 0) {
+    if (s->h_ctl->state == HS_STOPPED && s->sub_tasks.load(std::memory_order_acquire) != s->ret_tasks.load(std::memory_order_relaxed)) {
         // nobody kicked: every retire record already written is in the ring; anything else needs the kernel
         const Retire* nxt = &s->h_ret[s->ret_read & (s->slots - 1)];
         const uint32_t g = ((uint32_t)(s->ret_read / (unsigned long long)s->slots) + 1u) & 0x7fffffffu;
@@ -739,8 +748,8 @@ int pb2_stream_poll(pb2_stream_t* s, pb2_retire_t* out, int32_t max) {
         const uint64_t ft = s->freed_tail.load(std::memory_order_relaxed);
         s->freed[ft & (s->slots - 1)] = tk;
         s->freed_tail.store(ft + 1, std::memory_order_release);
-        s->entries_inflight.fetch_sub(s->tk_parts[(size_t)tk], std::memory_order_relaxed); s->inflight.fetch_sub(1, std::memory_order_relaxed);
-        s->n_retired.fetch_add(1, std::memory_order_relaxed);
+        s->ret_entries.store(s->ret_entries.load(std::memory_order_relaxed) + s->tk_parts[(size_t)tk], std::memory_order_release);
+        s->ret_tasks.store(s->ret_tasks.load(std::memory_order_relaxed) + 1, std::memory_order_release);
         s->ret_read++;
     }
     return n;
@@ -761,7 +770,7 @@ int pb2_stream_quiesce(pb2_stream_t* s) {
     return PB2_SUCCESS;
 }
 
-int pb2_stream_inflight(pb2_stream_t* s) { return s ? (int)s->inflight.load() : 0; }
+int pb2_stream_inflight(pb2_stream_t* s) { return s ? (int)(s->sub_tasks.load() - s->ret_tasks.load()) : 0; }
 
 int pb2_stream_stats(pb2_stream_t* s, pb2_stream_stats_t* out) {
     if (!s || !out) return PB2_ERR_BAD_PARAM;
@@ -776,7 +785,7 @@ int pb2_stream_stats(pb2_stream_t* s, pb2_stream_stats_t* out) {
         s->st.stage_ins = c.stage_ins.v; s->st.body_errors = c.body_errors.v;
         s->st.edges_late = sc.edges_late.v; s->st.released_on_device = sc.released.v;
     }
-    s->st.submitted = s->n_submitted.load(); s->st.retired = s->n_retired.load();
+    s->st.submitted = s->sub_tasks.load(); s->st.retired = s->ret_tasks.load();
     *out = s->st;
     return PB2_SUCCESS;
 }

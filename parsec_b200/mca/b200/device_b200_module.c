@@ -94,6 +94,9 @@ typedef struct b200_task_s {
     uint64_t             result;
     uint64_t             cold_bytes;      /* bytes this task stages in over PCIe / NVLink (throttle, see b200_start_task) */
     struct parsec_device_b200_module_s *dev;
+    int32_t              is_kernel;       /* PARSEC_GPU_TASK_TYPE_KERNEL (not a prefetch / warm-up pseudo task) */
+    int32_t              defer_tiles;     /* tile descriptions go to tdesc[]: the starter hands them to the device */
+    int32_t              ntdesc;
     pb2_task_t           cmd __attribute__((aligned(64)));   /* the engine command of this task (built by whoever settles its flows) */
     parsec_task_t        proxy __attribute__((aligned(64))); /* the completion task the worker pool runs for this one (b200_epilog_hook) */
     /* start path of tasks the manager has to look at, lane / copy-engine paths */
@@ -109,47 +112,74 @@ typedef struct b200_task_s {
     cudaEvent_t          ev;              /* created the first time a copy-engine / lane path needs it */
     int32_t              ev_dev;          /* CUDA device the event belongs to, -1: none */
     struct b200_task_s  *next_free;       /* per-thread free list */
+    struct b200_task_s  *next_done;       /* chain of finished tasks one proxy completes / lane_done stack */
+    struct { int32_t tile; pb2_tile_t desc; } tdesc[MAX_PARAM_COUNT];   /* see defer_tiles */
 } b200_task_t;
 
 typedef struct b200_host_range_s { char *base; size_t len; char *alias; int lazy; } b200_host_range_t;   /* lazy: unregistered by its owner, still pinned (registration cache) */
 
+#define B200_LINE __attribute__((aligned(64)))
+/* Laid out by who writes what: every group below starts on its own cache line. */
 typedef struct parsec_device_b200_module_s {
     parsec_device_cuda_module_t super;    /* generated CUDA bodies read cuda_index / the exec stream through this layout */
+    /* read-mostly */
     pb2_engine_t        *engine;
     pb2_stream_t        *stream;
     int                  dry_run;
     char                *slab_base;
     uint8_t             *tile_described;  /* per heap block: the device tile table entry of the replica that starts here is current */
-    /* inbox + election: callers take a slot index with one fetch-and-add and store their task record there; the
-     * manager reads the slots in order (pointers side by side: it can prefetch the records well ahead) */
-    b200_task_t * volatile *inbox_ring;
-    volatile int64_t     inbox_tail;      /* next slot a caller takes */
-    char                 pad0_[56];
-    volatile int64_t     inbox_head;      /* slots the manager has emptied (written by the manager only) */
-    volatile int32_t     owed;
-    volatile int32_t     callers_inside;
-    volatile int64_t     epilogs_done;    /* epilogs the worker threads have ended (their own cache line: the manager never writes it) */
-    char                 pad_[56];
-    b200_lock_t          lru_lock;        /* gpu_mem_lru / gpu_mem_owned_lru: the manager and the workers' epilogs */
-    /* manager-private */
-    parsec_list_t        stalled;         /* b200_task_t not started yet: new ones, and ones waiting for memory or ring space */
-    parsec_list_t        settled;         /* ... whose flows the caller settled (b200_prepare_resident): they only need ring space */
-    int32_t              nb_settled;
-    parsec_list_t        waiting_event;   /* b200_task_t in BT_DMA_IN / BT_LANE / BT_DMA_OUT, in event order */
-    int64_t              cold_inflight;   /* bytes of stage-in handed to the device and not retired yet */
-    int32_t              nb_stalled;
-    int32_t              again_window;    /* the last AGAIN of b200_start_task came from the stage-in window, not from memory */
-    volatile int32_t     retry_stalled;   /* something happened that may let a waiting task start (a retirement, a newcomer, the end of an epilog) */
-    int32_t              blocked_spins;   /* manager iterations since the last attempt to start a waiting task */
-    parsec_task_t       *completion_ring; /* proxies of finished tasks, handed to the worker pool once per iteration */
-    int64_t              epilogs_started; /* finished tasks handed to the worker pool */
-    uint64_t             tsc_start[4];    /* start phase by step: reserve, stage-in decisions, record, command */
-    int32_t              completed_now;   /* completions of the current manager iteration, subtracted from owed at its end */
+    b200_task_t * volatile *inbox_ring;   /* callers take a slot index with one fetch-and-add and store their task record there;
+                                           * the starter reads the slots in order (pointers side by side: it can prefetch the records) */
     cudaStream_t         dma_stream;
     parsec_cuda_exec_stream_t *lane;      /* exec_stream[0]: what submit functions receive */
-    parsec_b200_stats_t  st;
-    uint64_t             tsc[8];          /* manager time by phase (PARSEC_MCA_device_b200_profile): inbox, start, events, poll, finish, idle */
+    uint64_t             first_entry_ns, first_task_ns, last_done_ns;
+    /* callers of kernel_scheduler */
+    volatile int64_t     inbox_tail B200_LINE;       /* next slot a caller takes */
+    volatile int32_t     owed B200_LINE;             /* tasks handed over and not completed: 0 -> 1 elects the manager */
+    volatile int32_t     callers_inside B200_LINE;
+    volatile int32_t     max_callers_inside;
+    /* worker threads */
+    volatile int64_t     epilogs_done B200_LINE;     /* epilogs the worker threads have ended */
+    b200_lock_t          lru_lock B200_LINE;         /* gpu_mem_lru / gpu_mem_owned_lru: the starter and the workers' epilogs */
+    /* RESIDENCY of the flows of a task (device heap, choice of a source, tile descriptions) is decided under this lock,
+     * by the calling worker for engine tasks, by the starter for the others.  A caller pushes its task into the inbox
+     * BEFORE it lets the lock go: the inbox holds the decisions in the order they were taken. */
+    b200_lock_t          alloc_lock B200_LINE;
+    /* Two roles drive a device.  The STARTER (inbox, residency, stage-in decisions, command ring, events of the stage-in
+     * and lane paths) is whichever thread holds `starter_active`: a caller of kernel_scheduler takes it when it is free
+     * and keeps it while tasks keep arriving; the manager takes it when tasks that had to wait may go on.  The MANAGER
+     * (elected through `owed`) owns the retire side: retire ring, pushouts through the copy engine, completion. */
+    volatile int32_t     starter_active B200_LINE;
+    volatile int32_t     fatal;           /* the starter hit a fatal device problem: the manager gives the device up */
+    volatile int32_t     memory_pressure; /* the heap has been full since the last memory_release: LRU order is kept from here on */
+    struct b200_task_s * volatile lane_done;   /* finished lane tasks, starter -> manager (lock-free stack) */
+    volatile int32_t     retry_stalled B200_LINE;    /* something happened that may let a waiting task start (a retirement, a newcomer,
+                                                      * the end of an epilog): set by anybody, cleared by the starter */
+    volatile int64_t     cold_inflight B200_LINE;    /* bytes of stage-in handed to the device and not retired yet (starter adds, manager subtracts) */
+    /* starter-private */
+    volatile int64_t     inbox_head B200_LINE;       /* slots the starter has emptied (callers read it when the ring is full) */
+    parsec_list_t        stalled B200_LINE;          /* b200_task_t not started yet: new ones, and ones waiting for memory or ring space */
+    parsec_list_t        settled;         /* ... whose flows the caller settled (b200_prepare_resident): they only need ring space */
+    parsec_list_t        cold_q;          /* ... whose caller decided a stage-in: FIFO behind the stage-in window */
+    int32_t              nb_cold;
+    parsec_list_t        waiting_event;   /* b200_task_t in BT_DMA_IN / BT_LANE, in event order */
+    int32_t              nb_settled;
+    int32_t              nb_stalled;
+    int32_t              again_window;    /* the last AGAIN of b200_start_task came from the stage-in window, not from memory */
+    uint64_t             n_engine, n_lane, n_settled_by_caller;   /* statistics (folded into parsec_b200_stats_t on demand) */
+    uint64_t             tsc_start[4];    /* start phase by step: reserve, stage-in decisions, record, command */
+    uint64_t             tsc_s[3];        /* starter time by phase: inbox, start, events */
+    /* manager-private */
+    parsec_list_t        waiting_out B200_LINE;      /* b200_task_t in BT_DMA_OUT */
+    parsec_task_t       *completion_ring; /* proxies of finished tasks, handed to the worker pool once per iteration */
+    b200_task_t         *batch_head;      /* the finished tasks the next proxy will complete (a chain through next_done) */
+    int32_t              batch_len;
+    int32_t              completed_now;   /* completions of the current manager iteration, subtracted from owed at its end */
+    int32_t              blocked_spins;   /* manager iterations since the last forced attempt to start a waiting task */
+    int64_t              epilogs_started; /* finished tasks handed to the worker pool */
+    uint64_t             tsc[8];          /* manager time by phase: -, -, -, poll, finish, idle poll, schedule */
     pb2_retire_t         retbuf[256];
+    parsec_b200_stats_t  st B200_LINE;    /* rarely written counters */
 } parsec_device_b200_module_t;
 
 /* host ranges registered with memory_register: shared by the modules of the component (cudaHostRegisterPortable) */
@@ -239,7 +269,8 @@ static b200_task_t *b200_bt_new(parsec_device_b200_module_t *dev, parsec_gpu_tas
     bt->dev = dev;
     bt->gpu_task = gpu_task; bt->state = BT_NEW; bt->ticket = -1; bt->body = -1; bt->nb_args = 0;
     bt->peer_src_mask = 0; bt->dma_out_mask = 0; bt->result = 0; bt->retired = 0; bt->custom_stage = 0; bt->cold_bytes = 0;
-    bt->recorded = 0; bt->has_complete_stage = 0; bt->prepared = 0; bt->cmd_built = 0;
+    bt->recorded = 0; bt->has_complete_stage = 0; bt->prepared = 0; bt->cmd_built = 0; bt->defer_tiles = 0; bt->ntdesc = 0;
+    bt->is_kernel = (NULL == gpu_task) || (PARSEC_GPU_TASK_TYPE_KERNEL == gpu_task->task_type);
     if( NULL != gpu_task ) gpu_task->last_data_check_epoch = (uint64_t)(uintptr_t)bt;
     return bt;
 }
@@ -504,6 +535,7 @@ static int b200_reserve(parsec_device_b200_module_t *dev, b200_task_t *bt)
         if( NULL == gpu_elem ) {
             void *ptr;
             while( NULL == (ptr = zone_malloc(dev->super.super.memory, gpu_task->flow_info[i].flow_span)) ) {
+                dev->memory_pressure = 1;
                 if( !b200_evict_one(dev, gpu_task) ) {
                     /* nothing can be freed now: undo what this pass allocated and let the task wait for retirements */
                     for( int k = 0; k < nfresh; k++ ) {
@@ -552,6 +584,16 @@ static int b200_needs_memory(const parsec_device_b200_module_t *dev, const parse
 /* ------------------------------------------------------------------------------------------------------------------ */
 /* stage-in decisions (parsec_device_data_stage_in, device_gpu.c:1799-2165): who is the source, who moves the bytes     */
 /* ------------------------------------------------------------------------------------------------------------------ */
+/* a tile description decided by `bt`: straight to the device when the starter decides, kept in the record when the
+ * calling worker does (the starter sends the descriptions of a record before anything that was decided after them) */
+static int b200_emit_tile(parsec_device_b200_module_t *dev, b200_task_t *bt, int32_t tid, const pb2_tile_t *tile)
+{
+    if( !bt->defer_tiles ) return (PB2_SUCCESS == pb2_stream_set_tile(dev->stream, tid, tile)) ? 0 : -1;
+    if( bt->ntdesc >= MAX_PARAM_COUNT ) return -1;
+    bt->tdesc[bt->ntdesc].tile = tid; bt->tdesc[bt->ntdesc].desc = *tile; bt->ntdesc++;
+    return 0;
+}
+
 /* mode 0: engine task (the kernel pulls device-visible sources, the copy engine the others);
  * mode 1: lane task, default staging (copy engine on the lane stream); mode 2: lane task with a user stage_in: nothing is
  * copied here, the flows that need their bytes are left UNDER_TRANSFER for the callback.
@@ -606,7 +648,7 @@ static int b200_stage_in(parsec_device_b200_module_t *dev, b200_task_t *bt, int 
                 tile.version = (PARSEC_FLOW_ACCESS_WRITE & type) ? out->version - 1 : out->version;
                 if( NULL != original->device_copies[0] && NULL != original->device_copies[0]->device_private )
                     tile.src_ptr = b200_device_visible(original->device_copies[0]->device_private, span);
-                if( PB2_SUCCESS != pb2_stream_set_tile(dev->stream, b200_tile_of(dev, out), &tile) ) return PARSEC_HOOK_RETURN_ERROR;
+                if( 0 != b200_emit_tile(dev, bt, b200_tile_of(dev, out), &tile) ) return PARSEC_HOOK_RETURN_ERROR;
                 dev->tile_described[b200_tile_of(dev, out)] = 1;
             }
             continue;
@@ -712,7 +754,7 @@ static int b200_stage_in(parsec_device_b200_module_t *dev, b200_task_t *bt, int 
              * the kernel left it (STAGING), not a fresh "VALID" from the host. */
             const int32_t tid = b200_tile_of(dev, out);
             if( -1 != transfer_from || !dev->tile_described[tid] ) {
-                if( PB2_SUCCESS != pb2_stream_set_tile(dev->stream, tid, &tile) ) { parsec_atomic_unlock(&original->lock); return PARSEC_HOOK_RETURN_ERROR; }
+                if( 0 != b200_emit_tile(dev, bt, tid, &tile) ) { parsec_atomic_unlock(&original->lock); return PARSEC_HOOK_RETURN_ERROR; }
                 dev->tile_described[tid] = 1;
             }
         }
@@ -827,8 +869,10 @@ static int b200_epilog_flows(parsec_device_b200_module_t *dev, b200_task_t *bt, 
                 gpu_copy->coherency_state = PARSEC_DATA_COHERENCY_OWNED;
                 b200_lru_put(dev, &dev->super.super.gpu_mem_owned_lru, gpu_copy);
             }
-        } else if( 1 == gpu_copy->readers && 0 != (gpu_copy->flags & PARSEC_DATA_FLAG_PARSEC_OWNED) ) {
-            /* least recently used goes to the front: the last reader of a replica moves it to the back of its list */
+        } else if( dev->memory_pressure && 1 == gpu_copy->readers && 0 != (gpu_copy->flags & PARSEC_DATA_FLAG_PARSEC_OWNED) ) {
+            /* least recently used goes to the front: the last reader of a replica moves it to the back of its list.  The
+             * order only matters once something has to be evicted: until the heap has been full once the lists keep
+             * their insertion order and the readers of a replica do not queue up on the LRU lock. */
             b200_lru_touch(dev, gpu_copy);
         }
         if( locked ) parsec_atomic_unlock(&original->lock);
@@ -840,36 +884,56 @@ static parsec_hook_return_t b200_epilog_hook(parsec_execution_stream_t *es, pars
 {
     b200_task_t *bt = (b200_task_t*)((char*)task - offsetof(b200_task_t, proxy));
     parsec_device_b200_module_t *dev = bt->dev;
-    parsec_gpu_task_t *gpu_task = bt->gpu_task;
-    parsec_data_copy_t *held[MAX_PARAM_COUNT];
-    const int nheld = b200_epilog_flows(dev, bt, held);
-    (void)__parsec_complete_execution(es, gpu_task->ec);
-    for( int i = 0; i < nheld; i++ ) (void)parsec_atomic_fetch_dec_int32(&held[i]->readers);
-    gpu_task->last_data_check_epoch = 0;
-    gpu_task->release_device_task(gpu_task);
-    b200_bt_free(bt);          /* the proxy lives in the record: nothing of it is touched after this hook returns ASYNC */
-    if( dev->nb_stalled > 0 ) dev->retry_stalled = 1;      /* the readers just dropped may be what a waiting task needs evicted */
+    int64_t n = 0;
+    /* one proxy completes a short chain of finished tasks (B200_EPILOG_BATCH): scheduling a task costs the manager about
+     * as much as everything else it does for one */
+    while( NULL != bt ) {
+        b200_task_t *next = bt->next_done;
+        parsec_gpu_task_t *gpu_task = bt->gpu_task;
+        parsec_data_copy_t *held[MAX_PARAM_COUNT];
+        if( NULL != next ) { B200_PF(next); B200_PF(next->gpu_task); }
+        const int nheld = b200_epilog_flows(dev, bt, held);
+        (void)__parsec_complete_execution(es, gpu_task->ec);
+        for( int i = 0; i < nheld; i++ ) (void)parsec_atomic_fetch_dec_int32(&held[i]->readers);
+        gpu_task->last_data_check_epoch = 0;
+        gpu_task->release_device_task(gpu_task);
+        b200_bt_free(bt);          /* the proxy lives in the record: nothing of it is touched after this hook returns ASYNC */
+        bt = next;
+        n++;
+    }
+    if( dev->nb_stalled > 0 && !dev->retry_stalled ) dev->retry_stalled = 1;   /* the readers just dropped may be what a waiting task needs evicted */
     parsec_atomic_wmb();
-    (void)parsec_atomic_fetch_add_int64(&dev->epilogs_done, 1);
+    (void)parsec_atomic_fetch_add_int64(&dev->epilogs_done, n);
     return PARSEC_HOOK_RETURN_ASYNC;
+}
+
+#define B200_EPILOG_BATCH 4
+/* the chain collected so far becomes one proxy task of the completion ring */
+static inline void b200_close_batch(parsec_device_b200_module_t *dev)
+{
+    b200_task_t *bt = dev->batch_head;
+    if( NULL == bt ) return;
+    dev->batch_head = NULL; dev->batch_len = 0;
+    PARSEC_LIST_ITEM_SINGLETON(&bt->proxy);
+    if( NULL == dev->completion_ring ) dev->completion_ring = &bt->proxy;
+    else parsec_list_item_ring_push((parsec_list_item_t*)dev->completion_ring, (parsec_list_item_t*)&bt->proxy);
 }
 
 /* manager side of a finished kernel task */
 static void b200_complete(parsec_device_b200_module_t *dev, parsec_execution_stream_t *es, b200_task_t *bt)
 {
-    parsec_gpu_task_t *gpu_task = bt->gpu_task;
     dev->super.super.super.executed_tasks++;
     dev->completed_now++;
     if( parsec_b200_parallel_completion && !bt->has_complete_stage ) {
         /* nothing of the task but its record is touched here */
         dev->epilogs_started++;
-        PARSEC_LIST_ITEM_SINGLETON(&bt->proxy);
-        if( NULL == dev->completion_ring ) dev->completion_ring = &bt->proxy;
-        else parsec_list_item_ring_push((parsec_list_item_t*)dev->completion_ring, (parsec_list_item_t*)&bt->proxy);
+        bt->next_done = dev->batch_head; dev->batch_head = bt;
+        if( ++dev->batch_len >= B200_EPILOG_BATCH ) b200_close_batch(dev);
         return;
     }
     /* in line: a user completion hook (device_gpu.h:41-43; dtd_test_simple_gemm.c:538) is called by the thread that
      * drives the device, like the reference does, and device_b200_parallel_completion = 0 asks for it */
+    parsec_gpu_task_t *gpu_task = bt->gpu_task;
     parsec_data_copy_t *held[MAX_PARAM_COUNT];
     const int nheld = b200_epilog_flows(dev, bt, held);
     if( NULL != gpu_task->complete_stage ) {
@@ -962,7 +1026,7 @@ static int b200_push_engine(parsec_device_b200_module_t *dev, b200_task_t *bt)
         parsec_warning("device_b200: submit failed: %s", pb2_stream_last_error(dev->stream));
         return PARSEC_HOOK_RETURN_ERROR;
     }
-    dev->st.tasks_engine++;
+    dev->n_engine++;
     return PARSEC_HOOK_RETURN_DONE;
 }
 
@@ -1039,7 +1103,7 @@ static int b200_start_task(parsec_device_b200_module_t *dev, parsec_execution_st
         rc = b200_stage_in(dev, bt, 0);
         if( rc < 0 ) return rc;
         c1 = B200_TSC(); dev->tsc_start[1] += c1 - c0; c0 = c1;
-        dev->cold_inflight += (int64_t)bt->cold_bytes;
+        if( bt->cold_bytes ) (void)parsec_atomic_fetch_add_int64(&dev->cold_inflight, (int64_t)bt->cold_bytes);
         int src = 0;
         if( !bt->recorded ) {             /* normally done by the thread that called kernel_scheduler */
             b200_tl_recording = bt;
@@ -1071,7 +1135,7 @@ static int b200_start_task(parsec_device_b200_module_t *dev, parsec_execution_st
     const int user_in = (NULL != gpu_task->stage_in && gpu_task->stage_in != parsec_default_gpu_stage_in);
     rc = b200_stage_in(dev, bt, user_in ? 2 : 1);
     if( rc < 0 ) return rc;
-    dev->cold_inflight += (int64_t)bt->cold_bytes;
+    if( bt->cold_bytes ) (void)parsec_atomic_fetch_add_int64(&dev->cold_inflight, (int64_t)bt->cold_bytes);
     if( user_in ) {
         uint32_t mask = 0;
         for( uint32_t i = 0; i < gpu_task->nb_flows; i++ )
@@ -1119,7 +1183,7 @@ static int b200_start_task(parsec_device_b200_module_t *dev, parsec_execution_st
         }
     B200_CUDA(cudaEventRecord(b200_bt_event(dev, bt), dev->lane->cuda_stream), "cudaEventRecord", {});
     bt->state = BT_LANE;
-    dev->st.tasks_lane++;
+    dev->n_lane++;
     parsec_list_nolock_push_back(&dev->waiting_event, &bt->item);
     return PARSEC_HOOK_RETURN_DONE;
 }
@@ -1217,10 +1281,10 @@ static int b200_data_advise(parsec_device_module_t *module, parsec_data_t *data,
 /* ------------------------------------------------------------------------------------------------------------------ */
 static void b200_finish(parsec_device_b200_module_t *dev, parsec_execution_stream_t *es, b200_task_t *bt)
 {
+    if( bt->cold_bytes ) { (void)parsec_atomic_fetch_add_int64(&dev->cold_inflight, -(int64_t)bt->cold_bytes); bt->cold_bytes = 0; }
+    if( !dev->retry_stalled ) dev->retry_stalled = 1;     /* a retirement frees ring space, reopens the stage-in window, unpins replicas */
+    if( bt->is_kernel ) { b200_complete(dev, es, bt); return; }
     parsec_gpu_task_t *gpu_task = bt->gpu_task;
-    dev->cold_inflight -= (int64_t)bt->cold_bytes; bt->cold_bytes = 0;
-    dev->retry_stalled = 1;           /* a retirement frees ring space, reopens the stage-in window, unpins replicas */
-    if( PARSEC_GPU_TASK_TYPE_KERNEL == gpu_task->task_type ) { b200_complete(dev, es, bt); return; }
     /* pseudo task: the replica is resident and valid now; no runtime completion */
     parsec_data_copy_t *out = gpu_task->ec->data[0].data_out;
     if( NULL != out ) {
@@ -1240,45 +1304,62 @@ static void b200_finish(parsec_device_b200_module_t *dev, parsec_execution_strea
     dev->completed_now++;
 }
 
-/* The manager: inbox, starts, events of the copy-engine / lane paths, retire ring.
- * returns < 0 on a fatal device problem */
-static int b200_progress(parsec_device_b200_module_t *dev, parsec_execution_stream_t *es)
+/* inbox -> lists of tasks to start, in slot order (starter only).  A slot whose index has been taken but whose pointer
+ * is not there yet ends the pass: its caller is a few instructions away from storing it.  The tile descriptions a caller
+ * decided go to the device here, in the order of the decisions.  returns the number of records taken, < 0 on error */
+static int b200_drain_inbox(parsec_device_b200_module_t *dev)
+{
+    int64_t head = dev->inbox_head;
+    const int64_t head0 = head;
+    for(;;) {
+        b200_task_t * volatile *slot = &dev->inbox_ring[head & (B200_INBOX_SLOTS - 1)];
+        b200_task_t *bt = *slot;
+        if( NULL == bt ) break;
+        parsec_atomic_rmb();
+        *slot = NULL;
+        head++;
+        {   /* the records a few slots further on: written by other cores a moment ago */
+            const char *la = (const char*)dev->inbox_ring[(head + 6) & (B200_INBOX_SLOTS - 1)];
+            if( NULL != la ) { B200_PFW(la); B200_PFW(la + 64); B200_PF(la + offsetof(b200_task_t, cmd)); }
+        }
+        for( int k = 0; k < bt->ntdesc; k++ )
+            if( PB2_SUCCESS != pb2_stream_set_tile(dev->stream, bt->tdesc[k].tile, &bt->tdesc[k].desc) ) return -1;
+        bt->ntdesc = 0; bt->defer_tiles = 0;
+        switch( bt->prepared ) {
+        case 1:  parsec_list_nolock_push_back(&dev->settled, &bt->item); dev->nb_settled++; dev->n_settled_by_caller++; break;
+        case 2:  parsec_list_nolock_push_back(&dev->cold_q, &bt->item); dev->nb_cold++; dev->n_settled_by_caller++; break;
+        case 3:  bt->state = BT_DMA_IN; parsec_list_nolock_push_back(&dev->waiting_event, &bt->item);
+                 if( bt->cold_bytes ) (void)parsec_atomic_fetch_add_int64(&dev->cold_inflight, (int64_t)bt->cold_bytes);
+                 break;
+        default: parsec_list_nolock_push_back(&dev->stalled, &bt->item); dev->nb_stalled++; break;
+        }
+    }
+    if( head != head0 ) { dev->inbox_head = head; dev->retry_stalled = 1; }
+    return (int)(head - head0);
+}
+
+/* The STARTER's pass: inbox, starts, events of the stage-in / lane paths.  Called with `starter_active` held.
+ * returns the number of tasks it moved forward (0: nothing to do right now), < 0 on a fatal device problem */
+static int b200_start_pass(parsec_device_b200_module_t *dev, parsec_execution_stream_t *es)
 {
     uint64_t t0 = B200_TSC(), t1;
-    /* 1. inbox -> list of tasks to start, in slot order.  A slot whose index has been taken but whose pointer is not
-     *    there yet ends the pass: its caller is a few instructions away from storing it. */
+    int moved = 0;
+    /* 1. inbox */
     {
-        int64_t head = dev->inbox_head;
-        const int64_t head0 = head;
-        for(;;) {
-            b200_task_t * volatile *slot = &dev->inbox_ring[head & (B200_INBOX_SLOTS - 1)];
-            b200_task_t *bt = *slot;
-            if( NULL == bt ) break;
-            parsec_atomic_rmb();
-            *slot = NULL;
-            head++;
-            {   /* the records a few slots further on: written by other cores a moment ago */
-                const char *la = (const char*)dev->inbox_ring[(head + 6) & (B200_INBOX_SLOTS - 1)];
-                if( NULL != la ) { B200_PFW(la); B200_PFW(la + 64); B200_PF(la + offsetof(b200_task_t, cmd)); }
-            }
-            if( bt->prepared ) { parsec_list_nolock_push_back(&dev->settled, &bt->item); dev->nb_settled++; }
-            else { parsec_list_nolock_push_back(&dev->stalled, &bt->item); dev->nb_stalled++; }
-        }
-        if( head != head0 ) { dev->inbox_head = head; dev->retry_stalled = 1; }
+        const int n = b200_drain_inbox(dev);
+        if( n < 0 ) return -1;
+        moved += n;
     }
-    t1 = B200_TSC(); dev->tsc[0] += t1 - t0; t0 = t1;
+    t1 = B200_TSC(); dev->tsc_s[0] += t1 - t0; t0 = t1;
     /* 2. start tasks.  Settled tasks first (they only need a slot in the command ring; the stage-ins in flight are for
      *    them), then the others, oldest first.  A task that cannot get device memory stays where it is and the
      *    ones behind it are tried: their inputs may be resident already (they hold references that keep
      *    replicas from being evicted), and their retirement is what frees memory.  A full command ring stops the pass,
      *    and so does the stage-in window (a throttle, not a shortage: retirements reopen it). */
     int started = 0;
-    /* references that keep a replica from being evicted are also dropped where nobody tells the device (the data
-     * repositories of the runtime): a blocked task is retried every so often whatever happened */
-    if( (dev->nb_settled > 0 || dev->nb_stalled > 0) && !dev->retry_stalled && ++dev->blocked_spins >= 1024 ) dev->retry_stalled = 1;
-    if( dev->retry_stalled && (dev->nb_settled > 0 || dev->nb_stalled > 0) ) {
+    if( dev->retry_stalled && (dev->nb_settled > 0 || dev->nb_stalled > 0 || dev->nb_cold > 0) ) {
         int ring_full = 0, cut = 0;
-        dev->retry_stalled = 0; dev->blocked_spins = 0;
+        dev->retry_stalled = 0;
         while( dev->nb_settled > 0 ) {
             if( started >= 512 ) { cut = 1; break; }            /* then look at the retire ring again */
             b200_task_t *bt = (b200_task_t*)PARSEC_LIST_ITERATOR_FIRST(&dev->settled);
@@ -1292,6 +1373,25 @@ static int b200_progress(parsec_device_b200_module_t *dev, parsec_execution_stre
             if( PARSEC_HOOK_RETURN_AGAIN == rc ) { parsec_list_nolock_push_front(&dev->settled, &bt->item); ring_full = 1; break; }
             if( PARSEC_HOOK_RETURN_DONE != rc ) return -1;
             dev->nb_settled--;
+            started++;
+        }
+        /* tasks whose caller decided a stage-in: in order, behind the stage-in window.  The worker CTAs of the persistent
+         * kernel would happily start thousands of PCIe pulls at once; they would then all finish together, tens of
+         * milliseconds later, and their successors with them.  Keeping only a few link round-trips worth of cold bytes
+         * in flight makes tasks retire as a steady stream. */
+        while( !ring_full && !cut && dev->nb_cold > 0 ) {
+            if( started >= 512 ) { cut = 1; break; }
+            b200_task_t *bt = (b200_task_t*)PARSEC_LIST_ITERATOR_FIRST(&dev->cold_q);
+            if( bt->cold_bytes && dev->cold_inflight >= (int64_t)parsec_b200_stage_window ) break;
+            parsec_list_nolock_remove(&dev->cold_q, &bt->item);
+            PARSEC_LIST_ITEM_SINGLETON(&bt->item);
+            if( BT_NEW == bt->state ) bt->state = BT_STAGED;
+            const uint64_t cold = bt->cold_bytes;          /* the record may be recycled the moment the command is out */
+            const int rc = b200_push_engine(dev, bt);
+            if( PARSEC_HOOK_RETURN_AGAIN == rc ) { parsec_list_nolock_push_front(&dev->cold_q, &bt->item); ring_full = 1; break; }
+            if( PARSEC_HOOK_RETURN_DONE != rc ) return -1;
+            if( cold ) (void)parsec_atomic_fetch_add_int64(&dev->cold_inflight, (int64_t)cold);
+            dev->nb_cold--;
             started++;
         }
         parsec_list_item_t *it = PARSEC_LIST_ITERATOR_FIRST(&dev->stalled), *next;
@@ -1314,8 +1414,15 @@ static int b200_progress(parsec_device_b200_module_t *dev, parsec_execution_stre
             if( mem_blocked && BT_NEW == bt->state && b200_needs_memory(dev, bt->gpu_task) ) continue;
             parsec_list_nolock_remove(&dev->stalled, it);
             PARSEC_LIST_ITEM_SINGLETON(it);
-            if( BT_NEW == bt->state ) rc = b200_start_task(dev, es, bt);
-            else rc = b200_push_engine(dev, bt);            /* staged, waiting for ring space */
+            if( BT_NEW == bt->state ) {
+                /* residency is decided under the lock, after everything the callers have decided so far has reached the
+                 * device (their records are in the inbox: they push before they let the lock go) */
+                b200_lock(&dev->alloc_lock);
+                const int n = b200_drain_inbox(dev);
+                rc = (n < 0) ? PARSEC_HOOK_RETURN_ERROR : b200_start_task(dev, es, bt);
+                b200_unlock(&dev->alloc_lock);
+                if( n > 0 ) moved += n;
+            } else rc = b200_push_engine(dev, bt);            /* staged, waiting for ring space */
             if( PARSEC_HOOK_RETURN_AGAIN == rc ) {
                 /* back where it was */
                 if( next == PARSEC_LIST_ITERATOR_END(&dev->stalled) ) parsec_list_nolock_push_back(&dev->stalled, it);
@@ -1332,7 +1439,7 @@ static int b200_progress(parsec_device_b200_module_t *dev, parsec_execution_stre
         if( cut ) dev->retry_stalled = 1;
     }
     if( started && PB2_SUCCESS != pb2_stream_kick(dev->stream) ) return -1;
-    t1 = B200_TSC(); dev->tsc[1] += t1 - t0; t0 = t1;
+    t1 = B200_TSC(); dev->tsc_s[1] += t1 - t0; t0 = t1;
     /* 3. copy-engine / lane events */
     if( !parsec_list_nolock_is_empty(&dev->waiting_event) ) {
         parsec_list_item_t *it = PARSEC_LIST_ITERATOR_FIRST(&dev->waiting_event), *next;
@@ -1362,12 +1469,41 @@ static int b200_progress(parsec_device_b200_module_t *dev, parsec_execution_stre
                 else if( PARSEC_HOOK_RETURN_DONE != rc ) return -1;
                 else if( PB2_SUCCESS != pb2_stream_kick(dev->stream) ) return -1;
             } else {
-                b200_finish(dev, es, bt);               /* BT_LANE, BT_DMA_OUT */
+                /* BT_LANE: finished; completion belongs to the manager */
+                b200_task_t *old;
+                do { old = dev->lane_done; bt->next_done = old; } while( !parsec_atomic_cas_ptr(&dev->lane_done, old, bt) );
             }
+            moved++;
         }
     }
-    t1 = B200_TSC(); dev->tsc[2] += t1 - t0; t0 = t1;
-    /* 4. retire ring */
+    t1 = B200_TSC(); dev->tsc_s[2] += t1 - t0; t0 = t1;
+    return moved + started;
+}
+
+/* The MANAGER's pass: retire ring, copy-engine pushouts, lane tasks the starter saw finish.
+ * returns < 0 on a fatal device problem */
+static int b200_retire_pass(parsec_device_b200_module_t *dev, parsec_execution_stream_t *es)
+{
+    uint64_t t0 = B200_TSC(), t1;
+    if( dev->fatal ) return -1;
+    if( NULL != dev->lane_done ) {
+        b200_task_t *bt = dev->lane_done;
+        while( !parsec_atomic_cas_ptr(&dev->lane_done, bt, NULL) ) bt = dev->lane_done;
+        while( NULL != bt ) { b200_task_t *next = bt->next_done; b200_finish(dev, es, bt); bt = next; }
+    }
+    if( !parsec_list_nolock_is_empty(&dev->waiting_out) ) {
+        parsec_list_item_t *it = PARSEC_LIST_ITERATOR_FIRST(&dev->waiting_out), *next;
+        for( ; it != PARSEC_LIST_ITERATOR_END(&dev->waiting_out); it = next ) {
+            b200_task_t *bt = (b200_task_t*)it;
+            next = PARSEC_LIST_ITERATOR_NEXT(it);
+            cudaError_t q = cudaEventQuery(bt->ev);
+            if( cudaErrorNotReady == q ) { (void)cudaGetLastError(); continue; }
+            if( cudaSuccess != q ) { parsec_warning("device_b200: event failed: %s", cudaGetErrorString(q)); return -1; }
+            parsec_list_nolock_remove(&dev->waiting_out, it);
+            PARSEC_LIST_ITEM_SINGLETON(it);
+            b200_finish(dev, es, bt);
+        }
+    }
     for(;;) {
         int n = pb2_stream_poll(dev->stream, dev->retbuf, (int32_t)(sizeof(dev->retbuf) / sizeof(dev->retbuf[0])));
         if( n < 0 ) { parsec_warning("device_b200: %s", pb2_stream_last_error(dev->stream)); return -1; }
@@ -1381,19 +1517,46 @@ static int b200_progress(parsec_device_b200_module_t *dev, parsec_execution_stre
                 return -1;
             }
             bt->result = dev->retbuf[i].result;
-            if( PB2_BODY_CHECK_I32 == bt->body || PB2_BODY_CHECK_F32 == bt->body ) dev->st.check_mismatches += bt->result >> 32;
+            if( (PB2_BODY_CHECK_I32 == bt->body || PB2_BODY_CHECK_F32 == bt->body) && (bt->result >> 32) ) dev->st.check_mismatches += bt->result >> 32;
             bt->ticket = -1;
             if( PB2_SUCCESS != dev->retbuf[i].status ) { parsec_warning("device_b200: task ran an unknown engine body"); return -1; }
             if( bt->dma_out_mask && b200_dma_pushout(dev, bt) > 0 ) {
                 bt->state = BT_DMA_OUT;
-                parsec_list_nolock_push_back(&dev->waiting_event, &bt->item);
+                parsec_list_nolock_push_back(&dev->waiting_out, &bt->item);
             } else b200_finish(dev, es, bt);
         }
         t1 = B200_TSC(); dev->tsc[4] += t1 - t0; t0 = t1;
         if( n < (int)(sizeof(dev->retbuf) / sizeof(dev->retbuf[0])) ) break;
     }
+    b200_close_batch(dev);
     return 0;
 }
+
+/* is there anything a starter could do right now? (racy reads: a wrong answer costs one empty pass or one iteration) */
+static inline int b200_start_work(const parsec_device_b200_module_t *dev)
+{
+    return dev->inbox_tail != dev->inbox_head ||
+           ((dev->nb_stalled > 0 || dev->nb_settled > 0 || dev->nb_cold > 0) && dev->retry_stalled) ||
+           !parsec_list_nolock_is_empty((parsec_list_t*)&dev->waiting_event);
+}
+
+/* Take the starter role if it is free and run passes while they move something.  returns < 0 on a fatal problem. */
+static int b200_try_start(parsec_device_b200_module_t *dev, parsec_execution_stream_t *es, int sticky)
+{
+    for(;;) {
+        if( dev->starter_active || !parsec_atomic_cas_int32(&dev->starter_active, 0, 1) ) return 0;
+        int rc;
+        do { rc = b200_start_pass(dev, es); } while( rc > 0 && sticky );
+        if( rc < 0 ) dev->fatal = 1;
+        parsec_atomic_wmb();
+        dev->starter_active = 0;
+        parsec_mfence();
+        if( rc < 0 ) return -1;
+        /* a task that arrived between the last look at the inbox and the release of the role must not be left behind */
+        if( dev->inbox_tail == dev->inbox_head ) return 0;
+    }
+}
+
 
 static parsec_hook_return_t
 b200_kernel_scheduler(parsec_device_module_t *module, parsec_execution_stream_t *es, void *_gpu_task)
@@ -1401,9 +1564,9 @@ b200_kernel_scheduler(parsec_device_module_t *module, parsec_execution_stream_t 
     parsec_device_b200_module_t *dev = (parsec_device_b200_module_t*)module;
     parsec_gpu_task_t *gpu_task = (parsec_gpu_task_t*)_gpu_task;
 
-    if( 0 == dev->st.first_entry_ns ) dev->st.first_entry_ns = b200_now_ns();
+    if( 0 == dev->first_entry_ns ) dev->first_entry_ns = b200_now_ns();
     int32_t inside = parsec_atomic_fetch_inc_int32(&dev->callers_inside) + 1;
-    if( (uint64_t)inside > dev->st.max_concurrent_callers ) dev->st.max_concurrent_callers = (uint64_t)inside;
+    if( inside > dev->max_callers_inside ) dev->max_callers_inside = inside;
     /* 0. What does not need a decision of the manager is done here, by the calling thread, in parallel with every other
      *    caller -- it built the gpu_task a moment ago and ran prepare_input on the task: every line is in its cache,
      *    while the manager would have to pull each of them from here, and one thread paying a dozen cache-to-cache
@@ -1429,23 +1592,47 @@ b200_kernel_scheduler(parsec_device_module_t *module, parsec_execution_stream_t 
         else { bt->recorded = 1; bt->body = PB2_BODY_NOP; bt->nb_args = 0; }   /* dry run: an opaque body is a no-op */
     }
     bt->has_complete_stage = (NULL != gpu_task->complete_stage);     /* a body may install one (dtd_test_simple_gemm.c:538) */
-    if( bt->recorded && PARSEC_GPU_TASK_TYPE_KERNEL == gpu_task->task_type ) (void)b200_prepare_resident(dev, bt);
+    int decided = 0;
+    if( bt->recorded && bt->is_kernel && !b200_prepare_resident(dev, bt) && dev->nb_stalled < 64 &&
+        dev->inbox_tail - dev->inbox_head < B200_INBOX_SLOTS - 4096 /* never wait for an inbox slot with the lock held */ ) {
+        /*  - for an engine task that needs replicas made or filled: the same decisions the starter would take (heap,
+         *    source, versions), under the residency lock.  The tile descriptions ride in the record. */
+        b200_lock(&dev->alloc_lock);
+        decided = 1;
+        bt->defer_tiles = 1;
+        if( PARSEC_HOOK_RETURN_DONE == b200_reserve(dev, bt) ) {
+            const int rc = b200_stage_in(dev, bt, 0);
+            if( 0 == rc ) { b200_build_cmd(dev, bt); bt->prepared = 2; }
+            else if( rc > 0 ) {                      /* unregistered host memory: the copy engine brings it, the starter waits for the event */
+                B200_CUDA(cudaEventRecord(b200_bt_event(dev, bt), dev->dma_stream), "cudaEventRecord", {});
+                bt->prepared = 3;
+            } else if( PARSEC_HOOK_RETURN_AGAIN != rc ) dev->fatal = 1;
+            /* AGAIN: a peer replica is being reclaimed; nothing was changed, the starter retries */
+        }
+        if( 0 == bt->prepared ) bt->defer_tiles = (bt->ntdesc > 0);     /* descriptions decided before a failure still go first */
+    }
     /* 1. one more task is owed, THEN it is handed over.  In this order the manager can never complete a task whose debt
      *    has not been booked yet: booking first keeps `owed` from dropping to zero -- and a second manager from being
      *    elected -- while a task is on its way into the inbox. */
     int32_t before = parsec_atomic_fetch_add_int32(&dev->owed, 1);
     {
         const int64_t idx = parsec_atomic_fetch_add_int64(&dev->inbox_tail, 1);
-        while( idx - dev->inbox_head >= B200_INBOX_SLOTS ) { _mm_pause(); }   /* ring full: the manager is draining it */
+        while( idx - dev->inbox_head >= B200_INBOX_SLOTS ) { _mm_pause(); }   /* ring full: the starter is draining it */
         parsec_atomic_wmb();
         dev->inbox_ring[idx & (B200_INBOX_SLOTS - 1)] = bt;
     }
+    if( decided ) b200_unlock(&dev->alloc_lock);
     (void)parsec_atomic_fetch_dec_int32(&dev->callers_inside);
-    if( before > 0 ) return PARSEC_HOOK_RETURN_ASYNC;        /* somebody is driving the device and owes this task too */
+    if( before > 0 ) {
+        /* somebody manages the device and owes this task too.  If nobody is STARTING tasks right now, this thread does,
+         * for as long as tasks keep arriving: starts and retirements then proceed on two cores. */
+        (void)b200_try_start(dev, es, 1);
+        return PARSEC_HOOK_RETURN_ASYNC;
+    }
 
     /* 2. this thread is the manager until nothing is owed any more */
     dev->st.manager_entries++;
-    if( 0 == dev->st.first_task_ns ) dev->st.first_task_ns = b200_now_ns();
+    if( 0 == dev->first_task_ns ) dev->first_task_ns = b200_now_ns();
     if( NULL == es ) {
         /* data_advise comes without an execution stream and owes no runtime completion: it cannot complete other
          * threads' tasks, so it only drives the device until its own pseudo task is done */
@@ -1457,10 +1644,18 @@ b200_kernel_scheduler(parsec_device_module_t *module, parsec_execution_stream_t 
     for(;;) {
         dev->completed_now = 0;
         if( 0 == (++idle_spins & 0x3ffffff) && NULL != getenv("PARSEC_B200_DEBUG") ) {
-            fprintf(stderr, "b200 manager stuck? owed %d inbox %ld stalled %d stream inflight %d executed %lu\n",
-                    dev->owed, (long)(dev->inbox_tail - dev->inbox_head), dev->nb_stalled, pb2_stream_inflight(dev->stream), (unsigned long)module->executed_tasks);
+            fprintf(stderr, "b200 manager stuck? owed %d inbox %ld stalled %d settled %d starter %d retry %d stream inflight %d executed %lu\n",
+                    dev->owed, (long)(dev->inbox_tail - dev->inbox_head), dev->nb_stalled, dev->nb_settled, dev->starter_active, dev->retry_stalled,
+                    pb2_stream_inflight(dev->stream), (unsigned long)module->executed_tasks);
         }
-        if( b200_progress(dev, es) < 0 ) {
+        /* the starter role, when nobody has it: one pass, then back to the retire ring */
+        if( (dev->nb_stalled > 0 || dev->nb_settled > 0 || dev->nb_cold > 0) && ++dev->blocked_spins >= 1024 ) {
+            /* references that keep a replica from being evicted are also dropped where nobody tells the device (the data
+             * repositories of the runtime): a waiting task is retried every so often whatever happened */
+            dev->blocked_spins = 0; dev->retry_stalled = 1;
+        }
+        if( b200_start_work(dev) && b200_try_start(dev, es, 0) < 0 ) dev->fatal = 1;
+        if( b200_retire_pass(dev, es) < 0 ) {
             parsec_warning("GPU[%d:%s]: the device engine reported a fatal error; giving up", module->device_index, module->name);
             return PARSEC_HOOK_RETURN_DISABLE;
         }
@@ -1478,7 +1673,7 @@ b200_kernel_scheduler(parsec_device_module_t *module, parsec_execution_stream_t 
             idle_spins = 0;
             /* the subtraction that reaches zero is the LAST thing a manager does with the device */
             const int32_t left = parsec_atomic_fetch_sub_int32(&dev->owed, done_now) - done_now;
-            if( 0 == left ) { dev->st.last_done_ns = b200_now_ns(); return PARSEC_HOOK_RETURN_ASYNC; }
+            if( 0 == left ) { dev->last_done_ns = b200_now_ns(); return PARSEC_HOOK_RETURN_ASYNC; }
             if( left < 0 ) {
                 parsec_warning("GPU[%d:%s]: more tasks completed than were handed over (%d)", module->device_index, module->name, left);
                 return PARSEC_HOOK_RETURN_DISABLE;
@@ -1604,10 +1799,12 @@ static void b200_registration_cache_drop(parsec_device_b200_module_t *dev)
 static void b200_profile_print(parsec_device_b200_module_t *dev)
 {
     if( NULL == getenv("PARSEC_B200_PROFILE") ) return;
-    uint64_t tot = 0; for( int i = 0; i < 7; i++ ) tot += dev->tsc[i];
-    fprintf(stderr, "b200 manager Mcycles: inbox %.1f start %.1f events %.1f poll %.1f finish %.1f idle-poll %.1f schedule %.1f (total %.1f, %lu tasks so far, %lu manager entries)\n",
-            dev->tsc[0] * 1e-6, dev->tsc[1] * 1e-6, dev->tsc[2] * 1e-6, dev->tsc[3] * 1e-6, dev->tsc[4] * 1e-6, dev->tsc[5] * 1e-6, dev->tsc[6] * 1e-6,
+    uint64_t tot = 0; for( int i = 3; i < 7; i++ ) tot += dev->tsc[i];
+    fprintf(stderr, "b200 starter Mcycles: inbox %.1f start %.1f events %.1f (total %.1f, %lu settled by their caller) | manager Mcycles: poll %.1f finish %.1f idle-poll %.1f schedule %.1f (total %.1f, %lu tasks so far, %lu manager entries)\n",
+            dev->tsc_s[0] * 1e-6, dev->tsc_s[1] * 1e-6, dev->tsc_s[2] * 1e-6, (dev->tsc_s[0] + dev->tsc_s[1] + dev->tsc_s[2]) * 1e-6, (unsigned long)dev->n_settled_by_caller,
+            dev->tsc[3] * 1e-6, dev->tsc[4] * 1e-6, dev->tsc[5] * 1e-6, dev->tsc[6] * 1e-6,
             tot * 1e-6, (unsigned long)dev->super.super.super.executed_tasks, (unsigned long)dev->st.manager_entries);
+    memset(dev->tsc_s, 0, sizeof dev->tsc_s);
     fprintf(stderr, "b200 manager start Mcycles: reserve %.1f stage-in %.1f record %.1f command %.1f\n",
             dev->tsc_start[0] * 1e-6, dev->tsc_start[1] * 1e-6, dev->tsc_start[2] * 1e-6, dev->tsc_start[3] * 1e-6);
     memset(dev->tsc, 0, sizeof dev->tsc); memset(dev->tsc_start, 0, sizeof dev->tsc_start);
@@ -1617,13 +1814,14 @@ static int b200_memory_release(parsec_device_module_t *device)
 {
     parsec_device_b200_module_t *dev = (parsec_device_b200_module_t*)device;
     b200_profile_print(dev);
-    dev->st.first_task_ns = dev->st.first_entry_ns = 0;
+    dev->first_task_ns = dev->first_entry_ns = 0;
     /* the tail of an epilog (letting go of the readers it held) may still be running on a worker thread */
     while( dev->epilogs_done < dev->epilogs_started ) { parsec_atomic_rmb(); }
     /* dirty replicas go home first: flush_lru would drop them with a warning (device_gpu.c:1033-1037) */
     if( !dev->dry_run ) (void)pb2_stream_quiesce(dev->stream);
     while( b200_write_back_some(dev, 64) > 0 ) { }
     const int rc = parsec_device_flush_lru(device);
+    dev->memory_pressure = 0;
     if( NULL != dev->tile_described ) memset(dev->tile_described, 0, (size_t)dev->super.super.mem_nb_blocks);
     return rc;
 }
@@ -1653,6 +1851,9 @@ int parsec_b200_get_stats(const parsec_device_module_t *device, parsec_b200_stat
     parsec_device_b200_module_t *dev = (parsec_device_b200_module_t*)device;
     pb2_stream_stats_t ss;
     *stats = dev->st;
+    stats->tasks_engine = dev->n_engine; stats->tasks_lane = dev->n_lane;
+    stats->first_entry_ns = dev->first_entry_ns; stats->first_task_ns = dev->first_task_ns; stats->last_done_ns = dev->last_done_ns;
+    stats->max_concurrent_callers = (uint64_t)dev->max_callers_inside;
     if( PB2_SUCCESS == pb2_stream_stats(dev->stream, &ss) ) {
         stats->kernel_launches = ss.kernel_launches; stats->released_on_device = ss.released_on_device;
         stats->bytes_h2d_kernel = ss.bytes_h2d; stats->bytes_d2d_kernel = ss.bytes_d2d; stats->bytes_d2h_kernel = ss.bytes_d2h;
@@ -1662,7 +1863,9 @@ int parsec_b200_get_stats(const parsec_device_module_t *device, parsec_b200_stat
 
 int parsec_b200_module_init(int dev_id, parsec_device_module_t **module)
 {
-    parsec_device_b200_module_t *dev = (parsec_device_b200_module_t*)calloc(1, sizeof(parsec_device_b200_module_t));
+    parsec_device_b200_module_t *dev = NULL;
+    if( 0 != posix_memalign((void**)&dev, 64, sizeof(parsec_device_b200_module_t)) ) return PARSEC_ERR_OUT_OF_RESOURCE;
+    memset(dev, 0, sizeof(parsec_device_b200_module_t));
     parsec_device_gpu_module_t *gpu = &dev->super.super;
     parsec_device_module_t *device = &gpu->super;
     *module = NULL;
@@ -1722,6 +1925,8 @@ int parsec_b200_module_init(int dev_id, parsec_device_module_t **module)
     PARSEC_OBJ_CONSTRUCT(&gpu->pending, parsec_fifo_t);
     PARSEC_OBJ_CONSTRUCT(&dev->stalled, parsec_list_t);
     PARSEC_OBJ_CONSTRUCT(&dev->settled, parsec_list_t);
+    PARSEC_OBJ_CONSTRUCT(&dev->waiting_out, parsec_list_t);
+    PARSEC_OBJ_CONSTRUCT(&dev->cold_q, parsec_list_t);
     PARSEC_OBJ_CONSTRUCT(&dev->waiting_event, parsec_list_t);
     memset(&dev->lru_lock, 0, sizeof dev->lru_lock);
     dev->inbox_ring = (b200_task_t * volatile *)calloc(B200_INBOX_SLOTS, sizeof(b200_task_t*));
