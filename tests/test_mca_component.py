@@ -143,3 +143,42 @@ def test_component_two_gpus_in_one_process_peer_pulls():
     assert d["b200_modules"] == 2 and d["b200"]["peer_pulls"] > 0 and d["b200"]["peer_detours"] == 0
     rc, d, err = run("stage_b200", ["-m", "gpu", "-c", 4], {"PARSEC_MCA_device_b200_enabled": "2"})
     assert rc == 0 and d["check_errors"] == 0 and d["host_errors"] == 0, err[-1000:]
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# DTD task pools (parsec_dtd_task_class_add_chore(PARSEC_DEV_CUDA) + parsec_dtd_insert_task_with_task_class) through the
+# component: golden vectors of tests/dsl/dtd/dtd_test_cuda_task_insert.c (0xFFFFFFFF), dtd_test_new_tile (2*i) and a
+# CPU <-> GPU ping-pong (start + hops)
+# ------------------------------------------------------------------------------------------------------------------------
+def test_dtd_reference_runtime_cpu_chores_known_answers():
+    rc, d, err = run("dtd_b200", ["-C", "-M", 8, "-n", 1024, "-N", 6, "-c", 4], CPU_ENV)
+    assert rc == 0 and d["total_errors"] == 0 and d["executed_on_gpu"] == 0, err[-800:]
+
+
+def test_dtd_component_dry_run_takes_every_dtd_gpu_task():
+    """DTD builds the parsec_gpu_task_t (insert_function.c:2393-2425); the component completes each exactly once."""
+    M, hops = 8, 6
+    rc, d, err = run("dtd_b200", ["-M", M, "-n", 1024, "-N", hops, "-c", 4], {"PARSEC_MCA_device_b200_dry_run": "1"})
+    assert d["b200_modules"] == 1, err[-800:]
+    # memset: odd tiles; memset_and_read: all; new_tile: two tasks per tile; pingpong: every other hop
+    assert d["executed_on_gpu"] == M // 2 + M + 2 * M + M * hops // 2 == d["tasks_engine"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("opaque", [False, True])
+def test_dtd_component_gpu_known_answers(opaque):
+    M, hops = 16, 8
+    rc, d, err = run("dtd_b200", ["-M", M, "-n", 4096, "-N", hops, "-c", 8] + (["-o"] if opaque else []), {"PARSEC_MCA_device_b200_enabled": "1"})
+    assert rc == 0 and d["total_errors"] == 0, (d, err[-1000:])
+    assert d["b200_modules"] == 1 and d["executed_on_gpu"] == M // 2 + M + 2 * M + M * hops // 2
+    assert d["bytes_h2d_dma"] > 0 and d["bytes_d2h_dma"] > 0        # pageable collection: the copy engine moves it
+    if opaque:
+        assert d["tasks_lane"] >= M // 2 + M                        # the cudaMemsetAsync bodies ran on the stream lane
+    else:
+        assert d["tasks_lane"] <= 4                                 # only the first task of each class (it teaches the module its body)
+
+
+@pytest.mark.gpu
+def test_dtd_reference_cuda_component_agrees():
+    rc, d, err = run("dtd_b200", ["-M", 16, "-n", 4096, "-N", 8, "-c", 8, "-o"], {"PARSEC_MCA_device_cuda_enabled": "1"})
+    assert rc == 0 and d["total_errors"] == 0 and d["b200_modules"] == 0 and d["gpu_modules"] == 1, (d, err[-1000:])
