@@ -149,7 +149,8 @@ def e2e_mca(K, ngpus, steps, cores):
     """e2e through the reference-facing plug-in: reference runtime + parsec/mca/device/b200, host buffers."""
     env = {"PARSEC_MCA_device_b200_enabled": str(ngpus),
            # the bench process keeps its own slabs on the same GPUs: give the component's heap what the workload needs
-           "PARSEC_MCA_device_b200_memory_number_of_blocks": str(max(2 * K // max(ngpus, 1), 1024) + 1024)}
+           # (a GPU holds its own K/N tiles plus the replicas of up to three peers' tiles that its receivers read)
+           "PARSEC_MCA_device_b200_memory_number_of_blocks": str(max(4 * K // max(ngpus, 1), 1024) + 1024)}
     warm = 2
     d = run_app("ex05_b200", ["-m", "gpu", "-K", K, "-t", TILE // 4, "-r", steps + warm, "-c", cores], env, timeout=240)
     if d is None:

@@ -60,32 +60,42 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 }
 
 // ---------------------------------------------------------------------------------------------
-// TMA bulk mover (cp.async.bulk, 1-D): global -> shared -> global through a two-deep shared-memory ring with
+// TMA bulk mover (cp.async.bulk, 1-D): global -> shared -> global through a kBulkDepth-deep shared-memory ring with
 // mbarrier completion.  One elected thread drives the whole pipeline, so a copy costs no payload registers and
-// keeps 2 x kBulkChunk bytes in flight per CTA whatever the latency of the source (pinned host memory over PCIe,
-// a peer GPU over NVLink, local HBM).  Requires 16-byte aligned addresses and a byte count that is a multiple
-// of 16; callers fall back to the SIMT loops of pb2_bodies.cuh otherwise.
+// keeps up to kBulkDepth x kBulkChunk bytes of LOADS in flight per CTA whatever the latency of the source (pinned host
+// memory over PCIe, a peer GPU over NVLink, local HBM): what a link delivers is bytes in flight / round trip, and a
+// 64-thread worker that pulls a tile is one of a few hundred CTAs doing so at any moment.  The store of chunk i and
+// the reload of the slot of chunk i-1 overlap (wait_group.read 1), so depth-1 loads stay in flight all the time.
+// Depth 2 is the measured choice (r02): a 4-deep ring (16 KiB per worker, 203 KiB per SM) leaves the SM 28 KiB of L1 and
+// the resident Ex05 window drops from 60 to 46 M tasks/s, while the PCIe-bound e2e step does not move.
+// Requires 16-byte aligned addresses and a byte count that is a multiple of 16; callers fall back to the SIMT loops
+// of pb2_bodies.cuh otherwise.
 // This is the device-side replacement of the cudaMemcpyAsync per flow in parsec_default_gpu_stage_in / _stage_out
 // (parsec/mca/device/device_gpu.c:1623-1662, :1673-1724).
 // ---------------------------------------------------------------------------------------------
 #ifndef PB2_BULK_CHUNK
 #define PB2_BULK_CHUNK 4096
 #endif
+#ifndef PB2_BULK_DEPTH
+#define PB2_BULK_DEPTH 2
+#endif
 constexpr uint32_t kBulkChunk = PB2_BULK_CHUNK;
+constexpr int kBulkDepth = PB2_BULK_DEPTH;
+static_assert(kBulkDepth >= 2 && kBulkDepth <= 8, "bulk ring depth");
 
 struct alignas(128) BulkSmem {
-    uint8_t  buf[2][kBulkChunk];
-    uint64_t bar[2];
-    uint32_t parity[2];     // phase each barrier will complete next (persists across copies; owned by thread 0)
+    uint8_t  buf[kBulkDepth][kBulkChunk];
+    uint64_t bar[kBulkDepth];
+    uint32_t parity;        // bit s: the phase barrier s will complete next (persists across copies; owned by thread 0)
 };
 
 __device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void bulk_init(BulkSmem& b) {     // thread 0, once per kernel, followed by a barrier
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_addr_u32(&b.bar[0])) : "memory");
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_addr_u32(&b.bar[1])) : "memory");
+    for (int s = 0; s < kBulkDepth; ++s)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_addr_u32(&b.bar[s])) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    b.parity[0] = 0; b.parity[1] = 0;
+    b.parity = 0;
 }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr_u32(bar)), "r"(bytes) : "memory");
@@ -97,7 +107,7 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint3
                  :: "l"(gdst), "r"(smem_addr_u32(smem_src)), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all0()  { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_bar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok = 0;
@@ -114,23 +124,30 @@ __device__ __forceinline__ void cta_bulk_copy(void* dst, const void* src, size_t
         const uint8_t* s = reinterpret_cast<const uint8_t*>(src);
         uint8_t* d = reinterpret_cast<uint8_t*>(dst);
         const size_t n = (bytes + kBulkChunk - 1) / kBulkChunk;
-        uint32_t par0 = b.parity[0], par1 = b.parity[1];
-        bulk_g2s(b.buf[0], s, (uint32_t)(bytes < kBulkChunk ? bytes : kBulkChunk), &b.bar[0]);
+        uint32_t par = b.parity;
+        size_t issued = 0;                               // chunks whose load has been issued; chunk c uses slot c % depth
+        for (; issued < n && issued < (size_t)kBulkDepth; ++issued) {
+            const size_t off = issued * kBulkChunk;
+            bulk_g2s(b.buf[issued], s + off, (uint32_t)(bytes - off < kBulkChunk ? bytes - off : kBulkChunk), &b.bar[issued]);
+        }
         for (size_t i = 0; i < n; ++i) {
-            const int slot = (int)(i & 1);
-            if (i + 1 < n) {
-                if (i >= 1) bulk_wait_read0();          // the store that last read the other buffer has drained it
-                const size_t off = (i + 1) * kBulkChunk;
-                bulk_g2s(b.buf[slot ^ 1], s + off, (uint32_t)(bytes - off < kBulkChunk ? bytes - off : kBulkChunk), &b.bar[slot ^ 1]);
-            }
-            if (slot == 0) { bulk_bar_wait(&b.bar[0], par0); par0 ^= 1; }
-            else           { bulk_bar_wait(&b.bar[1], par1); par1 ^= 1; }
+            const int slot = (int)(i % kBulkDepth);
+            bulk_bar_wait(&b.bar[slot], (par >> slot) & 1u); par ^= (1u << slot);
             const size_t off = i * kBulkChunk;
             bulk_s2g(d + off, b.buf[slot], (uint32_t)(bytes - off < kBulkChunk ? bytes - off : kBulkChunk));
+            if (i >= 1 && issued < n) {
+                // the slot of chunk i-1: its store is the second most recent group, and it has finished READING the
+                // buffer once at most one group (the store just issued) still has reads pending
+                bulk_wait_read1();
+                const int fs = (int)((i - 1) % kBulkDepth);           // == issued % depth
+                const size_t noff = issued * kBulkChunk;
+                bulk_g2s(b.buf[fs], s + noff, (uint32_t)(bytes - noff < kBulkChunk ? bytes - noff : kBulkChunk), &b.bar[fs]);
+                ++issued;
+            }
         }
         bulk_wait_all0();
         asm volatile("fence.proxy.async;" ::: "memory");
-        b.parity[0] = par0; b.parity[1] = par1;
+        b.parity = par;
     }
     __syncthreads();
 }

@@ -60,8 +60,11 @@ int main(int argc, char *argv[])
     const int nthreads = parsec->virtual_processes[0]->nb_cores;
 
     parsec_matrix_block_cyclic_t dcA;
+    /* tiles of tile_mb x tile_nb elements stacked in one column of tiles: the matrix sizes of the reference API are ints,
+     * K * elems does not fit one for the 8-GPU workload (32768 tiles of 65536 elements) */
+    const int tile_nb = (0 == elems % 256) ? 256 : 1, tile_mb = elems / tile_nb;
     parsec_matrix_block_cyclic_init(&dcA, PARSEC_MATRIX_INTEGER, PARSEC_MATRIX_TILE, 0,
-                                    elems, 1, K * elems, 1, 0, 0, K * elems, 1, 1, 1, 1, 1, 0, 0);
+                                    tile_mb, tile_nb, K * tile_mb, tile_nb, 0, 0, K * tile_mb, tile_nb, 1, 1, 1, 1, 0, 0);
     dcA.mat = parsec_data_allocate((size_t)dcA.super.nb_local_tiles * (size_t)dcA.super.bsiz *
                                    (size_t)parsec_datadist_getsizeoftype(dcA.super.mtype));
     parsec_data_collection_set_key((parsec_data_collection_t*)&dcA, "dcA");

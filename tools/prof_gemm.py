@@ -11,7 +11,10 @@ with Engine(0) as e:
     dag = dags.dtd_gemm(NT, T)
     dag.tasks["access"][:, 2] &= ~np.uint8(L.FLOW_PUSHOUT)
     slab = e.malloc(dag.ntiles * tb)
-    e.h2d(slab, np.full(dag.ntiles * tb // 2, 0x3C00, np.uint16))
+    # random operands (uniform in [-1, 1), bf16): constant data toggles few bits and clocks higher than real data
+    from parsec_b200.bf16 import f32_to_bf16_bits
+    rng = np.random.default_rng(2026)
+    e.h2d(slab, f32_to_bf16_bits(rng.uniform(-1.0, 1.0, dag.ntiles * tb // 2).astype(np.float32)))
     tiles = np.zeros(dag.ntiles, L.TILE_DTYPE)
     tiles["dev_ptr"] = slab + np.arange(dag.ntiles, dtype=np.uint64) * np.uint64(tb)
     tiles["bytes"], tiles["state"] = tb, L.TILE_VALID
