@@ -166,6 +166,7 @@ typedef struct parsec_device_b200_module_s {
     int32_t              nb_settled;
     int32_t              nb_stalled;
     int32_t              again_window;    /* the last AGAIN of b200_start_task came from the stage-in window, not from memory */
+    int32_t              lane_pending;    /* staged batchable lane tasks waiting in lane->fifo_pending for b200_fire_lane */
     uint64_t             n_engine, n_lane, n_settled_by_caller;   /* statistics (folded into parsec_b200_stats_t on demand) */
     uint64_t             tsc_start[4];    /* start phase by step: reserve, stage-in decisions, record, command */
     uint64_t             tsc_s[3];        /* starter time by phase: inbox, start, events */
@@ -1071,6 +1072,98 @@ static int b200_prepare_resident(parsec_device_b200_module_t *dev, b200_task_t *
     return 1;
 }
 
+static int b200_chore_allows_batch(const parsec_task_t *task, const parsec_device_module_t *device)
+{
+    if( NULL == task || NULL == task->task_class || task->selected_chore < 0 ) return 0;
+    const __parsec_chore_t *chore = &task->task_class->incarnations[task->selected_chore];
+    return parsec_mca_device_type_supports_batch(device->type) && (0 != (chore->type & device->type)) &&
+           (0 != (chore->type & PARSEC_DEV_CHORE_ALLOW_BATCH));
+}
+
+/* after an opaque body has been enqueued on the lane stream: pushouts on the same stream, then the event */
+static int b200_lane_after_submit(parsec_device_b200_module_t *dev, b200_task_t *bt)
+{
+    parsec_gpu_task_t *gpu_task = bt->gpu_task;
+    for( uint32_t i = 0; i < gpu_task->nb_flows; i++ )
+        if( (gpu_task->pushout & (1 << i)) && (PARSEC_FLOW_ACCESS_WRITE & gpu_task->flow_info[i].flow->flow_flags) && NULL != gpu_task->ec->data[i].data_out ) {
+            if( NULL != gpu_task->stage_out && gpu_task->stage_out != parsec_default_gpu_stage_out ) {
+                if( PARSEC_SUCCESS != gpu_task->stage_out(gpu_task, 1u << i, &dev->lane->super) ) return PARSEC_HOOK_RETURN_ERROR;
+            } else {
+                parsec_data_copy_t *g = gpu_task->ec->data[i].data_out, *c = g->original->device_copies[0];
+                if( NULL != c && NULL != c->device_private )
+                    B200_CUDA(cudaMemcpyAsync(c->device_private, g->device_private, gpu_task->flow_info[i].flow_span, cudaMemcpyDeviceToHost, dev->lane->cuda_stream),
+                              "lane pushout", { return PARSEC_HOOK_RETURN_ERROR; });
+                dev->st.bytes_d2h_dma += gpu_task->flow_info[i].flow_span;
+            }
+        }
+    B200_CUDA(cudaEventRecord(b200_bt_event(dev, bt), dev->lane->cuda_stream), "cudaEventRecord", {});
+    bt->state = BT_LANE;
+    dev->n_lane++;
+    parsec_list_nolock_push_back(&dev->waiting_event, &bt->item);
+    return PARSEC_HOOK_RETURN_DONE;
+}
+
+/* the submit function of a staged lane task, and what follows it */
+static int b200_lane_submit(parsec_device_b200_module_t *dev, b200_task_t *bt)
+{
+    parsec_gpu_task_t *gpu_task = bt->gpu_task;
+    /* the submit hook may turn gpu_task into a batch ring: start from a clean singleton (device_gpu.c:2918-2922) */
+    PARSEC_LIST_ITEM_SINGLETON(&gpu_task->list_item);
+    b200_tl_recording = bt;
+    int src = gpu_task->submit(&dev->super.super, gpu_task, &dev->lane->super);
+    b200_tl_recording = NULL;
+    bt->has_complete_stage = (NULL != gpu_task->complete_stage);     /* a body may install one (dtd_test_simple_gemm.c:538) */
+    if( src < 0 && PARSEC_HOOK_RETURN_ASYNC != src ) return PARSEC_HOOK_RETURN_ERROR;
+    if( bt->body >= 0 ) {
+        /* first task of a class whose body names an engine body: remember it, and run THIS one in the kernel too
+         * once its copy-engine stage-in has landed */
+        parsec_b200_submit_set_engine(gpu_task->submit);
+        for( uint32_t i = 0; i < gpu_task->nb_flows; i++ ) {
+            parsec_data_copy_t *out = gpu_task->ec->data[i].data_out;
+            if( NULL == out || NULL == gpu_task->ec->data[i].data_in ) continue;
+            pb2_tile_t tile; memset(&tile, 0, sizeof tile);
+            tile.dev_ptr = out->device_private; tile.bytes = (uint32_t)gpu_task->flow_info[i].flow_span; tile.state = PB2_TILE_VALID;
+            const uint8_t type = (uint8_t)(gpu_task->flow_info[i].flow->flow_flags & PARSEC_FLOW_ACCESS_MASK);
+            tile.version = (PARSEC_FLOW_ACCESS_WRITE & type) ? out->version - 1 : out->version;
+            parsec_data_copy_t *cpu = out->original->device_copies[0];
+            tile.src_ptr = (NULL != cpu && NULL != cpu->device_private) ? b200_device_visible(cpu->device_private, tile.bytes) : NULL;
+            (void)pb2_stream_set_tile(dev->stream, b200_tile_of(dev, out), &tile);
+            dev->tile_described[b200_tile_of(dev, out)] = 1;
+        }
+        B200_CUDA(cudaEventRecord(b200_bt_event(dev, bt), dev->lane->cuda_stream), "cudaEventRecord", {});
+        bt->state = BT_DMA_IN;
+        parsec_list_nolock_push_back(&dev->waiting_event, &bt->item);
+        return PARSEC_HOOK_RETURN_DONE;
+    }
+    /* opaque: its kernels are on the lane stream behind the copies.  A batching body has chained the tasks it took from
+     * fifo_pending on the ring of its gpu_task: they ran with it, each of them completes like it. */
+    parsec_list_item_t *ring = (parsec_list_item_t*)gpu_task->list_item.list_next;
+    while( ring != &gpu_task->list_item ) {
+        parsec_list_item_t *next = (parsec_list_item_t*)ring->list_next;
+        parsec_gpu_task_t *member = (parsec_gpu_task_t*)ring;
+        PARSEC_LIST_ITEM_SINGLETON(ring);
+        dev->lane_pending--; dev->st.lane_batched++;
+        if( PARSEC_HOOK_RETURN_DONE != b200_lane_after_submit(dev, B200_BT(member)) ) return PARSEC_HOOK_RETURN_ERROR;
+        ring = next;
+    }
+    PARSEC_LIST_ITEM_SINGLETON(&gpu_task->list_item);
+    return b200_lane_after_submit(dev, bt);
+}
+
+/* the staged batchable tasks of this pass: oldest first, each call may take more of them along */
+static int b200_fire_lane(parsec_device_b200_module_t *dev)
+{
+    int n = 0;
+    while( dev->lane_pending > 0 ) {
+        parsec_gpu_task_t *head = (parsec_gpu_task_t*)parsec_list_nolock_pop_front(dev->lane->super.fifo_pending);
+        if( NULL == head ) { dev->lane_pending = 0; break; }
+        dev->lane_pending--;
+        if( PARSEC_HOOK_RETURN_DONE != b200_lane_submit(dev, B200_BT(head)) ) return -1;
+        n++;
+    }
+    return n;
+}
+
 static int b200_start_task(parsec_device_b200_module_t *dev, parsec_execution_stream_t *es, b200_task_t *bt)
 {
     parsec_gpu_task_t *gpu_task = bt->gpu_task;
@@ -1142,50 +1235,18 @@ static int b200_start_task(parsec_device_b200_module_t *dev, parsec_execution_st
             if( NULL != gpu_task->ec->data[i].data_out && PARSEC_DATA_STATUS_UNDER_TRANSFER == gpu_task->ec->data[i].data_out->data_transfer_status ) mask |= (1u << i);
         if( mask && PARSEC_SUCCESS != gpu_task->stage_in(gpu_task, mask, &dev->lane->super) ) return PARSEC_HOOK_RETURN_ERROR;
     }
-    b200_tl_recording = bt;
-    int src = gpu_task->submit(&dev->super.super, gpu_task, &dev->lane->super);
-    b200_tl_recording = NULL;
-    bt->has_complete_stage = (NULL != gpu_task->complete_stage);     /* a body may install one (dtd_test_simple_gemm.c:538) */
-    if( src < 0 && PARSEC_HOOK_RETURN_ASYNC != src ) return PARSEC_HOOK_RETURN_ERROR;
-    if( bt->body >= 0 ) {
-        /* first task of a class whose body names an engine body: remember it, and run THIS one in the kernel too
-         * once its copy-engine stage-in has landed */
-        parsec_b200_submit_set_engine(gpu_task->submit);
-        for( uint32_t i = 0; i < gpu_task->nb_flows; i++ ) {
-            parsec_data_copy_t *out = gpu_task->ec->data[i].data_out;
-            if( NULL == out || NULL == gpu_task->ec->data[i].data_in ) continue;
-            pb2_tile_t tile; memset(&tile, 0, sizeof tile);
-            tile.dev_ptr = out->device_private; tile.bytes = (uint32_t)gpu_task->flow_info[i].flow_span; tile.state = PB2_TILE_VALID;
-            const uint8_t type = (uint8_t)(gpu_task->flow_info[i].flow->flow_flags & PARSEC_FLOW_ACCESS_MASK);
-            tile.version = (PARSEC_FLOW_ACCESS_WRITE & type) ? out->version - 1 : out->version;
-            parsec_data_copy_t *cpu = out->original->device_copies[0];
-            tile.src_ptr = (NULL != cpu && NULL != cpu->device_private) ? b200_device_visible(cpu->device_private, tile.bytes) : NULL;
-            (void)pb2_stream_set_tile(dev->stream, b200_tile_of(dev, out), &tile);
-            dev->tile_described[b200_tile_of(dev, out)] = 1;
-        }
-        B200_CUDA(cudaEventRecord(b200_bt_event(dev, bt), dev->lane->cuda_stream), "cudaEventRecord", {});
-        bt->state = BT_DMA_IN;
-        parsec_list_nolock_push_back(&dev->waiting_event, &bt->item);
+    /* A body that may BATCH (chore flag PARSEC_DEV_CHORE_ALLOW_BATCH, `batch = true` in a JDF body) collects further
+     * staged tasks of its kind with parsec_gpu_task_collect_batch (device_gpu.c:2228-2285), which looks for them in
+     * the stream's fifo_pending.  Such a task is only STAGED here; its submit function is called when the pass has
+     * staged everything it could (b200_fire_lane), so that the tasks behind it are there to be collected. */
+    if( b200_chore_allows_batch(gpu_task->ec, &dev->super.super.super) && !parsec_b200_submit_is_engine(gpu_task->submit) ) {
+        bt->state = BT_LANE;
+        PARSEC_LIST_ITEM_SINGLETON(&gpu_task->list_item);
+        parsec_list_nolock_push_back(dev->lane->super.fifo_pending, &gpu_task->list_item);
+        dev->lane_pending++;
         return PARSEC_HOOK_RETURN_DONE;
     }
-    /* opaque: its kernels are on the lane stream behind the copies; pushouts follow on the same stream */
-    for( uint32_t i = 0; i < gpu_task->nb_flows; i++ )
-        if( (gpu_task->pushout & (1 << i)) && (PARSEC_FLOW_ACCESS_WRITE & gpu_task->flow_info[i].flow->flow_flags) && NULL != gpu_task->ec->data[i].data_out ) {
-            if( NULL != gpu_task->stage_out && gpu_task->stage_out != parsec_default_gpu_stage_out ) {
-                if( PARSEC_SUCCESS != gpu_task->stage_out(gpu_task, 1u << i, &dev->lane->super) ) return PARSEC_HOOK_RETURN_ERROR;
-            } else {
-                parsec_data_copy_t *g = gpu_task->ec->data[i].data_out, *c = g->original->device_copies[0];
-                if( NULL != c && NULL != c->device_private )
-                    B200_CUDA(cudaMemcpyAsync(c->device_private, g->device_private, gpu_task->flow_info[i].flow_span, cudaMemcpyDeviceToHost, dev->lane->cuda_stream),
-                              "lane pushout", { return PARSEC_HOOK_RETURN_ERROR; });
-                dev->st.bytes_d2h_dma += gpu_task->flow_info[i].flow_span;
-            }
-        }
-    B200_CUDA(cudaEventRecord(b200_bt_event(dev, bt), dev->lane->cuda_stream), "cudaEventRecord", {});
-    bt->state = BT_LANE;
-    dev->n_lane++;
-    parsec_list_nolock_push_back(&dev->waiting_event, &bt->item);
-    return PARSEC_HOOK_RETURN_DONE;
+    return b200_lane_submit(dev, bt);
 }
 
 /* ------------------------------------------------------------------------------------------------------------------ */
@@ -1438,6 +1499,7 @@ static int b200_start_pass(parsec_device_b200_module_t *dev, parsec_execution_st
         }
         if( cut ) dev->retry_stalled = 1;
     }
+    if( dev->lane_pending > 0 ) { const int n = b200_fire_lane(dev); if( n < 0 ) return -1; moved += n; }
     if( started && PB2_SUCCESS != pb2_stream_kick(dev->stream) ) return -1;
     t1 = B200_TSC(); dev->tsc_s[1] += t1 - t0; t0 = t1;
     /* 3. copy-engine / lane events */

@@ -182,3 +182,28 @@ def test_dtd_component_gpu_known_answers(opaque):
 def test_dtd_reference_cuda_component_agrees():
     rc, d, err = run("dtd_b200", ["-M", 16, "-n", 4096, "-N", 8, "-c", 8, "-o"], {"PARSEC_MCA_device_cuda_enabled": "1"})
     assert rc == 0 and d["total_errors"] == 0 and d["b200_modules"] == 0 and d["gpu_modules"] == 1, (d, err[-1000:])
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# parsec_gpu_task_collect_batch (device_gpu.c:2228-2285): a `batch = true` body takes further staged tasks of its class along
+# ------------------------------------------------------------------------------------------------------------------------
+def test_batch_reference_runtime_cpu_known_answer():
+    rc, d, err = run("batch_b200", ["-m", "cpu", "-M", 32], CPU_ENV)
+    assert rc == 0 and d["errors"] == 0 and d["executed_on_gpu"] == 0, err[-800:]
+
+
+@pytest.mark.gpu
+def test_batch_component_gpu_collects_staged_tasks():
+    M = 96
+    rc, d, err = run("batch_b200", ["-M", M, "-c", 8], {"PARSEC_MCA_device_b200_enabled": "1"})
+    assert rc == 0 and d["errors"] == 0, (d, err[-1000:])
+    assert d["b200_modules"] == 1 and d["executed_on_gpu"] == M and d["tasks_lane"] == M
+    assert d["tasks_in_batches"] == M                       # every task ran exactly once, in some batch
+    assert d["max_batch"] > 1 and d["submit_calls"] < M     # and batches did form (up to 5 per the body's callback)
+    assert d["lane_batched"] == M - d["submit_calls"]
+
+
+@pytest.mark.gpu
+def test_batch_reference_cuda_component_agrees():
+    rc, d, err = run("batch_b200", ["-M", 96, "-c", 8], {"PARSEC_MCA_device_cuda_enabled": "1"})
+    assert rc == 0 and d["errors"] == 0 and d["b200_modules"] == 0 and d["tasks_in_batches"] == 96, (d, err[-1000:])
