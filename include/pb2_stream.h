@@ -51,7 +51,7 @@ typedef struct pb2_stream_params_s {
     int32_t part_bytes;    /* tasks whose widest tile exceeds this are run as byte-slice parts by several workers
                             * (default 256 KiB; < 0: never split)                                                    */
     int32_t max_workers;   /* 0 = every resident CTA; 1 = one worker (deterministic FIFO order, tests)                */
-    int32_t reserved;
+    int32_t trace;         /* != 0: workers time-stamp every task with the device clock (pb2_retire_t.t_start_ns / t_end_ns) */
 } pb2_stream_params_t;
 
 /* One retired task, as the host reads it from the retire ring. */
@@ -61,6 +61,10 @@ typedef struct pb2_retire_s {
     uint32_t seen_version[PB2_MAX_FLOWS];   /* tile version each flow saw when the task started                        */
     int32_t  ticket;
     int32_t  status;            /* PB2_SUCCESS, or PB2_ERR_BAD_PARAM for an unknown body id                           */
+    uint64_t t_start_ns;        /* params.trace: %globaltimer when a worker popped the task (its last part), ...      */
+    uint64_t t_end_ns;          /* ... and when its body, pushout and successor release were done; else 0             */
+    uint32_t smid;              /* params.trace: the SM that ran it                                                    */
+    uint32_t pad;
 } pb2_retire_t;
 
 typedef struct pb2_stream_stats_s {

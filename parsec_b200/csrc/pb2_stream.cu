@@ -55,6 +55,9 @@ struct alignas(32) Retire {
 };
 static_assert(sizeof(Retire) == 32, "Retire must be 32 bytes");
 
+// params.trace: one per retire index, written before the retire record of the same index
+struct alignas(32) TraceRec { unsigned long long t_start, t_end; uint32_t smid; int32_t ticket; uint32_t pad[2]; };
+
 struct HostCtl {            // pinned host memory, written by both sides
     volatile uint32_t state;        // HS_*
     volatile uint32_t stop_req;     // host -> device: park as soon as nothing is in flight
@@ -85,6 +88,7 @@ struct StreamDev {
     uint16_t* nparts_rw;    // == w.nparts, writable alias for the dispatcher
     pb2_task_t* tasks_rw;   // == w.tasks
     unsigned long long idle_ns;
+    TraceRec* trace;        // pinned host memory, nullptr unless params.trace
 };
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const volatile uint32_t* p) { return *p; }
@@ -285,6 +289,7 @@ pb2_stream_kernel(StreamDev sd) {
         __syncthreads();
         const int32_t entry = s.entry;
         if (entry == kEmpty) break;
+        const unsigned long long t_pop = (sd.trace != nullptr && threadIdx.x == 0) ? globaltimer_ns() : 0ull;
         const int32_t id = PB2_ENT_TASK(entry);
         const int part = PB2_ENT_PART(entry);
         // the task table is rewritten when tickets are recycled: read it at L2, never through a read-only path
@@ -317,6 +322,10 @@ pb2_stream_kernel(StreamDev sd) {
                         atomicAdd(&sd.sctl->released.v, 1ull);
                     }
                     node = next;
+                }
+                if (sd.trace != nullptr) {
+                    TraceRec* tr = &sd.trace[ridx & sd.ret_mask];
+                    tr->t_start = t_pop; tr->t_end = globaltimer_ns(); tr->smid = smid(); tr->ticket = id;
                 }
                 Retire* rec = &sd.ret[ridx & sd.ret_mask];
                 const uint32_t gen = (uint32_t)(ridx / ((unsigned long long)sd.ret_mask + 1ull)) + 1u;
@@ -358,7 +367,7 @@ struct pb2_stream_s {
     std::string last_error;
     uint32_t slots = 0, ring_cap = 0;
     // pinned host memory
-    Cmd* h_cmd = nullptr; Retire* h_ret = nullptr; HostCtl* h_ctl = nullptr;
+    Cmd* h_cmd = nullptr; Retire* h_ret = nullptr; HostCtl* h_ctl = nullptr; TraceRec* h_trace = nullptr;
     StreamDev d{};
     std::vector<void*> dev_allocs;
     cudaStream_t kstream = nullptr;
@@ -468,6 +477,11 @@ int pb2_stream_create(pb2_engine_t* e, const pb2_stream_params_t* params, pb2_st
     STREAM_CUDA(s, cudaHostGetDevicePointer(&alias, s->h_ret, 0)); d.ret = reinterpret_cast<Retire*>(alias);
     STREAM_CUDA(s, cudaHostGetDevicePointer(&alias, (void*)s->h_ctl, 0)); d.hctl = reinterpret_cast<HostCtl*>(alias);
     d.cmd_mask = s->slots - 1; d.ret_mask = s->slots - 1;
+    if (p.trace) {
+        STREAM_CUDA(s, cudaHostAlloc(reinterpret_cast<void**>(&s->h_trace), sizeof(TraceRec) * s->slots, cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(s->h_trace, 0, sizeof(TraceRec) * s->slots);
+        STREAM_CUDA(s, cudaHostGetDevicePointer(&alias, s->h_trace, 0)); d.trace = reinterpret_cast<TraceRec*>(alias);
+    }
     int rc;
 #define TRY(x) do { rc = (x); if (rc != PB2_SUCCESS) { pb2_stream_destroy(s); return rc; } } while (0)
     WinDev& w = d.w;
@@ -519,6 +533,7 @@ int pb2_stream_destroy(pb2_stream_t* s) {
         if (s->h_cmd) cudaFreeHost(s->h_cmd);
         if (s->h_ret) cudaFreeHost(s->h_ret);
         if (s->h_ctl) cudaFreeHost((void*)s->h_ctl);
+        if (s->h_trace) cudaFreeHost(s->h_trace);
     }
     delete s;
     return PB2_SUCCESS;
@@ -739,6 +754,10 @@ int pb2_stream_poll(pb2_stream_t* s, pb2_retire_t* out, int32_t max) {
         r.cookie = s->cookie[(size_t)tk]; r.result = *reinterpret_cast<const volatile uint64_t*>(&rec->result);
         for (int f = 0; f < PB2_MAX_FLOWS; ++f) r.seen_version[f] = *reinterpret_cast<const volatile uint32_t*>(&rec->seen[f]);
         r.ticket = tk; r.status = (stamp & 0x80000000u) ? PB2_ERR_BAD_PARAM : PB2_SUCCESS;
+        if (s->h_trace) {
+            const volatile TraceRec* tr = &s->h_trace[s->ret_read & (s->slots - 1)];
+            r.t_start_ns = tr->t_start; r.t_end_ns = tr->t_end; r.smid = tr->smid; r.pad = 0;
+        } else { r.t_start_ns = 0; r.t_end_ns = 0; r.smid = 0; r.pad = 0; }
         if (!s->tk_nodes[(size_t)tk].empty()) {
             std::lock_guard<std::mutex> guard(s->nodes_mu);
             for (int32_t nd : s->tk_nodes[(size_t)tk]) s->free_nodes.push_back(nd);

@@ -32,6 +32,7 @@ int parsec_b200_cmd_slots = 65536;
 int parsec_b200_idle_us = 2000;
 int parsec_b200_lookahead = 1;
 int parsec_b200_max_workers = 0;
+char *parsec_b200_trace = NULL;
 int parsec_b200_parallel_completion = 1;
 int parsec_b200_stage_window = 32 * 1024 * 1024;
 int parsec_b200_registration_cache = 1;
@@ -109,6 +110,10 @@ static int device_b200_component_register(void)
                                         false, false, 1, &parsec_b200_registration_cache);
     (void)parsec_mca_param_reg_int_name("device_b200", "max_workers", "Debug: limit the worker CTAs of the persistent kernel (0: all)",
                                         false, false, 0, &parsec_b200_max_workers);
+    (void)parsec_mca_param_reg_string_name("device_b200", "trace",
+                                           "Write one Chrome-trace JSON file <value>.<device index>.json per device at finalize: every task with the "
+                                           "device-clock time a worker CTA started and finished it and the SM it ran on (empty: off)",
+                                           false, false, "", &parsec_b200_trace);
     return (0 == parsec_device_b200_enabled && 0 == parsec_b200_dry_run) ? MCA_ERROR : MCA_SUCCESS;
 }
 

@@ -118,6 +118,12 @@ typedef struct b200_task_s {
 
 typedef struct b200_host_range_s { char *base; size_t len; char *alias; int lazy; } b200_host_range_t;   /* lazy: unregistered by its owner, still pinned (registration cache) */
 
+typedef struct b200_trace_ev_s {
+    char     name[24];
+    int32_t  locals[2];
+    int32_t  body, smid;
+    uint64_t t_start_ns, t_end_ns, cold_bytes;
+} b200_trace_ev_t;
 #define B200_LINE __attribute__((aligned(64)))
 /* Laid out by who writes what: every group below starts on its own cache line. */
 typedef struct parsec_device_b200_module_s {
@@ -179,6 +185,10 @@ typedef struct parsec_device_b200_module_s {
     int32_t              blocked_spins;   /* manager iterations since the last forced attempt to start a waiting task */
     int64_t              epilogs_started; /* finished tasks handed to the worker pool */
     uint64_t             tsc[8];          /* manager time by phase: -, -, -, poll, finish, idle poll, schedule */
+    /* observability (device_b200_trace): what the reference reports through PINS / profiling keys around stage-in, exec
+     * and stage-out of a task (device_gpu.c:348-381) is kept here per task, stamped by the device clock */
+    struct b200_trace_ev_s *trace_ev;
+    size_t               trace_n, trace_cap;
     pb2_retire_t         retbuf[256];
     parsec_b200_stats_t  st B200_LINE;    /* rarely written counters */
 } parsec_device_b200_module_t;
@@ -1542,6 +1552,44 @@ static int b200_start_pass(parsec_device_b200_module_t *dev, parsec_execution_st
     return moved + started;
 }
 
+static void b200_trace_task(parsec_device_b200_module_t *dev, const b200_task_t *bt, const pb2_retire_t *r)
+{
+    if( dev->trace_n == dev->trace_cap ) {
+        dev->trace_cap = dev->trace_cap ? 2 * dev->trace_cap : 65536;
+        dev->trace_ev = (b200_trace_ev_t*)realloc(dev->trace_ev, dev->trace_cap * sizeof(b200_trace_ev_t));
+    }
+    b200_trace_ev_t *e = &dev->trace_ev[dev->trace_n++];
+    const parsec_task_t *t = bt->gpu_task->ec;
+    memset(e, 0, sizeof *e);
+    snprintf(e->name, sizeof e->name, "%s", (NULL != t && NULL != t->task_class && NULL != t->task_class->name) ? t->task_class->name : "?");
+    if( NULL != t ) { e->locals[0] = t->locals[0].value; e->locals[1] = t->locals[1].value; }
+    e->body = bt->body; e->smid = (int32_t)r->smid; e->t_start_ns = r->t_start_ns; e->t_end_ns = r->t_end_ns; e->cold_bytes = bt->cold_bytes;
+}
+
+/* <device_b200_trace>.<device index>.json, Chrome trace format (chrome://tracing, Perfetto): one complete event per
+ * task, pid = device, tid = SM, ts / dur in microseconds of the device clock relative to the first event */
+static void b200_trace_write(parsec_device_b200_module_t *dev)
+{
+    if( NULL == dev->trace_ev || 0 == dev->trace_n || NULL == parsec_b200_trace || '\0' == parsec_b200_trace[0] ) return;
+    char path[1024];
+    snprintf(path, sizeof path, "%s.%d.json", parsec_b200_trace, (int)dev->super.super.super.device_index);
+    FILE *f = fopen(path, "w");
+    if( NULL == f ) { parsec_warning("device_b200: cannot write the trace %s", path); return; }
+    uint64_t t0 = UINT64_MAX;
+    for( size_t i = 0; i < dev->trace_n; i++ ) if( dev->trace_ev[i].t_start_ns && dev->trace_ev[i].t_start_ns < t0 ) t0 = dev->trace_ev[i].t_start_ns;
+    fprintf(f, "{\"displayTimeUnit\": \"ns\", \"traceEvents\": [\n");
+    for( size_t i = 0; i < dev->trace_n; i++ ) {
+        const b200_trace_ev_t *e = &dev->trace_ev[i];
+        fprintf(f, "%s{\"name\": \"%s\", \"ph\": \"X\", \"pid\": %d, \"tid\": %d, \"ts\": %.3f, \"dur\": %.3f, "
+                   "\"args\": {\"l0\": %d, \"l1\": %d, \"body\": %d, \"stage_in_bytes\": %lu}}",
+                i ? ",\n" : "", e->name, (int)dev->super.super.super.device_index, e->smid,
+                (double)(e->t_start_ns - t0) * 1e-3, (double)(e->t_end_ns - e->t_start_ns) * 1e-3,
+                e->locals[0], e->locals[1], e->body, (unsigned long)e->cold_bytes);
+    }
+    fprintf(f, "\n]}\n");
+    fclose(f);
+}
+
 /* The MANAGER's pass: retire ring, copy-engine pushouts, lane tasks the starter saw finish.
  * returns < 0 on a fatal device problem */
 static int b200_retire_pass(parsec_device_b200_module_t *dev, parsec_execution_stream_t *es)
@@ -1579,6 +1627,7 @@ static int b200_retire_pass(parsec_device_b200_module_t *dev, parsec_execution_s
                 return -1;
             }
             bt->result = dev->retbuf[i].result;
+            if( NULL != dev->trace_ev || (NULL != parsec_b200_trace && '\0' != parsec_b200_trace[0]) ) b200_trace_task(dev, bt, &dev->retbuf[i]);
             if( (PB2_BODY_CHECK_I32 == bt->body || PB2_BODY_CHECK_F32 == bt->body) && (bt->result >> 32) ) dev->st.check_mismatches += bt->result >> 32;
             bt->ticket = -1;
             if( PB2_SUCCESS != dev->retbuf[i].status ) { parsec_warning("device_b200: task ran an unknown engine body"); return -1; }
@@ -2005,6 +2054,7 @@ int parsec_b200_module_init(int dev_id, parsec_device_module_t **module)
     sp.idle_us = parsec_b200_idle_us;
     sp.dry_run = dev->dry_run;
     sp.max_workers = parsec_b200_max_workers;
+    sp.trace = (NULL != parsec_b200_trace && '\0' != parsec_b200_trace[0]);
     if( PB2_SUCCESS != pb2_stream_create(dev->engine, &sp, &dev->stream) ) goto failed;
     *module = device;
     return PARSEC_SUCCESS;
@@ -2021,6 +2071,8 @@ int parsec_b200_module_fini(parsec_device_module_t *device)
     parsec_device_gpu_module_t *gpu = &dev->super.super;
     if( NULL != dev->stream ) { (void)pb2_stream_quiesce(dev->stream); }
     b200_profile_print(dev);
+    b200_trace_write(dev);
+    free(dev->trace_ev); dev->trace_ev = NULL; dev->trace_n = dev->trace_cap = 0;
     while( dev->epilogs_done < dev->epilogs_started ) { parsec_atomic_rmb(); }
     while( b200_write_back_some(dev, 64) > 0 ) { }
     parsec_device_memory_release(gpu);

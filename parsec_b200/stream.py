@@ -8,12 +8,13 @@ from . import _lib as L
 
 class StreamParams(C.Structure):
     _fields_ = [("cmd_slots", C.c_int32), ("max_tiles", C.c_int32), ("idle_us", C.c_int32), ("dry_run", C.c_int32),
-                ("timeout_ms", C.c_int32), ("part_bytes", C.c_int32), ("max_workers", C.c_int32), ("reserved", C.c_int32)]
+                ("timeout_ms", C.c_int32), ("part_bytes", C.c_int32), ("max_workers", C.c_int32), ("trace", C.c_int32)]
 
 
 class Retire(C.Structure):
     _fields_ = [("cookie", C.c_uint64), ("result", C.c_uint64), ("seen_version", C.c_uint32 * L.MAX_FLOWS),
-                ("ticket", C.c_int32), ("status", C.c_int32)]
+                ("ticket", C.c_int32), ("status", C.c_int32),
+                ("t_start_ns", C.c_uint64), ("t_end_ns", C.c_uint64), ("smid", C.c_uint32), ("pad", C.c_uint32)]
 
 
 class StreamStats(C.Structure):

@@ -207,3 +207,31 @@ def test_batch_component_gpu_collects_staged_tasks():
 def test_batch_reference_cuda_component_agrees():
     rc, d, err = run("batch_b200", ["-M", 96, "-c", 8], {"PARSEC_MCA_device_cuda_enabled": "1"})
     assert rc == 0 and d["errors"] == 0 and d["b200_modules"] == 0 and d["tasks_in_batches"] == 96, (d, err[-1000:])
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# observability: device_b200_trace (what PINS / the profiling keys of device_gpu.c:348-381 report, stamped by the device clock)
+# ------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_component_gpu_trace_shows_the_dependency_order_on_the_device_clock(tmp_path):
+    K = 128
+    base = str(tmp_path / "b200trace")
+    rc, d, err = run("ex05_b200", ["-K", K, "-t", 65536, "-m", "gpu", "-c", 8],
+                     {"PARSEC_MCA_device_b200_enabled": "1", "PARSEC_MCA_device_b200_trace": base})
+    assert rc == 0 and d["errors"] == 0, err[-1000:]
+    files = [f for f in os.listdir(tmp_path) if f.startswith("b200trace.") and f.endswith(".json")]
+    assert len(files) == 1
+    ev = json.load(open(tmp_path / files[0]))["traceEvents"]
+    assert len(ev) == K * 9
+    bcast_end, nrecv = {}, 0
+    for e in ev:
+        assert e["ph"] == "X" and e["dur"] > 0 and 0 <= e["tid"] < 160
+        if e["name"] == "TaskBcast":
+            bcast_end[e["args"]["l0"]] = e["ts"] + e["dur"]
+            assert e["args"]["stage_in_bytes"] == 262144                  # the broadcast tile came from the host
+    assert len(bcast_end) == K
+    for e in ev:
+        if e["name"] == "TaskRecv":
+            nrecv += 1
+            assert e["ts"] >= bcast_end[e["args"]["l0"]] and e["args"]["stage_in_bytes"] == 0   # a receiver starts after its broadcast ended
+    assert nrecv == K * 8
