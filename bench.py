@@ -386,6 +386,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-cores", type=int, default=32, help="worker threads of the reference runtime in the e2e run")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary records of the other BASELINE configs")
+    ap.add_argument("--kp", type=int, default=1, help="N>1: k-cyclic factor of the 1xN collection (1: the map of examples/Ex05_Broadcast)")
     ap.add_argument("--mgpu", default="direct", choices=["direct", "exchange"],
                     help="N>1: device-released cross-GPU edges (default) or two windows + one NCCL exchange")
     args = ap.parse_args()
@@ -398,7 +399,7 @@ def main():
     ntasks = K * (1 + F)
     algo_bytes = K * (1 + F) * TILE
     cfg = {"workload": "Ex05_Broadcast dataflow (BASELINE configs[1]), 256x256 fp32 tiles, K=%d groups/GPU, fan-out %d" % (K, F),
-           "tile_bytes": TILE, "groups_per_gpu": K, "tasks_per_gpu_step": ntasks, "distribution": "two_dim_block_cyclic 1x%d" % world,
+           "tile_bytes": TILE, "groups_per_gpu": K, "tasks_per_gpu_step": ntasks, "distribution": "two_dim_block_cyclic 1x%d, kp = 1 (tile k on rank k mod N: the map of mydata in examples/Ex05_Broadcast)" % world,
            "l2": "inputs larger than L2: %.2f GiB of tiles per GPU vs 126 MB L2, FIFO ready order" % (K * TILE / 2 ** 30),
            "value_path": "device-resident: the window the host runtime builds for the pool, run by the raw engine (tiles VALID in HBM); the device module's LRU stage-in is inside e2e"}
 
@@ -527,7 +528,9 @@ def main():
         launches_per_step = 2
         nworkers = eng.info()["nworkers"]
     elif args.mgpu == "direct":
-        step, finish, _, nt_rank = ex05_direct_step_factory(K, NB, TILE, rank, world, local_rank)
+        step, finish, _, nt_rank = ex05_direct_step_factory(K, NB, TILE, rank, world, local_rank, kp=args.kp)
+        if args.kp != 1:
+            cfg["distribution"] = "two_dim_block_cyclic 1x%d, kp = %d" % (world, args.kp)
         launches_per_step = 2                                     # re-arm + persistent kernel (the NCCL barrier kernel is not ours)
         assert nt_rank == ntasks
         cfg["multi_gpu"] = "one window per GPU; cross-GPU edges released by the producer's CTA (system-scope atomics over NVLink), tiles pulled by the consumers in 64 KiB slices (TMA bulk copies); NCCL only as the per-step barrier"
@@ -617,6 +620,30 @@ def main():
             except Exception as exc:
                 secondary["config2_gemm"] = {"error": repr(exc)}
     else:
+        if not args.no_secondary and args.mgpu == "direct":
+            # the same DAG on a collection with k-cyclic factor 64 (64 consecutive tiles per rank and cycle): one receiver
+            # in nine is remote and a rank pulls 0.22 GiB per step instead of 1 GiB (N=4) / 3 GiB (N=8)
+            try:
+                step2, finish2, _, nt2 = ex05_direct_step_factory(K, NB, TILE, rank, world, local_rank, kp=64)
+                for _ in range(args.warmup):
+                    step2()
+                finish2(); barrier()
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                f0.record()
+                for _ in range(args.steps):
+                    step2()
+                f1.record()
+                run2 = finish2(); torch.cuda.synchronize(); barrier()
+                ms2 = max_over_ranks(f0.elapsed_time(f1) / args.steps)
+                pulled = torch.tensor([float(run2.w.stats["bytes_d2d"])], dtype=torch.float64, device="cuda")
+                dist.all_reduce(pulled, op=dist.ReduceOp.MAX)
+                secondary["ex05_kcyclic64"] = {"config": "the Ex05 dataflow of `value` on a 1x%d two_dim_block_cyclic collection with k-cyclic factor kp = 64 (two_dim_rectangle_cyclic.h), K=%d groups/GPU" % (world, K),
+                                               "ms_per_step": ms2, "tasks_per_s": world * nt2 / (ms2 / 1e3), "tasks_per_gpu_step": nt2,
+                                               "peer_bytes_per_rank_step": float(pulled.item()), "body_errors": 0,
+                                               "weak_scaling_vs_value_at_this_N": (world * nt2 / (ms2 / 1e3)) / value}
+                del run2, step2, finish2
+            except Exception as exc:
+                secondary["ex05_kcyclic64"] = {"error": repr(exc)}
         # NVLink view of the step: bytes every rank pulled from its peers, against the per-direction link rate
         tot = torch.tensor([float(d2d_bytes)], dtype=torch.float64, device="cuda")
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)

@@ -15,6 +15,12 @@ __device__ __forceinline__ int32_t ld_acquire_sys(const int32_t* p) {
     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ int32_t ld_relaxed_sys(const int32_t* p) {
+    int32_t v;
+    asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ void st_release_sys(int32_t* p, int32_t v) {
     asm volatile("st.release.sys.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }

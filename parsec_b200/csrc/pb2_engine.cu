@@ -237,6 +237,8 @@ static int validate_window(pb2_engine_t* e, int kind, const pb2_task_t* tasks, i
                            const int32_t* ready, int32_t nready) {
     if (ntasks < 0 || nsucc < 0 || ntiles < 0 || nready < 0) return PB2_ERR_BAD_PARAM;
     if (ntasks >= (1 << 27)) return PB2_ERR_VALUE_OUT_OF_BOUNDS;
+    // ready-ring entries of the HBM kernel carry the task id in 22 bits (PB2_ENT_MAKE: part << 22 | task)
+    if (kind == 0 && ntasks >= (1 << 22)) { e->last_error = "an HBM window holds at most 4194303 tasks (22-bit task id in the ready ring)"; return PB2_ERR_VALUE_OUT_OF_BOUNDS; }
     for (int32_t i = 0; i < ntasks; ++i) {
         const pb2_task_t& t = tasks[i];
         if (t.nb_flows > PB2_MAX_FLOWS) { e->last_error = "task with more than PB2_MAX_FLOWS flows"; return PB2_ERR_BAD_PARAM; }

@@ -924,6 +924,8 @@ static int build_window(pb2_device_module_t* dev, Window& w, std::vector<pb2_gpu
     bool full = false;
     while (!queue.empty()) {
         pb2_htask_t* t = queue.front(); queue.pop_front();
+        // the ready-ring entries of an HBM window carry a 22-bit task id: a larger closure goes into the next window
+        if (w.kind == 0 && w.tasks.size() + 1 >= ((size_t)1 << 22)) full = true;
         bool ok = !full;
         std::vector<pb2_data_copy_t*> fresh;
         if (ok) {

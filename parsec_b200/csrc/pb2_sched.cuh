@@ -104,7 +104,11 @@ __device__ __forceinline__ int32_t pop_task(const WinDev& w) {
     int32_t* slot = &w.ring[ticket & w.cap_mask];
     uint32_t spins = 0;
     int32_t id;
+#ifdef PB2_EXPERIMENT_GPU_SCOPE_POLL
+    while ((id = ld_acquire_gpu(slot)) == kEmpty) {
+#else
     while ((id = (w.shared ? ld_acquire_sys(slot) : ld_acquire_gpu(slot))) == kEmpty) {
+#endif
         if (ld_relaxed_gpu(reinterpret_cast<const int32_t*>(&w.ctl->done.v)) != 0) return kEmpty;
         if ((++spins & 1023u) == 0) {
             // watchdog: a DAG whose dependency counts are wrong would spin forever

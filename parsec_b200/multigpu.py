@@ -86,11 +86,13 @@ class Partition:
             pass
 
 
-def ex05_global(K_total, NB, world, tile_bytes):
+def ex05_global(K_total, NB, world, tile_bytes, kp=1):
     """Ex05_Broadcast (examples/Ex05_Broadcast.jdf:24-58) over `world` ranks as ONE window + owner maps.
 
-    TaskBcast(k) : RW A <- mydata(k), -> A TaskRecv(k, 0..NB..2); runs on rank_of(mydata(k)) = k % world
+    TaskBcast(k) : RW A <- mydata(k), -> A TaskRecv(k, 0..NB..2); runs on rank_of(mydata(k))
     TaskRecv(k,n): READ A <- A TaskBcast(k);                       runs on rank_of(mydata(k + n)) (loc = k + n, :45-47)
+    rank_of(mydata(k)) = (k // kp) % world: a 1 x world grid whose k-cyclic factor kp (two_dim_rectangle_cyclic.h: `kp`
+    consecutive tiles per rank and cycle; two_dim_rectangle_cyclic.c:281-283) is 1 by default.
     Returns (tasks, succ, tiles, ready, task_rank, tile_rank)."""
     ns = np.arange(0, NB + 1, 2, dtype=np.int32)
     F = len(ns)
@@ -110,8 +112,9 @@ def ex05_global(K_total, NB, world, tile_bytes):
     succ = (K_total + np.arange(K_total * F)).astype(np.uint32)
     tiles = np.zeros(K_total, L.TILE_DTYPE)
     tiles["bytes"], tiles["state"] = tile_bytes, L.TILE_VALID
-    task_rank = np.concatenate([k % world, (kk + np.tile(ns, K_total)) % world]).astype(np.int32)
-    return t, succ, tiles, np.arange(K_total, dtype=np.int32), task_rank, (k % world).astype(np.int32)
+    owner = lambda x: ((x % K_total) // kp) % world
+    task_rank = np.concatenate([owner(k), owner(kk + np.tile(ns, K_total))]).astype(np.int32)
+    return t, succ, tiles, np.arange(K_total, dtype=np.int32), task_rank, owner(k).astype(np.int32)
 
 
 def rtt_global(nt, world, tile_bytes, frags=1):
@@ -421,7 +424,7 @@ def ex05_multi_gpu_step_factory(ctx, dev, dc, K, NB, tile_bytes, rank, world, lo
     return step, finish, (4 if wb is not None else 2)
 
 
-def ex05_direct_step_factory(K, NB, tile_bytes, rank, world, local_rank, eng=None, host_tiles=None):
+def ex05_direct_step_factory(K, NB, tile_bytes, rank, world, local_rank, eng=None, host_tiles=None, kp=1):
     """Ex05 over `world` GPUs, one window per GPU, cross-GPU edges released by the device ("direct" path).
 
     host_tiles: device-visible alias of this rank's K tiles in pinned host memory (pb2_engine_host_register); when
@@ -430,8 +433,9 @@ def ex05_direct_step_factory(K, NB, tile_bytes, rank, world, local_rank, eng=Non
     import torch.distributed as dist
     from .engine import Engine
 
-    g = list(ex05_global(K * world, NB, world, tile_bytes))
+    g = list(ex05_global(K * world, NB, world, tile_bytes, kp))
     if host_tiles is not None:
+        assert kp == 1
         tiles = g[2]
         mine = np.nonzero(g[5] == rank)[0]
         tiles["state"][:] = L.TILE_INVALID

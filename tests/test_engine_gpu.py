@@ -254,3 +254,17 @@ def test_big_tile_chain_uses_the_whole_gpu():
             times[pb] = st["kernel_ms"]
             e.host_unregister(host)
     assert times[0] < times[-1] / 4, times
+
+
+def test_hbm_window_larger_than_the_ring_entry_id_is_rejected(engine):
+    """Ready-ring entries of the HBM kernel carry the task id in 22 bits: a kind-0 window of 2^22 tasks must be refused
+    at creation, loudly, not run with truncated ids."""
+    n = 1 << 22
+    tasks = np.zeros(n, L.TASK_DTYPE)
+    tasks["tile"][:] = -1
+    tasks["body"] = L.BODY_NOP
+    tiles = np.zeros(1, L.TILE_DTYPE)
+    tiles["bytes"], tiles["state"] = 64, L.TILE_VALID
+    with pytest.raises(L.Pb2Error) as ei:
+        engine.window(0, tasks, np.zeros(0, np.uint32), tiles, np.arange(n, dtype=np.int32))
+    assert ei.value.rc == L.PB2_ERR_VALUE_OUT_OF_BOUNDS
