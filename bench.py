@@ -47,7 +47,8 @@ K_GROUPS = 4096
 NB = 14
 F = NB // 2 + 1
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "bin")
-NVLINK_GBS = 900.0          # per direction per GPU (B200_PROFILING.md); measured peer copy there: 770 GB/s
+NVLINK_GBS = 770.0          # per direction per GPU: the MEASURED peer copy B200_PROFILING.md gives as the NVLink denominator
+NVLINK_NOMINAL_GBS = 900.0  # nominal, for context
 
 
 def measured(key, fallback):
@@ -650,7 +651,8 @@ def main():
         ingress = float(tot.item())
         out["roofline"] = {"bound": "nvlink", "achieved": ingress / (ms_per_step / 1e3) / 1e9, "peak": NVLINK_GBS, "unit": "GB/s",
                            "frac": ingress / (ms_per_step / 1e3) / 1e9 / NVLINK_GBS, "traffic": ingress,
-                           "note": "bytes the busiest rank pulls from its peers per step (counted by the kernel) over 900 GB/s per direction; the step cannot be shorter than traffic / peak"}
+                           "frac_of_nominal_900": ingress / (ms_per_step / 1e3) / 1e9 / NVLINK_NOMINAL_GBS,
+                           "note": "bytes the busiest rank pulls from its peers per step (counted by the kernel) over the measured peer-copy rate of 770 GB/s per direction (B200_PROFILING.md; 900 nominal); the step cannot be shorter than traffic / peak"}
     if e2e_standalone is not None:
         out["e2e_standalone"] = e2e_standalone
     if secondary:

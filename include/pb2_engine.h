@@ -118,6 +118,8 @@ typedef struct pb2_tile_s {
 
 #define PB2_SRC_HOST 0
 #define PB2_SRC_PEER 1
+#define PB2_SRC_PUSH 2      /* the producer's worker writes the bytes into this slot over NVLink and publishes the state:
+                             * a local task never pulls it, it finds it VALID (pb2_window_set_push) */
 
 #define PB2_TILE_INVALID   0   /* PARSEC_DATA_COHERENCY_INVALID, must be staged in before a READ             */
 #define PB2_TILE_STAGING   1   /* PARSEC_DATA_STATUS_UNDER_TRANSFER                                          */
@@ -258,11 +260,11 @@ int  pb2_window_results(pb2_window_t* window,
  * without the host: the activation is a device atomic on the peer's dependency word plus a ring write over NVLink).
  * Handle of this window's scheduling arrays, to be given to the peers: */
 typedef struct pb2_window_handle_s {
-    unsigned char dep[64], ring[64], ctl[64];
+    unsigned char dep[64], ring[64], ctl[64], tiles[64];
     uint32_t cap_mask;
     int32_t  ntasks;
     int32_t  entry_kind;   /* 0: dep words and ring entries are per task, 1: per fused GEMM unit */
-    int32_t  reserved;
+    int32_t  ntiles;       /* entries of the exported tile table (producer-side pushes publish tile states in it) */
 } pb2_window_handle_t;
 /* entry[t] = what a remote producer must put in rs_target to release task t of THIS window (index of the
  * dependency word + number of ring entries, in this window's own encoding).  Exchange it with the peers. */
@@ -307,6 +309,25 @@ int  pb2_partition_get(const pb2_partition_t* partition, int32_t rank, const uin
                        pb2_task_t* tasks, uint32_t* succ, pb2_tile_t* tiles, int32_t* ready,
                        int32_t* rs_begin, int32_t* rs_rank, uint32_t* rs_target, int32_t* global_id,
                        int32_t* slot_tile, uint64_t* slot_offset);
+/* Producer-side push.  A version a rank reads out of another rank's slot can be written into the reader's slot by the
+ * PRODUCER, right after its body, when nothing on the reader's rank used that slot before (no write-after-read hazard):
+ * posted stores over NVLink instead of a pull whose every chunk pays a round trip.  pb2_partition_set_push(p, 1) makes
+ * pb2_partition_get describe such tiles with src_kind PB2_SRC_PUSH; pb2_partition_get_push returns, for the tasks of
+ * `rank`, what each has to push (CSR ps_begin[ntasks+1]); give it to the window with pb2_window_set_push AFTER
+ * pb2_window_set_remote (the destination tile tables come from the peers' handles). */
+typedef struct pb2_push_s {
+    uint64_t dst;          /* destination slot, as seen from the pushing rank (slab_base[rank] + offset)             */
+    uint32_t bytes;
+    int32_t  src_tile;     /* the pushing task's own descriptor of the tile                                           */
+    int32_t  rank;         /* destination rank                                                                        */
+    int32_t  desc;         /* destination descriptor (index in that rank's tile table)                                */
+    int32_t  pad[2];
+} pb2_push_t;
+int  pb2_partition_set_push(pb2_partition_t* partition, int on);
+int  pb2_partition_push_count(const pb2_partition_t* partition, int32_t rank, int32_t* npush);
+int  pb2_partition_get_push(const pb2_partition_t* partition, int32_t rank, const uint64_t* slab_base,
+                            int32_t* ps_begin, pb2_push_t* push);
+int  pb2_window_set_push(pb2_window_t* window, const int32_t* ps_begin, const pb2_push_t* push, int32_t npush);
 void pb2_partition_destroy(pb2_partition_t* partition);
 const char* pb2_partition_error(void);
 

@@ -85,8 +85,13 @@ class WindowStats(C.Structure):
 
 
 class WindowHandle(C.Structure):
-    _fields_ = [("dep", C.c_ubyte * 64), ("ring", C.c_ubyte * 64), ("ctl", C.c_ubyte * 64),
-                ("cap_mask", C.c_uint32), ("ntasks", C.c_int32), ("entry_kind", C.c_int32), ("reserved", C.c_int32)]
+    _fields_ = [("dep", C.c_ubyte * 64), ("ring", C.c_ubyte * 64), ("ctl", C.c_ubyte * 64), ("tiles", C.c_ubyte * 64),
+                ("cap_mask", C.c_uint32), ("ntasks", C.c_int32), ("entry_kind", C.c_int32), ("ntiles", C.c_int32)]
+
+
+PUSH_DTYPE = np.dtype([("dst", np.uint64), ("bytes", np.uint32), ("src_tile", np.int32), ("rank", np.int32), ("desc", np.int32),
+                       ("pad", np.int32, (2,))])
+assert PUSH_DTYPE.itemsize == 32
 
 
 class PartitionSizes(C.Structure):
@@ -112,6 +117,7 @@ ENGINE_SYMBOLS = [
     "pb2_window_create", "pb2_window_destroy", "pb2_window_launch", "pb2_window_wait",
     "pb2_window_results",
     "pb2_partition_create", "pb2_partition_sizes", "pb2_partition_get", "pb2_partition_destroy", "pb2_partition_error",
+    "pb2_partition_set_push", "pb2_partition_push_count", "pb2_partition_get_push", "pb2_window_set_push",
 ]
 
 
@@ -153,6 +159,10 @@ def load():
     lib.pb2_engine_set_stage_slice_bytes.argtypes = [vp, i32]
     lib.pb2_window_export.argtypes = [vp, vp]
     lib.pb2_window_set_remote.argtypes = [vp, i32, i32, vp, vp, vp, vp, i32]
+    lib.pb2_partition_set_push.argtypes = [vp, C.c_int]
+    lib.pb2_partition_push_count.argtypes = [vp, i32, vp]
+    lib.pb2_partition_get_push.argtypes = [vp, i32, vp, vp, vp]
+    lib.pb2_window_set_push.argtypes = [vp, vp, vp, i32]
     lib.pb2_window_arm.argtypes = [vp]
     lib.pb2_window_start.argtypes = [vp]
     lib.pb2_window_create.argtypes = [vp, P(vp), C.c_int, vp, i32, vp, i32, vp, i32, vp, i32]

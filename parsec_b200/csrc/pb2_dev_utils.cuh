@@ -72,8 +72,10 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 // memory over PCIe, a peer GPU over NVLink, local HBM): what a link delivers is bytes in flight / round trip, and a
 // 64-thread worker that pulls a tile is one of a few hundred CTAs doing so at any moment.  The store of chunk i and
 // the reload of the slot of chunk i-1 overlap (wait_group.read 1), so depth-1 loads stay in flight all the time.
-// Depth 2 is the measured choice (r02): a 4-deep ring (16 KiB per worker, 203 KiB per SM) leaves the SM 28 KiB of L1 and
-// the resident Ex05 window drops from 60 to 46 M tasks/s, while the PCIe-bound e2e step does not move.
+// Depth 3 x 4 KiB is the measured choice (r02, tools/r02_probe24.sh): the resident Ex05 window is unchanged against depth 2
+// (0.617 / 0.620 ms), a window that pulls 0.22 GiB per rank from its neighbour goes from 0.958 to 0.879 ms (4 x 2 KiB:
+// 0.918); a 4-deep ring of 4 KiB chunks (16 KiB per worker, 203 KiB per SM) leaves the SM 28 KiB of L1 and the resident
+// window drops from 60 to 46 M tasks/s.
 // Requires 16-byte aligned addresses and a byte count that is a multiple of 16; callers fall back to the SIMT loops
 // of pb2_bodies.cuh otherwise.
 // This is the device-side replacement of the cudaMemcpyAsync per flow in parsec_default_gpu_stage_in / _stage_out
@@ -83,7 +85,7 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 #define PB2_BULK_CHUNK 4096
 #endif
 #ifndef PB2_BULK_DEPTH
-#define PB2_BULK_DEPTH 2
+#define PB2_BULK_DEPTH 3
 #endif
 constexpr uint32_t kBulkChunk = PB2_BULK_CHUNK;
 constexpr int kBulkDepth = PB2_BULK_DEPTH;
@@ -131,6 +133,8 @@ __device__ __forceinline__ void cta_bulk_copy(void* dst, const void* src, size_t
         uint8_t* d = reinterpret_cast<uint8_t*>(dst);
         const size_t n = (bytes + kBulkChunk - 1) / kBulkChunk;
         uint32_t par = b.parity;
+        // the source may have been written by generic-proxy stores a barrier ago (a body's output that is pushed out)
+        asm volatile("fence.proxy.async;" ::: "memory");
         size_t issued = 0;                               // chunks whose load has been issued; chunk c uses slot c % depth
         for (; issued < n && issued < (size_t)kBulkDepth; ++issued) {
             const size_t off = issued * kBulkChunk;

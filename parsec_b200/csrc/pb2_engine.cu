@@ -128,6 +128,13 @@ pb2_engine_hbm_kernel(WinDev w) {
                 }
             }
             __syncwarp();
+        }
+        if (w.ps_begin != nullptr) {
+            // tiles this task wrote for readers on other GPUs go out before those readers are released
+            __syncthreads();
+            if (s.last && w.ps_begin[id + 1] > w.ps_begin[id]) push_written_tiles(w.tiles, w.ctl, w.ps_begin, w.ps, id, &bulk);
+        }
+        if (threadIdx.x < 32) {
             if (s.last) { release_successors_warp(w, s.task); release_remote_warp(w, id); }
             if (threadIdx.x == 0 && s.window_done) {
                 __threadfence();
@@ -216,6 +223,8 @@ struct pb2_window_s {
     std::vector<int32_t> task_entry;          // per task: its ring entry with (parts - 1) in the part field
     std::vector<void*> allocs;
     std::vector<void*> peer_ptrs;
+    std::vector<pb2_tile_t*> peer_tiles;     // per rank: its tile table as mapped here (nullptr: none / self)
+    std::vector<int32_t> peer_ntiles;
 };
 
 template <class T>
@@ -764,6 +773,7 @@ int pb2_window_create(pb2_engine_t* e, pb2_window_t** window, int kind,
     TRY(dev_alloc_copy(w, &d.result, (const unsigned long long*)nullptr, (size_t)ntasks));
     TRY(dev_alloc_copy(w, &d.worker, (const int32_t*)nullptr, (size_t)ntasks));
     d.parts_left = nullptr; d.rs_begin = nullptr; d.rs_rank = nullptr; d.rs_target = nullptr; d.peers = nullptr; d.shared = w->shared ? 1 : 0;
+    d.ps_begin = nullptr; d.ps = nullptr;
     d.slice_claim = nullptr; d.slice_done = nullptr; d.part_bytes = e->params.part_bytes;
     d.nparts = nullptr; d.remote_units = 0;
     if (kind == 0 && extra_parts) {
@@ -885,7 +895,33 @@ int pb2_window_export(pb2_window_t* w, pb2_window_handle_t* h) {
     PB2_CUDA(e, cudaIpcGetMemHandle(&ih, w->v2 ? w->g.udep : w->d.dep));  memcpy(h->dep, &ih, 64);   // fused-GEMM windows: unit words
     PB2_CUDA(e, cudaIpcGetMemHandle(&ih, w->d.ring)); memcpy(h->ring, &ih, 64);
     PB2_CUDA(e, cudaIpcGetMemHandle(&ih, w->d.ctl));  memcpy(h->ctl, &ih, 64);
+    if (w->d.tiles && w->ntiles > 0) { PB2_CUDA(e, cudaIpcGetMemHandle(&ih, w->d.tiles)); memcpy(h->tiles, &ih, 64); h->ntiles = w->ntiles; }
     h->cap_mask = w->d.cap_mask; h->ntasks = w->ntasks; h->entry_kind = w->v2 ? 1 : 0;
+    return PB2_SUCCESS;
+}
+
+int pb2_window_set_push(pb2_window_t* w, const int32_t* ps_begin, const pb2_push_t* push, int32_t npush) {
+    if (!w || !ps_begin || npush < 0 || (npush && !push)) return PB2_ERR_BAD_PARAM;
+    pb2_engine_t* e = w->e;
+    if (w->v2 || !w->d.peers) { e->last_error = "pushes need an HBM window whose remote edges are set (pb2_window_set_remote)"; return PB2_ERR_NOT_SUPPORTED; }
+    if (ps_begin[w->ntasks] != npush) return PB2_ERR_BAD_PARAM;
+    PB2_CUDA(e, cudaSetDevice(e->cuda_device));
+    std::vector<PushDev> pd((size_t)npush);
+    for (int32_t i = 0; i < npush; ++i) {
+        const pb2_push_t& p = push[i];
+        if (p.rank < 0 || (size_t)p.rank >= w->peer_tiles.size() || !w->peer_tiles[(size_t)p.rank]) { e->last_error = "push to a rank whose tile table is not mapped"; return PB2_ERR_BAD_PARAM; }
+        if (p.desc < 0 || p.desc >= w->peer_ntiles[(size_t)p.rank] || p.src_tile < 0 || p.src_tile >= w->ntiles) { e->last_error = "push descriptor out of bounds"; return PB2_ERR_VALUE_OUT_OF_BOUNDS; }
+        memset(&pd[(size_t)i], 0, sizeof(PushDev));
+        pd[(size_t)i].dst = reinterpret_cast<void*>(p.dst);
+        pd[(size_t)i].dst_state = &w->peer_tiles[(size_t)p.rank][p.desc].state;
+        pd[(size_t)i].bytes = p.bytes; pd[(size_t)i].src_tile = p.src_tile;
+    }
+    int rc;
+    int32_t* d_b = nullptr; PushDev* d_p = nullptr;
+    if ((rc = dev_alloc_copy(w, &d_b, ps_begin, (size_t)w->ntasks + 1)) != PB2_SUCCESS) return rc;
+    if ((rc = dev_alloc_copy(w, &d_p, pd.data(), pd.size())) != PB2_SUCCESS) return rc;
+    PB2_CUDA(e, cudaStreamSynchronize(e->up_stream));
+    w->d.ps_begin = npush ? d_b : nullptr; w->d.ps = d_p;
     return PB2_SUCCESS;
 }
 
@@ -907,12 +943,21 @@ int pb2_window_set_remote(pb2_window_t* w, int32_t my_rank, int32_t nranks, cons
     for (int32_t r = 0; r < nranks; ++r) {
         memset(&pw[r], 0, sizeof(PeerWin));
         if (r == my_rank) continue;
-        void *pd = nullptr, *pr = nullptr, *pc = nullptr;
+        void *pd = nullptr, *pr = nullptr, *pc = nullptr, *pt = nullptr;
         cudaIpcMemHandle_t ih;
         memcpy(&ih, peers[r].dep, 64);  PB2_CUDA(e, cudaIpcOpenMemHandle(&pd, ih, cudaIpcMemLazyEnablePeerAccess));
         memcpy(&ih, peers[r].ring, 64); PB2_CUDA(e, cudaIpcOpenMemHandle(&pr, ih, cudaIpcMemLazyEnablePeerAccess));
         memcpy(&ih, peers[r].ctl, 64);  PB2_CUDA(e, cudaIpcOpenMemHandle(&pc, ih, cudaIpcMemLazyEnablePeerAccess));
+        memcpy(&ih, peers[r].tiles, 64);
+        {   // a window without tiles exports an all-zero handle
+            bool any = false;
+            for (int b = 0; b < 64; ++b) any |= peers[r].tiles[b] != 0;
+            if (any) { PB2_CUDA(e, cudaIpcOpenMemHandle(&pt, ih, cudaIpcMemLazyEnablePeerAccess)); w->peer_ptrs.push_back(pt); }
+        }
         w->peer_ptrs.push_back(pd); w->peer_ptrs.push_back(pr); w->peer_ptrs.push_back(pc);
+        pw[r].tiles = reinterpret_cast<pb2_tile_t*>(pt);
+        w->peer_tiles.resize((size_t)nranks, nullptr); w->peer_tiles[(size_t)r] = reinterpret_cast<pb2_tile_t*>(pt);
+        w->peer_ntiles.resize((size_t)nranks, 0); w->peer_ntiles[(size_t)r] = peers[r].ntiles;
         pw[r].dep = reinterpret_cast<int32_t*>(pd); pw[r].ring = reinterpret_cast<int32_t*>(pr);
         pw[r].ctl = reinterpret_cast<Ctl*>(pc); pw[r].cap_mask = peers[r].cap_mask;
     }

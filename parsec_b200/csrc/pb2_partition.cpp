@@ -27,7 +27,9 @@ struct Desc {            // one tile descriptor of a rank's window
     int32_t src_slot;
     int32_t state;
     int32_t ver;         // writers of the tile before the first user of this descriptor: its version on arrival
+    int32_t pushable;    // nothing on this rank used the slot before: the producer may write the bytes itself
 };
+struct PushEnt { int32_t dst_rank, dst_desc, src_flow; };
 
 struct RankPart {
     std::vector<int32_t> gid;                 // local id -> global id
@@ -52,6 +54,8 @@ struct pb2_partition_s {
     std::vector<int32_t> rank, lid;
     std::vector<int32_t> flow_desc;           // [task][flow] -> descriptor index in the task's rank
     std::vector<RankPart> parts;
+    std::vector<std::vector<PushEnt>> push_of;   // per global task: what it may push
+    bool push_on = false;
 };
 
 static int slot_for(pb2_partition_s* P, int32_t r, int32_t tile) {
@@ -84,6 +88,7 @@ int pb2_partition_create(pb2_partition_t** out, const pb2_task_t* tasks, int32_t
     P->lid.assign((size_t)ntasks, -1);
     P->parts.resize((size_t)nranks);
     P->flow_desc.assign((size_t)ntasks * PB2_MAX_FLOWS, -1);
+    P->push_of.resize((size_t)ntasks);
 #define FAIL(code, msg) do { g_err = (msg); delete P; return (code); } while (0)
     for (int32_t t = 0; t < ntasks; ++t) {
         if (task_rank[t] < 0 || task_rank[t] >= nranks) FAIL(PB2_ERR_BAD_PARAM, "task_rank out of range");
@@ -235,9 +240,16 @@ int pb2_partition_create(pb2_partition_t** out, const pb2_task_t* tasks, int32_t
                 else {
                     const int32_t pr = task_rank[p];
                     d = (int32_t)rp.descs.size();
-                    rp.descs.push_back({tile, slot_for(P, r, tile), pr, slot_for(P, pr, tile), PB2_TILE_INVALID, v});
-                    pulled[(size_t)r][key] = d;
                     SlotUsers& su = slot_users[{r, tile}];
+                    // first content of this rank's slot: no earlier user can be overwritten by a push
+                    const int32_t pushable = (su.cur.empty() && su.prev.empty() && cur[(size_t)r].find(tile) == cur[(size_t)r].end()) ? 1 : 0;
+                    rp.descs.push_back({tile, slot_for(P, r, tile), pr, slot_for(P, pr, tile), PB2_TILE_INVALID, v, pushable});
+                    pulled[(size_t)r][key] = d;
+                    if (pushable) {
+                        int g = 0;
+                        while (g < tasks[p].nb_flows && !(tasks[p].tile[g] == tile && (tasks[p].access[g] & PB2_FLOW_ACCESS_WRITE))) ++g;
+                        P->push_of[(size_t)p].push_back({r, d, g});
+                    }
                     su.prev.swap(su.cur); su.cur.clear();
                 }
                 cur[(size_t)r][tile] = d;
@@ -258,10 +270,10 @@ int pb2_partition_create(pb2_partition_t** out, const pb2_task_t* tasks, int32_t
                 else {
                     const int32_t home = tile_rank[tile];
                     d = (int32_t)rp.descs.size();
-                    if (home == r) rp.descs.push_back({tile, slot_for(P, r, tile), -1, -1, tiles[tile].state, v});
-                    else if (!(k.access[f] & PB2_FLOW_ACCESS_READ)) rp.descs.push_back({tile, slot_for(P, r, tile), -1, -1, PB2_TILE_VALID, v});
+                    if (home == r) rp.descs.push_back({tile, slot_for(P, r, tile), -1, -1, tiles[tile].state, v, 0});
+                    else if (!(k.access[f] & PB2_FLOW_ACCESS_READ)) rp.descs.push_back({tile, slot_for(P, r, tile), -1, -1, PB2_TILE_VALID, v, 0});
                     else if (tiles[tile].state == PB2_TILE_VALID)
-                        rp.descs.push_back({tile, slot_for(P, r, tile), home, slot_for(P, home, tile), PB2_TILE_INVALID, v});
+                        rp.descs.push_back({tile, slot_for(P, r, tile), home, slot_for(P, home, tile), PB2_TILE_INVALID, v, 0});
                     else FAIL(PB2_ERR_NOT_SUPPORTED, "a rank reads the initial copy of a tile that is not resident on its home rank");
                     cur[(size_t)r][tile] = d;
                 }
@@ -340,12 +352,53 @@ int pb2_partition_get(const pb2_partition_t* P, int32_t rank, const uint64_t* sl
         t.version += (uint32_t)d.ver;                   // every task sees the version the unsplit window would show it
         if (d.src_rank >= 0) {
             t.src_ptr = reinterpret_cast<void*>(slab_base[d.src_rank] + P->parts[(size_t)d.src_rank].slot_off[(size_t)d.src_slot]);
-            t.src_kind = PB2_SRC_PEER;
+            t.src_kind = (P->push_on && d.pushable) ? PB2_SRC_PUSH : PB2_SRC_PEER;
         }
         tiles[i] = t;
     }
     if (slot_tile && !rp.slot_tile.empty()) memcpy(slot_tile, rp.slot_tile.data(), rp.slot_tile.size() * sizeof(int32_t));
     if (slot_offset && !rp.slot_off.empty()) memcpy(slot_offset, rp.slot_off.data(), rp.slot_off.size() * sizeof(uint64_t));
+    return PB2_SUCCESS;
+}
+
+int pb2_partition_set_push(pb2_partition_t* P, int on) {
+    if (!P) return PB2_ERR_BAD_PARAM;
+    P->push_on = on != 0;
+    return PB2_SUCCESS;
+}
+
+int pb2_partition_push_count(const pb2_partition_t* P, int32_t rank, int32_t* npush) {
+    if (!P || !npush || rank < 0 || rank >= P->nranks) return PB2_ERR_BAD_PARAM;
+    int32_t n = 0;
+    if (P->push_on) for (int32_t t : P->parts[(size_t)rank].gid) n += (int32_t)P->push_of[(size_t)t].size();
+    *npush = n;
+    return PB2_SUCCESS;
+}
+
+int pb2_partition_get_push(const pb2_partition_t* P, int32_t rank, const uint64_t* slab_base, int32_t* ps_begin, pb2_push_t* push) {
+    if (!P || rank < 0 || rank >= P->nranks || !slab_base || !ps_begin) return PB2_ERR_BAD_PARAM;
+    const RankPart& rp = P->parts[(size_t)rank];
+    int32_t n = 0;
+    for (size_t l = 0; l < rp.gid.size(); ++l) {
+        ps_begin[l] = n;
+        if (!P->push_on) continue;
+        const int32_t t = rp.gid[l];
+        for (const PushEnt& e : P->push_of[(size_t)t]) {
+            const RankPart& dp = P->parts[(size_t)e.dst_rank];
+            const Desc& dd = dp.descs[(size_t)e.dst_desc];
+            if (push) {
+                pb2_push_t o;
+                memset(&o, 0, sizeof o);
+                o.dst = slab_base[e.dst_rank] + dp.slot_off[(size_t)dd.slot];
+                o.bytes = P->tiles[(size_t)dd.tile].bytes;
+                o.src_tile = P->flow_desc[(size_t)t * PB2_MAX_FLOWS + e.src_flow];
+                o.rank = e.dst_rank; o.desc = e.dst_desc;
+                push[n] = o;
+            }
+            ++n;
+        }
+    }
+    ps_begin[rp.gid.size()] = n;
     return PB2_SUCCESS;
 }
 

@@ -48,6 +48,9 @@ struct WinDev {
     const int32_t*    rs_rank;
     const uint32_t*   rs_target;
     const struct PeerWin* peers;
+    // producer-side pushes (pb2_window_set_push): task t writes ps[ps_begin[t] .. ps_begin[t+1]) into its readers' slots
+    const int32_t*    ps_begin;
+    const struct PushDev* ps;
     int32_t           shared;         // scheduling arrays are written by peers: poll / publish at system scope
     // sliced stage-in of tiles larger than part_bytes (HBM windows): which slices are claimed / staged
     uint32_t*         slice_claim;
@@ -57,7 +60,8 @@ struct WinDev {
     int32_t           remote_units;   // remote targets are (parts-1) << 27 | unit of a fused-GEMM window, not << 22 | task
 };
 
-struct PeerWin { int32_t* dep; int32_t* ring; Ctl* ctl; uint32_t cap_mask; int32_t pad; };
+struct PeerWin { int32_t* dep; int32_t* ring; Ctl* ctl; uint32_t cap_mask; int32_t pad; pb2_tile_t* tiles; };
+struct alignas(32) PushDev { void* dst; int32_t* dst_state; uint32_t bytes; int32_t src_tile; int32_t pad[2]; };
 
 // A task whose tiles are large is executed as several PARTS (byte slices of its tiles) by different workers: one
 // tile at HBM / NVLink speed needs the whole GPU (a 64-thread CTA keeps 4 KiB in flight; a 4 MiB tile is 1.3 us of
@@ -201,6 +205,26 @@ __device__ __forceinline__ void release_remote_warp(const WinDev& w, int32_t id)
     }
 }
 
+// Whole CTA, after the body of a task whose written tile other GPUs read: write the tile into every reader rank's slot
+// (posted stores over NVLink through the bulk mover: local reads, remote writes, no round trip per chunk), then publish
+// the slot's state at system scope.  The release of the remote successors follows (release_remote_warp): they find
+// the tile VALID.  This is the PUT of remote_dep_mpi.c:2120 issued by the producer instead of a GET by each consumer.
+static __device__ __noinline__ void push_written_tiles(const pb2_tile_t* tiles, Ctl* ctl, const int32_t* ps_begin, const PushDev* ps,
+                                                       int32_t id, BulkSmem* bulk) {
+    const int32_t b = ps_begin[id], e = ps_begin[id + 1];
+    for (int32_t i = b; i < e; ++i) {
+        const PushDev p = ps[i];
+        cta_copy<false>(p.dst, tiles[p.src_tile].dev_ptr, p.bytes, bulk);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            st_release_sys(p.dst_state, PB2_TILE_VALID);
+            atomicAdd(&ctl->bytes_d2d.v, (unsigned long long)p.bytes);
+        }
+    }
+    __syncthreads();
+}
+
 // One thread: append to the retire log; returns true when this was the last task of the window.
 __device__ __forceinline__ bool retire_task(const WinDev& w, int32_t id) {
     const uint32_t seq = (uint32_t)atomicAdd(&w.ctl->retired.v, 1ull);
@@ -225,7 +249,10 @@ __device__ __forceinline__ StageCtx stage_ctx(const WinDev& w) {
 static __device__ __noinline__ void stage_in_flow(const StageCtx w, pb2_tile_t* tile, uint8_t access, int* s_decide, BulkSmem* bulk = nullptr) {
     if (threadIdx.x == 0) {
         int decide = 0;
-        if (access & PB2_FLOW_ACCESS_READ) {
+        if ((access & PB2_FLOW_ACCESS_READ) && tile->src_kind == PB2_SRC_PUSH) {
+            // the producer writes this slot and publishes its state before it releases us: nothing to move
+            while (ld_acquire_sys(&tile->state) != PB2_TILE_VALID) __nanosleep(64);
+        } else if (access & PB2_FLOW_ACCESS_READ) {
             // parsec_device_data_stage_in, device_gpu.c:1799-2165: only a READ access needs the bytes;
             // "finally we'll just overwrite w/o read" (data.c:427) for WRITE-only flows.
             int32_t st = atomicCAS(&tile->state, PB2_TILE_INVALID, PB2_TILE_STAGING);
@@ -269,6 +296,11 @@ __device__ __forceinline__ int tile_slices(const WinDev& w, uint32_t bytes) { re
 // for it.  The worker whose slice completes the tile publishes PB2_TILE_VALID.
 static __device__ __noinline__ void stage_in_slices(const StageCtx w, int32_t tile_id, int nslices, int s0, int s1, int* s_decide, BulkSmem* bulk = nullptr) {
     pb2_tile_t* tile = &w.tiles[tile_id];
+    if (tile->src_kind == PB2_SRC_PUSH) {       // written by its producer (see stage_in_flow)
+        if (threadIdx.x == 0) while (ld_acquire_sys(&tile->state) != PB2_TILE_VALID) __nanosleep(64);
+        __syncthreads();
+        return;
+    }
     const uint32_t bytes = tile->bytes;
     const uint32_t sper = ((bytes / (uint32_t)nslices) + 15u) & ~15u;
     uint32_t* claim = w.slice_claim + (size_t)tile_id * PB2_SLICE_WORDS;

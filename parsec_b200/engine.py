@@ -162,6 +162,12 @@ class Window:
         _check(self._lib.pb2_window_task_entries(self._h, _ptr(out)), "pb2_window_task_entries", self.engine)
         return out
 
+    def set_push(self, ps_begin, push):
+        """Producer-side pushes (pb2_window_set_push): call after set_remote."""
+        ps_begin = np.ascontiguousarray(ps_begin, np.int32)
+        push = np.ascontiguousarray(push, L.PUSH_DTYPE)
+        _check(self._lib.pb2_window_set_push(self._h, _ptr(ps_begin), _ptr(push), len(push)), "pb2_window_set_push", self.engine)
+
     def set_remote(self, my_rank, handles, rs_begin, rs_rank, rs_target):
         """handles: list of bytes (one exported WindowHandle per rank)."""
         arr = (L.WindowHandle * len(handles))(*[L.WindowHandle.from_buffer_copy(h) for h in handles])

@@ -21,6 +21,7 @@ Two data paths are kept:
 Host logic only (numpy + torch.distributed plumbing); the kernels are the engine's.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -73,6 +74,25 @@ class Partition:
             raise L.Pb2Error(rc, "pb2_partition_get", "")
         out["slab_bytes"] = z["slab_bytes"]
         return out
+
+    def set_push(self, on=True):
+        """Producer-side push of the versions a rank reads first in a slot (pb2_partition_set_push); call before get()."""
+        self._lib.pb2_partition_set_push(self._h, 1 if on else 0)
+
+    def get_push(self, rank, slab_base):
+        """(ps_begin[ntasks+1], push[npush]) of `rank` (empty when pushes are off)."""
+        n = C.c_int32(0)
+        rc = self._lib.pb2_partition_push_count(self._h, rank, C.byref(n))
+        if rc != L.PB2_SUCCESS:
+            raise L.Pb2Error(rc, "pb2_partition_push_count", "")
+        ps_begin = np.zeros(self.sizes(rank)["ntasks"] + 1, np.int32)
+        push = np.zeros(n.value, L.PUSH_DTYPE)
+        base = np.ascontiguousarray(slab_base, np.uint64)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        rc = self._lib.pb2_partition_get_push(self._h, rank, vp(base), vp(ps_begin), vp(push))
+        if rc != L.PB2_SUCCESS:
+            raise L.Pb2Error(rc, "pb2_partition_get_push", "")
+        return ps_begin, push
 
     def close(self):
         if self._h:
@@ -250,8 +270,14 @@ class SharedRun:
     `dist` is torch.distributed (any backend for the handle exchange; the per-step barrier is an all_reduce on
     torch's current CUDA stream, i.e. stream-ordered between the window reset and the worker kernel)."""
 
-    def __init__(self, eng, part, rank, world, dist, torch, kind=0):
+    def __init__(self, eng, part, rank, world, dist, torch, kind=0, push=None):
         self.eng, self.rank, self.world, self.dist, self.torch = eng, rank, world, dist, torch
+        # producer-side pushes (HBM windows only; the GEMM kernels pull operand slices): opt-in with PB2_MGPU_PUSH=1.
+        # Measured r02 (Ex05, 4 GPUs, 1 GiB of ingress per rank and step): pull 2.03 ms, push 2.19 ms -- the transfers run
+        # at the rate of a peer copy either way, the push only moves the copy onto the producers' critical path.
+        if push is None:
+            push = (kind == 0) and os.environ.get("PB2_MGPU_PUSH", "0") == "1"
+        part.set_push(push)
         z = part.sizes(rank)
         self.slab_bytes = max(int(z["slab_bytes"]), 256)
         self.slab = eng.malloc(self.slab_bytes)
@@ -268,6 +294,11 @@ class SharedRun:
         dist.all_gather_object(wh, (self.w.export(), self.w.task_entries()))
         tgt = translate_remote_targets(self.p, [h[1] for h in wh])
         self.w.set_remote(rank, [h[0] for h in wh], self.p["rs_begin"], self.p["rs_rank"], tgt)
+        self.npush = 0
+        if push:
+            ps_begin, pushes = part.get_push(rank, self.base)
+            self.npush = len(pushes)
+            self.w.set_push(ps_begin, pushes)
         self._flag = torch.zeros(1, dtype=torch.int32, device="cuda")
         dist.barrier()
 

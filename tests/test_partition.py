@@ -267,3 +267,46 @@ def test_partition_rejects_bad_input():
     g[0] = g[0].copy(); g[0]["dep_goal"][10] = 3                 # mask that no edge satisfies
     with pytest.raises(L.Pb2Error):
         M.Partition(*g, nranks=2)
+
+
+def test_producer_side_push_lists():
+    """pb2_partition_set_push: a version a rank reads FIRST in a slot is written there by its producer.  Ex05 on 4 ranks:
+    every (tile, remote reader rank) pair is one push of the broadcast task; the rtt ring reuses one slot per rank, so only
+    the first hop into each rank can be pushed, the later ones are pulled."""
+    from parsec_b200 import multigpu as M
+    from parsec_b200 import _lib as L
+    world, K = 4, 32
+    g = M.ex05_global(K * world, 14, world, 4096)
+    part = M.Partition(*g, nranks=world)
+    part.set_push(True)
+    base = np.arange(world, dtype=np.uint64) * np.uint64(1 << 40)
+    tasks, succ, tiles, ready, task_rank, tile_rank = g
+    total = 0
+    parts = [part.get(r, base) for r in range(world)]
+    for r in range(world):
+        ps_begin, push = part.get_push(r, base)
+        p = parts[r]
+        assert ps_begin[0] == 0 and ps_begin[-1] == len(push) and np.all(np.diff(ps_begin) >= 0)
+        total += len(push)
+        for l in range(len(p["tasks"])):
+            for e in push[ps_begin[l]:ps_begin[l + 1]]:
+                gid = p["global_id"][l]
+                assert tasks["body"][gid] == L.BODY_FILL_I32                    # only the broadcasts write
+                dst = parts[e["rank"]]["tiles"][e["desc"]]
+                assert dst["src_kind"] == 2 and dst["state"] == L.TILE_INVALID   # PB2_SRC_PUSH, filled by the producer
+                assert int(dst["dev_ptr"]) == int(e["dst"]) and dst["bytes"] == e["bytes"] == 4096
+                assert int(dst["src_ptr"]) == int(p["tiles"][e["src_tile"]]["dev_ptr"])   # the slot a pull would have read
+    # n even: (k + n) % 4 is k % 4 or (k + 2) % 4 -- one remote reader rank per tile
+    assert total == K * world
+    npush_kinds = sum(int((parts[r]["tiles"]["src_kind"] == 2).sum()) for r in range(world))
+    assert npush_kinds == total
+    # pushes off: the same descriptors are pulls
+    part.set_push(False)
+    assert all(int((part.get(r, base)["tiles"]["src_kind"] == 2).sum()) == 0 for r in range(world))
+    assert all(len(part.get_push(r, base)[1]) == 0 for r in range(world))
+    # rtt: one slot per rank, reused at every lap
+    g = M.rtt_global(16, world, 4096)
+    part = M.Partition(*g, nranks=world)
+    part.set_push(True)
+    n = sum(len(part.get_push(r, base)[1]) for r in range(world))
+    assert n == world - 1          # hops 1, 2, 3 enter a fresh slot; rank 0's slot holds the initial tile
