@@ -50,7 +50,6 @@ typedef struct parsec_b200_stats_s {
     uint64_t tasks_lane;            /* opaque submit bodies run on the stream lane                                   */
     uint64_t kernel_launches;       /* (re)starts of the persistent kernel                                           */
     uint64_t released_on_device;    /* successors made ready by a device-side decrement (look-ahead)                 */
-    uint64_t lookahead_submitted;   /* tasks handed to the device before the host made them ready                    */
     uint64_t bytes_h2d_kernel, bytes_d2d_kernel, bytes_d2h_kernel;  /* moved by the persistent kernel               */
     uint64_t bytes_h2d_dma, bytes_d2h_dma;                          /* moved by the copy engine (unregistered memory)*/
     uint64_t evictions, w2r_copies;

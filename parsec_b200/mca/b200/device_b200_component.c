@@ -30,7 +30,6 @@ int parsec_b200_memory_percentage = 95;
 int parsec_b200_memory_number_of_blocks = -1;
 int parsec_b200_cmd_slots = 65536;
 int parsec_b200_idle_us = 2000;
-int parsec_b200_lookahead = 1;
 int parsec_b200_max_workers = 0;
 char *parsec_b200_trace = NULL;
 int parsec_b200_parallel_completion = 1;
@@ -96,9 +95,6 @@ static int device_b200_component_register(void)
                                         false, false, 65536, &parsec_b200_cmd_slots);
     (void)parsec_mca_param_reg_int_name("device_b200", "idle_us", "The persistent kernel parks after this many idle microseconds",
                                         false, false, 2000, &parsec_b200_idle_us);
-    (void)parsec_mca_param_reg_int_name("device_b200", "lookahead",
-                                        "Hand single-input successors to the device before the host made them ready (device-side release)",
-                                        false, false, 1, &parsec_b200_lookahead);
     (void)parsec_mca_param_reg_int_name("device_b200", "parallel_completion",
                                         "Let the worker pool run __parsec_complete_execution of finished GPU tasks instead of the manager thread",
                                         false, false, 1, &parsec_b200_parallel_completion);

@@ -74,15 +74,14 @@ enum {
     BT_DMA_IN,         /* copy-engine stage-in of unregistered host memory in progress (event)          */
     BT_INFLIGHT,       /* descriptor in the command ring / running in the persistent kernel             */
     BT_LANE,           /* opaque submit body enqueued on the lane stream (event)                        */
-    BT_DMA_OUT,        /* copy-engine pushout in progress (event)                                       */
-    BT_SHADOW          /* look-ahead: runs on the device, the host has not scheduled it yet             */
+    BT_DMA_OUT         /* copy-engine pushout in progress (event)                                       */
 };
 
 /* One record per task handed to the device.  Laid out by who touches what: the manager's hot path (inbox, submit,
  * retire) reads the first two lines and `cmd`, the worker that runs the epilog reads `proxy` and the task itself. */
 typedef struct b200_task_s {
     parsec_list_item_t   item;
-    parsec_gpu_task_t   *gpu_task;        /* NULL while a shadow task waits for the host to schedule it */
+    parsec_gpu_task_t   *gpu_task;
     int32_t              state;
     int32_t              ticket;          /* pb2_stream ticket, -1 when none */
     int32_t              body;            /* enum pb2_body_e recorded by parsec_b200_task_body, -1: opaque body */
@@ -104,10 +103,8 @@ typedef struct b200_task_s {
     int32_t              arg_flow[PB2_MAX_FLOWS];
     int32_t              iparam[3];
     float                fparam;
-    uint32_t             tile_of_arg[PB2_MAX_FLOWS];
     uint32_t             peer_src_mask;   /* flows whose source copy on a peer GPU holds a reader for us */
     parsec_data_copy_t  *peer_src[MAX_PARAM_COUNT];
-    int32_t              retired;         /* shadow: the device is done with it */
     int32_t              custom_stage;    /* the task brought its own stage_in / stage_out (device_gpu.h:75-91) */
     cudaEvent_t          ev;              /* created the first time a copy-engine / lane path needs it */
     int32_t              ev_dev;          /* CUDA device the event belongs to, -1: none */
@@ -279,7 +276,7 @@ static b200_task_t *b200_bt_new(parsec_device_b200_module_t *dev, parsec_gpu_tas
     PARSEC_LIST_ITEM_SINGLETON(&bt->item);
     bt->dev = dev;
     bt->gpu_task = gpu_task; bt->state = BT_NEW; bt->ticket = -1; bt->body = -1; bt->nb_args = 0;
-    bt->peer_src_mask = 0; bt->dma_out_mask = 0; bt->result = 0; bt->retired = 0; bt->custom_stage = 0; bt->cold_bytes = 0;
+    bt->peer_src_mask = 0; bt->dma_out_mask = 0; bt->result = 0; bt->custom_stage = 0; bt->cold_bytes = 0;
     bt->recorded = 0; bt->has_complete_stage = 0; bt->prepared = 0; bt->cmd_built = 0; bt->defer_tiles = 0; bt->ntdesc = 0;
     bt->is_kernel = (NULL == gpu_task) || (PARSEC_GPU_TASK_TYPE_KERNEL == gpu_task->task_type);
     if( NULL != gpu_task ) gpu_task->last_data_check_epoch = (uint64_t)(uintptr_t)bt;
