@@ -183,6 +183,13 @@ def secondary_chain():
     if g:
         out["b200_component"] = {"tasks_per_s": g["tasks_per_s"], "ns_per_edge": g["ns_per_edge"],
                                  "ok": g["errors"] == 0 and g["executed_on_gpu"] == 5000}
+    try:        # the same binary under the reference's OWN GPU module (parsec/mca/device/cuda): the drop-in comparison
+        r = run_app("ex02_b200", ["-m", "gpu", "-N", 999, "-c", 2, "-r", 5], {"PARSEC_MCA_device_cuda_enabled": "1"}, timeout=120)
+        if r:
+            out["reference_cuda_component"] = {"tasks_per_s": r["tasks_per_s"], "ns_per_edge": r["ns_per_edge"],
+                                               "ok": r["errors"] == 0 and r["b200_modules"] == 0 and r["executed_on_gpu"] == 5000}
+    except Exception as exc:
+        out["reference_cuda_component"] = {"error": repr(exc)}
     from oracle import orc_dags as dags
     from parsec_b200 import _lib as L
     from parsec_b200.engine import Engine
@@ -201,6 +208,22 @@ def secondary_chain():
                                 "ok": bool(np.array_equal(res["retire_order"], np.arange(1000)))}
         w.close()
     return out
+
+
+def secondary_reference_cuda(K, cores):
+    """The e2e workload under the reference's OWN GPU device module (parsec/mca/device/cuda, one cudaMemcpyAsync per flow,
+    one kernel launch and three events per task): the same binary, the same generated task pool, the same GPU -- what the
+    b200 component is a drop-in for.  Bodies are the same kernels, launched stand-alone (pb2_body_launch)."""
+    warm, steps = 1, 3
+    d = run_app("ex05_b200", ["-m", "gpu", "-K", K, "-t", TILE // 4, "-r", steps + warm, "-c", cores],
+                {"PARSEC_MCA_device_cuda_enabled": "1"}, timeout=120)
+    if d is None:
+        return None
+    times = d["times_s"][warm:]
+    sec = sum(times) / len(times)
+    return {"config": "BASELINE configs[1] through the reference's cuda device module, %d worker threads" % d["cores"],
+            "tasks_per_s": d["tasks"] / sec, "ms_per_step": sec * 1e3, "best_ms": d["best_s"] * 1e3,
+            "ok": d["errors"] == 0 and d["b200_modules"] == 0 and d["gpu_modules"] == 1 and d["executed_on_gpu"] == d["tasks"] * (steps + warm)}
 
 
 def secondary_gemm(clock_index):
@@ -615,6 +638,10 @@ def main():
                 secondary["config0_chain"] = secondary_chain()
             except Exception as exc:
                 secondary["config0_chain"] = {"error": repr(exc)}
+            try:
+                secondary["e2e_reference_cuda_component"] = secondary_reference_cuda(K, args.e2e_cores)
+            except Exception as exc:
+                secondary["e2e_reference_cuda_component"] = {"error": repr(exc)}
             try:
                 w.close(); eng.free(slab)
                 secondary["config2_gemm"] = secondary_gemm(local_rank)

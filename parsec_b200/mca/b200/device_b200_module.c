@@ -180,6 +180,8 @@ typedef struct parsec_device_b200_module_s {
     int32_t              batch_len;
     int32_t              completed_now;   /* completions of the current manager iteration, subtracted from owed at its end */
     int32_t              blocked_spins;   /* manager iterations since the last forced attempt to start a waiting task */
+    int32_t              complete_inline; /* this retire pass found ONE finished task and an empty device: a serial stretch of the
+                                           * DAG, where handing the completion to another thread only adds a hop to every edge */
     int64_t              epilogs_started; /* finished tasks handed to the worker pool */
     uint64_t             tsc[8];          /* manager time by phase: -, -, -, poll, finish, idle poll, schedule */
     /* observability (device_b200_trace): what the reference reports through PINS / profiling keys around stage-in, exec
@@ -932,7 +934,7 @@ static void b200_complete(parsec_device_b200_module_t *dev, parsec_execution_str
 {
     dev->super.super.super.executed_tasks++;
     dev->completed_now++;
-    if( parsec_b200_parallel_completion && !bt->has_complete_stage ) {
+    if( parsec_b200_parallel_completion && !bt->has_complete_stage && !dev->complete_inline ) {
         /* nothing of the task but its record is touched here */
         dev->epilogs_started++;
         bt->next_done = dev->batch_head; dev->batch_head = bt;
@@ -1615,6 +1617,7 @@ static int b200_retire_pass(parsec_device_b200_module_t *dev, parsec_execution_s
         int n = pb2_stream_poll(dev->stream, dev->retbuf, (int32_t)(sizeof(dev->retbuf) / sizeof(dev->retbuf[0])));
         if( n < 0 ) { parsec_warning("device_b200: %s", pb2_stream_last_error(dev->stream)); return -1; }
         t1 = B200_TSC(); dev->tsc[n ? 3 : 5] += t1 - t0; t0 = t1;
+        dev->complete_inline = (1 == n) && (0 == pb2_stream_inflight(dev->stream)) && (dev->inbox_tail == dev->inbox_head);
         for( int i = 0; i < n; i++ ) {
             b200_task_t *bt = (b200_task_t*)(uintptr_t)dev->retbuf[i].cookie;
             if( i + 5 < n ) { const char *la = (const char*)(uintptr_t)dev->retbuf[i + 5].cookie; B200_PFW(la); B200_PFW(la + 64); B200_PFW(la + offsetof(b200_task_t, proxy)); }
@@ -1636,6 +1639,7 @@ static int b200_retire_pass(parsec_device_b200_module_t *dev, parsec_execution_s
         t1 = B200_TSC(); dev->tsc[4] += t1 - t0; t0 = t1;
         if( n < (int)(sizeof(dev->retbuf) / sizeof(dev->retbuf[0])) ) break;
     }
+    dev->complete_inline = 0;
     b200_close_batch(dev);
     return 0;
 }
