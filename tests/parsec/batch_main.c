@@ -5,6 +5,7 @@
 #include "parsec/mca/device/b200/device_b200.h"
 #include "parsec/parsec_internal.h"
 #include "batch_b200.h"
+#include "checksum.h"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -62,9 +63,10 @@ int main(int argc, char *argv[])
     parsec_devices_release_memory();
     long errors = 0;
     for( size_t i = 0; i < (size_t)MT * MB * NB; i++ ) errors += (mat[i] != (int32_t)(i % 100003) + 5);
-    printf("{\"app\": \"batch_b200\", \"tiles\": %d, \"gpu_modules\": %d, \"b200_modules\": %d, \"errors\": %ld, \"executed_on_gpu\": %lu, "
+    const uint64_t checksum = fnv1a64(mat, (size_t)MT * MB * NB * sizeof(int32_t), 0);
+    printf("{\"app\": \"batch_b200\", \"checksum\": \"%016lx\", \"tiles\": %d, \"gpu_modules\": %d, \"b200_modules\": %d, \"errors\": %ld, \"executed_on_gpu\": %lu, "
            "\"submit_calls\": %d, \"tasks_in_batches\": %d, \"max_batch\": %d, \"tasks_lane\": %lu, \"lane_batched\": %lu}\n",
-           MT, ngpu, b200, errors, (unsigned long)on_gpu, batch_b200_submit_calls, batch_b200_tasks_in_batches, batch_b200_max_batch,
+           (unsigned long)checksum, MT, ngpu, b200, errors, (unsigned long)on_gpu, batch_b200_submit_calls, batch_b200_tasks_in_batches, batch_b200_max_batch,
            (unsigned long)lane, (unsigned long)batched);
     parsec_taskpool_free((parsec_taskpool_t*)tp);
     parsec_data_free(dcA.mat);

@@ -25,6 +25,7 @@
 #include "parsec/parsec_internal.h"
 #include "pb2_engine.h"
 #include <cuda_runtime_api.h>
+#include "checksum.h"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -147,6 +148,7 @@ int main(int argc, char *argv[])
     parsec_dtd_attach_arena_datatype(parsec, adt, &TILE_FULL);
 
     int errors[4] = {0, 0, 0, 0};
+    uint64_t checksum[4] = {0, 0, 0, 0};
     const char *names[4] = { "memset", "memset_and_read", "new_tile", "pingpong" };
     uint64_t gpu_tasks_before = 0, gpu_tasks = 0;
 
@@ -224,6 +226,7 @@ int main(int argc, char *argv[])
                 if( p[j] != want ) { if( errors[test] < 3 ) fprintf(stderr, "%s: A(%d)[%d] = %d, expected %d\n", names[test], i, j, p[j], want); errors[test]++; }
             }
         }
+        checksum[test] = fnv1a64(dcA.mat, (size_t)MT * nb * sizeof(int32_t), 0);
         if( 1 == test ) errors[1] += read_errors;
         for( int k = 0; k < 3; k++ ) if( NULL != tc[k] ) parsec_dtd_task_class_release(tp, tc[k]);
         parsec_taskpool_free(tp);
@@ -243,9 +246,10 @@ int main(int argc, char *argv[])
     }
     (void)gpu_tasks_before;
     const int total = errors[0] + errors[1] + errors[2] + errors[3];
-    printf("{\"app\": \"dtd_b200\", \"tiles\": %d, \"nb\": %d, \"hops\": %d, \"opaque\": %d, \"gpu_modules\": %d, \"b200_modules\": %d, "
+    printf("{\"app\": \"dtd_b200\", \"checksums\": [\"%016lx\", \"%016lx\", \"%016lx\", \"%016lx\"], \"tiles\": %d, \"nb\": %d, \"hops\": %d, \"opaque\": %d, \"gpu_modules\": %d, \"b200_modules\": %d, "
            "\"errors\": {\"memset\": %d, \"memset_and_read\": %d, \"new_tile\": %d, \"pingpong\": %d}, \"total_errors\": %d, "
            "\"executed_on_gpu\": %lu, \"tasks_engine\": %lu, \"tasks_lane\": %lu, \"bytes_h2d_dma\": %lu, \"bytes_d2h_dma\": %lu}\n",
+           (unsigned long)checksum[0], (unsigned long)checksum[1], (unsigned long)checksum[2], (unsigned long)checksum[3],
            MT, nb, NT, opaque, ngpu, b200, errors[0], errors[1], errors[2], errors[3], total,
            (unsigned long)gpu_tasks, (unsigned long)engine, (unsigned long)lane, (unsigned long)h2d_dma, (unsigned long)d2h_dma);
 

@@ -8,6 +8,7 @@
 #include "parsec/parsec_internal.h"
 #include "parsec/execution_stream.h"
 #include "ex02_b200.h"
+#include "checksum.h"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -37,6 +38,7 @@ int main(int argc, char *argv[])
     dcA.mat = parsec_data_allocate((size_t)elems * sizeof(int32_t));
     parsec_data_collection_set_key((parsec_data_collection_t*)&dcA, "dcA");
     int32_t *mat = (int32_t*)dcA.mat;
+    for( int i = 0; i < elems; i++ ) mat[i] = 7;      /* a defined start value: the golden vectors checksum the final tile */
     int ngpu = 0, b200 = 0;
     for( int i = 0; i < (int)parsec_nb_devices; i++ ) {
         parsec_device_module_t *d = parsec_mca_device_get(i);
@@ -72,9 +74,10 @@ int main(int argc, char *argv[])
         parsec_device_module_t *d = parsec_mca_device_get(i);
         if( NULL != d && PARSEC_DEV_IS_GPU(d->type) ) on_gpu += d->executed_tasks;
     }
-    printf("{\"app\": \"ex02_b200\", \"mode\": \"%s\", \"NB\": %d, \"tasks\": %d, \"tile_bytes\": %ld, \"repeats\": %d, \"cores\": %d, "
+    const uint64_t checksum = fnv1a64(mat, (size_t)elems * sizeof(int32_t), 0);
+    printf("{\"app\": \"ex02_b200\", \"checksum\": \"%016lx\", \"mode\": \"%s\", \"NB\": %d, \"tasks\": %d, \"tile_bytes\": %ld, \"repeats\": %d, \"cores\": %d, "
            "\"gpu_modules\": %d, \"b200_modules\": %d, \"best_s\": %.6f, \"mean_s\": %.6f, \"tasks_per_s\": %.1f, \"ns_per_edge\": %.1f, "
-           "\"errors\": %ld, \"executed_on_gpu\": %lu}\n", gpu ? "gpu" : "cpu", NB, NB + 1, (long)elems * 4, repeats,
+           "\"errors\": %ld, \"executed_on_gpu\": %lu}\n", (unsigned long)checksum, gpu ? "gpu" : "cpu", NB, NB + 1, (long)elems * 4, repeats,
            parsec->virtual_processes[0]->nb_cores, ngpu, b200, best, total / repeats, (NB + 1) / best, best / NB * 1e9, bad, (unsigned long)on_gpu);
     for( int i = 0; i < (int)parsec_nb_devices; i++ ) {
         parsec_device_module_t *d = parsec_mca_device_get(i);

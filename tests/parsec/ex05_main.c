@@ -19,6 +19,7 @@
 #include "parsec/execution_stream.h"
 #include "ex05_b200.h"
 #include "pb2_engine.h"
+#include "checksum.h"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -171,13 +172,14 @@ int main(int argc, char *argv[])
     }
     bad_total += (int64_t)st.check_mismatches;
     const long ntasks = (long)K * (1 + F);
-    printf("{\"app\": \"ex05_b200\", \"mode\": \"%s\", \"wb\": %d, \"K\": %d, \"NB\": %d, \"F\": %d, \"tile_bytes\": %ld, \"tasks\": %ld, \"repeats\": %d, "
+    const uint64_t checksum = wb ? fnv1a64(mat, (size_t)K * elems * sizeof(int32_t), 0) : 0;   /* the host tiles are final only with -w */
+    printf("{\"app\": \"ex05_b200\", \"checksum\": \"%016lx\", \"mode\": \"%s\", \"wb\": %d, \"K\": %d, \"NB\": %d, \"F\": %d, \"tile_bytes\": %ld, \"tasks\": %ld, \"repeats\": %d, "
            "\"cores\": %d, \"gpu_modules\": %d, \"b200_modules\": %d, \"best_s\": %.6f, \"mean_s\": %.6f, \"times_s\": [%s], \"tasks_per_s\": %.1f, "
            "\"errors\": %ld, \"executed_on_gpu\": %lu, \"required_in\": %lu, \"h2d_bytes\": %lu, \"h2d_prefetch_bytes\": %lu, "
            "\"b200\": {\"tasks_engine\": %lu, \"tasks_lane\": %lu, \"kernel_launches\": %lu, \"released_on_device\": %lu, "
            "\"bytes_h2d_kernel\": %lu, \"bytes_h2d_dma\": %lu, \"bytes_d2h_dma\": %lu, "
            "\"check_mismatches\": %lu, \"manager_entries\": %lu, \"max_concurrent_callers\": %lu, \"evictions\": %lu, \"w2r_copies\": %lu, \"peer_pulls\": %lu, \"peer_detours\": %lu}}\n",
-           gpu ? "gpu" : "cpu", wb, K, NB, F, (long)elems * 4, ntasks, repeats, nthreads, ngpu, b200, best, total / repeats, times,
+           (unsigned long)checksum, gpu ? "gpu" : "cpu", wb, K, NB, F, (long)elems * 4, ntasks, repeats, nthreads, ngpu, b200, best, total / repeats, times,
            ntasks / best, (long)bad_total, (unsigned long)executed_gpu, (unsigned long)required_in, (unsigned long)h2d, (unsigned long)h2d_prefetch,
            (unsigned long)st.tasks_engine, (unsigned long)st.tasks_lane, (unsigned long)st.kernel_launches,
            (unsigned long)st.released_on_device, (unsigned long)st.bytes_h2d_kernel,

@@ -7,6 +7,7 @@
 #include "parsec/parsec_internal.h"
 #include "parsec/execution_stream.h"
 #include "stage_b200.h"
+#include "checksum.h"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -97,9 +98,11 @@ int main(int argc, char *argv[])
         if( parsec_b200_is_b200_device(d) ) { parsec_b200_stats_t s1; parsec_b200_get_stats(d, &s1);
             st.tasks_engine += s1.tasks_engine; st.tasks_lane += s1.tasks_lane; st.bytes_h2d_dma += s1.bytes_h2d_dma; st.bytes_d2h_dma += s1.bytes_d2h_dma; }
     }
-    printf("{\"app\": \"stage_b200\", \"mode\": \"%s\", \"tiles\": %d, \"check_errors\": %d, \"host_errors\": %ld, \"executed_on_gpu\": %lu, "
+    uint64_t checksum = fnv1a64(dcA.mat, bytes, 0);
+    checksum = fnv1a64(dcB.mat, bytes, checksum); checksum = fnv1a64(dcC.mat, bytes, checksum);
+    printf("{\"app\": \"stage_b200\", \"checksum\": \"%016lx\", \"mode\": \"%s\", \"tiles\": %d, \"check_errors\": %d, \"host_errors\": %ld, \"executed_on_gpu\": %lu, "
            "\"gpu_modules\": %d, \"b200_modules\": %d, \"tasks_engine\": %lu, \"tasks_lane\": %lu, \"bytes_h2d_dma\": %lu, \"bytes_d2h_dma\": %lu, "
-           "\"complete_stage_calls\": %d}\n", gpu ? "gpu" : "cpu", MT * NT, out, host_bad, (unsigned long)on_gpu, ngpu, b200,
+           "\"complete_stage_calls\": %d}\n", (unsigned long)checksum, gpu ? "gpu" : "cpu", MT * NT, out, host_bad, (unsigned long)on_gpu, ngpu, b200,
            (unsigned long)st.tasks_engine, (unsigned long)st.tasks_lane, (unsigned long)st.bytes_h2d_dma, (unsigned long)st.bytes_d2h_dma,
            stage_b200_complete_stage_calls);
     PARSEC_OBJ_DESTRUCT(&tp->arenas_datatypes[PARSEC_stage_b200_DEFAULT_ADT_IDX]);
