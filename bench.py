@@ -430,9 +430,12 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        # capped so that the arm ends within minutes whatever --steps says: a step is the FULL workload on all cores
-        steps = min(args.steps, 20)
-        r = reference_cpu_arm(K, steps, args.warmup) or port_cpu_arm(K, steps, args.warmup)
+        # capped so that the arm ends within minutes whatever --steps says: a step is the FULL workload of the N-GPU arm
+        # (K groups per GPU x N) on all host cores
+        steps = min(args.steps, max(3, 20 // max(args.gpus, 1)))
+        Kref = K * max(args.gpus, 1)
+        cfg["reference_workload"] = "%d groups (%d tasks) per step: the whole job of the %d-GPU arm" % (Kref, Kref * (1 + F), max(args.gpus, 1))
+        r = reference_cpu_arm(Kref, steps, args.warmup) or port_cpu_arm(Kref, steps, args.warmup)
         print(json.dumps({"impl": "reference", "metric": "tasks/s", "value": r["value"], "unit": "tasks/s", "n_gpus": args.gpus,
                           "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic", "config": cfg,
