@@ -20,13 +20,17 @@ pass of that DAG.
   cpu_baseline / --impl reference
                the reference's OWN CPU implementation: the same generated task pool restricted to its CPU incarnations,
                scheduled by the reference runtime on all host cores (cpu_baseline.kind = "reference").
-  secondary    in-run records of the other BASELINE configs with their parity checks: configs[0] chain (tasks/s,
-               ns/edge), configs[2] DTD tile-GEMM NT=32 (TFLOP/s vs the measured bf16 peak, sampled value check),
-               at N=4 configs[3] rtt ring, at N=8 configs[4] Cholesky-shaped DAG, and the multi-GPU parity cases.
+  secondary    in-run records of the other BASELINE configs with their parity checks: configs[0] chain (tasks/s, ns/edge;
+               also under the reference's own cuda device module), configs[2] DTD tile-GEMM NT=32 (TFLOP/s vs the measured
+               bf16 peak, sampled value check), the e2e workload under the reference's own cuda device module (the drop-in
+               comparison), at N=4 configs[3] rtt ring, at N=8 configs[4] Cholesky-shaped DAG, the multi-GPU parity
+               cases, and the Ex05 DAG on a collection with k-cyclic factor 64.
 N > 1 (torchrun, one rank per GPU): weak scaling of the device-resident value -- every rank owns K groups of a K*N-group
-collection on a 1 x N block-cyclic grid, TaskRecv(k, n) lives on the owner of mydata(k+n); cross-GPU edges are released
-by the producer's CTA over NVLink and tiles are pulled by the consumers (NCCL is only the per-step barrier).  e2e at
-N > 1 is the SAME path as at N = 1 (the reference runtime driving N b200 device modules from one process, rank 0).
+collection on a 1 x N block-cyclic grid (kp = 1: tile k on rank k mod N, the map of mydata in examples/Ex05_Broadcast;
+--kp changes it), TaskRecv(k, n) lives on the owner of mydata(k+n); cross-GPU edges are released by the producer's CTA over
+NVLink and tiles are pulled by the consumers (NCCL is only the per-step barrier).  e2e at N > 1 is the SAME path as at
+N = 1: the reference runtime driving N b200 device modules from one process, run by rank 0 after the process group is gone.
+--impl reference: the reference's CPU implementation of the WHOLE job of the N-GPU arm (K*N groups) on the host cores.
 """
 import argparse
 import ctypes as C

@@ -23,8 +23,14 @@
  * so that a quiet device never holds SMs and blocking CUDA calls (cudaFree, cudaHostUnregister, ...) cannot
  * deadlock against it; the next submission relaunches it.
  *
- * Threading: ONE thread at a time may call the functions of a given stream (the device module's manager thread;
- * election happens above this layer, like gpu_device->mutex in device_gpu.c:3408-3424).
+ * Threading: a stream has a SUBMIT side (pb2_stream_set_tile / _submit / _add_edge / _kick) and a POLL side
+ * (pb2_stream_poll).  One thread at a time may be on each side, and the two sides may run at the same time on
+ * different threads: tickets travel back through a single-producer single-consumer ring, each side keeps its own
+ * counters on its own cache line, either side may find the kernel parked and relaunch it.  The caller's record
+ * (`*ticket`, whatever `cookie` points to) must be final BEFORE pb2_stream_submit: the task may retire, and be polled
+ * by the other thread, before the call returns.  Election of the two threads happens above this layer (the starter
+ * and the manager of the device module; gpu_device->mutex in device_gpu.c:3408-3424).  pb2_stream_quiesce, _stats,
+ * _destroy: with both sides idle.
  *
  * dry_run streams touch no CUDA API: tasks "retire" in dependency order without running their bodies.  They exist
  * for host-logic tests in GPU-less containers and are never a fallback: a stream is dry-run only when its creator

@@ -112,3 +112,11 @@ def test_stream_unknown_body_is_reported(engine):
                 if recs:
                     assert recs[0][4] != 0
                     raise L.Pb2Error(recs[0][4], "bad body")
+
+
+def test_submit_and_poll_from_two_threads(engine):
+    """The submit side and the poll side of a stream on two threads at once (what the device module's starter and manager
+    do): 50 000 empty tasks through a 1024-slot ring, every cookie retired exactly once."""
+    from test_stream_host import _two_sided
+    with Stream(engine, cmd_slots=1024) as s:
+        _two_sided(s, 50000)

@@ -84,3 +84,45 @@ def test_bad_arguments():
             s.submit(row)                  # tile id outside the table
         with pytest.raises(L.Pb2Error):
             s.add_edge(1, 2)               # tickets that are not in flight
+
+
+def _two_sided(stream, n):
+    """One thread submits n empty tasks (retrying when tickets or ring space run out), another polls at the same time:
+    every cookie comes back exactly once (the threading contract of include/pb2_stream.h)."""
+    import threading
+    from parsec_b200 import _lib as L
+    task = np.zeros(1, L.TASK_DTYPE)
+    task["tile"][:] = -1
+    task["body"] = L.BODY_NOP
+    seen, errors = [], []
+
+    def submitter():
+        try:
+            i = 0
+            while i < n:
+                if stream.submit(task, cookie=i + 1, allow_full=True) is None:
+                    continue
+                i += 1
+                if (i & 63) == 0:
+                    stream.kick()
+            stream.kick()
+        except Exception as exc:                       # pragma: no cover
+            errors.append(exc)
+
+    th = threading.Thread(target=submitter)
+    th.start()
+    spins = 0
+    while len(seen) < n and spins < 50_000_000 and not errors:
+        got = stream.poll()
+        seen.extend(r[0] for r in got)
+        spins += 1
+    th.join()
+    assert not errors, errors
+    assert len(seen) == n and sorted(seen) == list(range(1, n + 1))
+    assert stream.inflight() == 0
+
+
+def test_submit_and_poll_from_two_threads_dry_run():
+    from parsec_b200.stream import Stream
+    with Stream(None, dry_run=1, cmd_slots=1024) as s:
+        _two_sided(s, 20000)
