@@ -92,6 +92,10 @@ struct StreamDev {
 };
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const volatile uint32_t* p) { return *p; }
+__device__ __forceinline__ void st_volatile_v8(void* p, const uint4& a, const uint4& b) {      // 32-byte aligned
+    asm volatile("st.volatile.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
 __device__ __forceinline__ void st_volatile_v4(void* p, const uint4& v) {
     asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -331,12 +335,17 @@ pb2_stream_kernel(StreamDev sd) {
                 const uint32_t gen = (uint32_t)(ridx / ((unsigned long long)sd.ret_mask + 1ull)) + 1u;
                 const uint4 lo = __ldcg(reinterpret_cast<const uint4*>(&w.seen_version[(size_t)id * PB2_MAX_FLOWS]));
                 const unsigned long long res = *reinterpret_cast<volatile unsigned long long*>(&w.result[id]);
-                st_volatile_v4(&rec->seen[0], lo);
-                __threadfence_system();
                 uint4 hi;
                 hi.x = (uint32_t)res; hi.y = (uint32_t)(res >> 32); hi.z = (uint32_t)id;
                 hi.w = (gen & 0x7fffffffu) | (r == ~0ull ? 0x80000000u : 0u);
-                st_volatile_v4(&rec->result, hi);
+                // What the host must see BEFORE the record -- bytes this task pushed out to host memory, its trace entry --
+                // is ordered by one system-scope fence; a task that wrote nothing the host reads skips it.  The record
+                // itself is ONE 32-byte store (a single sector write over PCIe): the host, which reads the stamp first,
+                // never sees half of it, and the record is visible one posted write after the task ended.
+                bool host_reads = sd.trace != nullptr;
+                for (int f = 0; f < (int)t.nb_flows; ++f) host_reads |= (t.access[f] & PB2_FLOW_PUSHOUT) != 0;
+                if (host_reads) __threadfence_system();
+                st_volatile_v8(rec, lo, hi);
                 __threadfence_system();
                 atomicAdd(&sd.sctl->published.v, 1ull);
             }
