@@ -60,6 +60,7 @@ typedef struct parsec_b200_stats_s {
     uint64_t check_mismatches;      /* elements the CHECK bodies found different from what they expected             */
     uint64_t manager_entries;       /* how often a worker thread became the manager                                  */
     uint64_t lane_batched;          /* lane tasks a batching body took along (parsec_gpu_task_collect_batch)          */
+    uint64_t forwarded;             /* tasks short of memory here that were handed to the peer device holding their inputs */
     uint64_t max_concurrent_callers;
 } parsec_b200_stats_t;
 int parsec_b200_get_stats(const parsec_device_module_t *device, parsec_b200_stats_t *stats);

@@ -152,6 +152,8 @@ typedef struct parsec_device_b200_module_s {
      * and lane paths) is whichever thread holds `starter_active`: a caller of kernel_scheduler takes it when it is free
      * and keeps it while tasks keep arriving; the manager takes it when tasks that had to wait may go on.  The MANAGER
      * (elected through `owed`) owns the retire side: retire ring, pushouts through the copy engine, completion. */
+    volatile int32_t     handed_back B200_LINE;      /* tasks the starter gave back to the runtime (b200_forward_peer): the manager
+                                                      * subtracts them from `owed` like completions */
     volatile int32_t     starter_active B200_LINE;
     volatile int32_t     fatal;           /* the starter hit a fatal device problem: the manager gives the device up */
     volatile int32_t     memory_pressure; /* the heap has been full since the last memory_release: LRU order is kept from here on */
@@ -1374,6 +1376,57 @@ static void b200_finish(parsec_device_b200_module_t *dev, parsec_execution_strea
     dev->completed_now++;
 }
 
+/* A task that cannot get memory here, all of whose non-resident inputs are replicas of ONE peer b200 device where it
+ * needs no memory at all, runs THERE: two devices whose heaps are full of replicas that only tasks queued on the other
+ * device still reference would otherwise wait for each other for ever (each replica is retained until its readers
+ * have run).  Returns that device, or NULL. */
+static parsec_device_b200_module_t *b200_forward_peer(parsec_device_b200_module_t *dev, const parsec_gpu_task_t *gpu_task)
+{
+    const uint8_t my = dev->super.super.super.device_index;
+    parsec_device_b200_module_t *peer = NULL;
+    if( PARSEC_GPU_TASK_TYPE_KERNEL != gpu_task->task_type ) return NULL;
+    for( uint32_t i = 0; i < gpu_task->nb_flows; i++ ) {
+        const parsec_flow_t *flow = gpu_task->flow_info[i].flow;
+        if( PARSEC_FLOW_ACCESS_NONE == (PARSEC_FLOW_ACCESS_MASK & flow->flow_flags) ) continue;
+        const parsec_data_copy_t *in = gpu_task->ec->data[i].data_in;
+        if( NULL == in || in->device_index == my ) continue;
+        if( !parsec_mca_device_is_gpu(in->device_index) ) {
+            if( NULL != PARSEC_DATA_GET_COPY(in->original, my) ) continue;        /* resident here, would have to be there too */
+            return NULL;
+        }
+        parsec_device_module_t *m = parsec_mca_device_get(in->device_index);
+        if( !parsec_b200_is_b200_device(m) ) return NULL;
+        if( NULL != peer && (parsec_device_module_t*)peer != m ) return NULL;
+        peer = (parsec_device_b200_module_t*)m;
+    }
+    if( NULL == peer || peer->dry_run != dev->dry_run || b200_needs_memory(peer, gpu_task) ) return NULL;
+    return peer;
+}
+
+/* starter: `bt` (in `stalled`, BT_NEW) is short of memory here.  If its inputs sit on a peer device where it needs none, the task
+ * goes BACK TO THE RUNTIME with that peer as its selected device: the runtime runs its hook again (what a hook that returns
+ * AGAIN gets, scheduling.c:445-467) and keeps an a-priori selected device (device.c:113-118).  returns 1 when the task left. */
+static int b200_hand_back(parsec_device_b200_module_t *dev, parsec_execution_stream_t *es, b200_task_t *bt)
+{
+    parsec_device_b200_module_t *peer;
+    if( NULL == es || BT_NEW != bt->state || NULL == (peer = b200_forward_peer(dev, bt->gpu_task)) ) return 0;
+    parsec_gpu_task_t *gt = bt->gpu_task;
+    parsec_task_t *task = gt->ec;
+    parsec_list_nolock_remove(&dev->stalled, &bt->item);
+    PARSEC_LIST_ITEM_SINGLETON(&bt->item);
+    dev->nb_stalled--;
+    b200_bt_free(bt);
+    gt->last_data_check_epoch = UINT64_MAX;
+    gt->release_device_task(gt);                       /* the hook builds a new one */
+    (void)parsec_atomic_fetch_add_int64(&task->selected_device->device_load, -task->load);   /* __parsec_execute adds it again ... */
+    task->selected_device = &peer->super.super.super;                 /* ... to the device it keeps (device.c: "a-priori selected_device") */
+    (void)parsec_atomic_fetch_add_int32(&dev->handed_back, 1);      /* the manager takes it off `owed` */
+    dev->st.forwarded++;
+    PARSEC_LIST_ITEM_SINGLETON(&task->super);
+    (void)__parsec_reschedule(es, task);
+    return 1;
+}
+
 /* inbox -> lists of tasks to start, in slot order (starter only).  A slot whose index has been taken but whose pointer
  * is not there yet ends the pass: its caller is a few instructions away from storing it.  The tile descriptions a caller
  * decided go to the device here, in the order of the decisions.  returns the number of records taken, < 0 on error */
@@ -1481,7 +1534,10 @@ static int b200_start_pass(parsec_device_b200_module_t *dev, parsec_execution_st
             }
             /* once a task has failed to get memory in this pass, only tasks that need none are tried -- all of them:
              * the task whose retirement frees memory may be anywhere behind */
-            if( mem_blocked && BT_NEW == bt->state && b200_needs_memory(dev, bt->gpu_task) ) continue;
+            if( mem_blocked && BT_NEW == bt->state && b200_needs_memory(dev, bt->gpu_task) ) {
+                if( b200_hand_back(dev, es, bt) ) moved++;
+                continue;
+            }
             parsec_list_nolock_remove(&dev->stalled, it);
             PARSEC_LIST_ITEM_SINGLETON(it);
             if( BT_NEW == bt->state ) {
@@ -1499,6 +1555,7 @@ static int b200_start_pass(parsec_device_b200_module_t *dev, parsec_execution_st
                 else parsec_list_nolock_add_before(&dev->stalled, next, it);
                 if( BT_NEW != bt->state ) break;            /* ring full */
                 if( dev->again_window ) break;              /* throttled: every cold task behind this one is, too */
+                if( b200_hand_back(dev, es, bt) ) { moved++; continue; }
                 mem_blocked = 1;
                 continue;
             }
@@ -1705,7 +1762,7 @@ b200_kernel_scheduler(parsec_device_module_t *module, parsec_execution_stream_t 
     }
     bt->has_complete_stage = (NULL != gpu_task->complete_stage);     /* a body may install one (dtd_test_simple_gemm.c:538) */
     int decided = 0;
-    if( bt->recorded && bt->is_kernel && !b200_prepare_resident(dev, bt) && dev->nb_stalled < 64 &&
+    if( bt->recorded && bt->is_kernel && !b200_prepare_resident(dev, bt) && dev->nb_stalled < 64 && !dev->memory_pressure &&
         dev->inbox_tail - dev->inbox_head < B200_INBOX_SLOTS - 4096 /* never wait for an inbox slot with the lock held */ ) {
         /*  - for an engine task that needs replicas made or filled: the same decisions the starter would take (heap,
          *    source, versions), under the residency lock.  The tile descriptions ride in the record. */
@@ -1780,7 +1837,8 @@ b200_kernel_scheduler(parsec_device_module_t *module, parsec_execution_stream_t 
         }
         /* `completed_now` belongs to the manager: take a private copy BEFORE the subtraction -- the instant `owed`
          * reaches zero another thread may become the manager and reset the field */
-        const int32_t done_now = dev->completed_now;
+        int32_t done_now = dev->completed_now;
+        if( dev->handed_back ) done_now += parsec_atomic_fetch_and_int32(&dev->handed_back, 0);
         if( done_now ) {
             idle_spins = 0;
             /* the subtraction that reaches zero is the LAST thing a manager does with the device */

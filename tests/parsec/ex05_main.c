@@ -159,7 +159,7 @@ int main(int argc, char *argv[])
         if( parsec_b200_is_b200_device(d) ) {
             parsec_b200_stats_t s1; parsec_b200_get_stats(d, &s1);
             st.tasks_engine += s1.tasks_engine; st.tasks_lane += s1.tasks_lane; st.kernel_launches += s1.kernel_launches;
-            st.released_on_device += s1.released_on_device;
+            st.released_on_device += s1.released_on_device; st.forwarded += s1.forwarded;
             st.bytes_h2d_kernel += s1.bytes_h2d_kernel; st.bytes_h2d_dma += s1.bytes_h2d_dma; st.bytes_d2h_dma += s1.bytes_d2h_dma;
             st.manager_entries += s1.manager_entries; st.evictions += s1.evictions; st.w2r_copies += s1.w2r_copies;
             st.check_mismatches += s1.check_mismatches; st.peer_pulls += s1.peer_pulls; st.peer_detours += s1.peer_detours;
@@ -177,12 +177,12 @@ int main(int argc, char *argv[])
            "\"cores\": %d, \"gpu_modules\": %d, \"b200_modules\": %d, \"best_s\": %.6f, \"mean_s\": %.6f, \"times_s\": [%s], \"tasks_per_s\": %.1f, "
            "\"errors\": %ld, \"executed_on_gpu\": %lu, \"required_in\": %lu, \"h2d_bytes\": %lu, \"h2d_prefetch_bytes\": %lu, "
            "\"b200\": {\"tasks_engine\": %lu, \"tasks_lane\": %lu, \"kernel_launches\": %lu, \"released_on_device\": %lu, "
-           "\"bytes_h2d_kernel\": %lu, \"bytes_h2d_dma\": %lu, \"bytes_d2h_dma\": %lu, "
+           "\"forwarded\": %lu, \"bytes_h2d_kernel\": %lu, \"bytes_h2d_dma\": %lu, \"bytes_d2h_dma\": %lu, "
            "\"check_mismatches\": %lu, \"manager_entries\": %lu, \"max_concurrent_callers\": %lu, \"evictions\": %lu, \"w2r_copies\": %lu, \"peer_pulls\": %lu, \"peer_detours\": %lu}}\n",
            (unsigned long)checksum, gpu ? "gpu" : "cpu", wb, K, NB, F, (long)elems * 4, ntasks, repeats, nthreads, ngpu, b200, best, total / repeats, times,
            ntasks / best, (long)bad_total, (unsigned long)executed_gpu, (unsigned long)required_in, (unsigned long)h2d, (unsigned long)h2d_prefetch,
            (unsigned long)st.tasks_engine, (unsigned long)st.tasks_lane, (unsigned long)st.kernel_launches,
-           (unsigned long)st.released_on_device, (unsigned long)st.bytes_h2d_kernel,
+           (unsigned long)st.released_on_device, (unsigned long)st.forwarded, (unsigned long)st.bytes_h2d_kernel,
            (unsigned long)st.bytes_h2d_dma, (unsigned long)st.bytes_d2h_dma, (unsigned long)st.check_mismatches, (unsigned long)st.manager_entries,
            (unsigned long)st.max_concurrent_callers, (unsigned long)st.evictions, (unsigned long)st.w2r_copies, (unsigned long)st.peer_pulls, (unsigned long)st.peer_detours);
 

@@ -235,3 +235,15 @@ def test_component_gpu_trace_shows_the_dependency_order_on_the_device_clock(tmp_
             nrecv += 1
             assert e["ts"] >= bcast_end[e["args"]["l0"]] and e["args"]["stage_in_bytes"] == 0   # a receiver starts after its broadcast ended
     assert nrecv == K * 8
+
+
+@pytest.mark.parametrize("attempt", [0, 1, 2])
+def test_component_dry_run_two_devices_with_small_heaps_do_not_wait_for_each_other(attempt):
+    """4096 tiles through two heaps of 48 blocks: each heap fills with replicas that only tasks queued on the OTHER device
+    still reference.  A task that is short of memory where it is, and whose inputs sit on the peer where it needs none, is
+    handed back to the runtime with that peer as its device (this configuration hung two runs in three before)."""
+    K = 4096
+    rc, d, err = run("ex05_b200", ["-K", K, "-t", 65536, "-m", "gpu", "-c", 3],
+                     {"PARSEC_MCA_device_b200_dry_run": "2", "PARSEC_MCA_device_b200_memory_number_of_blocks": "48"}, timeout=120)
+    assert d["b200_modules"] == 2 and d["executed_on_gpu"] == K * 9, err[-500:]
+    assert d["b200"]["evictions"] > 0
