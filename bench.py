@@ -170,6 +170,7 @@ def e2e_mca(K, ngpus, steps, cores):
             "d2h_bytes_per_step": 32 * d["tasks"],                                      # retire records (result, versions)
             "tile_gbs": K * (1 + F) * TILE / sec / 1e9, "path": "reference runtime + MCA component parsec/mca/device/b200 (%d module%s), %d worker threads" % (ngpus, "" if ngpus == 1 else "s", d["cores"]),
             "tasks": d["tasks"], "kernel_launches_total": d["b200"]["kernel_launches"], "best_ms": d["best_s"] * 1e3,
+            "median_ms": sorted(times)[len(times) // 2] * 1e3, "steps": len(times),
             "max_concurrent_callers": d["b200"]["max_concurrent_callers"]}
 
 
@@ -411,7 +412,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--groups", type=int, default=K_GROUPS, help="broadcast groups per GPU (config value: 4096)")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=10, help="timed passes of the e2e run (the host side shares the box: more passes, steadier mean)")
     ap.add_argument("--e2e-cores", type=int, default=32, help="worker threads of the reference runtime in the e2e run")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary records of the other BASELINE configs")
     ap.add_argument("--kp", type=int, default=1, help="N>1: k-cyclic factor of the 1xN collection (1: the map of examples/Ex05_Broadcast)")
