@@ -14,10 +14,14 @@
  *     parsec_device_memory_reserve / _release / parsec_device_flush_lru (device_gpu.c:866-1100), exactly like the
  *     cuda, hip and level_zero components use them.
  *
- * Threading (SURVEY.md 8b "Threading"): any worker thread may call kernel_scheduler concurrently.  Callers push their
- * gpu_task on a lock-free inbox and add one to `owed`; the caller that takes `owed` from 0 to 1 becomes the MANAGER and
- * keeps driving the device until `owed` is back to 0 (every completed task subtracts one).  Only the manager touches
- * the LRUs, the command ring and the retire ring, and it completes tasks with its own execution stream.
+ * Threading (SURVEY.md 8b "Threading"): any worker thread may call kernel_scheduler concurrently.  A caller does for its
+ * own task whatever needs no device-wide decision (task record, recording of the body, residency of the flows -- under
+ * `alloc_lock` when replicas have to be made or filled), puts the record into the slot-ring inbox and adds one to `owed`.
+ * Two roles then drive the device.  The STARTER (whoever holds `starter_active`) drains the inbox in order and owns the
+ * submit side of the stream: tile descriptions, command ring, events of the copy-engine and lane paths.  The MANAGER (the
+ * caller that takes `owed` from 0 to 1, until it is back to 0: every completed task subtracts one) owns the poll side:
+ * retire ring, copy-engine pushouts, and the hand-over of finished tasks to the worker pool, where their epilog and
+ * __parsec_complete_execution run (b200_epilog_hook).  The LRUs are shared by the starter and the epilogs (`lru_lock`).
  */
 #include "parsec/parsec_config.h"
 #include "parsec/parsec_internal.h"
