@@ -65,6 +65,17 @@ def test_component_dry_run_memory_pressure_evicts_and_writes_back():
     assert d["b200"]["w2r_copies"] > 0
 
 
+@pytest.mark.parametrize("pins", ["iterators_checker", "print_steals", "alperf"])
+def test_component_dry_run_under_pins_modules(pins):
+    """(f)4: the runtime's PINS events (EXEC_BEGIN/END around the hook, COMPLETE_EXEC_BEGIN/END inside
+    __parsec_complete_execution, scheduling.c:185-192, :477-502) fire for tasks the component runs, and for the proxy
+    tasks that carry their completion: the reference's PINS modules run over them unchanged.  iterators_checker walks
+    iterate_successors / iterate_predecessors of every task it sees at EXEC_BEGIN."""
+    rc, d, err = run("ex05_b200", ["-K", 64, "-t", 1024, "-m", "gpu", "-c", 4],
+                     {"PARSEC_MCA_device_b200_dry_run": "1", "PARSEC_MCA_mca_pins": pins})
+    assert d["executed_on_gpu"] == 64 * 9 and d["b200_modules"] == 1, err[-500:]
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("wb", [False, True])
 def test_component_gpu_ex05_known_answer(wb):
