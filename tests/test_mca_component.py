@@ -65,6 +65,16 @@ def test_component_dry_run_memory_pressure_evicts_and_writes_back():
     assert d["b200"]["w2r_copies"] > 0
 
 
+@pytest.mark.parametrize("sched", ["ap", "gd", "ip", "lfq", "lhq", "ll", "llp", "ltq", "pbq", "rnd", "spq"])
+def test_component_dry_run_under_every_scheduler_module(sched):
+    """The completion proxies go through the runtime's scheduler like any task (__parsec_schedule of a ring of tasks with
+    priority INT32_MAX): every scheduler module of the reference (parsec/mca/sched/*) has to take them."""
+    K, rep = 256, 3
+    rc, d, err = run("ex05_b200", ["-K", K, "-t", 1024, "-m", "gpu", "-c", 8, "-r", rep],
+                     {"PARSEC_MCA_device_b200_dry_run": "1", "PARSEC_MCA_mca_sched": sched}, timeout=120)
+    assert d["executed_on_gpu"] == K * 9 * rep and d["b200_modules"] == 1, err[-500:]
+
+
 @pytest.mark.parametrize("pins", ["iterators_checker", "print_steals", "alperf"])
 def test_component_dry_run_under_pins_modules(pins):
     """(f)4: the runtime's PINS events (EXEC_BEGIN/END around the hook, COMPLETE_EXEC_BEGIN/END inside
