@@ -2,10 +2,12 @@
  * ex05_main.c -- driver of tests/parsec/ex05_b200.jdf: plays the role the reference's test mains play
  * (examples/Ex05_Broadcast.jdf main, tests/runtime/cuda/stage_main.c).  Prints one JSON line.
  *
- *   ex05_b200 [-K groups] [-N NB] [-t tile_elems] [-r repeats] [-c cores] [-m cpu|gpu] [-v] [-- parsec args]
+ *   ex05_b200 [-K groups] [-N NB] [-t tile_elems] [-r repeats] [-c cores] [-m cpu|gpu] [-P pools] [-v] [-- parsec args]
  *
  * -m cpu: restrict the taskpool to the CPU incarnations (the reference's own scheduler + CPU bodies: the CPU baseline);
  * -m gpu: every task class has a CUDA incarnation, whichever GPU component is active drives it.
+ * -P n: n task pools, each on a collection of its own, are handed to the context TOGETHER (one start / wait): the device
+ *       modules see the tasks of several pools interleaved.
  * The check is the example's known answer: every TaskRecv(k, n) sees k in the whole tile; with -m gpu the verdict comes
  * from the engine's CHECK body through a complete_stage-free path: the final host tiles (pushed out because the
  * collection is flushed at the end) must hold k, and the device statistics must show each tile staged in once.
@@ -34,8 +36,8 @@ static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &
 
 int main(int argc, char *argv[])
 {
-    int K = 64, NB = 14, elems = 256 * 256, repeats = 1, cores = -1, verbose = 0, gpu = 1, wb = 0, prefetch = 0, c;
-    while( -1 != (c = getopt(argc, argv, "K:N:t:r:c:m:vwp")) ) {
+    int K = 64, NB = 14, elems = 256 * 256, repeats = 1, cores = -1, verbose = 0, gpu = 1, wb = 0, prefetch = 0, pools = 1, c;
+    while( -1 != (c = getopt(argc, argv, "K:N:t:r:c:m:P:vwp")) ) {
         switch(c) {
         case 'K': K = atoi(optarg); break;
         case 'N': NB = atoi(optarg); break;
@@ -46,6 +48,7 @@ int main(int argc, char *argv[])
         case 'v': verbose = 1; break;
         case 'w': wb = 1; break;
         case 'p': prefetch = 1; break;
+        case 'P': pools = atoi(optarg); if( pools < 1 ) pools = 1; if( pools > 8 ) pools = 8; break;
         default: break;
         }
     }
@@ -60,7 +63,8 @@ int main(int argc, char *argv[])
     const int F = NB / 2 + 1;
     const int nthreads = parsec->virtual_processes[0]->nb_cores;
 
-    parsec_matrix_block_cyclic_t dcA;
+    parsec_matrix_block_cyclic_t dcs[8];
+#define dcA dcs[0]
     /* tiles of tile_mb x tile_nb elements stacked in one column of tiles: the matrix sizes of the reference API are ints,
      * K * elems does not fit one for the 8-GPU workload (32768 tiles of 65536 elements) */
     const int tile_nb = (0 == elems % 256) ? 256 : 1, tile_mb = elems / tile_nb;
@@ -69,14 +73,22 @@ int main(int argc, char *argv[])
     dcA.mat = parsec_data_allocate((size_t)dcA.super.nb_local_tiles * (size_t)dcA.super.bsiz *
                                    (size_t)parsec_datadist_getsizeoftype(dcA.super.mtype));
     parsec_data_collection_set_key((parsec_data_collection_t*)&dcA, "dcA");
-    int32_t *mat = (int32_t*)dcA.mat;
+    static char dc_names[8][8];
+    for( int q = 1; q < pools; q++ ) {
+        parsec_matrix_block_cyclic_init(&dcs[q], PARSEC_MATRIX_INTEGER, PARSEC_MATRIX_TILE, 0,
+                                        tile_mb, tile_nb, K * tile_mb, tile_nb, 0, 0, K * tile_mb, tile_nb, 1, 1, 1, 1, 0, 0);
+        dcs[q].mat = parsec_data_allocate((size_t)dcs[q].super.nb_local_tiles * (size_t)dcs[q].super.bsiz *
+                                          (size_t)parsec_datadist_getsizeoftype(dcs[q].super.mtype));
+        snprintf(dc_names[q], sizeof dc_names[q], "dc%c", 'A' + q);
+        parsec_data_collection_set_key((parsec_data_collection_t*)&dcs[q], dc_names[q]);
+    }
 
     int ngpu = 0, b200 = 0;
     for( int i = 0; i < (int)parsec_nb_devices; i++ ) {
         parsec_device_module_t *d = parsec_mca_device_get(i);
         if( NULL == d || !PARSEC_DEV_IS_GPU(d->type) ) continue;
         ngpu++; b200 += parsec_b200_is_b200_device(d);
-        if( gpu ) dcA.super.super.register_memory(&dcA.super.super, d);
+        for( int q = 0; gpu && q < pools; q++ ) dcs[q].super.super.register_memory(&dcs[q].super.super, d);
     }
     if( gpu && 0 == ngpu ) { fprintf(stderr, "-m gpu but no GPU device module is active\n"); return 3; }
 
@@ -100,19 +112,24 @@ int main(int argc, char *argv[])
     char times[4096]; int tl = 0; times[0] = 0;
     int64_t bad_total = 0;
     for( int r = 0; r < repeats; r++ ) {
-        for( size_t i = 0; i < (size_t)K * elems; i++ ) mat[i] = -7;
-        parsec_ex05_b200_taskpool_t *tp = parsec_ex05_b200_new(&dcA.super, NB, errors, wb);
-        parsec_arena_datatype_set_type(&tp->arenas_datatypes[PARSEC_ex05_b200_DEFAULT_ADT_IDX],
-                                       (size_t)elems * sizeof(int32_t), PARSEC_ARENA_ALIGNMENT_SSE, parsec_datatype_int_t);
-        if( !gpu ) {
-            for( int i = 0; i < (int)parsec_nb_devices; i++ ) {
-                parsec_device_module_t *d = parsec_mca_device_get(i);
-                if( NULL != d && PARSEC_DEV_IS_GPU(d->type) ) tp->super.devices_index_mask &= ~(1u << i);
+        parsec_ex05_b200_taskpool_t *tps[8];
+        for( int q = 0; q < pools; q++ ) {
+            int32_t *m = (int32_t*)dcs[q].mat;
+            for( size_t i = 0; i < (size_t)K * elems; i++ ) m[i] = -7;
+            tps[q] = parsec_ex05_b200_new(&dcs[q].super, NB, errors, wb);
+            parsec_arena_datatype_set_type(&tps[q]->arenas_datatypes[PARSEC_ex05_b200_DEFAULT_ADT_IDX],
+                                           (size_t)elems * sizeof(int32_t), PARSEC_ARENA_ALIGNMENT_SSE, parsec_datatype_int_t);
+            if( !gpu ) {
+                for( int i = 0; i < (int)parsec_nb_devices; i++ ) {
+                    parsec_device_module_t *d = parsec_mca_device_get(i);
+                    if( NULL != d && PARSEC_DEV_IS_GPU(d->type) ) tps[q]->super.devices_index_mask &= ~(1u << i);
+                }
             }
         }
         struct timespec ts0, ts1; clock_gettime(CLOCK_MONOTONIC, &ts0);
         const double t0 = now_s();
-        if( 0 > parsec_context_add_taskpool(parsec, (parsec_taskpool_t*)tp) ) return 4;
+        for( int q = 0; q < pools; q++ )
+            if( 0 > parsec_context_add_taskpool(parsec, (parsec_taskpool_t*)tps[q]) ) return 4;
         const double ta = now_s();
         if( 0 > parsec_context_start(parsec) ) return 4;
         const double tst = now_s();
@@ -138,14 +155,17 @@ int main(int argc, char *argv[])
         /* the host tiles hold k when a CPU body wrote them, or when the GPU result was written back (-w, or a module whose
          * memory_release brings dirty replicas home) */
         if( !gpu || wb || b200 )
-            for( int k = 0; k < K; k++ )
-                for( int i = 0; i < elems; i += (elems > 64 ? elems / 64 : 1) ) bad_total += (mat[(size_t)k * elems + i] != k);
+            for( int q = 0; q < pools; q++ )
+                for( int k = 0; k < K; k++ )
+                    for( int i = 0; i < elems; i += (elems > 64 ? elems / 64 : 1) ) bad_total += (((int32_t*)dcs[q].mat)[(size_t)k * elems + i] != k);
         if( verbose ) fprintf(stderr, "repeat %d: dag %.3f ms, flush %.3f ms\n", r, 1e3 * (t1 - t0), 1e3 * (t2 - t1));
         if( tl < 4000 ) tl += snprintf(times + tl, sizeof(times) - (size_t)tl, "%s%.6f", r ? ", " : "", t1 - t0);
         if( t1 - t0 < best ) best = t1 - t0;
         total += t1 - t0;
-        PARSEC_OBJ_DESTRUCT(&tp->arenas_datatypes[PARSEC_ex05_b200_DEFAULT_ADT_IDX]);
-        parsec_taskpool_free((parsec_taskpool_t*)tp);
+        for( int q = 0; q < pools; q++ ) {
+            PARSEC_OBJ_DESTRUCT(&tps[q]->arenas_datatypes[PARSEC_ex05_b200_DEFAULT_ADT_IDX]);
+            parsec_taskpool_free((parsec_taskpool_t*)tps[q]);
+        }
     }
     for( int t = 0; t < nthreads; t++ ) bad_total += errors[t];
 
@@ -171,15 +191,16 @@ int main(int argc, char *argv[])
         if( 0 == pb2_body_launch_errors(&e, 1) ) st.check_mismatches += e;
     }
     bad_total += (int64_t)st.check_mismatches;
-    const long ntasks = (long)K * (1 + F);
-    const uint64_t checksum = wb ? fnv1a64(mat, (size_t)K * elems * sizeof(int32_t), 0) : 0;   /* the host tiles are final only with -w */
-    printf("{\"app\": \"ex05_b200\", \"checksum\": \"%016lx\", \"mode\": \"%s\", \"wb\": %d, \"K\": %d, \"NB\": %d, \"F\": %d, \"tile_bytes\": %ld, \"tasks\": %ld, \"repeats\": %d, "
+    const long ntasks = (long)K * (1 + F) * pools;
+    uint64_t checksum = 0;                       /* the host tiles are final only with -w */
+    for( int q = 0; wb && q < pools; q++ ) checksum = fnv1a64(dcs[q].mat, (size_t)K * elems * sizeof(int32_t), checksum);
+    printf("{\"app\": \"ex05_b200\", \"checksum\": \"%016lx\", \"mode\": \"%s\", \"wb\": %d, \"K\": %d, \"NB\": %d, \"F\": %d, \"tile_bytes\": %ld, \"tasks\": %ld, \"repeats\": %d, \"pools\": %d, "
            "\"cores\": %d, \"gpu_modules\": %d, \"b200_modules\": %d, \"best_s\": %.6f, \"mean_s\": %.6f, \"times_s\": [%s], \"tasks_per_s\": %.1f, "
            "\"errors\": %ld, \"executed_on_gpu\": %lu, \"required_in\": %lu, \"h2d_bytes\": %lu, \"h2d_prefetch_bytes\": %lu, "
            "\"b200\": {\"tasks_engine\": %lu, \"tasks_lane\": %lu, \"kernel_launches\": %lu, \"released_on_device\": %lu, "
            "\"forwarded\": %lu, \"bytes_h2d_kernel\": %lu, \"bytes_h2d_dma\": %lu, \"bytes_d2h_dma\": %lu, "
            "\"check_mismatches\": %lu, \"manager_entries\": %lu, \"max_concurrent_callers\": %lu, \"evictions\": %lu, \"w2r_copies\": %lu, \"peer_pulls\": %lu, \"peer_detours\": %lu}}\n",
-           (unsigned long)checksum, gpu ? "gpu" : "cpu", wb, K, NB, F, (long)elems * 4, ntasks, repeats, nthreads, ngpu, b200, best, total / repeats, times,
+           (unsigned long)checksum, gpu ? "gpu" : "cpu", wb, K, NB, F, (long)elems * 4, ntasks, repeats, pools, nthreads, ngpu, b200, best, total / repeats, times,
            ntasks / best, (long)bad_total, (unsigned long)executed_gpu, (unsigned long)required_in, (unsigned long)h2d, (unsigned long)h2d_prefetch,
            (unsigned long)st.tasks_engine, (unsigned long)st.tasks_lane, (unsigned long)st.kernel_launches,
            (unsigned long)st.released_on_device, (unsigned long)st.forwarded, (unsigned long)st.bytes_h2d_kernel,
@@ -188,10 +209,12 @@ int main(int argc, char *argv[])
 
     for( int i = 0; i < (int)parsec_nb_devices; i++ ) {
         parsec_device_module_t *d = parsec_mca_device_get(i);
-        if( gpu && NULL != d && PARSEC_DEV_IS_GPU(d->type) ) dcA.super.super.unregister_memory(&dcA.super.super, d);
+        for( int q = 0; gpu && NULL != d && PARSEC_DEV_IS_GPU(d->type) && q < pools; q++ ) dcs[q].super.super.unregister_memory(&dcs[q].super.super, d);
     }
-    parsec_data_free(dcA.mat);
-    parsec_tiled_matrix_destroy((parsec_tiled_matrix_t*)&dcA);
+    for( int q = 0; q < pools; q++ ) {
+        parsec_data_free(dcs[q].mat);
+        parsec_tiled_matrix_destroy((parsec_tiled_matrix_t*)&dcs[q]);
+    }
     free(errors);
     parsec_fini(&parsec);
     return bad_total ? 1 : 0;

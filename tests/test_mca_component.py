@@ -65,6 +65,18 @@ def test_component_dry_run_memory_pressure_evicts_and_writes_back():
     assert d["b200"]["w2r_copies"] > 0
 
 
+@pytest.mark.parametrize("ndev", [1, 2])
+def test_component_dry_run_several_taskpools_at_once(ndev):
+    """Three task pools, each on a collection of its own, handed to the context together: the module sees their tasks
+    interleaved (proxies carry the task pool of the task they complete; taskpool_register / unregister per pool)."""
+    K, P, rep = 128, 3, 2
+    rc, d, _ = run("ex05_b200", ["-K", K, "-t", 1024, "-m", "cpu", "-c", 8, "-w", "-P", P, "-r", rep], CPU_ENV)
+    assert rc == 0 and d["errors"] == 0 and d["tasks"] == K * 9 * P and d["pools"] == P
+    rc, d, err = run("ex05_b200", ["-K", K, "-t", 1024, "-m", "gpu", "-c", 8, "-P", P, "-r", rep],
+                     {"PARSEC_MCA_device_b200_dry_run": str(ndev)}, timeout=120)
+    assert d["executed_on_gpu"] == K * 9 * P * rep and d["b200_modules"] == ndev, err[-500:]
+
+
 @pytest.mark.parametrize("sched", ["ap", "gd", "ip", "lfq", "lhq", "ll", "llp", "ltq", "pbq", "rnd", "spq"])
 def test_component_dry_run_under_every_scheduler_module(sched):
     """The completion proxies go through the runtime's scheduler like any task (__parsec_schedule of a ring of tasks with
