@@ -32,6 +32,7 @@ int parsec_b200_cmd_slots = 65536;
 int parsec_b200_idle_us = 2000;
 int parsec_b200_max_workers = 0;
 char *parsec_b200_trace = NULL;
+int parsec_b200_nvtx = 0;
 int parsec_b200_parallel_completion = 1;
 int parsec_b200_stage_window = 32 * 1024 * 1024;
 int parsec_b200_registration_cache = 1;
@@ -110,6 +111,11 @@ static int device_b200_component_register(void)
                                            "Write one Chrome-trace JSON file <value>.<device index>.json per device at finalize: every task with the "
                                            "device-clock time a worker CTA started and finished it and the SM it ran on (empty: off)",
                                            false, false, "", &parsec_b200_trace);
+    (void)parsec_mca_param_reg_int_name("device_b200", "nvtx",
+                                        "Wrap the host side of the device in NVTX ranges (domain \"parsec_b200\": start pass, retire pass, "
+                                        "epilog batch) and mark every manager election; what profiling_nvtx.c does for the profiling keys "
+                                        "of the reference's stream engine",
+                                        false, false, 0, &parsec_b200_nvtx);
     return (0 == parsec_device_b200_enabled && 0 == parsec_b200_dry_run) ? MCA_ERROR : MCA_SUCCESS;
 }
 

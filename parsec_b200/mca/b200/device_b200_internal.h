@@ -12,6 +12,7 @@ extern int parsec_device_b200_enabled, parsec_device_b200_enabled_index, parsec_
 extern int parsec_b200_memory_block_size, parsec_b200_memory_percentage, parsec_b200_memory_number_of_blocks;
 extern int parsec_b200_parallel_completion, parsec_b200_stage_window, parsec_b200_registration_cache;
 extern char *parsec_b200_trace;
+extern int parsec_b200_nvtx;
 extern int parsec_b200_cmd_slots, parsec_b200_idle_us, parsec_b200_max_workers;
 
 int  parsec_b200_device_count(void);

@@ -52,6 +52,29 @@ static inline uint64_t b200_now_ns(void) { struct timespec ts; clock_gettime(CLO
 #include <x86intrin.h>
 #define B200_TSC() __rdtsc()
 
+/* device_b200_nvtx: the host side of a device as NVTX ranges of the domain "parsec_b200" (header-only NVTX3: the calls are
+ * no-ops unless a tool injected itself; what parsec/profiling_nvtx.c does for the profiling keys of device_gpu.c:348-381) */
+#include <nvtx3/nvToolsExt.h>
+static nvtxDomainHandle_t b200_nvtx_domain = NULL;
+static inline void b200_nvtx_attr(nvtxEventAttributes_t *a, const char *name)
+{
+    memset(a, 0, sizeof *a);
+    a->version = NVTX_VERSION; a->size = NVTX_EVENT_ATTRIB_STRUCT_SIZE;
+    a->messageType = NVTX_MESSAGE_TYPE_ASCII; a->message.ascii = name;
+}
+static inline void b200_nvtx_push(const char *name)
+{
+    if( parsec_b200_nvtx ) { nvtxEventAttributes_t a; b200_nvtx_attr(&a, name); (void)nvtxDomainRangePushEx(b200_nvtx_domain, &a); }
+}
+static inline void b200_nvtx_pop(void)
+{
+    if( parsec_b200_nvtx ) (void)nvtxDomainRangePop(b200_nvtx_domain);
+}
+static inline void b200_nvtx_mark(const char *name)
+{
+    if( parsec_b200_nvtx ) { nvtxEventAttributes_t a; b200_nvtx_attr(&a, name); nvtxDomainMarkEx(b200_nvtx_domain, &a); }
+}
+
 /* ------------------------------------------------------------------------------------------------------------------ */
 /* types                                                                                                                */
 /* ------------------------------------------------------------------------------------------------------------------ */
@@ -901,6 +924,7 @@ static parsec_hook_return_t b200_epilog_hook(parsec_execution_stream_t *es, pars
     b200_task_t *bt = (b200_task_t*)((char*)task - offsetof(b200_task_t, proxy));
     parsec_device_b200_module_t *dev = bt->dev;
     int64_t n = 0;
+    b200_nvtx_push("b200 epilog batch");
     /* one proxy completes a short chain of finished tasks (B200_EPILOG_BATCH): scheduling a task costs the manager about
      * as much as everything else it does for one */
     while( NULL != bt ) {
@@ -920,6 +944,7 @@ static parsec_hook_return_t b200_epilog_hook(parsec_execution_stream_t *es, pars
     if( dev->nb_stalled > 0 && !dev->retry_stalled ) dev->retry_stalled = 1;   /* the readers just dropped may be what a waiting task needs evicted */
     parsec_atomic_wmb();
     (void)parsec_atomic_fetch_add_int64(&dev->epilogs_done, n);
+    b200_nvtx_pop();
     return PARSEC_HOOK_RETURN_ASYNC;
 }
 
@@ -1426,6 +1451,7 @@ static int b200_hand_back(parsec_device_b200_module_t *dev, parsec_execution_str
     task->selected_device = &peer->super.super.super;                 /* ... to the device it keeps (device.c: "a-priori selected_device") */
     (void)parsec_atomic_fetch_add_int32(&dev->handed_back, 1);      /* the manager takes it off `owed` */
     dev->st.forwarded++;
+    b200_nvtx_mark("b200 task handed back to the runtime for a peer device");
     PARSEC_LIST_ITEM_SINGLETON(&task->super);
     (void)__parsec_reschedule(es, task);
     return 1;
@@ -1679,6 +1705,7 @@ static int b200_retire_pass(parsec_device_b200_module_t *dev, parsec_execution_s
         if( n < 0 ) { parsec_warning("device_b200: %s", pb2_stream_last_error(dev->stream)); return -1; }
         t1 = B200_TSC(); dev->tsc[n ? 3 : 5] += t1 - t0; t0 = t1;
         dev->complete_inline = (1 == n) && (0 == pb2_stream_inflight(dev->stream)) && (dev->inbox_tail == dev->inbox_head);
+        if( n > 0 ) b200_nvtx_push("b200 retire pass");
         for( int i = 0; i < n; i++ ) {
             b200_task_t *bt = (b200_task_t*)(uintptr_t)dev->retbuf[i].cookie;
             if( i + 5 < n ) { const char *la = (const char*)(uintptr_t)dev->retbuf[i + 5].cookie; B200_PFW(la); B200_PFW(la + 64); B200_PFW(la + offsetof(b200_task_t, proxy)); }
@@ -1697,6 +1724,7 @@ static int b200_retire_pass(parsec_device_b200_module_t *dev, parsec_execution_s
                 parsec_list_nolock_push_back(&dev->waiting_out, &bt->item);
             } else b200_finish(dev, es, bt);
         }
+        if( n > 0 ) b200_nvtx_pop();
         t1 = B200_TSC(); dev->tsc[4] += t1 - t0; t0 = t1;
         if( n < (int)(sizeof(dev->retbuf) / sizeof(dev->retbuf[0])) ) break;
     }
@@ -1719,7 +1747,7 @@ static int b200_try_start(parsec_device_b200_module_t *dev, parsec_execution_str
     for(;;) {
         if( dev->starter_active || !parsec_atomic_cas_int32(&dev->starter_active, 0, 1) ) return 0;
         int rc;
-        do { rc = b200_start_pass(dev, es); } while( rc > 0 && sticky );
+        do { b200_nvtx_push("b200 start pass"); rc = b200_start_pass(dev, es); b200_nvtx_pop(); } while( rc > 0 && sticky );
         if( rc < 0 ) dev->fatal = 1;
         parsec_atomic_wmb();
         dev->starter_active = 0;
@@ -1805,6 +1833,7 @@ b200_kernel_scheduler(parsec_device_module_t *module, parsec_execution_stream_t 
 
     /* 2. this thread is the manager until nothing is owed any more */
     dev->st.manager_entries++;
+    b200_nvtx_mark("b200 manager elected");
     if( 0 == dev->first_task_ns ) dev->first_task_ns = b200_now_ns();
     if( NULL == es ) {
         /* data_advise comes without an execution stream and owes no runtime completion: it cannot complete other
@@ -2118,6 +2147,7 @@ int parsec_b200_module_init(int dev_id, parsec_device_module_t **module)
     sp.dry_run = dev->dry_run;
     sp.max_workers = parsec_b200_max_workers;
     sp.trace = (NULL != parsec_b200_trace && '\0' != parsec_b200_trace[0]);
+    if( parsec_b200_nvtx && NULL == b200_nvtx_domain ) b200_nvtx_domain = nvtxDomainCreateA("parsec_b200");
     if( PB2_SUCCESS != pb2_stream_create(dev->engine, &sp, &dev->stream) ) goto failed;
     *module = device;
     return PARSEC_SUCCESS;

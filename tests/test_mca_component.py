@@ -65,6 +65,29 @@ def test_component_dry_run_memory_pressure_evicts_and_writes_back():
     assert d["b200"]["w2r_copies"] > 0
 
 
+def test_component_dry_run_nvtx_ranges(tmp_path):
+    """device_b200_nvtx: the host side of the device as NVTX ranges of the domain "parsec_b200".  nsys is not in the image:
+    tests/c/nvtx_counter.c is a minimal NVTX injection library (what a profiler is to the application) that counts them."""
+    lib = tmp_path / "libnvtx_counter.so"
+    subprocess.run(["gcc", "-shared", "-fPIC", "-O2", "-I/usr/local/cuda/include", "-o", str(lib),
+                    os.path.join(ROOT, "tests", "c", "nvtx_counter.c"), "-lpthread"], check=True)
+    K = 128
+    out = tmp_path / "nvtx.json"
+    env = {"PARSEC_MCA_device_b200_dry_run": "1", "NVTX_INJECTION64_PATH": str(lib), "PB2_NVTX_COUNT_FILE": str(out)}
+    rc, d, err = run("ex05_b200", ["-K", K, "-t", 1024, "-m", "gpu", "-c", 8], env)            # off by default: no NVTX call at all
+    assert d["executed_on_gpu"] == K * 9 and not out.exists(), err[-500:]
+    rc, d, err = run("ex05_b200", ["-K", K, "-t", 1024, "-m", "gpu", "-c", 8], dict(env, PARSEC_MCA_device_b200_nvtx="1"))
+    assert d["executed_on_gpu"] == K * 9, err[-500:]
+    j = json.loads(out.read_text())
+    ev = j["events"]
+    assert j["domain"] == "parsec_b200" and j["unbalanced_pops"] == 0
+    assert j["pops"] == sum(e["pushes"] for e in ev.values())
+    assert ev["b200 manager elected"]["marks"] >= 1
+    assert ev["b200 start pass"]["pushes"] >= 1 and ev["b200 retire pass"]["pushes"] >= 1
+    # a task is completed by an epilog batch of up to four (B200_EPILOG_BATCH) on the worker pool, or in line by the manager
+    assert 1 <= ev["b200 epilog batch"]["pushes"] <= K * 9
+
+
 @pytest.mark.parametrize("ndev", [1, 2])
 def test_component_dry_run_several_taskpools_at_once(ndev):
     """Three task pools, each on a collection of its own, handed to the context together: the module sees their tasks
