@@ -65,6 +65,20 @@ def test_component_dry_run_memory_pressure_evicts_and_writes_back():
     assert d["b200"]["w2r_copies"] > 0
 
 
+@pytest.mark.parametrize("knobs", [
+    {"parallel_completion": 0},                         # the manager completes every task in line (device_gpu.c:3562-3590)
+    {"cmd_slots": 1024},                                # the command ring fills: staged tasks wait for retirements
+    {"stage_window": 1},                                # every cold task waits for the one before it
+    {"cmd_slots": 1024, "stage_window": 4096, "parallel_completion": 0, "memory_number_of_blocks": 64},
+])
+def test_component_dry_run_mca_knobs(knobs):
+    K, rep = 512, 2
+    env = {"PARSEC_MCA_device_b200_dry_run": "1"}
+    env.update({"PARSEC_MCA_device_b200_" + k: str(v) for k, v in knobs.items()})
+    rc, d, err = run("ex05_b200", ["-K", K, "-t", 131072, "-m", "gpu", "-c", 8, "-r", rep], env, timeout=120)
+    assert d["executed_on_gpu"] == K * 9 * rep, err[-500:]
+
+
 def test_component_dry_run_nvtx_ranges(tmp_path):
     """device_b200_nvtx: the host side of the device as NVTX ranges of the domain "parsec_b200".  nsys is not in the image:
     tests/c/nvtx_counter.c is a minimal NVTX injection library (what a profiler is to the application) that counts them."""
