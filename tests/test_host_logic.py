@@ -295,6 +295,18 @@ def test_select_best_device_load_balance_matches_oracle():
         assert sorted(dev.tolist()) == sorted(chosen)
 
 
+def test_tiles_of_4_gib_or_more_are_refused_not_truncated():
+    """pb2_tile_t::bytes is 32 bits: a datum whose span does not fit makes the window builder fail loudly instead of
+    describing a truncated tile to the device."""
+    with R.Context(cuda_devices=(0,), dry_run=True,
+                   mca={"device_cuda_memory_number_of_blocks": 16, "device_cuda_memory_block_size": 1 << 30}) as ctx:
+        dc = ctx.block_cyclic(4, 1 << 30, 1, 1 << 30, 1)              # one tile of exactly 4 GiB
+        C.c_void_p(ctx.l.pb2_ptg_ex05_broadcast_new(ctx.h, dc, 1, 4))
+        with pytest.raises(L.Pb2Error) as ei:
+            ctx.wait()
+        assert ei.value.rc == L.PB2_ERR_VALUE_OUT_OF_BOUNDS
+
+
 def test_cpu_only_chain_is_config1():
     """BASELINE config 1: Ex02_Chain, 1000 tasks, CPU-only: task k sees k, final value 999."""
     with R.Context(cuda_devices=(), dry_run=True) as ctx:
